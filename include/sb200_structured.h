@@ -1,0 +1,169 @@
+/*
+ * strumpack_b200 -- C ABI of the B200-native HSS/BLR engine.
+ *
+ * Drop-in boundary: the SP_d_struct_* entry points below have
+ * exactly the names, argument meaning, ownership and error behaviour of the
+ * reference's C interface in
+ *     reference src/structured/StructuredMatrix.h:46-85 (types),
+ *     :118-607 (functions), glue src/structured/StructuredMatrixC.cpp:39-119
+ * so a program written against StructuredMatrix.h links against
+ * libstrumpack_b200.so unchanged.  All pointers passed to SP_* functions are
+ * HOST pointers (reference doc/doxygen/pages/GPU_support.txt:24-26), matrices
+ * are column-major with a leading dimension, `solve` overwrites B in place,
+ * every function returns 0 on success and 1 after printing
+ * "Operation failed: <what>" (StructuredMatrixC.cpp:107-119).
+ *
+ * The SB200_* entry points are engine extensions (device-resident operands,
+ * generator import, statistics); they never change the meaning of SP_*.
+ *
+ * There is no CPU fallback behind this interface: every function that does
+ * arithmetic launches sm_100a kernels and fails (return 1) without a GPU.
+ */
+#ifndef SB200_STRUCTURED_C_H
+#define SB200_STRUCTURED_C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference StructuredMatrix.h:46-55 */
+typedef enum {
+  SP_TYPE_HSS = 0,
+  SP_TYPE_BLR,
+  SP_TYPE_HODLR,
+  SP_TYPE_HODBF,
+  SP_TYPE_BUTTERFLY,
+  SP_TYPE_LR,
+  SP_TYPE_LOSSY,
+  SP_TYPE_LOSSLESS
+} SP_STRUCTURED_TYPE;
+
+/* reference StructuredMatrix.h:68-75 */
+typedef struct CSPOptions {
+  SP_STRUCTURED_TYPE type;
+  double rel_tol;
+  double abs_tol;
+  int leaf_size;
+  int max_rank;
+  int verbose;
+} CSPOptions;
+
+/* reference StructuredMatrix.h:85 */
+typedef void* CSPStructMat;
+
+/* ---- reference interface, double precision ------------------------------ */
+/* StructuredMatrix.h:118  (defaults of StructuredOptions.hpp:106-162:
+ * type BLR, rel_tol 1e-4, abs_tol 1e-10, leaf 128, max_rank 5000) */
+void SP_d_struct_default_options(CSPOptions* opts);
+/* StructuredMatrix.h:131 */
+void SP_d_struct_destroy(CSPStructMat* S);
+/* StructuredMatrix.h:143,153,164,175,186 */
+int SP_d_struct_rows(const CSPStructMat S);
+int SP_d_struct_cols(const CSPStructMat S);
+long long int SP_d_struct_memory(const CSPStructMat S);
+long long int SP_d_struct_nonzeros(const CSPStructMat S);
+int SP_d_struct_rank(const CSPStructMat S);
+/* StructuredMatrix.h:210  -- compress a host column-major dense matrix.
+ * Supported types: SP_TYPE_HSS, SP_TYPE_BLR (others: return 1, like the
+ * reference built without the optional back ends). */
+int SP_d_struct_from_dense(CSPStructMat* S, int rows, int cols,
+                           const double* A, int ldA, const CSPOptions* opts);
+/* StructuredMatrix.h:244  -- compress from an element callback. The callback
+ * runs on the host; the engine samples it into device buffers. */
+int SP_d_struct_from_elements(CSPStructMat* S, int rows, int cols,
+                              double A(int i, int j), const CSPOptions* opts);
+/* StructuredMatrix.h:292  C = op(S) * B, trans in {N,n,T,t,C,c}; m = columns
+ * of B and C. */
+int SP_d_struct_mult(const CSPStructMat S, char trans, int m,
+                     const double* B, int ldB, double* C, int ldC);
+/* StructuredMatrix.h:340 */
+int SP_d_struct_factor(CSPStructMat S);
+/* StructuredMatrix.h:360  B <- S^{-1} B */
+int SP_d_struct_solve(const CSPStructMat S, int nrhs, double* B, int ldB);
+/* StructuredMatrix.h:395  S <- S + s*I (invalidates the factorization) */
+int SP_d_struct_shift(CSPStructMat S, double s);
+
+/* ---- engine extensions --------------------------------------------------- */
+
+/* Kernel-matrix types for SB200_d_hss_from_kernel
+ * (reference src/kernel/Kernel.hpp:333-357 GaussKernel, :370-396 Laplace). */
+typedef enum {
+  SB200_KERNEL_GAUSS = 0,    /* exp(-|x-y|_2^2 / (2 h^2)) + lambda [i==j] */
+  SB200_KERNEL_LAPLACE = 1,  /* exp(-|x-y|_1 / h)         + lambda [i==j] */
+  SB200_KERNEL_TOEPLITZ_INVDIST = 2 /* 1/(1+|i-j|), d=1, pts ignored:
+                                       test/test_HSS_seq.cpp:69-79 */
+} SB200_KERNEL_TYPE;
+
+/* Mirrors HSSMatrix(kernel::Kernel&, opts), reference HSSMatrix.cpp:88-106:
+ * clusters the n points (d x n, column-major, one point per column), reorders
+ * them IN PLACE into the cluster ordering, writes the 0-based permutation to
+ * perm (may be NULL; perm[new] = old) and compresses on the GPU.  All later
+ * mult/solve calls act in the permuted ordering, as in the reference. */
+int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
+                            int kernel_type, double h, double lambda,
+                            const CSPOptions* opts, int* perm);
+
+/* Reads a reference HSS dump (HSSMatrix<double>::write, reference
+ * HSSMatrix.cpp:438-486) and uploads its generators. */
+int SB200_d_hss_read(CSPStructMat* S, const char* path);
+/* Writes the generators in that same format (HSSMatrix.cpp:474-480). */
+int SB200_d_hss_write(const CSPStructMat S, const char* path);
+
+/* Import generators from flat host arrays (pre-order node numbering, root=0).
+ * node_tab: n_nodes x SB200_NODE_FIELDS int64, see sb200 DESIGN.md section 3:
+ *   [0] parent [1] child0 [2] child1 [3] rows [4] cols
+ *   [5] U_rows [6] U_rank [7] V_rows [8] V_rank
+ *   [9] off_D [10] off_Eu [11] off_Ev [12] off_B01 [13] off_B10  (into vals,
+ *        column-major blocks, -1 when absent)
+ *   [14] off_Pu [15] off_Pv   (into perms; 0-based GATHER index of length
+ *        U_rows / V_rows such that (P^T b)[i] = b[perm[i]])
+ */
+#define SB200_NODE_FIELDS 16
+int SB200_d_hss_from_generators(CSPStructMat* S, int n_nodes,
+                                const int64_t* node_tab, const double* vals,
+                                int64_t n_vals, const int32_t* perms,
+                                int64_t n_perms);
+
+/* Device-resident operands: dB/dC are DEVICE pointers, work is queued on
+ * `stream` (a cudaStream_t, 0 = legacy default stream) and NOT synchronised. */
+int SB200_d_struct_mult_device(const CSPStructMat S, char trans, int m,
+                               const double* dB, int ldB, double* dC, int ldC,
+                               void* stream);
+int SB200_d_struct_factor_device(CSPStructMat S, void* stream);
+int SB200_d_struct_solve_device(const CSPStructMat S, int nrhs, double* dB,
+                                int ldB, void* stream);
+
+/* Statistics (HSSMatrix::levels, factor_nonzeros; reference
+ * HSSMatrix.cpp:326-332, HSSMatrixBase.cpp:74). */
+int SB200_d_struct_levels(const CSPStructMat S);
+long long int SB200_d_struct_factor_nonzeros(const CSPStructMat S);
+/* Algorithmic flop counts in the reference's own accounting:
+ * which = 0: apply with 1 rhs (2*nnz terms of HSSMatrix.apply.hpp),
+ *         1: ULV factor  (params::ULV_factor_flops formula, factor.hpp:78-141)
+ *         2: ULV solve, 1 rhs (params::hss_solve_flops, solve.hpp:94-223)
+ *         3: flops the engine actually executes in factor (no explicit Q) */
+long long int SB200_d_struct_flops(const CSPStructMat S, int which);
+/* Number of kernels launched by this object since creation. */
+long long int SB200_d_struct_launches(const CSPStructMat S);
+/* H.print_info() equivalent to stdout (HSSMatrix.cpp:333-356). */
+int SB200_d_struct_print_info(const CSPStructMat S);
+/* Dense reconstruction into a host buffer (HSSMatrix::dense). */
+int SB200_d_struct_dense(const CSPStructMat S, double* A, int ldA);
+
+/* Host-only helpers (no GPU needed): parse a reference HSS dump and report
+ * out[0..9] = rows, cols, n_nodes, levels, max rank, nonzeros (reference
+ * accounting), apply flops, ULV factor flops, ULV solve flops (1 rhs; both in
+ * the reference's accounting), flops the engine executes in factor. */
+int SB200_d_hss_file_info(const char* path, long long int* out);
+/* Read a reference HSS dump and write it back (round trip of the format). */
+int SB200_d_hss_file_copy(const char* in_path, const char* out_path);
+
+/* Library identification: returns "strumpack_b200 <ver> sm_100a". */
+const char* SB200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

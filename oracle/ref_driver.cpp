@@ -1,0 +1,222 @@
+/*
+ * ORACLE / TEST INFRASTRUCTURE ONLY -- never linked into the product.
+ *
+ * Thin C-ABI driver around the UNMODIFIED reference classes, compiled from
+ * the sources where they lie under /root/reference (see oracle/Makefile).
+ * It lets tests/ and bench.py's cpu_baseline / --impl reference legs
+ *   - build an HSS matrix with the reference's own compression
+ *     (HSSMatrix(A,opts)            reference src/HSS/HSSMatrix.cpp:49-54,
+ *      HSSMatrix(Kernel&,opts)      reference src/HSS/HSSMatrix.cpp:88-106),
+ *   - dump it with the reference's own HSSMatrix::write
+ *                                   (reference src/HSS/HSSMatrix.cpp:438-486),
+ *   - run mult / factor / solve     (reference src/HSS/HSSMatrix.apply.hpp:34,
+ *                                    .factor.hpp:35, .solve.hpp:35),
+ *   - read the reference's flop counters (src/StrumpackParameters.hpp:85-98),
+ *   - run BLR compress_and_factor + solve (src/BLR/BLRMatrix.cpp:113, .hpp:118).
+ * Nothing here restates an algorithm: every numeric result comes from the
+ * reference code itself.
+ */
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+#include "HSS/HSSMatrix.hpp"
+#include "BLR/BLRMatrix.hpp"
+#include "kernel/Kernel.hpp"
+#include "structured/ClusterTree.hpp"
+#include "StrumpackParameters.hpp"
+
+using namespace strumpack;
+using HSS::HSSMatrix;
+using HSS::HSSOptions;
+using DenseD = DenseMatrix<double>;
+using DenseW = DenseMatrixWrapper<double>;
+
+namespace {
+  struct HSSHandle {
+    std::unique_ptr<HSSMatrix<double>> H;
+  };
+  struct BLRHandle {
+    std::unique_ptr<BLR::BLRMatrix<double>> B;
+    int n = 0;
+  };
+
+  // "--hss_leaf_size 128 --hss_rel_tol 1e-4" -> argc/argv for the reference's
+  // own getopt parser (HSSOptions.cpp:67-240)
+  template<typename Opts> void parse(Opts& o, const char* args) {
+    std::vector<std::string> tok{"oracle"};
+    std::istringstream is(args ? args : "");
+    for (std::string t; is >> t;) tok.push_back(t);
+    std::vector<char*> argv;
+    for (auto& t : tok) argv.push_back(const_cast<char*>(t.c_str()));
+    argv.push_back(nullptr);
+    o.set_from_command_line(int(tok.size()), argv.data());
+  }
+}
+
+extern "C" {
+
+  void ref_set_num_threads(int t) { omp_set_num_threads(t); }
+  int ref_get_max_threads() { return omp_get_max_threads(); }
+
+  void ref_flops_reset() {
+    params::flops = 0;
+    params::ULV_factor_flops = 0;
+    params::hss_solve_flops = 0;
+  }
+  long long ref_flops_total() { return params::flops.load(); }
+  long long ref_flops_ulv_factor() { return params::ULV_factor_flops.load(); }
+  long long ref_flops_hss_solve() { return params::hss_solve_flops.load(); }
+
+  /* kind: 'T' Toeplitz A(i,j)=1/(1+|i-j|), diag 1 (test_HSS_seq.cpp:69-79)
+   *       'U' upper triangular Toeplitz            (test_HSS_seq.cpp:80-91) */
+  void* ref_hss_toeplitz(int n, int kind, const char* hss_args) {
+    DenseD A(n, n);
+    for (int j=0; j<n; j++)
+      for (int i=0; i<n; i++) {
+        double v = (i==j) ? 1. : 1./(1+std::abs(i-j));
+        if (kind == 'U' && i > j) v = 0.;
+        A(i, j) = v;
+      }
+    HSSOptions<double> opts;
+    opts.set_verbose(false);
+    parse(opts, hss_args);
+    auto h = new HSSHandle;
+    h->H.reset(new HSSMatrix<double>(A, opts));
+    return h;
+  }
+
+  void* ref_hss_dense(int m, int n, const double* A, int lda,
+                      const char* hss_args) {
+    DenseD Ad(m, n, A, lda);
+    HSSOptions<double> opts;
+    opts.set_verbose(false);
+    parse(opts, hss_args);
+    auto h = new HSSHandle;
+    h->H.reset(new HSSMatrix<double>(Ad, opts));
+    return h;
+  }
+
+  /* Gaussian kernel exp(-|x-y|^2/(2h^2)) + lambda*I on n points of dimension
+   * d (pts: d x n column-major, PERMUTED IN PLACE by the clustering,
+   * HSSMatrix.cpp:93-95). perm1 (length n) receives the reference's 1-based
+   * permutation vector (Kernel::permutation()). */
+  void* ref_hss_gauss(int n, int d, double* pts, double h, double lambda,
+                      const char* hss_args, int* perm1) {
+    DenseW data(d, n, pts, d);
+    kernel::GaussKernel<double> K(data, h, lambda);
+    HSSOptions<double> opts;
+    opts.set_verbose(false);
+    parse(opts, hss_args);
+    auto hd = new HSSHandle;
+    hd->H.reset(new HSSMatrix<double>(K, opts));
+    if (perm1)
+      for (int i=0; i<n; i++) perm1[i] = K.permutation()[i];
+    return hd;
+  }
+
+  void* ref_hss_read(const char* path) {
+    auto h = new HSSHandle;
+    h->H.reset(new HSSMatrix<double>(HSSMatrix<double>::read(path)));
+    return h;
+  }
+
+  int ref_hss_write(void* hv, const char* path) {
+    static_cast<HSSHandle*>(hv)->H->write(std::string(path));
+    return 0;
+  }
+
+  /* out[0..7] = rows, cols, rank, levels, nonzeros, factor_nonzeros, memory,
+   *             is_compressed */
+  void ref_hss_info(void* hv, long long* out) {
+    auto& H = *static_cast<HSSHandle*>(hv)->H;
+    out[0] = H.rows(); out[1] = H.cols(); out[2] = H.rank();
+    out[3] = H.levels(); out[4] = H.nonzeros();
+    out[5] = H.factor_nonzeros(); out[6] = H.memory();
+    out[7] = H.is_compressed();
+  }
+
+  void ref_hss_print_info(void* hv) {
+    static_cast<HSSHandle*>(hv)->H->print_info();
+  }
+
+  /* y = op(H) x ; trans: 0 = N, 1 = C */
+  void ref_hss_mult(void* hv, int trans, int s, const double* x, int ldx,
+                    double* y, int ldy) {
+    auto& H = *static_cast<HSSHandle*>(hv)->H;
+    int nx = trans ? H.rows() : H.cols(), ny = trans ? H.cols() : H.rows();
+    DenseW X(nx, s, const_cast<double*>(x), ldx), Y(ny, s, y, ldy);
+    H.mult(trans ? Trans::C : Trans::N, X, Y);
+  }
+
+  void ref_hss_factor(void* hv) { static_cast<HSSHandle*>(hv)->H->factor(); }
+
+  void ref_hss_solve(void* hv, int s, double* b, int ldb) {
+    auto& H = *static_cast<HSSHandle*>(hv)->H;
+    DenseW B(H.rows(), s, b, ldb);
+    H.solve(B);
+  }
+
+  void ref_hss_shift(void* hv, double sigma) {
+    static_cast<HSSHandle*>(hv)->H->shift(sigma);
+  }
+
+  void ref_hss_dense_out(void* hv, double* A, int lda) {
+    auto& H = *static_cast<HSSHandle*>(hv)->H;
+    auto D = H.dense();
+    for (std::size_t j=0; j<D.cols(); j++)
+      std::memcpy(A + j*std::size_t(lda), D.ptr(0, j), sizeof(double)*D.rows());
+  }
+
+  double ref_hss_get(void* hv, int i, int j) {
+    return static_cast<HSSHandle*>(hv)->H->get(i, j);
+  }
+
+  void ref_hss_destroy(void* hv) { delete static_cast<HSSHandle*>(hv); }
+
+  /* ---- BLR: compress_and_factor on a dense matrix, weak admissibility,
+   *      tiles from ClusterTree(n).refine(leaf)   (test_BLR_seq.cpp:136-156) */
+  void* ref_blr_factor_dense(int n, const double* A, int lda,
+                             const char* blr_args, int* ntiles_out,
+                             int* tiles_out /* may be null; >= n entries */) {
+    DenseD Ad(n, n, A, lda);
+    BLR::BLROptions<double> opts;
+    opts.set_verbose(false);
+    parse(opts, blr_args);
+    structured::ClusterTree tree(n);
+    tree.refine(opts.leaf_size());
+    auto tiles = tree.template leaf_sizes<std::size_t>();
+    int nt = tiles.size();
+    DenseMatrix<bool> adm(nt, nt);
+    adm.fill(true);
+    for (int t=0; t<nt; t++) adm(t, t) = false;
+    auto h = new BLRHandle;
+    h->n = n;
+    h->B.reset(new BLR::BLRMatrix<double>(n, tiles, n, tiles));
+    h->B->compress_and_factor(Ad, adm, opts);
+    if (ntiles_out) *ntiles_out = nt;
+    if (tiles_out) for (int t=0; t<nt; t++) tiles_out[t] = int(tiles[t]);
+    return h;
+  }
+
+  void ref_blr_solve(void* hv, int s, double* b, int ldb) {
+    auto* h = static_cast<BLRHandle*>(hv);
+    DenseW B(h->n, s, b, ldb);
+    h->B->solve(B);
+  }
+
+  /* out[0..3] = rows, cols, rank, nonzeros */
+  void ref_blr_info(void* hv, long long* out) {
+    auto* h = static_cast<BLRHandle*>(hv);
+    out[0] = h->B->rows(); out[1] = h->B->cols();
+    out[2] = h->B->rank(); out[3] = h->B->nonzeros();
+  }
+
+  void ref_blr_destroy(void* hv) { delete static_cast<BLRHandle*>(hv); }
+}

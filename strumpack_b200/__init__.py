@@ -1,0 +1,349 @@
+"""strumpack_b200 -- host-side Python mirror of the engine's C ABI.
+
+The product is ``libstrumpack_b200.so`` (C ABI in ``include/sb200_structured.h``,
+the drop-in for the reference's ``src/structured/StructuredMatrix.h``).  This
+module is a thin ctypes view of it whose names follow the reference's
+``structured::StructuredMatrix`` / ``HSS::HSSMatrix`` interface
+(reference src/structured/StructuredMatrix.hpp:209-418,
+src/HSS/HSSMatrix.hpp:95-511): ``rows, cols, rank, memory, nonzeros, levels,
+mult, factor, solve, shift``.
+
+There is no CPU fallback: if the shared library is missing, or no GPU is
+visible when a compute entry point is called, the call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libstrumpack_b200.so")
+_lib = None
+
+SP_TYPE_HSS, SP_TYPE_BLR = 0, 1
+KERNEL_GAUSS, KERNEL_LAPLACE, KERNEL_TOEPLITZ_INVDIST = 0, 1, 2
+NODE_FIELDS = 16
+
+
+class CSPOptions(C.Structure):
+    """reference StructuredMatrix.h:68-75"""
+    _fields_ = [("type", C.c_int), ("rel_tol", C.c_double),
+                ("abs_tol", C.c_double), ("leaf_size", C.c_int),
+                ("max_rank", C.c_int), ("verbose", C.c_int)]
+
+
+# every symbol include/sb200_structured.h declares: name -> (restype, argtypes)
+_vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+_pvp = C.POINTER(C.c_void_p)
+_po = C.POINTER(CSPOptions)
+SYMBOLS = {
+    "SB200_version": (C.c_char_p, []),
+    "SP_d_struct_default_options": (None, [_po]),
+    "SP_d_struct_destroy": (None, [_pvp]),
+    "SP_d_struct_rows": (_i, [_vp]),
+    "SP_d_struct_cols": (_i, [_vp]),
+    "SP_d_struct_memory": (_ll, [_vp]),
+    "SP_d_struct_nonzeros": (_ll, [_vp]),
+    "SP_d_struct_rank": (_i, [_vp]),
+    "SP_d_struct_from_dense": (_i, [_pvp, _i, _i, _vp, _i, _po]),
+    "SP_d_struct_from_elements": (_i, [_pvp, _i, _i, _vp, _po]),
+    "SP_d_struct_mult": (_i, [_vp, C.c_char, _i, _vp, _i, _vp, _i]),
+    "SP_d_struct_factor": (_i, [_vp]),
+    "SP_d_struct_solve": (_i, [_vp, _i, _vp, _i]),
+    "SP_d_struct_shift": (_i, [_vp, _d]),
+    "SB200_d_hss_from_kernel": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp]),
+    "SB200_d_hss_read": (_i, [_pvp, C.c_char_p]),
+    "SB200_d_hss_write": (_i, [_vp, C.c_char_p]),
+    "SB200_d_hss_from_generators": (_i, [_pvp, _i, _vp, _vp, C.c_int64, _vp,
+                                        C.c_int64]),
+    "SB200_d_struct_mult_device": (_i, [_vp, C.c_char, _i, _vp, _i, _vp, _i, _vp]),
+    "SB200_d_struct_factor_device": (_i, [_vp, _vp]),
+    "SB200_d_struct_solve_device": (_i, [_vp, _i, _vp, _i, _vp]),
+    "SB200_d_hss_file_info": (_i, [C.c_char_p, _vp]),
+    "SB200_d_hss_file_copy": (_i, [C.c_char_p, C.c_char_p]),
+    "SB200_d_struct_levels": (_i, [_vp]),
+    "SB200_d_struct_factor_nonzeros": (_ll, [_vp]),
+    "SB200_d_struct_flops": (_ll, [_vp, _i]),
+    "SB200_d_struct_launches": (_ll, [_vp]),
+    "SB200_d_struct_print_info": (_i, [_vp]),
+    "SB200_d_struct_dense": (_i, [_vp, _vp, _i]),
+}
+
+
+def lib():
+    """dlopen the engine; raise (never fall back) if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise RuntimeError(
+                f"{_SO} not built: run `python __graft_entry__.py` "
+                "(strumpack_b200 has no CPU fallback)")
+        L = C.CDLL(_SO)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)      # AttributeError if a symbol is missing
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def default_options(type=SP_TYPE_HSS, **kw):
+    o = CSPOptions()
+    lib().SP_d_struct_default_options(C.byref(o))
+    o.type = type
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"strumpack_b200: {what} failed (see stderr)")
+
+
+def _fortran(a):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    return np.asfortranarray(a)
+
+
+def pack_generators(nodes):
+    """Pack a pre-order list of node records (attributes: parent, ch (list of
+    child indices), rows, cols, U_rows, U_rank, V_rows, V_rank, Pu/Pv (LAPACK
+    ipiv, 1-based), Eu, Ev, D, B01, B10) into the flat arrays of
+    ``SB200_d_hss_from_generators``."""
+    tab = np.full((len(nodes), NODE_FIELDS), -1, dtype=np.int64)
+    vals, perms = [], []
+    nv = npm = 0
+
+    def put(a):
+        nonlocal nv
+        a = np.asarray(a, dtype=np.float64)
+        if a.size == 0:
+            return -1
+        off = nv
+        vals.append(np.asfortranarray(a).ravel(order="F"))
+        nv += a.size
+        return off
+
+    def putp(ipiv):
+        nonlocal npm
+        ipiv = np.asarray(ipiv)
+        if ipiv.size == 0:
+            return -1
+        g = np.arange(ipiv.size, dtype=np.int32)
+        for i, p in enumerate(ipiv):
+            p = int(p) - 1
+            if p != i:
+                g[i], g[p] = g[p], g[i]
+        off = npm
+        perms.append(g)
+        npm += g.size
+        return off
+
+    for i, n in enumerate(nodes):
+        t = tab[i]
+        t[0] = n.parent
+        t[1], t[2] = (n.ch[0], n.ch[1]) if n.ch else (-1, -1)
+        t[3], t[4] = n.rows, n.cols
+        has_u, has_v = len(n.Pu) > 0, len(n.Pv) > 0
+        t[5], t[6] = (len(n.Pu), n.Eu.shape[1]) if has_u else (0, 0)
+        t[7], t[8] = (len(n.Pv), n.Ev.shape[1]) if has_v else (0, 0)
+        t[9] = put(n.D)
+        t[10], t[11] = put(n.Eu), put(n.Ev)
+        t[12], t[13] = put(n.B01), put(n.B10)
+        t[14], t[15] = putp(n.Pu), putp(n.Pv)
+    v = np.concatenate(vals) if vals else np.zeros(0)
+    p = np.concatenate(perms) if perms else np.zeros(0, dtype=np.int32)
+    return tab, v, p
+
+
+def hss_file_info(path):
+    """Host-only: statistics and flop counts of a reference HSS dump."""
+    out = np.zeros(10, dtype=np.int64)
+    _check(lib().SB200_d_hss_file_info(str(path).encode(), out.ctypes.data),
+           "hss_file_info")
+    keys = ("rows", "cols", "nodes", "levels", "rank", "nonzeros",
+            "apply_flops", "factor_flops", "solve_flops", "factor_flops_exec")
+    return dict(zip(keys, (int(v) for v in out)))
+
+
+def hss_file_copy(src, dst):
+    _check(lib().SB200_d_hss_file_copy(str(src).encode(), str(dst).encode()),
+           "hss_file_copy")
+
+
+class StructuredMatrix:
+    """Mirror of ``structured::StructuredMatrix<double>``
+    (reference src/structured/StructuredMatrix.hpp:209-418)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    # -- factories (reference StructuredMatrix.cpp:53-127, 193-312) ---------
+    @classmethod
+    def from_dense(cls, A, opts=None):
+        A = _fortran(A)
+        opts = opts or default_options()
+        h = C.c_void_p()
+        _check(lib().SP_d_struct_from_dense(
+            C.byref(h), A.shape[0], A.shape[1], A.ctypes.data, A.shape[0],
+            C.byref(opts)), "construct_from_dense")
+        return cls(h.value)
+
+    @classmethod
+    def from_elements(cls, rows, cols, fn, opts=None):
+        opts = opts or default_options()
+        cb = C.CFUNCTYPE(C.c_double, C.c_int, C.c_int)(fn)
+        h = C.c_void_p()
+        _check(lib().SP_d_struct_from_elements(
+            C.byref(h), rows, cols, C.cast(cb, C.c_void_p), C.byref(opts)),
+            "construct_from_elements")
+        return cls(h.value)
+
+    # -- queries --------------------------------------------------------------
+    @property
+    def rows(self):
+        return lib().SP_d_struct_rows(self._h)
+
+    @property
+    def cols(self):
+        return lib().SP_d_struct_cols(self._h)
+
+    @property
+    def rank(self):
+        return lib().SP_d_struct_rank(self._h)
+
+    @property
+    def memory(self):
+        return lib().SP_d_struct_memory(self._h)
+
+    @property
+    def nonzeros(self):
+        return lib().SP_d_struct_nonzeros(self._h)
+
+    @property
+    def levels(self):
+        return lib().SB200_d_struct_levels(self._h)
+
+    @property
+    def factor_nonzeros(self):
+        return lib().SB200_d_struct_factor_nonzeros(self._h)
+
+    @property
+    def launches(self):
+        return lib().SB200_d_struct_launches(self._h)
+
+    def flops(self, which):
+        """'apply' | 'factor' | 'solve' (reference accounting) | 'factor_exec'"""
+        k = {"apply": 0, "factor": 1, "solve": 2, "factor_exec": 3}[which]
+        return lib().SB200_d_struct_flops(self._h, k)
+
+    def print_info(self):
+        _check(lib().SB200_d_struct_print_info(self._h), "print_info")
+
+    def dense(self):
+        A = np.zeros((self.rows, self.cols), order="F")
+        _check(lib().SB200_d_struct_dense(self._h, A.ctypes.data, A.shape[0]),
+               "dense")
+        return A
+
+    # -- the hot path, host operands (the reference-facing call) --------------
+    def mult(self, x, trans="N"):
+        """y = op(S) x  (StructuredMatrix::mult, StructuredMatrix.hpp:280-300)"""
+        x = _fortran(x)
+        t = trans.upper() != "N"
+        ny = self.cols if t else self.rows
+        y = np.zeros((ny, x.shape[1]), order="F")
+        _check(lib().SP_d_struct_mult(self._h, trans.encode()[:1], x.shape[1],
+                                      x.ctypes.data, x.shape[0],
+                                      y.ctypes.data, ny), "mult")
+        return y
+
+    def factor(self):
+        _check(lib().SP_d_struct_factor(self._h), "factor")
+
+    def solve(self, b):
+        """x = S^{-1} b (StructuredMatrix::solve, StructuredMatrix.hpp:340-360;
+        the C call overwrites its argument, this wrapper returns a copy)."""
+        x = _fortran(b).copy(order="F")
+        _check(lib().SP_d_struct_solve(self._h, x.shape[1], x.ctypes.data,
+                                       x.shape[0]), "solve")
+        return x
+
+    def shift(self, sigma):
+        _check(lib().SP_d_struct_shift(self._h, float(sigma)), "shift")
+
+    # -- device operands (torch CUDA tensors, column-major = .t() of a
+    #    contiguous (s, n) tensor); queued on torch's current stream ----------
+    @staticmethod
+    def _stream():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def mult_device(self, xT, yT, trans="N"):
+        """xT, yT: torch float64 CUDA tensors of shape (s, n) contiguous, i.e.
+        column-major n x s with ld = n."""
+        s, n = xT.shape
+        _check(lib().SB200_d_struct_mult_device(
+            self._h, trans.encode()[:1], s, C.c_void_p(xT.data_ptr()), n,
+            C.c_void_p(yT.data_ptr()), yT.shape[1], self._stream()),
+            "mult_device")
+
+    def factor_device(self):
+        _check(lib().SB200_d_struct_factor_device(self._h, self._stream()),
+               "factor_device")
+
+    def solve_device(self, bT):
+        s, n = bT.shape
+        _check(lib().SB200_d_struct_solve_device(
+            self._h, s, C.c_void_p(bT.data_ptr()), n, self._stream()),
+            "solve_device")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().SP_d_struct_destroy(C.byref(self._h))
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HSSMatrix(StructuredMatrix):
+    """Mirror of ``HSS::HSSMatrix<double>`` (reference src/HSS/HSSMatrix.hpp)."""
+
+    @classmethod
+    def read(cls, path):
+        """HSSMatrix::read (reference HSSMatrix.cpp:488-510)."""
+        h = C.c_void_p()
+        _check(lib().SB200_d_hss_read(C.byref(h), str(path).encode()), "read")
+        return cls(h.value)
+
+    def write(self, path):
+        _check(lib().SB200_d_hss_write(self._h, str(path).encode()), "write")
+
+    @classmethod
+    def from_generators(cls, nodes):
+        tab, vals, perms = pack_generators(nodes)
+        h = C.c_void_p()
+        _check(lib().SB200_d_hss_from_generators(
+            C.byref(h), len(nodes), tab.ctypes.data, vals.ctypes.data,
+            vals.size, perms.ctypes.data, perms.size), "from_generators")
+        return cls(h.value)
+
+    @classmethod
+    def from_kernel(cls, pts, kernel=KERNEL_GAUSS, h=1.0, lam=0.0, opts=None):
+        """HSSMatrix(kernel::Kernel&, opts) (reference HSSMatrix.cpp:88-106).
+        pts: d x n.  Returns (H, perm, pts_permuted)."""
+        pts = np.asfortranarray(np.array(pts, dtype=np.float64))
+        d, n = pts.shape
+        opts = opts or default_options()
+        perm = np.zeros(n, dtype=np.int32)
+        hd = C.c_void_p()
+        _check(lib().SB200_d_hss_from_kernel(
+            C.byref(hd), n, d, pts.ctypes.data, kernel, h, lam, C.byref(opts),
+            perm.ctypes.data), "from_kernel")
+        return cls(hd.value), perm, pts

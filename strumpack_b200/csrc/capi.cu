@@ -1,0 +1,312 @@
+// strumpack_b200 -- C ABI (include/sb200_structured.h).
+// Mirrors reference src/structured/StructuredMatrixC.cpp:39-119: opaque handle
+// owning the matrix, try/catch around every call, "Operation failed: ..." on
+// stderr and return code 1 on error.
+#include "../../include/sb200_structured.h"
+
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "hss_compress.hpp"
+#include "hss_engine.hpp"
+#include "hss_tree.hpp"
+
+using namespace sb200;
+
+namespace {
+
+struct Mat {
+  SP_STRUCTURED_TYPE type = SP_TYPE_HSS;
+  std::unique_ptr<HSSEngine> hss;
+  // staging buffers for the host-pointer entry points
+  DevBuf<double> dB, dC;
+};
+
+void require_gpu() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw std::runtime_error(
+        "no CUDA device: strumpack_b200 has no CPU fallback (sm_100a only)");
+}
+
+template <typename F> int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << "Operation failed: " << e.what() << std::endl;
+    return 1;
+  } catch (...) {
+    std::cerr << "Operation failed: unknown exception" << std::endl;
+    return 1;
+  }
+}
+
+Mat* M(const CSPStructMat S) {
+  if (!S) throw std::invalid_argument("null CSPStructMat");
+  return static_cast<Mat*>(S);
+}
+
+HSSEngine& hss(const CSPStructMat S) {
+  Mat* m = M(S);
+  if (!m->hss) throw std::logic_error("operation not supported for this type");
+  return *m->hss;
+}
+
+// copy a host column-major block to a packed device buffer and back
+void h2d(DevBuf<double>& d, const double* h, int rows, int cols, int ld,
+         cudaStream_t st) {
+  d.ensure((size_t)rows * cols);
+  SB200_CUDA(cudaMemcpy2DAsync(d.p, sizeof(double) * rows, h, sizeof(double) * ld,
+                               sizeof(double) * rows, cols,
+                               cudaMemcpyHostToDevice, st));
+}
+void d2h(double* h, const DevBuf<double>& d, int rows, int cols, int ld,
+         cudaStream_t st) {
+  SB200_CUDA(cudaMemcpy2DAsync(h, sizeof(double) * ld, d.p, sizeof(double) * rows,
+                               sizeof(double) * rows, cols,
+                               cudaMemcpyDeviceToHost, st));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* SB200_version(void) { return "strumpack_b200 0.1 sm_100a"; }
+
+void SP_d_struct_default_options(CSPOptions* o) {
+  // StructuredOptions defaults, reference StructuredOptions.hpp:106-162
+  o->type = SP_TYPE_BLR;
+  o->rel_tol = 1e-4;
+  o->abs_tol = 1e-10;
+  o->leaf_size = 128;
+  o->max_rank = 5000;
+  o->verbose = 0;
+}
+
+void SP_d_struct_destroy(CSPStructMat* S) {
+  if (!S || !*S) return;
+  delete static_cast<Mat*>(*S);
+  *S = nullptr;
+}
+
+int SP_d_struct_rows(const CSPStructMat S) { return S ? hss(S).rows() : 0; }
+int SP_d_struct_cols(const CSPStructMat S) { return S ? hss(S).cols() : 0; }
+long long int SP_d_struct_memory(const CSPStructMat S) {
+  return S ? hss(S).host().memory_bytes() : 0;
+}
+long long int SP_d_struct_nonzeros(const CSPStructMat S) {
+  return S ? hss(S).host().nonzeros() : 0;
+}
+int SP_d_struct_rank(const CSPStructMat S) {
+  return S ? hss(S).host().max_rank() : 0;
+}
+
+int SP_d_struct_from_dense(CSPStructMat* S, int rows, int cols, const double* A,
+                           int ldA, const CSPOptions* opts) {
+  return guarded([&] {
+    require_gpu();
+    if (opts->type != SP_TYPE_HSS)
+      throw std::invalid_argument("structured type not supported (HSS only)");
+    auto m = std::make_unique<Mat>();
+    m->type = opts->type;
+    CompressOptions co;
+    co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
+    co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
+    co.verbose = opts->verbose;
+    m->hss = std::make_unique<HSSEngine>(compress_dense(rows, cols, A, ldA, co));
+    *S = m.release();
+  });
+}
+
+int SP_d_struct_from_elements(CSPStructMat* S, int rows, int cols,
+                              double A(int i, int j), const CSPOptions* opts) {
+  return guarded([&] {
+    require_gpu();
+    if (opts->type != SP_TYPE_HSS)
+      throw std::invalid_argument("structured type not supported (HSS only)");
+    auto m = std::make_unique<Mat>();
+    m->type = opts->type;
+    CompressOptions co;
+    co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
+    co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
+    co.verbose = opts->verbose;
+    m->hss = std::make_unique<HSSEngine>(compress_elements(rows, cols, A, co));
+    *S = m.release();
+  });
+}
+
+int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
+                            int kernel_type, double h, double lambda,
+                            const CSPOptions* opts, int* perm) {
+  return guarded([&] {
+    require_gpu();
+    auto m = std::make_unique<Mat>();
+    m->type = SP_TYPE_HSS;
+    CompressOptions co;
+    co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
+    co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
+    co.verbose = opts->verbose;
+    m->hss = std::make_unique<HSSEngine>(
+        compress_kernel(n, d, pts, kernel_type, h, lambda, co, perm));
+    *S = m.release();
+  });
+}
+
+int SB200_d_hss_read(CSPStructMat* S, const char* path) {
+  return guarded([&] {
+    require_gpu();
+    auto m = std::make_unique<Mat>();
+    m->hss = std::make_unique<HSSEngine>(HSSHost::read_file(path));
+    *S = m.release();
+  });
+}
+
+int SB200_d_hss_write(const CSPStructMat S, const char* path) {
+  return guarded([&] {
+    hss(S).sync_host_values();
+    hss(S).host().write_file(path);
+  });
+}
+
+int SB200_d_hss_from_generators(CSPStructMat* S, int n_nodes,
+                                const int64_t* node_tab, const double* vals,
+                                int64_t n_vals, const int32_t* perms,
+                                int64_t n_perms) {
+  return guarded([&] {
+    require_gpu();
+    auto m = std::make_unique<Mat>();
+    m->hss = std::make_unique<HSSEngine>(
+        HSSHost::from_flat(n_nodes, node_tab, vals, n_vals, perms, n_perms));
+    *S = m.release();
+  });
+}
+
+int SP_d_struct_mult(const CSPStructMat S, char trans, int m, const double* B,
+                     int ldB, double* C, int ldC) {
+  return guarded([&] {
+    auto& H = hss(S);
+    Mat* mm = M(S);
+    const bool T = !(trans == 'N' || trans == 'n');
+    const int nb = T ? H.rows() : H.cols(), nc = T ? H.cols() : H.rows();
+    cudaStream_t st = 0;
+    h2d(mm->dB, B, nb, m, ldB, st);
+    mm->dC.ensure((size_t)nc * m);
+    H.mult(trans, m, mm->dB.p, nb, mm->dC.p, nc, st);
+    d2h(C, mm->dC, nc, m, ldC, st);
+    SB200_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int SP_d_struct_factor(CSPStructMat S) {
+  return guarded([&] {
+    hss(S).factor(0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SP_d_struct_solve(const CSPStructMat S, int nrhs, double* B, int ldB) {
+  return guarded([&] {
+    auto& H = hss(S);
+    Mat* mm = M(S);
+    cudaStream_t st = 0;
+    h2d(mm->dB, B, H.rows(), nrhs, ldB, st);
+    H.solve(nrhs, mm->dB.p, H.rows(), st);
+    d2h(B, mm->dB, H.rows(), nrhs, ldB, st);
+    SB200_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int SP_d_struct_shift(CSPStructMat S, double s) {
+  return guarded([&] {
+    hss(S).shift(s, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_struct_mult_device(const CSPStructMat S, char trans, int m,
+                               const double* dB, int ldB, double* dC, int ldC,
+                               void* stream) {
+  return guarded([&] {
+    hss(S).mult(trans, m, dB, ldB, dC, ldC, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int SB200_d_struct_factor_device(CSPStructMat S, void* stream) {
+  return guarded([&] { hss(S).factor(static_cast<cudaStream_t>(stream)); });
+}
+
+int SB200_d_struct_solve_device(const CSPStructMat S, int nrhs, double* dB,
+                                int ldB, void* stream) {
+  return guarded([&] {
+    hss(S).solve(nrhs, dB, ldB, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int SB200_d_hss_file_info(const char* path, long long int* out) {
+  return guarded([&] {
+    HSSHost h = HSSHost::read_file(path);
+    out[0] = h.rows(); out[1] = h.cols(); out[2] = (long long)h.nodes.size();
+    out[3] = h.levels(); out[4] = h.max_rank(); out[5] = h.nonzeros();
+    out[6] = h.apply_flops(); out[7] = h.factor_flops_ref();
+    out[8] = h.solve_flops_ref(); out[9] = h.factor_flops_exec();
+  });
+}
+
+int SB200_d_hss_file_copy(const char* in_path, const char* out_path) {
+  return guarded([&] { HSSHost::read_file(in_path).write_file(out_path); });
+}
+
+int SB200_d_struct_levels(const CSPStructMat S) {
+  return S ? hss(S).host().levels() : 0;
+}
+long long int SB200_d_struct_factor_nonzeros(const CSPStructMat S) {
+  return S ? hss(S).factor_nonzeros() : 0;
+}
+long long int SB200_d_struct_flops(const CSPStructMat S, int which) {
+  if (!S) return 0;
+  const auto& h = hss(S).host();
+  switch (which) {
+    case 0: return h.apply_flops();
+    case 1: return h.factor_flops_ref();
+    case 2: return h.solve_flops_ref();
+    case 3: return h.factor_flops_exec();
+  }
+  return 0;
+}
+long long int SB200_d_struct_launches(const CSPStructMat S) {
+  return S ? hss(S).launches() : 0;
+}
+int SB200_d_struct_print_info(const CSPStructMat S) {
+  return guarded([&] { hss(S).host().print_info(); });
+}
+int SB200_d_struct_dense(const CSPStructMat S, double* A, int ldA) {
+  return guarded([&] {
+    auto& H = hss(S);
+    const int n = H.cols(), m = H.rows();
+    // H * I, in slabs of 256 columns
+    DevBuf<double> I, Y;
+    const int sb = 256;
+    I.alloc((size_t)n * sb);
+    Y.alloc((size_t)m * sb);
+    std::vector<double> hI((size_t)n * sb);
+    for (int c0 = 0; c0 < n; c0 += sb) {
+      const int nc = std::min(sb, n - c0);
+      std::fill(hI.begin(), hI.end(), 0.);
+      for (int c = 0; c < nc; c++) hI[(size_t)c * n + c0 + c] = 1.;
+      SB200_CUDA(cudaMemcpy(I.p, hI.data(), sizeof(double) * (size_t)n * nc,
+                            cudaMemcpyHostToDevice));
+      H.mult('N', nc, I.p, n, Y.p, m, 0);
+      SB200_CUDA(cudaMemcpy2D(A + (size_t)c0 * ldA, sizeof(double) * ldA, Y.p,
+                              sizeof(double) * m, sizeof(double) * m, nc,
+                              cudaMemcpyDeviceToHost));
+    }
+  });
+}
+
+}  // extern "C"

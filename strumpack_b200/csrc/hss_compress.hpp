@@ -1,0 +1,33 @@
+// strumpack_b200 -- HSS construction on the GPU.
+//
+// Produces the generators consumed by HSSEngine.  Replaces (reference, CPU):
+//   HSSMatrix(const DenseM_t&, opts) / compress   src/HSS/HSSMatrix.cpp:49-54,148-161
+//   HSSMatrix(kernel::Kernel&, opts)              src/HSS/HSSMatrix.cpp:88-106
+//   compress_kernel / ANN sampling                src/HSS/HSSMatrix.compress_kernel.hpp:39-293
+// The algorithm here is NOT the reference's randomized sampling: see
+// hss_compress.cu (sampled-column interpolative decomposition, batched per
+// height class on the device).
+#pragma once
+#include "hss_tree.hpp"
+
+namespace sb200 {
+
+struct CompressOptions {
+  double rel_tol = 1e-2, abs_tol = 1e-8;  // HSSOptions defaults (HSSOptions.hpp:465-490)
+  int leaf_size = 512;
+  int max_rank = 50000;
+  int verbose = 0;
+};
+
+// A: host column-major rows x cols
+HSSHost compress_dense(int rows, int cols, const double* A, int ldA,
+                       const CompressOptions& o);
+// element callback evaluated on the host
+HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
+                          const CompressOptions& o);
+// kernel matrix on n points (d x n, column-major); pts is reordered in place,
+// perm[new] = old (may be null). kernel_type: SB200_KERNEL_TYPE.
+HSSHost compress_kernel(int n, int d, double* pts, int kernel_type, double h,
+                        double lambda, const CompressOptions& o, int* perm);
+
+}  // namespace sb200

@@ -1,0 +1,1055 @@
+// strumpack_b200 -- HSS apply / ULV factor / ULV solve on sm_100a.
+// See hss_engine.hpp for the reference routines each kernel family replaces.
+#include "hss_engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace sb200 {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// sum over the CTA; every thread gets the result. red: >= 32 doubles of smem.
+// Contains two __syncthreads().
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double s = 0.;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) s += red[w];
+  return s;
+}
+
+// ===========================================================================
+//                                  APPLY
+// ===========================================================================
+// Workspace convention: node block = base + w_off * s, column c of a block
+// with `len` rows starts at + c * len.
+
+// Up-sweep, one height class (root excluded):  t1 = top(P^T in) + E^H bot(P^T in)
+//   reference apply_fwd   HSSMatrix.apply.hpp:55-82 (leaf :58-63, inner :76-80)
+//   HSSBasisID::applyC    HSSBasisID.hpp:189-203
+template <bool TRANS>
+__global__ void __launch_bounds__(kThreads)
+hss_up_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+              const double* __restrict__ vals, const int* __restrict__ perms,
+              const double* __restrict__ x, int ldx, double* __restrict__ t1,
+              int s) {
+  extern __shared__ double sm[];
+  const DNode nd = nodes[list[blockIdx.x]];
+  const int c = blockIdx.y, tid = threadIdx.x;
+  const int r = TRANS ? nd.u_rank : nd.v_rank;
+  const int n = TRANS ? nd.u_rows : nd.v_rows;
+  if (r == 0) return;
+  const int* P = perms + (TRANS ? nd.Pu : nd.Pv);
+  double* pb = sm;
+  if (nd.leaf) {
+    const double* xin = x + (TRANS ? nd.row_off : nd.col_off) + (size_t)c * ldx;
+    for (int i = tid; i < n; i += kThreads) pb[i] = xin[P[i]];
+  } else {
+    const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
+    const int q0 = TRANS ? c0.u_rank : c0.v_rank;
+    const int q1 = TRANS ? c1.u_rank : c1.v_rank;
+    const double* a = t1 + (size_t)c0.w_off * s + (size_t)c * q0;
+    const double* b = t1 + (size_t)c1.w_off * s + (size_t)c * q1;
+    for (int i = tid; i < n; i += kThreads) {
+      int p = P[i];
+      pb[i] = p < q0 ? a[p] : b[p - q0];
+    }
+  }
+  __syncthreads();
+  const int k = n - r;
+  const double* E = vals + (TRANS ? nd.Eu : nd.Ev);
+  double* out = t1 + (size_t)nd.w_off * s + (size_t)c * r;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int j = warp; j < r; j += kWarps) {
+    double acc = 0.;
+    const double* Ej = E + (size_t)j * k;
+    for (int i = lane; i < k; i += 32) acc += Ej[i] * pb[r + i];
+    acc = warp_sum(acc);
+    if (lane == 0) out[j] = pb[j] + acc;
+  }
+}
+
+// Down-sweep over inner nodes of one height class (root included):
+//   u = U t2 (= P [t2; E t2]) split over the children, plus B01/B10 coupling.
+//   reference apply_bwd   HSSMatrix.apply.hpp:101-124, HSSBasisID::apply :155-169
+template <bool TRANS>
+__global__ void __launch_bounds__(kThreads)
+hss_down_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                const double* __restrict__ vals, const int* __restrict__ perms,
+                const double* __restrict__ t1, double* __restrict__ t2, int s) {
+  extern __shared__ double sm[];
+  const int id = list[blockIdx.x];
+  const DNode nd = nodes[id];
+  if (nd.leaf) return;
+  const int c = blockIdx.y, tid = threadIdx.x;
+  const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
+  // ranks of the children on the way down (o*) and on the way up (q*)
+  const int o0 = TRANS ? c0.v_rank : c0.u_rank, o1 = TRANS ? c1.v_rank : c1.u_rank;
+  const int q0 = TRANS ? c0.u_rank : c0.v_rank, q1 = TRANS ? c1.u_rank : c1.v_rank;
+  const int rout = TRANS ? nd.v_rank : nd.u_rank;
+  const int nout = o0 + o1;
+  double* u = sm;            // nout
+  double* tin = sm + nout;   // rout : this node's t2
+  const bool has_u = (nd.parent >= 0) && rout > 0;
+  if (has_u) {
+    const double* my = t2 + (size_t)nd.w_off * s + (size_t)c * rout;
+    for (int i = tid; i < rout; i += kThreads) tin[i] = my[i];
+    __syncthreads();
+    const int* P = perms + (TRANS ? nd.Pv : nd.Pu);
+    const double* E = vals + (TRANS ? nd.Ev : nd.Eu);
+    const int k = nout - rout;
+    for (int i = tid; i < nout; i += kThreads) {
+      double v;
+      if (i < rout) v = tin[i];
+      else {
+        v = 0.;
+        for (int l = 0; l < rout; l++) v += E[(i - rout) + (size_t)l * k] * tin[l];
+      }
+      u[P[i]] = v;
+    }
+  } else {
+    for (int i = tid; i < nout; i += kThreads) u[i] = 0.;
+  }
+  __syncthreads();
+  const double* ta = t1 + (size_t)c0.w_off * s + (size_t)c * q0;  // t1(c0)
+  const double* tb = t1 + (size_t)c1.w_off * s + (size_t)c * q1;  // t1(c1)
+  double* oa = t2 + (size_t)c0.w_off * s + (size_t)c * o0;
+  double* ob = t2 + (size_t)c1.w_off * s + (size_t)c * o1;
+  const double* B01 = vals + nd.B01;  // u_rank(c0) x v_rank(c1)
+  const double* B10 = vals + nd.B10;  // u_rank(c1) x v_rank(c0)
+  for (int i = tid; i < nout; i += kThreads) {
+    double v = u[i];
+    if (!TRANS) {
+      if (i < o0) { for (int j = 0; j < q1; j++) v += B01[i + (size_t)j * o0] * tb[j]; oa[i] = v; }
+      else { int ii = i - o0; for (int j = 0; j < q0; j++) v += B10[ii + (size_t)j * o1] * ta[j]; ob[ii] = v; }
+    } else {
+      // t2(c0) += B10^H t1(c1) ; t2(c1) += B01^H t1(c0)   (apply.hpp:194-211)
+      if (i < o0) { for (int j = 0; j < q1; j++) v += B10[j + (size_t)i * q1] * tb[j]; oa[i] = v; }
+      else { int ii = i - o0; for (int j = 0; j < q0; j++) v += B01[j + (size_t)ii * q0] * ta[j]; ob[ii] = v; }
+    }
+  }
+}
+
+// Leaves:  y = D x + U t2    (apply_bwd leaf, HSSMatrix.apply.hpp:87-99)
+template <bool TRANS>
+__global__ void __launch_bounds__(kThreads)
+hss_leaf_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                const double* __restrict__ vals, const int* __restrict__ perms,
+                const double* __restrict__ x, int ldx, const double* __restrict__ t2,
+                double* __restrict__ y, int ldy, int s) {
+  extern __shared__ double sm[];
+  const DNode nd = nodes[list[blockIdx.x]];
+  const int c = blockIdx.y, tid = threadIdx.x;
+  const int nin = TRANS ? nd.rows : nd.cols;    // length of the x slice
+  const int nout = TRANS ? nd.cols : nd.rows;   // length of the y slice
+  const int rout = TRANS ? nd.v_rank : nd.u_rank;
+  double* xs = sm;           // nin
+  double* u = sm + nin;      // nout
+  double* tin = u + nout;    // rout
+  const double* xin = x + (TRANS ? nd.row_off : nd.col_off) + (size_t)c * ldx;
+  for (int i = tid; i < nin; i += kThreads) xs[i] = xin[i];
+  const bool has_u = (nd.parent >= 0) && rout > 0;
+  if (has_u) {
+    const double* my = t2 + (size_t)nd.w_off * s + (size_t)c * rout;
+    for (int i = tid; i < rout; i += kThreads) tin[i] = my[i];
+    __syncthreads();
+    const int* P = perms + (TRANS ? nd.Pv : nd.Pu);
+    const double* E = vals + (TRANS ? nd.Ev : nd.Eu);
+    const int k = nout - rout;
+    for (int i = tid; i < nout; i += kThreads) {
+      double v;
+      if (i < rout) v = tin[i];
+      else {
+        v = 0.;
+        for (int l = 0; l < rout; l++) v += E[(i - rout) + (size_t)l * k] * tin[l];
+      }
+      u[P[i]] = v;
+    }
+  } else {
+    for (int i = tid; i < nout; i += kThreads) u[i] = 0.;
+  }
+  __syncthreads();
+  const double* D = vals + nd.D;  // rows x cols, ld = rows
+  double* yo = y + (TRANS ? nd.col_off : nd.row_off) + (size_t)c * ldy;
+  if (!TRANS) {
+    const int m = nd.rows;
+    for (int i = tid; i < m; i += kThreads) {
+      double a0 = u[i], a1 = 0., a2 = 0., a3 = 0.;
+      const double* Di = D + i;
+      int j = 0;
+      for (; j + 4 <= nin; j += 4) {
+        a0 += Di[(size_t)j * m] * xs[j];
+        a1 += Di[(size_t)(j + 1) * m] * xs[j + 1];
+        a2 += Di[(size_t)(j + 2) * m] * xs[j + 2];
+        a3 += Di[(size_t)(j + 3) * m] * xs[j + 3];
+      }
+      for (; j < nin; j++) a0 += Di[(size_t)j * m] * xs[j];
+      yo[i] = (a0 + a1) + (a2 + a3);
+    }
+  } else {
+    const int m = nd.rows;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < nout; j += kWarps) {
+      const double* Dj = D + (size_t)j * m;
+      double acc = 0.;
+      for (int i = lane; i < m; i += 32) acc += Dj[i] * xs[i];
+      acc = warp_sum(acc);
+      if (lane == 0) yo[j] = u[j] + acc;
+    }
+  }
+}
+
+__global__ void hss_shift_kernel(const DNode* __restrict__ nodes,
+                                 const int* __restrict__ list, double* vals,
+                                 double sigma) {
+  const DNode nd = nodes[list[blockIdx.x]];
+  if (!nd.leaf) return;
+  double* D = vals + nd.D;
+  const int n = min(nd.rows, nd.cols);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) D[i + (size_t)i * nd.rows] += sigma;
+}
+
+// ===========================================================================
+//                               ULV FACTOR
+// ===========================================================================
+// Per non-root node the factor block F is m x naug (ld = m), columns
+//   [0,k)            A = W0^T          -> R (upper) + Householder vectors V
+//   [k,k+rv)         Vh                -> Q^T Vh  = [Vt0 ; Vt1]
+//   [k+rv,k+rv+r)    W1^T              -> Q^T W1^T = [(W1 Q0^H)^T ; Dt^T]
+// W0 = (P_u^T D)_bot - E_u (P_u^T D)_top, W1 = (P_u^T D)_top
+// (reference factor.hpp:109-121).  The reference forms Q explicitly
+// (DenseMatrix::LQ, DenseMatrix.cpp:693-719); here Q stays in compact-WY form.
+
+// Vh = dense(V) = P_v [I; E_v] for leaves        (factor.hpp:100-103)
+__global__ void __launch_bounds__(kThreads)
+ulv_vh_leaf_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                   const double* __restrict__ vals, const int* __restrict__ perms,
+                   double* __restrict__ fact) {
+  const DNode nd = nodes[list[blockIdx.x]];
+  if (!nd.leaf || nd.parent < 0) return;
+  const int m = nd.m, rv = nd.v_rank, kv = m - rv;
+  const int* P = perms + nd.Pv;
+  const double* E = vals + nd.Ev;
+  double* Vh = fact + nd.F + (size_t)nd.k * m;
+  for (int idx = threadIdx.x; idx < m * rv; idx += kThreads) {
+    int i = idx % m, c = idx / m;
+    double v = i < rv ? (i == c ? 1. : 0.) : E[(i - rv) + (size_t)c * kv];
+    Vh[P[i] + (size_t)c * m] = v;
+  }
+}
+
+__device__ __forceinline__ double child_Dt(const double* f, const DNode& c, int a, int b) {
+  // Dt[a,b] = F[(k+b) + (k+rv+a) m]
+  return f[c.F + (c.k + b) + (size_t)(c.k + c.v_rank + a) * c.m];
+}
+__device__ __forceinline__ double child_Vt1(const double* f, const DNode& c, int a, int j) {
+  // Vt1[a,j] = F[(k+a) + (k+j) m]
+  return f[c.F + (c.k + a) + (size_t)(c.k + j) * c.m];
+}
+
+// Inner nodes: Dfull = [Dt0, B01 Vt1(c1)^H; B10 Vt1(c0)^H, Dt1] into `dst`
+// (ld = m) and, for non-root nodes, Vh = [Vt1(c0) Vd_top; Vt1(c1) Vd_bot]
+// into the factor block                         (factor.hpp:68-98)
+__global__ void __launch_bounds__(kThreads)
+ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                       const double* __restrict__ vals, const int* __restrict__ perms,
+                       double* __restrict__ fact, double* __restrict__ scratch,
+                       const long long* __restrict__ scratch_off) {
+  extern __shared__ double sm[];
+  const int id = list[blockIdx.x];
+  const DNode nd = nodes[id];
+  if (nd.leaf) return;
+  const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
+  const int ru0 = c0.u_rank, ru1 = c1.u_rank, rv0 = c0.v_rank, rv1 = c1.v_rank;
+  const int m = ru0 + ru1, tid = threadIdx.x;
+  double* Df = scratch + scratch_off[blockIdx.x];
+  const double* B01 = vals + nd.B01;
+  const double* B10 = vals + nd.B10;
+  for (int idx = tid; idx < m * m; idx += kThreads) {
+    int i = idx % m, j = idx / m;
+    double v;
+    if (i < ru0 && j < ru0) v = child_Dt(fact, c0, i, j);
+    else if (i >= ru0 && j >= ru0) v = child_Dt(fact, c1, i - ru0, j - ru0);
+    else if (i < ru0) {  // B01 * Vt1(c1)^H
+      int b = j - ru0;
+      v = 0.;
+      for (int q = 0; q < rv1; q++) v += B01[i + (size_t)q * ru0] * child_Vt1(fact, c1, b, q);
+    } else {             // B10 * Vt1(c0)^H
+      int a = i - ru0;
+      v = 0.;
+      for (int q = 0; q < rv0; q++) v += B10[a + (size_t)q * ru1] * child_Vt1(fact, c0, j, q);
+    }
+    Df[i + (size_t)j * m] = v;
+  }
+  if (nd.parent < 0) return;
+  // Vd = dense(V) in smem (v_rows x rv)
+  const int rv = nd.v_rank, nv = rv0 + rv1, kv = nv - rv;
+  const int* P = perms + nd.Pv;
+  const double* E = vals + nd.Ev;
+  double* Vd = sm;
+  for (int idx = tid; idx < nv * rv; idx += kThreads) {
+    int i = idx % nv, c = idx / nv;
+    Vd[P[i] + c * nv] = i < rv ? (i == c ? 1. : 0.) : E[(i - rv) + (size_t)c * kv];
+  }
+  __syncthreads();
+  double* Vh = fact + nd.F + (size_t)nd.k * m;
+  for (int idx = tid; idx < m * rv; idx += kThreads) {
+    int i = idx % m, c = idx / m;
+    double v = 0.;
+    if (i < ru0) for (int q = 0; q < rv0; q++) v += child_Vt1(fact, c0, i, q) * Vd[q + c * nv];
+    else for (int q = 0; q < rv1; q++) v += child_Vt1(fact, c1, i - ru0, q) * Vd[rv0 + q + c * nv];
+    Vh[i + (size_t)c * m] = v;
+  }
+}
+
+// Elimination step: writes A = W0^T and W1^T into the factor block.
+// Dsrc = leaf ? D generator : Dfull scratch; tiles of TJ columns of Dsrc are
+// staged in smem so the row gather by P_u is a shared-memory gather.
+template <int TJ>
+__global__ void __launch_bounds__(kThreads)
+ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                     const double* __restrict__ vals, const int* __restrict__ perms,
+                     double* __restrict__ fact, const double* __restrict__ scratch,
+                     const long long* __restrict__ scratch_off) {
+  extern __shared__ double sm[];
+  const DNode nd = nodes[list[blockIdx.x]];
+  if (nd.parent < 0) return;
+  const int m = nd.m, r = nd.u_rank, k = nd.k, rv = nd.v_rank, tid = threadIdx.x;
+  const double* Dsrc = nd.leaf ? vals + nd.D : scratch + scratch_off[blockIdx.x];
+  const int* P = perms + nd.Pu;
+  const double* E = vals + nd.Eu;  // k x r
+  double* A = fact + nd.F;
+  double* W1t = A + (size_t)(k + rv) * m;
+  constexpr int LD = TJ + 1;
+  double* Dn = sm;  // m x LD (row-major-ish: Dn[i*LD + jj])
+  for (int j0 = 0; j0 < m; j0 += TJ) {
+    const int tj = min(TJ, m - j0);
+    __syncthreads();
+    for (int idx = tid; idx < m * tj; idx += kThreads) {
+      int i = idx % m, jj = idx / m;
+      Dn[i * LD + jj] = Dsrc[i + (size_t)(j0 + jj) * m];
+    }
+    __syncthreads();
+    // W1^T[j, l] = Dp[l, j]
+    for (int idx = tid; idx < r * tj; idx += kThreads) {
+      int jj = idx % tj, l = idx / tj;
+      W1t[(j0 + jj) + (size_t)l * m] = Dn[P[l] * LD + jj];
+    }
+    // W0^T[j, i] = Dp[r+i, j] - sum_l E[i,l] Dp[l, j]
+    for (int i = tid; i < k; i += kThreads) {
+      double acc[TJ];
+      const double* src = Dn + P[r + i] * LD;
+#pragma unroll
+      for (int jj = 0; jj < TJ; jj++) acc[jj] = src[jj];
+      for (int l = 0; l < r; l++) {
+        const double e = E[i + (size_t)l * k];
+        const double* top = Dn + P[l] * LD;
+#pragma unroll
+        for (int jj = 0; jj < TJ; jj++) acc[jj] -= e * top[jj];
+      }
+      double* dst = A + j0 + (size_t)i * m;
+#pragma unroll
+      for (int jj = 0; jj < TJ; jj++)
+        if (jj < tj) dst[jj] = acc[jj];
+    }
+  }
+}
+
+// Blocked Householder QR of the first k columns of the m x naug factor block,
+// reflectors applied to all naug columns (right-looking, panel width NB).
+// One CTA per node.  All GEMM-shaped work (V^T C, T^T W, C -= V W, V^T V)
+// runs on the fp64 tensor pipe from shared memory.
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+              double* __restrict__ fact, double* __restrict__ tfac, int ldv) {
+  extern __shared__ double sm[];
+  const DNode nd = nodes[list[blockIdx.x]];
+  if (nd.parent < 0 || nd.k == 0) return;
+  const int m = nd.m, k = nd.k, naug = nd.naug, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
+  double* Vs = sm;                       // ldv x NB
+  double* Cs = Vs + (size_t)ldv * NB;    // ldv x NB
+  double* Ws = Cs + (size_t)ldv * NB;    // LDW x NB
+  double* W2 = Ws + LDW * NB;            // LDW x NB
+  double* Ts = W2 + LDW * NB;            // LDW x NB
+  double* tau = Ts + LDW * NB;           // NB
+  double* red = tau + NB;                // 32
+  double* A = fact + nd.F;
+  double* Tg = tfac + nd.T;
+  for (int j0 = 0; j0 < k; j0 += NB) {
+    const int jb = min(NB, k - j0), mp = m - j0;
+    // ---- load panel
+    for (int idx = tid; idx < mp * jb; idx += kThreads) {
+      int i = idx % mp, c = idx / mp;
+      Vs[i + c * ldv] = A[(j0 + i) + (size_t)(j0 + c) * m];
+    }
+    __syncthreads();
+    // ---- unblocked Householder on the panel (dgeqr2)
+    for (int c = 0; c < jb; c++) {
+      double part = 0.;
+      for (int i = c + 1 + tid; i < mp; i += kThreads) {
+        double v = Vs[i + c * ldv];
+        part += v * v;
+      }
+      const double xn2 = block_sum(part, red, tid);
+      const double alpha = Vs[c + c * ldv];
+      double tc = 0., scal = 0., beta = alpha;
+      if (xn2 > 0.) {
+        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        tc = (beta - alpha) / beta;
+        scal = 1. / (alpha - beta);
+      }
+      __syncthreads();  // everyone has read alpha
+      if (xn2 > 0.)
+        for (int i = c + 1 + tid; i < mp; i += kThreads) Vs[i + c * ldv] *= scal;
+      if (tid == 0) { Vs[c + c * ldv] = beta; tau[c] = tc; }
+      __syncthreads();
+      if (tc != 0.) {
+        for (int cc = c + 1 + warp; cc < jb; cc += kWarps) {
+          double* col = Vs + cc * ldv;
+          const double* v = Vs + c * ldv;
+          double w = 0.;
+          for (int i = c + 1 + lane; i < mp; i += 32) w += v[i] * col[i];
+          w = warp_sum(w);
+          w = tc * (w + col[c]);
+          for (int i = c + 1 + lane; i < mp; i += 32) col[i] -= w * v[i];
+          __syncwarp();
+          if (lane == 0) col[c] -= w;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- R block to global, make V explicit (unit diagonal, zeros above)
+    for (int idx = tid; idx < jb * jb; idx += kThreads) {
+      int i = idx % jb, c = idx / jb;
+      if (i <= c) {
+        A[(j0 + i) + (size_t)(j0 + c) * m] = Vs[i + c * ldv];
+        Vs[i + c * ldv] = (i == c) ? 1. : 0.;
+      }
+    }
+    __syncthreads();
+    // ---- T factor (dlarft, forward/columnwise): S = V^T V, then per row
+    smem_gemm<true, false>(jb, jb, mp, 1., Vs, ldv, Vs, ldv, 0., Ws, LDW, warp, kWarps, lane);
+    for (int idx = tid; idx < NB * NB; idx += kThreads) Ts[(idx % NB) + (idx / NB) * LDW] = 0.;
+    __syncthreads();
+    if (warp == 0 && lane < jb) {
+      const int a = lane;
+      Ts[a + a * LDW] = tau[a];
+      for (int c = a + 1; c < jb; c++) {
+        double acc = 0.;
+        for (int b = a; b < c; b++) acc += Ts[a + b * LDW] * Ws[b + c * LDW];
+        Ts[a + c * LDW] = -tau[c] * acc;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < jb * jb; idx += kThreads) {
+      int a = idx % jb, c = idx / jb;
+      Tg[a + (size_t)(j0 + c) * NB] = Ts[a + c * LDW];
+    }
+    // ---- V (strictly lower part) back to global
+    for (int idx = tid; idx < mp * jb; idx += kThreads) {
+      int i = idx % mp, c = idx / mp;
+      if (i > c) A[(j0 + i) + (size_t)(j0 + c) * m] = Vs[i + c * ldv];
+    }
+    // ---- trailing update: C <- (I - V T^T V^T) C, NB columns at a time
+    for (int c0 = j0 + jb; c0 < naug; c0 += NB) {
+      const int nc = min(NB, naug - c0);
+      for (int idx = tid; idx < mp * nc; idx += kThreads) {
+        int i = idx % mp, c = idx / mp;
+        Cs[i + c * ldv] = A[(j0 + i) + (size_t)(c0 + c) * m];
+      }
+      __syncthreads();
+      smem_gemm<true, false>(jb, nc, mp, 1., Vs, ldv, Cs, ldv, 0., Ws, LDW, warp, kWarps, lane);
+      __syncthreads();
+      smem_gemm<true, false>(jb, nc, jb, 1., Ts, LDW, Ws, LDW, 0., W2, LDW, warp, kWarps, lane);
+      __syncthreads();
+      smem_gemm<false, false>(mp, nc, jb, -1., Vs, ldv, W2, LDW, 1., Cs, ldv, warp, kWarps, lane);
+      __syncthreads();
+      for (int idx = tid; idx < mp * nc; idx += kThreads) {
+        int i = idx % mp, c = idx / mp;
+        A[(j0 + i) + (size_t)(c0 + c) * m] = Cs[i + c * ldv];
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
+// Root: Dfull (already assembled in the root factor block by
+// ulv_build_inner_kernel, or D itself for a single-node tree) -> LU with
+// partial pivoting, in place.                       (factor.hpp:104-107)
+__global__ void __launch_bounds__(kThreads)
+ulv_root_lu_kernel(double* __restrict__ A, int n, int* __restrict__ piv) {
+  __shared__ double rv[kWarps];
+  __shared__ int ri[kWarps];
+  __shared__ int pivrow;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int j = 0; j < n; j++) {
+    // pivot search in column j
+    double best = -1.;
+    int bi = j;
+    for (int i = j + tid; i < n; i += kThreads) {
+      double v = fabs(A[i + (size_t)j * n]);
+      if (v > best) { best = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { rv[warp] = best; ri[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = rv[0]; int p = ri[0];
+      for (int w = 1; w < kWarps; w++)
+        if (rv[w] > b || (rv[w] == b && ri[w] < p)) { b = rv[w]; p = ri[w]; }
+      pivrow = p;
+      piv[j] = p;
+    }
+    __syncthreads();
+    const int p = pivrow;
+    if (p != j)
+      for (int c = tid; c < n; c += kThreads) {
+        double t = A[j + (size_t)c * n];
+        A[j + (size_t)c * n] = A[p + (size_t)c * n];
+        A[p + (size_t)c * n] = t;
+      }
+    __syncthreads();
+    const double d = A[j + (size_t)j * n];
+    const double inv = d != 0. ? 1. / d : 0.;
+    __syncthreads();
+    for (int i = j + 1 + tid; i < n; i += kThreads) A[i + (size_t)j * n] *= inv;
+    __syncthreads();
+    // rank-1 update of the trailing block
+    const int nt = n - j - 1;
+    for (int idx = tid; idx < nt * nt; idx += kThreads) {
+      int i = j + 1 + idx % nt, c = j + 1 + idx / nt;
+      A[i + (size_t)c * n] -= A[i + (size_t)j * n] * A[j + (size_t)c * n];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void copy_block_kernel(const double* __restrict__ src, double* __restrict__ dst, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// ===========================================================================
+//                                ULV SOLVE
+// ===========================================================================
+// Forward sweep over one height class (root excluded)   solve.hpp:69-197
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+ulv_fwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+               const double* __restrict__ vals, const int* __restrict__ perms,
+               const double* __restrict__ fact, const double* __restrict__ b, int ldb,
+               double* __restrict__ ysol, double* __restrict__ zsol,
+               double* __restrict__ fsol, int s) {
+  extern __shared__ double sm[];
+  const DNode nd = nodes[list[blockIdx.x]];
+  if (nd.parent < 0) return;
+  const int col = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = nd.m, r = nd.u_rank, k = nd.k, rv = nd.v_rank;
+  double* f = sm;            // m
+  double* fp = f + m;        // m   (P^T f) ; fp[0:r] = ft1, then y in fp[r:]
+  double* zc = fp + m;       // v_rows (children z concat) for inner nodes
+  double* Rd = zc + max(nd.v_rows, 1);  // 32 x 33 diagonal block
+  // ---- gather f
+  if (nd.leaf) {
+    const double* bb = b + nd.row_off + (size_t)col * ldb;
+    for (int i = tid; i < m; i += kThreads) f[i] = bb[i];
+  } else {
+    const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
+    const int ru0 = c0.u_rank, ru1 = c1.u_rank, rv0 = c0.v_rank, rv1 = c1.v_rank;
+    const double* f0 = fsol + (size_t)c0.f_off * s + (size_t)col * ru0;
+    const double* f1 = fsol + (size_t)c1.f_off * s + (size_t)col * ru1;
+    const double* z0 = zsol + (size_t)c0.z_off * s + (size_t)col * rv0;
+    const double* z1 = zsol + (size_t)c1.z_off * s + (size_t)col * rv1;
+    const double* B01 = vals + nd.B01;
+    const double* B10 = vals + nd.B10;
+    for (int i = tid; i < m; i += kThreads) {
+      double v;
+      if (i < ru0) { v = f0[i]; for (int j = 0; j < rv1; j++) v -= B01[i + (size_t)j * ru0] * z1[j]; }
+      else { int ii = i - ru0; v = f1[ii]; for (int j = 0; j < rv0; j++) v -= B10[ii + (size_t)j * ru1] * z0[j]; }
+      f[i] = v;
+    }
+    for (int i = tid; i < rv0 + rv1; i += kThreads) zc[i] = i < rv0 ? z0[i] : z1[i - rv0];
+  }
+  __syncthreads();
+  const int* P = perms + nd.Pu;
+  for (int i = tid; i < m; i += kThreads) fp[i] = f[P[i]];
+  __syncthreads();
+  double* y = fp + r;
+  const double* A = fact + nd.F;
+  if (k > 0) {
+    // rhs = fp[r:] - E ft1
+    const double* E = vals + nd.Eu;
+    for (int i = tid; i < k; i += kThreads) {
+      double v = fp[r + i];
+      for (int l = 0; l < r; l++) v -= E[i + (size_t)l * k] * fp[l];
+      f[i] = v;  // reuse f as rhs
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += kThreads) y[i] = f[i];
+    __syncthreads();
+    // y = R^{-T} rhs, blocked by 32 columns (L = R^T, solve.hpp:160-161)
+    for (int i0 = 0; i0 < k; i0 += 32) {
+      const int ib = min(32, k - i0);
+      for (int c = warp; c < ib; c += kWarps) {
+        const double* Rc = A + (size_t)(i0 + c) * m;
+        double acc = 0.;
+        for (int j = lane; j < i0; j += 32) acc += Rc[j] * y[j];
+        acc = warp_sum(acc);
+        if (lane == 0) y[i0 + c] -= acc;
+      }
+      for (int idx = tid; idx < ib * ib; idx += kThreads) {
+        int a = idx % ib, c = idx / ib;
+        Rd[a + c * 33] = (a <= c) ? A[(i0 + a) + (size_t)(i0 + c) * m] : 0.;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        double val = lane < ib ? y[i0 + lane] : 0.;
+        for (int a = 0; a < ib; a++) {
+          if (lane == a) val = val / Rd[a + a * 33];
+          const double ya = __shfl_sync(0xffffffffu, val, a);
+          if (lane > a && lane < ib) val -= Rd[a + lane * 33] * ya;
+        }
+        if (lane < ib) y[i0 + lane] = val;
+      }
+      __syncthreads();
+    }
+    double* yo = ysol + (size_t)nd.y_off * s + (size_t)col * k;
+    for (int i = tid; i < k; i += kThreads) yo[i] = y[i];
+  }
+  // ---- z = Vt0^H y (+ V^H [z0; z1]) ; ft1 -= (W1 Q0^H) y
+  double* zo = zsol + (size_t)nd.z_off * s + (size_t)col * rv;
+  double* fo = fsol + (size_t)nd.f_off * s + (size_t)col * r;
+  const int* Pv = perms + nd.Pv;
+  const double* Ev = vals + nd.Ev;
+  const int kv = nd.v_rows - rv;
+  for (int c = warp; c < rv + r; c += kWarps) {
+    double acc = 0.;
+    if (k > 0) {
+      const double* col_ = A + (size_t)(k + c) * m;
+      for (int i = lane; i < k; i += 32) acc += col_[i] * y[i];
+    }
+    if (c < rv && !nd.leaf) {
+      // basis part: zc[Pv[c]] + sum_i Ev[i,c] zc[Pv[rv+i]]   (solve.hpp:166-167)
+      for (int i = lane; i < kv; i += 32) acc += Ev[i + (size_t)c * kv] * zc[Pv[rv + i]];
+      if (lane == 0) acc += zc[Pv[c]];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (c < rv) zo[c] = acc;
+      else fo[c - rv] = fp[c - rv] - acc;
+    }
+  }
+}
+
+// Root: f = [ft1(c0) - B01 z(c1); ft1(c1) - B10 z(c0)], x = LU^{-1} f
+//                                                   (solve.hpp:88-135)
+__global__ void __launch_bounds__(kThreads)
+ulv_root_solve_kernel(const DNode* __restrict__ nodes, const double* __restrict__ vals,
+                      const double* __restrict__ fact, const int* __restrict__ piv,
+                      double* __restrict__ b, int ldb, const double* __restrict__ zsol,
+                      const double* __restrict__ fsol, double* __restrict__ xsol, int s) {
+  extern __shared__ double sm[];
+  const DNode nd = nodes[0];
+  const int col = blockIdx.x, tid = threadIdx.x;
+  const int n = nd.m;
+  double* x = sm;
+  if (nd.leaf) {
+    const double* bb = b + (size_t)col * ldb;
+    for (int i = tid; i < n; i += kThreads) x[i] = bb[i];
+  } else {
+    const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
+    const int ru0 = c0.u_rank, ru1 = c1.u_rank, rv0 = c0.v_rank, rv1 = c1.v_rank;
+    const double* f0 = fsol + (size_t)c0.f_off * s + (size_t)col * ru0;
+    const double* f1 = fsol + (size_t)c1.f_off * s + (size_t)col * ru1;
+    const double* z0 = zsol + (size_t)c0.z_off * s + (size_t)col * rv0;
+    const double* z1 = zsol + (size_t)c1.z_off * s + (size_t)col * rv1;
+    const double* B01 = vals + nd.B01;
+    const double* B10 = vals + nd.B10;
+    for (int i = tid; i < n; i += kThreads) {
+      double v;
+      if (i < ru0) { v = f0[i]; for (int j = 0; j < rv1; j++) v -= B01[i + (size_t)j * ru0] * z1[j]; }
+      else { int ii = i - ru0; v = f1[ii]; for (int j = 0; j < rv0; j++) v -= B10[ii + (size_t)j * ru1] * z0[j]; }
+      x[i] = v;
+    }
+  }
+  __syncthreads();
+  const double* A = fact + nd.F;
+  if (tid == 0)
+    for (int j = 0; j < n; j++) {
+      int p = piv[j];
+      if (p != j) { double t = x[j]; x[j] = x[p]; x[p] = t; }
+    }
+  __syncthreads();
+  for (int j = 0; j < n; j++) {   // unit lower
+    const double xj = x[j];
+    for (int i = j + 1 + tid; i < n; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; j--) {  // upper
+    if (tid == 0) x[j] /= A[j + (size_t)j * n];
+    __syncthreads();
+    const double xj = x[j];
+    for (int i = tid; i < j; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+    __syncthreads();
+  }
+  if (nd.leaf) {
+    double* bb = b + (size_t)col * ldb;
+    for (int i = tid; i < n; i += kThreads) bb[i] = x[i];
+  } else {
+    double* xo = xsol + (size_t)nd.x_off * s + (size_t)col * n;
+    for (int i = tid; i < n; i += kThreads) xo[i] = x[i];
+  }
+}
+
+// Backward sweep over one height class (root excluded): x = Q^H [y; x_c]
+//                                                   (solve.hpp:199-238)
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+               const double* __restrict__ fact, const double* __restrict__ tfac,
+               double* __restrict__ b, int ldb, const double* __restrict__ ysol,
+               double* __restrict__ xsol, int s) {
+  extern __shared__ double sm[];
+  const int id = list[blockIdx.x];
+  const DNode nd = nodes[id];
+  if (nd.parent < 0) return;
+  const DNode par = nodes[nd.parent];
+  const int col = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = nd.m, r = nd.u_rank, k = nd.k;
+  double* v = sm;        // m
+  double* w = v + m;     // NB
+  double* w2 = w + NB;   // NB
+  const int xoff = (par.ch0 == id) ? 0 : nodes[par.ch0].u_rank;
+  const double* xp = xsol + (size_t)par.x_off * s + (size_t)col * par.m + xoff;
+  const double* yi = ysol + (size_t)nd.y_off * s + (size_t)col * k;
+  for (int i = tid; i < m; i += kThreads) v[i] = i < k ? yi[i] : xp[i - k];
+  __syncthreads();
+  const double* A = fact + nd.F;
+  const double* Tg = tfac + nd.T;
+  const int nblk = (k + NB - 1) / NB;
+  for (int bi = nblk - 1; bi >= 0; bi--) {
+    const int j0 = bi * NB, jb = min(NB, k - j0);
+    for (int a = warp; a < jb; a += kWarps) {
+      const double* Va = A + (size_t)(j0 + a) * m;
+      double acc = 0.;
+      for (int i = j0 + a + 1 + lane; i < m; i += 32) acc += Va[i] * v[i];
+      acc = warp_sum(acc);
+      if (lane == 0) w[a] = acc + v[j0 + a];
+    }
+    __syncthreads();
+    if (tid < jb) {
+      double acc = 0.;
+      for (int c = tid; c < jb; c++) acc += Tg[tid + (size_t)(j0 + c) * NB] * w[c];
+      w2[tid] = acc;
+    }
+    __syncthreads();
+    for (int i = j0 + tid; i < m; i += kThreads) {
+      double acc = 0.;
+      const int amax = min(jb, i - j0);  // a with j0+a < i
+      for (int a = 0; a < amax; a++) acc += A[i + (size_t)(j0 + a) * m] * w2[a];
+      if (i - j0 < jb) acc += w2[i - j0];
+      v[i] -= acc;
+    }
+    __syncthreads();
+  }
+  if (nd.leaf) {
+    double* bb = b + nd.row_off + (size_t)col * ldb;
+    for (int i = tid; i < m; i += kThreads) bb[i] = v[i];
+  } else {
+    double* xo = xsol + (size_t)nd.x_off * s + (size_t)col * m;
+    for (int i = tid; i < m; i += kThreads) xo[i] = v[i];
+  }
+}
+
+}  // namespace
+
+// ===========================================================================
+//                                 HOST SIDE
+// ===========================================================================
+
+HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) { build_tables(); }
+HSSEngine::~HSSEngine() {}
+
+void HSSEngine::build_tables() {
+  const int N = int(H_.nodes.size());
+  hn_.resize(N);
+  int woff = 0;
+  long long foff = 0, toff = 0;
+  int yoff = 0, zoff = 0, fo = 0, xo = 0;
+  int maxm = 0;
+  for (int i = 0; i < N; i++) {
+    const auto& n = H_.nodes[i];
+    maxm = std::max(maxm, n.leaf() ? std::max(n.rows, n.cols)
+                                   : H_.nodes[n.ch0].u_rank + H_.nodes[n.ch1].u_rank);
+  }
+  nb_ = maxm <= 340 ? 32 : (maxm <= 800 ? 16 : 8);
+  if (maxm > 1600)
+    throw std::invalid_argument("HSS block larger than 1600 not supported");
+  for (int i = 0; i < N; i++) {
+    const auto& n = H_.nodes[i];
+    DNode& d = hn_[i];
+    d.ch0 = n.ch0; d.ch1 = n.ch1; d.parent = n.parent; d.leaf = n.leaf();
+    d.rows = n.rows; d.cols = n.cols; d.row_off = n.row_off; d.col_off = n.col_off;
+    d.u_rows = n.u_rows; d.u_rank = n.u_rank; d.v_rows = n.v_rows; d.v_rank = n.v_rank;
+    d.D = n.off_D; d.Eu = n.off_Eu; d.Ev = n.off_Ev; d.B01 = n.off_B01; d.B10 = n.off_B10;
+    d.Pu = n.off_Pu; d.Pv = n.off_Pv;
+    d.w_off = woff;
+    woff += std::max(n.u_rank, n.v_rank);
+    d.m = n.leaf() ? n.rows : H_.nodes[n.ch0].u_rank + H_.nodes[n.ch1].u_rank;
+    if (i == 0) {
+      d.k = 0; d.naug = d.m;  // root: m x m LU block
+    } else {
+      d.k = d.m - n.u_rank;
+      d.naug = d.k + n.v_rank + n.u_rank;
+    }
+    d.F = foff;
+    foff += (long long)d.m * d.naug;
+    d.T = toff;
+    toff += (long long)nb_ * d.k;
+    d.y_off = yoff; yoff += d.k;
+    d.z_off = zoff; zoff += n.v_rank;
+    d.f_off = fo; fo += n.u_rank;
+    d.x_off = xo; xo += d.m;
+  }
+  ws_total_ = woff;
+  tot_k_ = yoff; tot_rv_ = zoff; tot_ru_ = fo; tot_m_ = xo;
+  fact_nnz_ = foff + toff;
+  hptr_ = H_.hptr;
+  const int nh = int(hptr_.size()) - 1;
+  cls_max_m_.assign(nh, 0);
+  cls_max_naug_.assign(nh, 0);
+  for (int h = 0; h < nh; h++)
+    for (int q = hptr_[h]; q < hptr_[h + 1]; q++) {
+      const DNode& d = hn_[H_.by_height[q]];
+      cls_max_m_[h] = std::max(cls_max_m_[h], std::max(d.m, std::max(d.rows * d.leaf, d.cols * d.leaf)));
+      cls_max_m_[h] = std::max(cls_max_m_[h], std::max(d.u_rows, d.v_rows));
+      cls_max_naug_[h] = std::max(cls_max_naug_[h], d.naug);
+    }
+  dn_.upload(hn_.data(), hn_.size());
+  vals_.upload(H_.vals.data(), H_.vals.size());
+  perms_.upload(H_.perms.data(), H_.perms.size());
+  by_height_.upload(H_.by_height.data(), H_.by_height.size());
+  SB200_CUDA(cudaStreamSynchronize(0));
+}
+
+void HSSEngine::ensure_apply_ws(int s) {
+  if (s <= apply_s_) return;
+  t1_.alloc((size_t)std::max(ws_total_, 1) * s);
+  t2_.alloc((size_t)std::max(ws_total_, 1) * s);
+  apply_s_ = s;
+}
+
+void HSSEngine::ensure_solve_ws(int s) {
+  if (s <= solve_s_) return;
+  ysol_.alloc((size_t)std::max<long long>(tot_k_, 1) * s);
+  zsol_.alloc((size_t)std::max<long long>(tot_rv_, 1) * s);
+  fsol_.alloc((size_t)std::max<long long>(tot_ru_, 1) * s);
+  xsol_.alloc((size_t)std::max<long long>(tot_m_, 1) * s);
+  solve_s_ = s;
+}
+
+template <typename K> static void set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    SB200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+void HSSEngine::mult(char trans, int s, const double* dB, int ldB, double* dC,
+                     int ldC, cudaStream_t st) {
+  const bool T = !(trans == 'N' || trans == 'n');
+  if (s <= 0) return;
+  ensure_apply_ws(s);
+  const int nh = int(hptr_.size()) - 1;
+  const int* list = by_height_.p;
+  // up-sweep: classes 0 .. nh-2 (the root, alone in class nh-1, is skipped)
+  for (int h = 0; h < nh - 1; h++) {
+    const int cnt = hptr_[h + 1] - hptr_[h];
+    size_t smem = sizeof(double) * (size_t)std::max(cls_max_m_[h], 1);
+    dim3 grid(cnt, s);
+    if (T) { set_smem(hss_up_kernel<true>, smem);
+      hss_up_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, dB, ldB, t1_.p, s);
+    } else { set_smem(hss_up_kernel<false>, smem);
+      hss_up_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, dB, ldB, t1_.p, s);
+    }
+    launches_++;
+  }
+  // down-sweep over inner nodes, top class first
+  for (int h = nh - 1; h >= 1; h--) {
+    const int cnt = hptr_[h + 1] - hptr_[h];
+    size_t smem = sizeof(double) * (size_t)(2 * std::max(cls_max_m_[h], 1) + 8);
+    dim3 grid(cnt, s);
+    if (T) { set_smem(hss_down_kernel<true>, smem);
+      hss_down_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, t1_.p, t2_.p, s);
+    } else { set_smem(hss_down_kernel<false>, smem);
+      hss_down_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, t1_.p, t2_.p, s);
+    }
+    launches_++;
+  }
+  {
+    const int cnt = hptr_[1] - hptr_[0];
+    size_t smem = sizeof(double) * (size_t)(3 * std::max(cls_max_m_[0], 1) + 8);
+    dim3 grid(cnt, s);
+    if (T) { set_smem(hss_leaf_kernel<true>, smem);
+      hss_leaf_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, list, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s);
+    } else { set_smem(hss_leaf_kernel<false>, smem);
+      hss_leaf_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, list, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s);
+    }
+    launches_++;
+  }
+  SB200_CUDA(cudaGetLastError());
+}
+
+void HSSEngine::shift(double sigma, cudaStream_t st) {
+  const int cnt = hptr_[1] - hptr_[0];
+  hss_shift_kernel<<<cnt, 128, 0, st>>>(dn_.p, by_height_.p, vals_.p, sigma);
+  launches_++;
+  SB200_CUDA(cudaGetLastError());
+  factored_ = false;
+}
+
+void HSSEngine::sync_host_values() {
+  SB200_CUDA(cudaMemcpy(H_.vals.data(), vals_.p, H_.vals.size() * sizeof(double),
+                        cudaMemcpyDeviceToHost));
+}
+
+template <int NB> static size_t qr_smem(int ldv) {
+  constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
+  return sizeof(double) * ((size_t)2 * ldv * NB + 3 * LDW * NB + NB + 32);
+}
+
+void HSSEngine::factor(cudaStream_t st) {
+  if (H_.rows() != H_.cols())
+    throw std::invalid_argument("ULV factorization needs a square matrix");
+  for (auto& n : H_.nodes)
+    if (n.leaf() && n.rows != n.cols)
+      throw std::invalid_argument("ULV factorization needs square diagonal blocks");
+  const int nh = int(hptr_.size()) - 1;
+  const int N = int(hn_.size());
+  fact_.ensure((size_t)std::max<long long>(fact_nnz_, 1));
+  tfac_.ensure((size_t)std::max<long long>((long long)nb_ * tot_k_, 1));
+  rootpiv_.ensure(std::max(hn_[0].m, 1));
+  // scratch for the Dfull of inner nodes: one slab per class, reused
+  std::vector<long long> soff(N, 0);
+  long long smax = 0;
+  for (int h = 1; h < nh; h++) {
+    long long o = 0;
+    for (int q = hptr_[h]; q < hptr_[h + 1]; q++) {
+      const DNode& d = hn_[H_.by_height[q]];
+      soff[q] = o;
+      o += (long long)d.m * d.m;
+    }
+    smax = std::max(smax, o);
+  }
+  scratch_.ensure((size_t)std::max<long long>(smax, 1));
+  DevBuf<long long> dsoff;
+  dsoff.upload(soff.data(), soff.size(), st);
+  const int* list = by_height_.p;
+  for (int h = 0; h < nh; h++) {
+    const int cnt = hptr_[h + 1] - hptr_[h];
+    const int* lst = list + hptr_[h];
+    const long long* so = dsoff.p + hptr_[h];
+    const int mm = std::max(cls_max_m_[h], 1);
+    if (h == 0) {
+      ulv_vh_leaf_kernel<<<cnt, kThreads, 0, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p);
+      launches_++;
+    } else {
+      size_t smem = sizeof(double) * (size_t)mm * mm;  // Vd: v_rows x rv <= mm^2
+      smem = std::min(smem, sizeof(double) * (size_t)mm * std::max(H_.max_rank(), 1));
+      set_smem(ulv_build_inner_kernel, smem);
+      ulv_build_inner_kernel<<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
+      launches_++;
+    }
+    if (h == nh - 1) break;  // root class: LU below
+    // elimination
+    if (mm <= 640) {
+      size_t smem = sizeof(double) * (size_t)mm * 33;
+      set_smem(ulv_eliminate_kernel<32>, smem);
+      ulv_eliminate_kernel<32><<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
+    } else {
+      size_t smem = sizeof(double) * (size_t)mm * 9;
+      set_smem(ulv_eliminate_kernel<8>, smem);
+      ulv_eliminate_kernel<8><<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
+    }
+    launches_++;
+    const int ldv = smem_ld(mm);
+    if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32>, smem);
+      ulv_qr_kernel<32><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
+    } else if (nb_ == 16) { size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16>, smem);
+      ulv_qr_kernel<16><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
+    } else { size_t smem = qr_smem<8>(ldv); set_smem(ulv_qr_kernel<8>, smem);
+      ulv_qr_kernel<8><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
+    }
+    launches_++;
+  }
+  // root LU
+  const DNode& root = hn_[0];
+  if (root.leaf) {
+    long long n2 = (long long)root.m * root.m;
+    copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(vals_.p + root.D, fact_.p + root.F, n2);
+  } else {
+    long long n2 = (long long)root.m * root.m;
+    // Dfull of the root was written to scratch slab offset 0 of its class
+    copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(scratch_.p, fact_.p + root.F, n2);
+  }
+  launches_++;
+  ulv_root_lu_kernel<<<1, kThreads, 0, st>>>(fact_.p + root.F, root.m, rootpiv_.p);
+  launches_++;
+  SB200_CUDA(cudaGetLastError());
+  SB200_CUDA(cudaStreamSynchronize(st));  // dsoff lifetime
+  factored_ = true;
+}
+
+void HSSEngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
+  if (!factored_) throw std::logic_error("solve called before factor");
+  if (s <= 0) return;
+  ensure_solve_ws(s);
+  const int nh = int(hptr_.size()) - 1;
+  const int* list = by_height_.p;
+  for (int h = 0; h < nh - 1; h++) {
+    const int cnt = hptr_[h + 1] - hptr_[h];
+    const int mm = std::max(cls_max_m_[h], 1);
+    size_t smem = sizeof(double) * (size_t)(3 * mm + 32 * 33 + 8);
+    dim3 grid(cnt, s);
+    set_smem(ulv_fwd_kernel<32>, smem);
+    ulv_fwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, fact_.p, dB, ldB, ysol_.p, zsol_.p, fsol_.p, s);
+    launches_++;
+  }
+  {
+    size_t smem = sizeof(double) * (size_t)std::max(hn_[0].m, 1);
+    set_smem(ulv_root_solve_kernel, smem);
+    ulv_root_solve_kernel<<<s, kThreads, smem, st>>>(dn_.p, vals_.p, fact_.p, rootpiv_.p, dB, ldB, zsol_.p, fsol_.p, xsol_.p, s);
+    launches_++;
+  }
+  for (int h = nh - 2; h >= 0; h--) {
+    const int cnt = hptr_[h + 1] - hptr_[h];
+    const int mm = std::max(cls_max_m_[h], 1);
+    size_t smem = sizeof(double) * (size_t)(mm + 2 * 32 + 8);
+    dim3 grid(cnt, s);
+    if (nb_ == 32) { set_smem(ulv_bwd_kernel<32>, smem);
+      ulv_bwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
+    } else if (nb_ == 16) { set_smem(ulv_bwd_kernel<16>, smem);
+      ulv_bwd_kernel<16><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
+    } else { set_smem(ulv_bwd_kernel<8>, smem);
+      ulv_bwd_kernel<8><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
+    }
+    launches_++;
+  }
+  SB200_CUDA(cudaGetLastError());
+}
+
+}  // namespace sb200

@@ -1,0 +1,86 @@
+// strumpack_b200 -- device-resident HSS matrix: apply, ULV factor, ULV solve.
+//
+// Replaces (reference, CPU/OpenMP-task recursion, one BLAS call per block):
+//   apply_HSS / apply_fwd / apply_bwd / applyT_*  src/HSS/HSSMatrix.apply.hpp:34-220
+//   factor / factor_recursive                     src/HSS/HSSMatrix.factor.hpp:35-147
+//   solve / solve_fwd / solve_bwd                 src/HSS/HSSMatrix.solve.hpp:35-238
+// with per-height-class batched sm_100a kernels over a flat node table.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+#include "hss_tree.hpp"
+#include "sb200_common.cuh"
+
+namespace sb200 {
+
+// One record per node, read by the CTA that owns the node.
+struct DNode {
+  int ch0, ch1, parent, leaf;
+  int rows, cols, row_off, col_off;
+  int u_rows, u_rank, v_rows, v_rank;
+  long long D, Eu, Ev, B01, B10;  // offsets into the generator arena (-1: none)
+  long long Pu, Pv;               // offsets into the permutation arena
+  int w_off;                      // apply workspace: prefix of max(u_rank,v_rank)
+  // ---- ULV ----
+  int m, k;            // reduced-system size, eliminated unknowns (m - u_rank)
+  int naug;            // k + v_rank + u_rank columns of the factor block
+  long long F;         // factor block m x naug (ld = m) in the factor arena
+  long long T;         // block-reflector T factors, NB x k (ld = NB)
+  int y_off, z_off, f_off, x_off;  // solve workspace prefixes (k, v_rank, u_rank, m)
+};
+
+class HSSEngine {
+ public:
+  explicit HSSEngine(HSSHost&& host);
+  ~HSSEngine();
+
+  const HSSHost& host() const { return H_; }
+  int rows() const { return H_.rows(); }
+  int cols() const { return H_.cols(); }
+
+  // C = op(H) B ; dB, dC device pointers (column-major)
+  void mult(char trans, int s, const double* dB, int ldB, double* dC, int ldC,
+            cudaStream_t st);
+  void factor(cudaStream_t st);
+  void solve(int s, double* dB, int ldB, cudaStream_t st);
+  void shift(double sigma, cudaStream_t st);
+  bool factored() const { return factored_; }
+
+  long long factor_nonzeros() const { return fact_nnz_; }
+  long long launches() const { return launches_; }
+  // download the generator arena (after shift) for write_file / dense
+  void sync_host_values();
+
+ private:
+  void build_tables();
+  void ensure_apply_ws(int s);
+  void ensure_solve_ws(int s);
+
+  HSSHost H_;
+  std::vector<DNode> hn_;
+  DevBuf<DNode> dn_;
+  DevBuf<double> vals_;
+  DevBuf<int32_t> perms_;
+  DevBuf<int> by_height_;
+  std::vector<int> hptr_;
+  // per height class: max sizes (launch configuration)
+  std::vector<int> cls_max_m_, cls_max_naug_;
+  // apply workspace
+  DevBuf<double> t1_, t2_;
+  int ws_total_ = 0, apply_s_ = 0;
+  // ULV
+  DevBuf<double> fact_, tfac_, scratch_;
+  DevBuf<int> rootpiv_;
+  DevBuf<double> ysol_, zsol_, fsol_, xsol_;
+  int solve_s_ = 0;
+  long long tot_k_ = 0, tot_rv_ = 0, tot_ru_ = 0, tot_m_ = 0;
+  long long fact_nnz_ = 0;
+  long long scratch_per_node_max_ = 0;
+  bool factored_ = false;
+  long long launches_ = 0;
+  int nb_ = 32;
+};
+
+}  // namespace sb200

@@ -1,0 +1,143 @@
+"""GPU parity tests (through the C ABI): HSS apply / ULV factor / ULV solve
+vs the golden vectors produced by the reference and vs the CPU oracle.
+
+Tolerances: the reference's own test demands ||B - H(H\\B)||/||B|| <= 1e-12
+(test/test_HSS_seq.cpp:39,247-250) in fp64; apply is the same arithmetic in a
+different summation order -> 1e-13."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASES, GOLDEN, have_ref
+from oracle import hss_file, hss_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def sb(built):
+    import torch
+    assert torch.cuda.is_available()
+    return built
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_apply_matches_reference(sb, case):
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    H = sb.HSSMatrix.read(os.path.join(GOLDEN, case + ".hss"))
+    assert (H.rows, H.cols, H.rank, H.levels) == tuple(g["info"][:4])
+    assert rel(H.mult(g["x"]), g["y"]) < 1e-13
+    assert rel(H.mult(g["x"], "T"), g["yt"]) < 1e-13
+    assert rel(H.mult(g["x"][:, 0]), g["y"][:, :1]) < 1e-13   # single rhs
+    assert H.launches > 0
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_ulv_matches_reference(sb, case):
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    H = sb.HSSMatrix.read(os.path.join(GOLDEN, case + ".hss"))
+    H.factor()
+    xs = H.solve(g["y"])
+    assert rel(xs, g["xs"]) < 1e-10
+    assert rel(H.mult(xs), g["y"]) < 1e-12      # reference's acceptance bound
+    assert H.flops("factor") == g["flops"][0]
+
+
+def test_solve_before_factor_fails(sb, capfd):
+    H = sb.HSSMatrix.read(os.path.join(GOLDEN, CASES[0] + ".hss"))
+    with pytest.raises(RuntimeError):
+        H.solve(np.ones(H.rows))
+    assert "Operation failed" in capfd.readouterr().err
+
+
+def test_from_generators_and_dense(sb):
+    nodes, _ = hss_file.read_hss(os.path.join(GOLDEN, CASES[1] + ".hss"))
+    H = sb.HSSMatrix.from_generators(nodes)
+    A = H.dense()
+    assert rel(A, ho.to_dense(nodes)) < 1e-13
+
+
+def test_shift_and_write(sb, tmp_path):
+    path = os.path.join(GOLDEN, CASES[0] + ".hss")
+    nodes, _ = hss_file.read_hss(path)
+    H = sb.HSSMatrix.read(path)
+    x = np.random.default_rng(3).standard_normal((H.rows, 2))
+    y0 = H.mult(x)
+    H.shift(2.5)
+    assert rel(H.mult(x), y0 + 2.5 * x) < 1e-13
+    H.factor()
+    y = H.mult(x)
+    assert rel(H.solve(y), x) < 1e-10
+    out = tmp_path / "shifted.hss"
+    H.write(out)
+    n2, _ = hss_file.read_hss(out)
+    leaf = next(i for i, n in enumerate(nodes) if n.leaf)
+    assert np.allclose(n2[leaf].D, nodes[leaf].D + 2.5 * np.eye(nodes[leaf].rows))
+
+
+def test_device_resident_path(sb):
+    import torch
+    path = os.path.join(GOLDEN, CASES[2] + ".hss")
+    g = np.load(os.path.join(GOLDEN, CASES[2] + ".npz"))
+    H = sb.HSSMatrix.read(path)
+    xT = torch.tensor(g["x"].T.copy(), device="cuda", dtype=torch.float64)
+    yT = torch.empty_like(xT)
+    H.mult_device(xT, yT)
+    H.factor_device()
+    bT = yT.clone()
+    H.solve_device(bT)
+    torch.cuda.synchronize()
+    assert rel(yT.cpu().numpy().T, g["y"]) < 1e-13
+    assert rel(bT.cpu().numpy().T, g["xs"]) < 1e-10
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("n,leaf,tol,kind", [(4096, 128, 1e-4, "T"),
+                                              (2000, 100, 1e-8, "U"),
+                                              (1000, 16, 1e-2, "T"),
+                                              (97, 128, 1e-4, "T")])
+def test_live_reference_toeplitz(sb, tmp_path, n, leaf, tol, kind):
+    """BASELINE configs[0] (4096 Toeplitz, leaf 128, tol 1e-4) and the ragged /
+    tiny-leaf / single-node edge cases of test/CMakeLists.txt:57-159."""
+    from oracle import ref
+    ref.set_num_threads(8)
+    R = ref.RefHSS.toeplitz(n, kind, f"--hss_leaf_size {leaf} --hss_rel_tol {tol}")
+    p = tmp_path / "h.hss"
+    R.write(p)
+    H = sb.HSSMatrix.read(p)
+    x = np.random.default_rng(n).standard_normal((n, 2))
+    y_ref = R.mult(x)
+    assert rel(H.mult(x), y_ref) < 1e-13
+    assert rel(H.mult(x, "T"), R.mult(x, trans=True)) < 1e-13
+    ref.flops_reset()
+    R.factor()
+    assert H.flops("factor") == ref.flops()["ulv_factor"]
+    H.factor()
+    xs = H.solve(y_ref)
+    assert rel(xs, R.solve(y_ref)) < 1e-9
+    assert rel(H.mult(xs), y_ref) < 1e-12
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_live_reference_gauss_ragged(sb, tmp_path):
+    """Gaussian kernel, 2-means clustering -> ragged leaves."""
+    from oracle import ref
+    ref.set_num_threads(8)
+    pts = np.random.default_rng(42).random((2, 8192))
+    R = ref.RefHSS.gauss(pts, 0.1, 1.0, "--hss_leaf_size 256 --hss_rel_tol 1e-4")
+    p = tmp_path / "h.hss"
+    R.write(p)
+    H = sb.HSSMatrix.read(p)
+    x = np.random.default_rng(0).standard_normal((8192, 3))
+    y_ref = R.mult(x)
+    assert rel(H.mult(x), y_ref) < 1e-13
+    R.factor()
+    H.factor()
+    xs = H.solve(y_ref)
+    assert rel(xs, R.solve(y_ref)) < 1e-9
+    assert rel(H.mult(xs), y_ref) < 1e-12

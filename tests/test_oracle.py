@@ -1,0 +1,86 @@
+"""CPU tests: pin the numpy oracle (oracle/hss_oracle.py).
+
+(1) against the committed golden vectors (outputs of the reference itself,
+    tests/golden/make_golden.py), (2) against the live reference library
+    oracle/_ref when it is present, including the reference's own acceptance
+    checks of test/test_HSS_seq.cpp (compression error <= 1e2*tol, :143-152;
+    ULV residual <= 1e-12, :235-250)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASES, GOLDEN, have_ref
+from oracle import hss_file, hss_oracle as ho
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_golden(case):
+    nodes, ver = hss_file.read_hss(os.path.join(GOLDEN, case + ".hss"))
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    assert tuple(ver) == (8, 0, 0)
+    assert nodes[0].rows == g["info"][0] and nodes[0].cols == g["info"][1]
+    assert max(max(n.U_rank, n.V_rank) for n in nodes) == g["info"][2]
+    # apply, both directions: bit-for-bit the same algorithm -> ~1e-15
+    assert rel(ho.apply(nodes, g["x"]), g["y"]) < 1e-13
+    assert rel(ho.apply(nodes, g["x"], trans=True), g["yt"]) < 1e-13
+    # ULV factor + solve
+    f = ho.factor(nodes)
+    xs = ho.solve(nodes, f, g["y"])
+    assert rel(xs, g["xs"]) < 1e-11
+    # reference's own acceptance: ||B - H (H\B)|| / ||B|| <= 1e-12
+    assert rel(ho.apply(nodes, xs), g["y"]) < 1e-12
+
+
+def test_basis_identities():
+    nodes, _ = hss_file.read_hss(os.path.join(GOLDEN, CASES[0] + ".hss"))
+    nd = next(n for n in nodes if n.leaf)
+    U = ho.basis_dense(nd.Pu, nd.Eu)
+    b = np.random.default_rng(0).standard_normal((nd.U_rank, 2))
+    assert np.allclose(ho.basis_apply(nd.Pu, nd.Eu, b), U @ b)
+    c = np.random.default_rng(1).standard_normal((nd.U_rows, 2))
+    assert np.allclose(ho.basis_applyC(nd.Pu, nd.Eu, c), U.T @ c)
+    # interpolative: U contains the identity on the skeleton rows
+    g = hss_file.ipiv_to_gather(nd.Pu)
+    assert np.allclose(U[g[:nd.U_rank], :], np.eye(nd.U_rank))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_oracle_matches_live_reference(tmp_path):
+    from oracle import ref
+    ref.set_num_threads(2)
+    n = 768
+    H = ref.RefHSS.toeplitz(n, "T", "--hss_leaf_size 48 --hss_rel_tol 1e-5")
+    p = tmp_path / "h.hss"
+    H.write(p)
+    nodes, _ = hss_file.read_hss(p)
+    x = np.random.default_rng(5).standard_normal((n, 2))
+    assert rel(ho.apply(nodes, x), H.mult(x)) < 1e-13
+    H.factor()
+    y = H.mult(x)
+    f = ho.factor(nodes)
+    assert rel(ho.solve(nodes, f, y), H.solve(y)) < 1e-11
+    # test_HSS_seq.cpp:143-152 compression check on the dense matrix
+    i = np.arange(n)
+    A = 1.0 / (1.0 + np.abs(i[:, None] - i[None, :]))
+    assert rel(ho.to_dense(nodes), A) < 1e2 * 1e-5
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_reference_selftests_pass():
+    """The oracle build of the reference passes the reference's own tests."""
+    import subprocess
+    from oracle import ref
+    d = os.path.dirname(ref._SO)
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="2")
+    out = subprocess.run([os.path.join(d, "test_HSS_seq"), "T", "200",
+                          "--hss_leaf_size", "16", "--hss_rel_tol", "1e-5"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-500:]
+    out = subprocess.run([os.path.join(d, "test_BLR_seq"), "512"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-500:]
