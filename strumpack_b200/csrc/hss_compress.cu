@@ -1,15 +1,560 @@
-// strumpack_b200 -- HSS construction on the GPU (placeholder, see header).
+// strumpack_b200 -- HSS construction on the GPU.
+//
+// What it replaces (reference, CPU): HSSMatrix(A,opts)/compress
+// (src/HSS/HSSMatrix.cpp:49-54,148-161), HSSMatrix(Kernel&,opts)
+// (src/HSS/HSSMatrix.cpp:88-106), compress_kernel + ANN sampling
+// (src/HSS/HSSMatrix.compress_kernel.hpp:39-293).  Same output object -- the
+// ID generators U = P[I;E], V, D, B01, B10 of every node -- but a different,
+// GPU-shaped algorithm:
+//
+//  * cluster tree: median bisection along the widest coordinate (a kd-tree,
+//    one of the reference's clustering options, Clustering.hpp:51-57) for
+//    point data; index bisection (HSSMatrix.cpp:60-70) for plain matrices;
+//  * per node a SAMPLE of the complement columns is chosen top-down on the
+//    host: the nearest points of the sibling cluster and of the parent's
+//    sample, plus random far ones (multi-scale: every level contributes);
+//    small dense inputs use the whole complement (exact);
+//  * bottom-up by height class, batched on the device: evaluate the sampled
+//    block A(I_t, J_t) entry-wise, column-pivoted Gram-Schmidt QR with the
+//    reference's stopping rule |R_jj|/|R_00| <= rel_tol or |R_jj| <= abs_tol
+//    (src/dense/lapack/dgeqp3tol.f:203-209), E = (R11^{-1} R12)^T
+//    (DenseMatrix::ID_column_GEQP3, src/dense/DenseMatrix.cpp:764-790);
+//    skeleton rows propagate to the parent (nested bases);
+//  * B01/B10/D are sub-blocks of A at skeleton indices, evaluated directly.
 #include "hss_compress.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <numeric>
+#include <random>
 #include <stdexcept>
+
+#include "sb200_common.cuh"
+
 namespace sb200 {
-HSSHost compress_dense(int, int, const double*, int, const CompressOptions&) {
-  throw std::runtime_error("compress_dense: not implemented yet");
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+
+// ---- matrix element on the device ------------------------------------------
+struct ElemSrc {
+  int type;            // 0 gauss, 1 laplace, 2 toeplitz 1/(1+|i-j|), 3 dense
+  int d;               // point dimension
+  const double* pts;   // d x n (device), permuted ordering
+  double h, lambda;
+  const double* A;     // dense (device), column-major
+  long long lda;
+};
+
+__device__ __forceinline__ double elem(const ElemSrc& s, int i, int j) {
+  switch (s.type) {
+    case 0: {
+      double r2 = 0.;
+      for (int q = 0; q < s.d; q++) {
+        double t = s.pts[q + (size_t)i * s.d] - s.pts[q + (size_t)j * s.d];
+        r2 += t * t;
+      }
+      return exp(-r2 / (2. * s.h * s.h)) + (i == j ? s.lambda : 0.);
+    }
+    case 1: {
+      double r1 = 0.;
+      for (int q = 0; q < s.d; q++)
+        r1 += fabs(s.pts[q + (size_t)i * s.d] - s.pts[q + (size_t)j * s.d]);
+      return exp(-r1 / s.h) + (i == j ? s.lambda : 0.);
+    }
+    case 2:
+      return i == j ? 1. + s.lambda : 1. / (1. + fabs((double)i - (double)j));
+    default:
+      return s.A[i + (size_t)j * s.lda];
+  }
 }
-HSSHost compress_elements(int, int, double (*)(int, int), const CompressOptions&) {
-  throw std::runtime_error("compress_elements: not implemented yet");
+
+// One block task: out (nr x nc, ld) = A(rows[.], cols[.]) or its transpose.
+struct BlockTask {
+  const int* rows;   // device index list (global indices)
+  const int* cols;
+  int nr, nc;
+  double* out;       // device
+  long long ld;
+  int transpose;     // 1: out[j + i*ld] = A(rows[i], cols[j])
+};
+
+__global__ void __launch_bounds__(kThreads)
+eval_blocks_kernel(ElemSrc src, const BlockTask* __restrict__ tasks) {
+  const BlockTask t = tasks[blockIdx.x];
+  const long long tot = (long long)t.nr * t.nc;
+  for (long long idx = blockIdx.y * (long long)kThreads + threadIdx.x; idx < tot;
+       idx += (long long)gridDim.y * kThreads) {
+    if (!t.transpose) {
+      int i = (int)(idx % t.nr), j = (int)(idx / t.nr);
+      t.out[i + (size_t)j * t.ld] = elem(src, t.rows[i], t.cols[j]);
+    } else {
+      int j = (int)(idx % t.nc), i = (int)(idx / t.nc);
+      t.out[j + (size_t)i * t.ld] = elem(src, t.rows[i], t.cols[j]);
+    }
+  }
 }
-HSSHost compress_kernel(int, int, double*, int, double, double,
-                        const CompressOptions&, int*) {
-  throw std::runtime_error("compress_kernel: not implemented yet");
+
+// ---- batched column-pivoted QR -> interpolative decomposition ----------------
+struct IDTask {
+  double* M;       // ns x nc, column-major, ld = ns (destroyed)
+  double* R;       // rcap x nc workspace, ld = rcap
+  int ns, nc, rcap;
+  int* order;      // nc: pivot order (output): order[0:rank] = skeleton columns
+  int* rank;       // 1
+  double* E;       // (nc - rank) x rank column-major (output), capacity (nc x rcap)
+};
+
+__global__ void __launch_bounds__(kThreads)
+id_cpqr_kernel(const IDTask* __restrict__ tasks, double rtol, double atol,
+               int max_rank) {
+  const IDTask t = tasks[blockIdx.x];
+  extern __shared__ double sm[];
+  double* nrm2 = sm;                 // nc
+  int* ord = (int*)(nrm2 + t.nc);    // nc
+  __shared__ double redv[kWarps];
+  __shared__ int redi[kWarps];
+  __shared__ int s_piv;
+  __shared__ double s_r00;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ns = t.ns, nc = t.nc;
+  for (int c = tid; c < nc; c += kThreads) ord[c] = c;
+  for (int c = warp; c < nc; c += kWarps) {
+    const double* col = t.M + (size_t)c * ns;
+    double a = 0.;
+    for (int i = lane; i < ns; i += 32) a += col[i] * col[i];
+    a = warp_sum(a);
+    if (lane == 0) nrm2[c] = a;
+  }
+  __syncthreads();
+  const int rmax = min(min(ns, nc), min(t.rcap, max_rank));
+  int rank = 0;
+  for (int j = 0; j < rmax; j++) {
+    // pivot = remaining column (position >= j) with the largest norm
+    double best = -1.;
+    int bp = j;
+    for (int p = j + tid; p < nc; p += kThreads) {
+      double v = nrm2[ord[p]];
+      if (v > best) { best = v; bp = p; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (ov > best || (ov == best && op < bp)) { best = ov; bp = op; }
+    }
+    if (lane == 0) { redv[warp] = best; redi[warp] = bp; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = redv[0]; int p = redi[0];
+      for (int w = 1; w < kWarps; w++)
+        if (redv[w] > b || (redv[w] == b && redi[w] < p)) { b = redv[w]; p = redi[w]; }
+      int tmp = ord[j]; ord[j] = ord[p]; ord[p] = tmp;
+      s_piv = ord[j];
+      if (j == 0) s_r00 = sqrt(fmax(b, 0.));
+    }
+    __syncthreads();
+    const int pc = s_piv;
+    const double rjj = sqrt(fmax(nrm2[pc], 0.));
+    // stopping rule of xGEQP3TOL: the new diagonal entry is tested first
+    if (rjj / s_r00 <= rtol || rjj <= atol || !(rjj > 0.)) break;
+    rank = j + 1;
+    double* q = t.M + (size_t)pc * ns;
+    const double inv = 1. / rjj;
+    for (int i = tid; i < ns; i += kThreads) q[i] *= inv;
+    if (tid == 0) t.R[j + (size_t)pc * t.rcap] = rjj;
+    __syncthreads();
+    // orthogonalise the remaining columns against q, refresh their norms
+    for (int p = j + 1 + warp; p < nc; p += kWarps) {
+      const int c = ord[p];
+      double* col = t.M + (size_t)c * ns;
+      double r = 0.;
+      for (int i = lane; i < ns; i += 32) r += q[i] * col[i];
+      r = warp_sum(r);
+      double a = 0.;
+      for (int i = lane; i < ns; i += 32) {
+        double v = col[i] - r * q[i];
+        col[i] = v;
+        a += v * v;
+      }
+      a = warp_sum(a);
+      if (lane == 0) { t.R[j + (size_t)c * t.rcap] = r; nrm2[c] = a; }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) *t.rank = rank;
+  for (int c = tid; c < nc; c += kThreads) t.order[c] = ord[c];
+  // E^T = R11^{-1} R12 : back substitution, one thread per remaining column
+  const int k = nc - rank;
+  for (int p = tid; p < k; p += kThreads) {
+    const int c = ord[rank + p];
+    double* x = t.R + (size_t)c * t.rcap;   // in place in column c of R
+    for (int a = rank - 1; a >= 0; a--) {
+      double v = x[a];
+      for (int b = a + 1; b < rank; b++) v -= t.R[a + (size_t)ord[b] * t.rcap] * x[b];
+      x[a] = v / t.R[a + (size_t)ord[a] * t.rcap];
+    }
+    for (int a = 0; a < rank; a++) t.E[p + (size_t)a * k] = x[a];
+  }
 }
+
+// ---- host-side cluster tree --------------------------------------------------
+struct TNode {
+  int lo, hi;          // index range [lo, hi) in the permuted ordering
+  int parent = -1, ch0 = -1, ch1 = -1;
+  int height = 0;
+};
+
+void build_tree_index(std::vector<TNode>& T, int lo, int hi, int parent, int leaf) {
+  int me = (int)T.size();
+  T.push_back({lo, hi, parent, -1, -1, 0});
+  if (hi - lo > leaf) {
+    int mid = lo + (hi - lo) / 2;   // m/2 | m - m/2, HSSMatrix.cpp:60-70
+    int c0 = (int)T.size(); build_tree_index(T, lo, mid, me, leaf);
+    int c1 = (int)T.size(); build_tree_index(T, mid, hi, me, leaf);
+    T[me].ch0 = c0; T[me].ch1 = c1;
+  }
+}
+
+void build_tree_kd(std::vector<TNode>& T, std::vector<int>& perm, const double* pts,
+                   int d, int lo, int hi, int parent, int leaf) {
+  int me = (int)T.size();
+  T.push_back({lo, hi, parent, -1, -1, 0});
+  if (hi - lo > leaf) {
+    // widest coordinate
+    int best = 0; double bw = -1;
+    for (int q = 0; q < d; q++) {
+      double mn = 1e300, mx = -1e300;
+      for (int i = lo; i < hi; i++) {
+        double v = pts[q + (size_t)perm[i] * d];
+        mn = std::min(mn, v); mx = std::max(mx, v);
+      }
+      if (mx - mn > bw) { bw = mx - mn; best = q; }
+    }
+    int mid = lo + (hi - lo) / 2;
+    std::nth_element(perm.begin() + lo, perm.begin() + mid, perm.begin() + hi,
+                     [&](int a, int b) {
+                       double va = pts[best + (size_t)a * d], vb = pts[best + (size_t)b * d];
+                       return va < vb || (va == vb && a < b);
+                     });
+    int c0 = (int)T.size(); build_tree_kd(T, perm, pts, d, lo, mid, me, leaf);
+    int c1 = (int)T.size(); build_tree_kd(T, perm, pts, d, mid, hi, me, leaf);
+    T[me].ch0 = c0; T[me].ch1 = c1;
+  }
+}
+
+struct Problem {
+  int n = 0, d = 1;
+  int type = 3;
+  std::vector<double> pts;     // d x n in permuted ordering (may be 1-D indices)
+  double h = 1, lambda = 0;
+  const double* hostA = nullptr; long long lda = 0;   // dense input (host)
+  bool symmetric = false;
+  bool full_complement = false;
+};
+
+HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& o) {
+  const int N = (int)T.size(), n = P.n;
+  // heights and classes
+  int maxh = 0;
+  for (int i = N - 1; i >= 0; i--) {
+    T[i].height = T[i].ch0 < 0 ? 0 : 1 + std::max(T[T[i].ch0].height, T[T[i].ch1].height);
+    maxh = std::max(maxh, T[i].height);
+  }
+  std::vector<std::vector<int>> cls(maxh + 1);
+  for (int i = 0; i < N; i++) cls[T[i].height].push_back(i);
+
+  // ---- sample sets, top-down ------------------------------------------------
+  const int d = P.d;
+  auto center = [&](int t, std::vector<double>& c) {
+    c.assign(d, 0.);
+    for (int i = T[t].lo; i < T[t].hi; i++)
+      for (int q = 0; q < d; q++) c[q] += P.pts[q + (size_t)i * d];
+    for (int q = 0; q < d; q++) c[q] /= std::max(1, T[t].hi - T[t].lo);
+  };
+  std::vector<std::vector<int>> J(N);
+  std::mt19937 rng(12345);
+  const int k_near = P.full_complement ? 0 : 128, k_far = P.full_complement ? 0 : 96;
+  if (P.full_complement) {
+    for (int t = 1; t < N; t++) {
+      J[t].reserve(n - (T[t].hi - T[t].lo));
+      for (int i = 0; i < T[t].lo; i++) J[t].push_back(i);
+      for (int i = T[t].hi; i < n; i++) J[t].push_back(i);
+    }
+  } else {
+    std::vector<double> c;
+    std::vector<std::pair<double, int>> cand;
+    for (int t = 1; t < N; t++) {  // pre-order: the parent's sample exists
+      const int p = T[t].parent;
+      const int s = (T[p].ch0 == t) ? T[p].ch1 : T[p].ch0;
+      center(t, c);
+      cand.clear();
+      auto push = [&](int i) {
+        double r2 = 0.;
+        for (int q = 0; q < d; q++) {
+          double v = P.pts[q + (size_t)i * d] - c[q];
+          r2 += v * v;
+        }
+        cand.emplace_back(r2, i);
+      };
+      for (int i = T[s].lo; i < T[s].hi; i++) push(i);
+      for (int i : J[p]) push(i);
+      const int want = k_near + k_far;
+      if ((int)cand.size() <= want) {
+        for (auto& e : cand) J[t].push_back(e.second);
+      } else {
+        std::nth_element(cand.begin(), cand.begin() + k_near, cand.end());
+        for (int i = 0; i < k_near; i++) J[t].push_back(cand[i].second);
+        // random far samples from the rest
+        for (int i = 0; i < k_far; i++) {
+          std::uniform_int_distribution<int> U(k_near + i, (int)cand.size() - 1);
+          int pick = U(rng);
+          std::swap(cand[k_near + i], cand[pick]);
+          J[t].push_back(cand[k_near + i].second);
+        }
+      }
+      std::sort(J[t].begin(), J[t].end());
+    }
+  }
+
+  // ---- device problem description ---------------------------------------------
+  DevBuf<double> dpts, dA;
+  ElemSrc src{};
+  src.type = P.type; src.d = d; src.h = P.h; src.lambda = P.lambda;
+  if (P.type == 3) {
+    dA.alloc((size_t)n * n);
+    SB200_CUDA(cudaMemcpy2D(dA.p, sizeof(double) * n, P.hostA, sizeof(double) * P.lda,
+                            sizeof(double) * n, n, cudaMemcpyHostToDevice));
+    src.A = dA.p; src.lda = n;
+  } else {
+    dpts.upload(P.pts.data(), P.pts.size());
+    src.pts = dpts.p;
+  }
+
+  // ---- bottom-up ID -------------------------------------------------------------
+  // per node results (host)
+  struct Basis { std::vector<int> skel;      // global indices of the skeleton
+                 std::vector<int> order;     // local pivot order (gather perm)
+                 std::vector<double> E; int rank = 0, rows = 0; };
+  std::vector<Basis> BU(N), BV(N);
+  const int nbasis = P.symmetric ? 1 : 2;
+  for (int h = 0; h < maxh; h++) {       // the root (alone in class maxh) has no basis
+    const auto& nodes = cls[h];
+    const int cnt = (int)nodes.size();
+    for (int which = 0; which < nbasis; which++) {
+      // index lists I_t
+      std::vector<std::vector<int>> I(cnt);
+      size_t totI = 0, totJ = 0, totM = 0, totR = 0, totE = 0;
+      std::vector<int> rcap(cnt);
+      for (int q = 0; q < cnt; q++) {
+        const int t = nodes[q];
+        auto& B = which == 0 ? BU : BV;
+        if (T[t].ch0 < 0) {
+          I[q].resize(T[t].hi - T[t].lo);
+          std::iota(I[q].begin(), I[q].end(), T[t].lo);
+        } else {
+          I[q] = B[T[t].ch0].skel;
+          I[q].insert(I[q].end(), B[T[t].ch1].skel.begin(), B[T[t].ch1].skel.end());
+        }
+        const int nc = (int)I[q].size(), ns = (int)J[t].size();
+        rcap[q] = std::max(1, std::min(nc, ns));
+        totI += nc; totJ += ns; totM += (size_t)ns * nc;
+        totR += (size_t)rcap[q] * nc; totE += (size_t)nc * rcap[q];
+      }
+      std::vector<int> hI(totI), hJ(totJ);
+      DevBuf<int> dI(totI ? totI : 1), dJ(totJ ? totJ : 1), dOrder(totI ? totI : 1), dRank(cnt);
+      DevBuf<double> dM(totM ? totM : 1), dR(totR ? totR : 1), dE(totE ? totE : 1);
+      SB200_CUDA(cudaMemset(dR.p, 0, sizeof(double) * (totR ? totR : 1)));
+      std::vector<BlockTask> bt(cnt);
+      std::vector<IDTask> it(cnt);
+      size_t oI = 0, oJ = 0, oM = 0, oR = 0, oE = 0;
+      int max_nc = 1;
+      std::vector<size_t> offI(cnt), offE(cnt);
+      for (int q = 0; q < cnt; q++) {
+        const int t = nodes[q];
+        const int nc = (int)I[q].size(), ns = (int)J[t].size();
+        std::copy(I[q].begin(), I[q].end(), hI.begin() + oI);
+        std::copy(J[t].begin(), J[t].end(), hJ.begin() + oJ);
+        // M^T (ns x nc): row basis: M^T[s,i] = A(I[i], J[s])  -> rows=I cols=J transposed
+        //                col basis: M  [s,i] = A(J[s], I[i])  -> rows=J cols=I plain
+        if (which == 0) bt[q] = {dI.p + oI, dJ.p + oJ, nc, ns, dM.p + oM, ns, 1};
+        else            bt[q] = {dJ.p + oJ, dI.p + oI, ns, nc, dM.p + oM, ns, 0};
+        it[q] = {dM.p + oM, dR.p + oR, ns, nc, rcap[q], dOrder.p + oI, dRank.p + q, dE.p + oE};
+        offI[q] = oI; offE[q] = oE;
+        oI += nc; oJ += ns; oM += (size_t)ns * nc; oR += (size_t)rcap[q] * nc;
+        oE += (size_t)nc * rcap[q];
+        max_nc = std::max(max_nc, nc);
+      }
+      dI.upload(hI.data(), totI);
+      dJ.upload(hJ.data(), totJ);
+      DevBuf<BlockTask> dbt; dbt.upload(bt.data(), cnt);
+      DevBuf<IDTask> dit; dit.upload(it.data(), cnt);
+      eval_blocks_kernel<<<dim3(cnt, 16), kThreads>>>(src, dbt.p);
+      size_t smem = (sizeof(double) + sizeof(int)) * (size_t)max_nc + 16;
+      if (smem > 48 * 1024)
+        SB200_CUDA(cudaFuncSetAttribute(id_cpqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      id_cpqr_kernel<<<cnt, kThreads, smem>>>(dit.p, o.rel_tol, o.abs_tol, o.max_rank);
+      SB200_CUDA(cudaGetLastError());
+      std::vector<int> hOrder(totI), hRank(cnt);
+      SB200_CUDA(cudaMemcpy(hOrder.data(), dOrder.p, sizeof(int) * totI, cudaMemcpyDeviceToHost));
+      SB200_CUDA(cudaMemcpy(hRank.data(), dRank.p, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+      std::vector<double> hE(totE);
+      SB200_CUDA(cudaMemcpy(hE.data(), dE.p, sizeof(double) * totE, cudaMemcpyDeviceToHost));
+      for (int q = 0; q < cnt; q++) {
+        const int t = nodes[q];
+        auto& b = (which == 0 ? BU : BV)[t];
+        const int nc = (int)I[q].size(), r = hRank[q];
+        b.rank = r; b.rows = nc;
+        b.order.assign(hOrder.begin() + offI[q], hOrder.begin() + offI[q] + nc);
+        b.skel.resize(r);
+        for (int a = 0; a < r; a++) b.skel[a] = I[q][b.order[a]];
+        b.E.assign(hE.begin() + offE[q], hE.begin() + offE[q] + (size_t)(nc - r) * r);
+        if (o.verbose && r == rcap[q] && r < nc)
+          std::printf("# sb200 compress: node %d rank %d hit the sample cap\n", t, r);
+      }
+    }
+    if (P.symmetric)
+      for (int t : nodes) BV[t] = BU[t];
+  }
+
+  // ---- assemble HSSHost (pre-order = tree order) ----------------------------------
+  HSSHost Hh;
+  Hh.nodes.resize(N);
+  std::vector<BlockTask> bt;
+  std::vector<std::vector<int>> rowsL, colsL;   // index lists for D/B blocks
+  struct Pending { int node; int which; size_t nr, nc; };  // which: 0 D, 1 B01, 2 B10
+  std::vector<Pending> pend;
+  auto put_perm = [&](const std::vector<int>& ord) {
+    int64_t off = (int64_t)Hh.perms.size();
+    Hh.perms.insert(Hh.perms.end(), ord.begin(), ord.end());
+    return off;
+  };
+  auto put_vals = [&](const std::vector<double>& v) {
+    if (v.empty()) return (int64_t)-1;
+    int64_t off = (int64_t)Hh.vals.size();
+    Hh.vals.insert(Hh.vals.end(), v.begin(), v.end());
+    return off;
+  };
+  for (int t = 0; t < N; t++) {
+    auto& hn = Hh.nodes[t];
+    hn.parent = T[t].parent; hn.ch0 = T[t].ch0; hn.ch1 = T[t].ch1;
+    hn.rows = hn.cols = T[t].hi - T[t].lo;
+    if (t > 0) {
+      hn.u_rows = BU[t].rows; hn.u_rank = BU[t].rank;
+      hn.v_rows = BV[t].rows; hn.v_rank = BV[t].rank;
+      hn.off_Pu = put_perm(BU[t].order); hn.off_Eu = put_vals(BU[t].E);
+      hn.off_Pv = put_perm(BV[t].order); hn.off_Ev = put_vals(BV[t].E);
+    }
+  }
+  // blocks evaluated on the device, appended to the arena in one go
+  size_t total = 0;
+  for (int t = 0; t < N; t++) {
+    if (T[t].ch0 < 0) {
+      std::vector<int> idx(T[t].hi - T[t].lo);
+      std::iota(idx.begin(), idx.end(), T[t].lo);
+      pend.push_back({t, 0, idx.size(), idx.size()});
+      rowsL.push_back(idx); colsL.push_back(idx);
+      total += idx.size() * idx.size();
+    } else {
+      const int a = T[t].ch0, b = T[t].ch1;
+      pend.push_back({t, 1, BU[a].skel.size(), BV[b].skel.size()});
+      rowsL.push_back(BU[a].skel); colsL.push_back(BV[b].skel);
+      total += BU[a].skel.size() * BV[b].skel.size();
+      pend.push_back({t, 2, BU[b].skel.size(), BV[a].skel.size()});
+      rowsL.push_back(BU[b].skel); colsL.push_back(BV[a].skel);
+      total += BU[b].skel.size() * BV[a].skel.size();
+    }
+  }
+  {
+    size_t nidx = 0;
+    for (size_t q = 0; q < pend.size(); q++) nidx += rowsL[q].size() + colsL[q].size();
+    std::vector<int> hidx(nidx);
+    DevBuf<int> didx(nidx ? nidx : 1);
+    DevBuf<double> dout(total ? total : 1);
+    bt.resize(pend.size());
+    size_t oi = 0, oo = 0;
+    const int64_t base = (int64_t)Hh.vals.size();
+    for (size_t q = 0; q < pend.size(); q++) {
+      const int nr = (int)rowsL[q].size(), nc = (int)colsL[q].size();
+      std::copy(rowsL[q].begin(), rowsL[q].end(), hidx.begin() + oi);
+      std::copy(colsL[q].begin(), colsL[q].end(), hidx.begin() + oi + nr);
+      bt[q] = {didx.p + oi, didx.p + oi + nr, nr, nc, dout.p + oo, std::max(nr, 1), 0};
+      auto& hn = Hh.nodes[pend[q].node];
+      int64_t off = (size_t)nr * nc ? base + (int64_t)oo : -1;
+      if (pend[q].which == 0) hn.off_D = off;
+      else if (pend[q].which == 1) hn.off_B01 = off;
+      else hn.off_B10 = off;
+      oi += nr + nc; oo += (size_t)nr * nc;
+    }
+    didx.upload(hidx.data(), nidx);
+    DevBuf<BlockTask> dbt; dbt.upload(bt.data(), bt.size());
+    if (!bt.empty()) eval_blocks_kernel<<<dim3((unsigned)bt.size(), 8), kThreads>>>(src, dbt.p);
+    SB200_CUDA(cudaGetLastError());
+    Hh.vals.resize(base + total);
+    SB200_CUDA(cudaMemcpy(Hh.vals.data() + base, dout.p, sizeof(double) * total,
+                          cudaMemcpyDeviceToHost));
+  }
+  Hh.finalize();
+  return Hh;
+}
+
+}  // namespace
+
+HSSHost compress_dense(int rows, int cols, const double* A, int ldA,
+                       const CompressOptions& o) {
+  if (rows != cols)
+    throw std::invalid_argument("compress_dense: only square matrices are supported");
+  Problem P;
+  P.n = rows; P.d = 1; P.type = 3; P.hostA = A; P.lda = ldA;
+  P.pts.resize(rows);
+  for (int i = 0; i < rows; i++) P.pts[i] = i;
+  P.full_complement = rows <= 8192;
+  std::vector<TNode> T;
+  build_tree_index(T, 0, rows, -1, std::max(1, o.leaf_size));
+  return compress_impl(P, T, o);
+}
+
+HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
+                          const CompressOptions& o) {
+  if (rows != cols)
+    throw std::invalid_argument("compress_elements: only square matrices are supported");
+  if (rows > 16384)
+    throw std::invalid_argument("compress_elements: host callbacks are limited to "
+                                "n <= 16384; use SB200_d_hss_from_kernel for large kernel matrices");
+  std::vector<double> D((size_t)rows * cols);
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < rows; i++) D[i + (size_t)j * rows] = A(i, j);
+  return compress_dense(rows, cols, D.data(), rows, o);
+}
+
+HSSHost compress_kernel(int n, int d, double* pts, int kernel_type, double h,
+                        double lambda, const CompressOptions& o, int* perm) {
+  if (kernel_type < 0 || kernel_type > 2) throw std::invalid_argument("unknown kernel type");
+  Problem P;
+  P.n = n; P.type = kernel_type; P.h = h; P.lambda = lambda; P.symmetric = true;
+  std::vector<TNode> T;
+  std::vector<int> pm(n);
+  std::iota(pm.begin(), pm.end(), 0);
+  if (kernel_type == 2) {
+    P.d = 1;
+    P.pts.resize(n);
+    for (int i = 0; i < n; i++) P.pts[i] = i;
+    build_tree_index(T, 0, n, -1, std::max(1, o.leaf_size));
+  } else {
+    P.d = d;
+    build_tree_kd(T, pm, pts, d, 0, n, -1, std::max(1, o.leaf_size));
+    P.pts.resize((size_t)d * n);
+    for (int i = 0; i < n; i++)
+      for (int q = 0; q < d; q++) P.pts[q + (size_t)i * d] = pts[q + (size_t)pm[i] * d];
+    std::memcpy(pts, P.pts.data(), sizeof(double) * (size_t)d * n);
+  }
+  if (perm) std::copy(pm.begin(), pm.end(), perm);
+  return compress_impl(P, T, o);
+}
+
 }  // namespace sb200
