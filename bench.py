@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- HSS apply + ULV factor + ULV solve throughput (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one synthetic Gaussian-kernel
+matrix already compressed to HSS generators:  y = H x (1 rhs),  H = ULV,
+x = H^{-1} b (1 rhs).  GFLOP/s uses the REFERENCE's flop accounting
+(params::ULV_factor_flops / hss_solve_flops formulas + 2*nnz for apply,
+SURVEY.md 8d), so CPU and GPU numbers are comparable.
+
+  python bench.py --gpus 1 --steps K --warmup W            # our engine
+  python bench.py --impl reference --steps K --warmup W    # reference CPU path
+
+value  : device-resident operands, CUDA events on the launching stream
+e2e    : the same step through the reference-facing C ABI with HOST buffers
+         (SP_d_struct_mult / _factor / _solve: H2D + D2H inside the timing)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.setrecursionlimit(100000)
+
+FP64_DMMA_PEAK_TFLOPS = 37.1   # profiles/microbench/fp64_peak (this pool's B200)
+LEAF, TOL, H_GAUSS, LAMBDA = 256, 1e-4, 0.1, 1.0
+
+
+def points(n, seed=42):
+    return np.random.default_rng(seed).random((2, n))
+
+
+def clocks_start():
+    f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                              "-lms", "100", "-i", os.environ.get("LOCAL_RANK", "0")],
+                             stdout=f, stderr=subprocess.DEVNULL)
+    except OSError:
+        return None, f.name
+    return p, f.name
+
+
+def clocks_stop(p, path):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    if p is not None:
+        p.terminate()
+        try:
+            p.wait(timeout=5)
+        except Exception:
+            p.kill()
+    try:
+        rows = [r.split(",") for r in open(path).read().strip().splitlines() if r.strip()]
+        sm = [float(r[1]) for r in rows]
+        out["sm_mhz"] = float(np.median(sm)) if sm else None
+        out["sm_max_mhz"] = float(rows[0][2]) if rows else None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        seen = set()
+        for r in rows:
+            for k, nm in enumerate(names):
+                if r[5 + k].strip().lower().startswith("active"):
+                    seen.add(nm)
+        out["reasons"] = sorted(seen)
+        out["samples"] = len(rows)
+    except Exception:
+        pass
+    try:
+        os.unlink(path)
+    except OSError:
+        pass
+    return out
+
+
+# ------------------------------------------------------------------ reference
+def reference_problem(n, threads):
+    from oracle import ref
+    ref.set_num_threads(threads)
+    t0 = time.perf_counter()
+    H = ref.RefHSS.gauss(points(n), H_GAUSS, LAMBDA,
+                         f"--hss_leaf_size {LEAF} --hss_rel_tol {TOL}")
+    tc = time.perf_counter() - t0
+    return H, tc
+
+
+def reference_flops(H, n):
+    """apply flops from the generators, factor/solve from the reference's own
+    counters (one factor + one 1-rhs solve)."""
+    from oracle import ref
+    import strumpack_b200 as sb
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "h.hss")
+        H.write(p)
+        inf = sb.hss_file_info(p)     # host-only parser, no GPU involved
+    return inf["apply_flops"], inf["factor_flops"], inf["solve_flops"]
+
+
+def reference_step(H, x):
+    y = H.mult(x)
+    H.factor()
+    return H.solve(y)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own OpenMP CPU implementation (oracle/_ref,
+    compiled from /root/reference) on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+        return
+    cores = os.cpu_count() or 1
+    n = args.ref_n
+    H, tc = reference_problem(n, cores)
+    fa, ff, fs = reference_flops(H, n)
+    x = np.random.default_rng(0).standard_normal((n, 1))
+    for _ in range(args.warmup):
+        reference_step(H, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_step(H, x)
+    dt = (time.perf_counter() - t0) / args.steps
+    gf = (fa + ff + fs) / dt / 1e9
+    print(json.dumps({
+        "impl": "reference", "metric": "HSS apply+ULV GFLOP/s", "value": gf, "unit": "GFLOP/s",
+        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"HSS apply+ULV factor+solve, 2-D Gaussian kernel (h={H_GAUSS}, "
+                               f"lambda={LAMBDA}), leaf {LEAF}, tol {TOL}, 1 rhs; bounded sample "
+                               f"N={n} of the N=2^20 workload", "N": n},
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "reference",
+                         "sample": f"N={n} (compress {tc:.1f}s untimed), {args.steps} steps"},
+        "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def cpu_baseline(n, budget_s=25.0):
+    from oracle import ref
+    if not ref.available():
+        return None
+    cores = os.cpu_count() or 1
+    H, tc = reference_problem(n, cores)
+    fa, ff, fs = reference_flops(H, n)
+    x = np.random.default_rng(0).standard_normal((n, 1))
+    reference_step(H, x)  # warm-up
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < 5 and time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        reference_step(H, x)
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.median(ts))
+    return {"value": (fa + ff + fs) / dt / 1e9, "unit": "GFLOP/s", "cores": cores,
+            "kind": "reference",
+            "sample": f"N={n} Gaussian 2-D, leaf {LEAF}, tol {TOL}: median of {len(ts)} "
+                      f"apply+factor+solve passes ({dt*1e3:.1f} ms each), compress {tc:.1f}s untimed"}
+
+
+# ----------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import strumpack_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no GPU visible (strumpack_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sb.lib()
+
+    n = args.n
+    # every rank owns one independent N-point problem (distinct seeds): the
+    # subtree-sharded single-matrix path is the next multi-GPU milestone.
+    pts = points(n, seed=42 + rank)
+    opts = sb.default_options(type=sb.SP_TYPE_HSS, rel_tol=TOL, abs_tol=1e-10, leaf_size=LEAF)
+    t0 = time.perf_counter()
+    H, perm, pts_p = sb.HSSMatrix.from_kernel(pts, sb.KERNEL_GAUSS, H_GAUSS, LAMBDA, opts)
+    t_compress = time.perf_counter() - t0
+    fa, ff, fs = H.flops("apply"), H.flops("factor"), H.flops("solve")
+    flops_step = fa + ff + fs
+
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    x_host = torch.randn(1, n, dtype=torch.float64, generator=g).pin_memory()
+    xT = x_host.to(dev)
+    yT = torch.empty_like(xT)
+    bT = torch.empty_like(xT)
+    H.set_profile(True)
+
+    def step_device():
+        H.mult_device(xT, yT)
+        H.factor_device()
+        bT.copy_(yT)
+        H.solve_device(bT)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    # parity inside the bench: x must come back (ULV is a direct solver for H)
+    resid = float((bT - xT).norm() / xT.norm())
+
+    launches0 = H.launches
+    cp, cpath = clocks_start()
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    qr_ms = []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+        qr_ms.append(H.kernel_ms(0))   # events recorded on this stream inside factor
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = clocks_stop(cp, cpath)
+    launches = H.launches - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        fl = torch.tensor([float(flops_step)], device=dev, dtype=torch.float64)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
+        total_flops = float(fl.item())
+    else:
+        total_flops = float(flops_step)
+    value = total_flops / (ms * 1e-3) / 1e9
+
+    # ---- end to end through the reference-facing C ABI, host buffers ----------
+    xh = x_host.numpy().reshape(n, 1)
+    yh = None
+    for _ in range(2):
+        yh = H.mult(xh); H.factor(); H.solve(yh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        yh = H.mult(xh)      # H2D x, D2H y
+        H.factor()
+        xs = H.solve(yh)     # H2D b, D2H x
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = total_flops / (e2e_ms * 1e-3) / 1e9
+    e2e_resid = float(np.linalg.norm(xs - xh) / np.linalg.norm(xh))
+
+    # ---- roofline of the dominant kernel (leaf-class Householder QR) ----------
+    qr_alg = H.flops("qr_leaf")
+    qr_exec = H.flops("qr_leaf_exec")
+    qr_avg_ms = float(np.mean(qr_ms))
+    achieved = qr_alg / (qr_avg_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS,
+                "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                "kernel": "ulv_qr_kernel (leaf class)", "kernel_ms": qr_avg_ms,
+                "executed_tflops": qr_exec / (qr_avg_ms * 1e-3) / 1e12,
+                "peak_source": "fp64 mma.sync (DMMA) peak measured on this pool's B200 by "
+                               "profiles/microbench/fp64_peak.cu; MEASURED_PEAKS.json holds "
+                               "no fp64 figure (tcgen05 has no f64 kind)"}
+
+    if rank == 0:
+        base = None
+        if world == 1 and not args.no_cpu_baseline:
+            base = cpu_baseline(args.ref_n)
+        line = {
+            "metric": "HSS apply+ULV GFLOP/s", "value": value, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"HSS apply (1 rhs) + ULV factor + ULV solve (1 rhs), 2-D Gaussian "
+                            f"kernel (h={H_GAUSS}, lambda={LAMBDA}), N={n}, leaf {LEAF}, tol {TOL}",
+                "N": n, "leaf": LEAF, "rel_tol": TOL, "rank": H.rank, "levels": H.levels,
+                "parallelism": "1 matrix per GPU (independent replicas)" if world > 1 else "1 GPU",
+                "l2": "inputs larger than L2 (generators %.2f GB + ULV factors %.2f GB)" % (
+                    H.memory / 1e9, H.factor_nonzeros * 8 / 1e9),
+                "flops_per_step": {"apply": fa, "factor": ff, "solve": fs,
+                                   "factor_executed": H.flops("factor_exec")},
+                "compress_s": t_compress, "solve_residual": resid},
+            "e2e": {"value": e2e, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 2 * 8 * n,
+                    "residual": e2e_resid},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 20, help="matrix size (default 2^20)")
+    ap.add_argument("--ref-n", type=int, default=1 << 16,
+                    help="size of the bounded CPU sample of the workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,8 +143,16 @@ long long int SB200_d_struct_factor_nonzeros(const CSPStructMat S);
  * which = 0: apply with 1 rhs (2*nnz terms of HSSMatrix.apply.hpp),
  *         1: ULV factor  (params::ULV_factor_flops formula, factor.hpp:78-141)
  *         2: ULV solve, 1 rhs (params::hss_solve_flops, solve.hpp:94-223)
- *         3: flops the engine actually executes in factor (no explicit Q) */
+ *         3: flops the engine actually executes in factor (no explicit Q)
+ *         4: the leaf-class Householder-QR launch (dominant kernel), reference
+ *            accounting: LQ_flops + the three Q GEMMs (factor.hpp:122-141)
+ *         5: the same launch, flops actually executed */
 long long int SB200_d_struct_flops(const CSPStructMat S, int which);
+/* Live kernel timing: when enabled, factor records CUDA events around the
+ * leaf-class QR launch on the launching stream; kernel_ms(S, 0) returns the
+ * duration (ms) of that launch in the last factor call. */
+int SB200_d_struct_set_profile(CSPStructMat S, int on);
+double SB200_d_struct_kernel_ms(const CSPStructMat S, int which);
 /* Number of kernels launched by this object since creation. */
 long long int SB200_d_struct_launches(const CSPStructMat S);
 /* H.print_info() equivalent to stdout (HSSMatrix.cpp:333-356). */

@@ -64,6 +64,8 @@ SYMBOLS = {
     "SB200_d_struct_levels": (_i, [_vp]),
     "SB200_d_struct_factor_nonzeros": (_ll, [_vp]),
     "SB200_d_struct_flops": (_ll, [_vp, _i]),
+    "SB200_d_struct_set_profile": (_i, [_vp, _i]),
+    "SB200_d_struct_kernel_ms": (_d, [_vp, _i]),
     "SB200_d_struct_launches": (_ll, [_vp]),
     "SB200_d_struct_print_info": (_i, [_vp]),
     "SB200_d_struct_dense": (_i, [_vp, _vp, _i]),
@@ -236,8 +238,15 @@ class StructuredMatrix:
 
     def flops(self, which):
         """'apply' | 'factor' | 'solve' (reference accounting) | 'factor_exec'"""
-        k = {"apply": 0, "factor": 1, "solve": 2, "factor_exec": 3}[which]
+        k = {"apply": 0, "factor": 1, "solve": 2, "factor_exec": 3,
+             "qr_leaf": 4, "qr_leaf_exec": 5}[which]
         return lib().SB200_d_struct_flops(self._h, k)
+
+    def set_profile(self, on=True):
+        _check(lib().SB200_d_struct_set_profile(self._h, int(on)), "set_profile")
+
+    def kernel_ms(self, which=0):
+        return lib().SB200_d_struct_kernel_ms(self._h, which)
 
     def print_info(self):
         _check(lib().SB200_d_struct_print_info(self._h), "print_info")

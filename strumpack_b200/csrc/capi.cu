@@ -276,8 +276,18 @@ long long int SB200_d_struct_flops(const CSPStructMat S, int which) {
     case 1: return h.factor_flops_ref();
     case 2: return h.solve_flops_ref();
     case 3: return h.factor_flops_exec();
+    case 4: return h.qr_class_flops_ref(0);
+    case 5: return h.qr_class_flops_exec(0);
   }
   return 0;
+}
+int SB200_d_struct_set_profile(CSPStructMat S, int on) {
+  return guarded([&] { hss(S).set_profile(on != 0); });
+}
+double SB200_d_struct_kernel_ms(const CSPStructMat S, int which) {
+  double ms = 0.;
+  guarded([&] { if (which == 0) ms = hss(S).qr_leaf_ms(); });
+  return ms;
 }
 long long int SB200_d_struct_launches(const CSPStructMat S) {
   return S ? hss(S).launches() : 0;

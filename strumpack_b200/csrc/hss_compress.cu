@@ -279,7 +279,6 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
   };
   std::vector<std::vector<int>> J(N);
   std::mt19937 rng(12345);
-  const int k_near = P.full_complement ? 0 : 128, k_far = P.full_complement ? 0 : 96;
   if (P.full_complement) {
     for (int t = 1; t < N; t++) {
       J[t].reserve(n - (T[t].hi - T[t].lo));
@@ -287,14 +286,101 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
       for (int i = T[t].hi; i < n; i++) J[t].push_back(i);
     }
   } else {
+    // Sample of the complement of every node, four strata:
+    //  (a) the K1 outside points nearest to the node's bounding box,
+    //  (b) K2 random ones among the next 8*K1 nearest   (near field, all sides)
+    //  (c) the K3 points of (sibling U parent's sample) nearest to the centre,
+    //  (d) K4 random ones of that set                   (every coarser scale)
+    const int K1 = o.sample_near, K2 = o.sample_near, K3 = o.sample_far, K4 = o.sample_far;
+    // bounding boxes, bottom-up
+    std::vector<double> bmin((size_t)N * d), bmax((size_t)N * d);
+    for (int t = N - 1; t >= 0; t--) {
+      double* mn = &bmin[(size_t)t * d];
+      double* mx = &bmax[(size_t)t * d];
+      if (T[t].ch0 < 0) {
+        for (int q = 0; q < d; q++) { mn[q] = 1e300; mx[q] = -1e300; }
+        for (int i = T[t].lo; i < T[t].hi; i++)
+          for (int q = 0; q < d; q++) {
+            double v = P.pts[q + (size_t)i * d];
+            mn[q] = std::min(mn[q], v); mx[q] = std::max(mx[q], v);
+          }
+      } else {
+        for (int q = 0; q < d; q++) {
+          mn[q] = std::min(bmin[(size_t)T[t].ch0 * d + q], bmin[(size_t)T[t].ch1 * d + q]);
+          mx[q] = std::max(bmax[(size_t)T[t].ch0 * d + q], bmax[(size_t)T[t].ch1 * d + q]);
+        }
+      }
+    }
+    auto box_box = [&](int a, int b) {
+      double r2 = 0.;
+      for (int q = 0; q < d; q++) {
+        double g = std::max(0., std::max(bmin[(size_t)a * d + q] - bmax[(size_t)b * d + q],
+                                         bmin[(size_t)b * d + q] - bmax[(size_t)a * d + q]));
+        r2 += g * g;
+      }
+      return r2;
+    };
+    auto pt_box = [&](int i, int a) {
+      double r2 = 0.;
+      for (int q = 0; q < d; q++) {
+        double v = P.pts[q + (size_t)i * d];
+        double g = std::max(0., std::max(bmin[(size_t)a * d + q] - v, v - bmax[(size_t)a * d + q]));
+        r2 += g * g;
+      }
+      return r2;
+    };
     std::vector<double> c;
-    std::vector<std::pair<double, int>> cand;
+    std::vector<std::pair<double, int>> cand, heap, pq;
+    std::vector<char> taken(n, 0);
     for (int t = 1; t < N; t++) {  // pre-order: the parent's sample exists
+      const int lo = T[t].lo, hi = T[t].hi;
+      // ---- (a)+(b): best-first search of the Kc nearest outside points
+      const int Kc = std::min(n - (hi - lo), 9 * K1);
+      heap.clear();   // max-heap on distance of the current Kc best
+      pq.clear();     // min-heap (negated distance) of tree nodes to visit
+      pq.emplace_back(-0., 0);
+      while (!pq.empty()) {
+        std::pop_heap(pq.begin(), pq.end());
+        auto top = pq.back(); pq.pop_back();
+        const double dn = -top.first;
+        if ((int)heap.size() == Kc && dn >= heap.front().first) break;
+        const int u = top.second;
+        if (T[u].lo >= lo && T[u].hi <= hi) continue;   // inside t
+        if (T[u].ch0 < 0) {
+          for (int i = T[u].lo; i < T[u].hi; i++) {
+            double r2 = pt_box(i, t);
+            if ((int)heap.size() < Kc) {
+              heap.emplace_back(r2, i); std::push_heap(heap.begin(), heap.end());
+            } else if (r2 < heap.front().first) {
+              std::pop_heap(heap.begin(), heap.end());
+              heap.back() = {r2, i};
+              std::push_heap(heap.begin(), heap.end());
+            }
+          }
+        } else {
+          for (int ch : {T[u].ch0, T[u].ch1}) {
+            if (T[ch].lo >= lo && T[ch].hi <= hi) continue;
+            pq.emplace_back(-box_box(ch, t), ch);
+            std::push_heap(pq.begin(), pq.end());
+          }
+        }
+      }
+      std::sort(heap.begin(), heap.end());
+      auto take = [&](int i) { if (!taken[i]) { taken[i] = 1; J[t].push_back(i); } };
+      const int n1 = std::min<int>(K1, heap.size());
+      for (int i = 0; i < n1; i++) take(heap[i].second);
+      for (int i = 0; i < K2 && n1 + i < (int)heap.size(); i++) {
+        std::uniform_int_distribution<int> U(n1 + i, (int)heap.size() - 1);
+        std::swap(heap[n1 + i], heap[U(rng)]);
+        take(heap[n1 + i].second);
+      }
+      // ---- (c)+(d): coarser scales through the sibling and the parent's sample
       const int p = T[t].parent;
       const int s = (T[p].ch0 == t) ? T[p].ch1 : T[p].ch0;
       center(t, c);
       cand.clear();
       auto push = [&](int i) {
+        if (taken[i]) return;
         double r2 = 0.;
         for (int q = 0; q < d; q++) {
           double v = P.pts[q + (size_t)i * d] - c[q];
@@ -303,22 +389,20 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
         cand.emplace_back(r2, i);
       };
       for (int i = T[s].lo; i < T[s].hi; i++) push(i);
-      for (int i : J[p]) push(i);
-      const int want = k_near + k_far;
-      if ((int)cand.size() <= want) {
-        for (auto& e : cand) J[t].push_back(e.second);
+      for (int i : J[p]) if (i < lo || i >= hi) push(i);
+      if ((int)cand.size() <= K3 + K4) {
+        for (auto& e : cand) take(e.second);
       } else {
-        std::nth_element(cand.begin(), cand.begin() + k_near, cand.end());
-        for (int i = 0; i < k_near; i++) J[t].push_back(cand[i].second);
-        // random far samples from the rest
-        for (int i = 0; i < k_far; i++) {
-          std::uniform_int_distribution<int> U(k_near + i, (int)cand.size() - 1);
-          int pick = U(rng);
-          std::swap(cand[k_near + i], cand[pick]);
-          J[t].push_back(cand[k_near + i].second);
+        std::nth_element(cand.begin(), cand.begin() + K3, cand.end());
+        for (int i = 0; i < K3; i++) take(cand[i].second);
+        for (int i = 0; i < K4; i++) {
+          std::uniform_int_distribution<int> U(K3 + i, (int)cand.size() - 1);
+          std::swap(cand[K3 + i], cand[U(rng)]);
+          take(cand[K3 + i].second);
         }
       }
       std::sort(J[t].begin(), J[t].end());
+      for (int i : J[t]) taken[i] = 0;
     }
   }
 

@@ -17,6 +17,9 @@ struct CompressOptions {
   int leaf_size = 512;
   int max_rank = 50000;
   int verbose = 0;
+  // sampled-ID parameters: points per near-field / coarse-scale stratum
+  // (the role HSSOptions::d0/ann_number play in the reference)
+  int sample_near = 96, sample_far = 128;
 };
 
 // A: host column-major rows x cols

@@ -290,22 +290,25 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
     Df[i + (size_t)j * m] = v;
   }
   if (nd.parent < 0) return;
-  // Vd = dense(V) in smem (v_rows x rv)
+  // Vd = dense(V) = P_v [I; E_v] is never formed: row j of Vd is row
+  // pinv[j] of [I; E_v]; only the inverse permutation sits in smem.
   const int rv = nd.v_rank, nv = rv0 + rv1, kv = nv - rv;
   const int* P = perms + nd.Pv;
   const double* E = vals + nd.Ev;
-  double* Vd = sm;
-  for (int idx = tid; idx < nv * rv; idx += kThreads) {
-    int i = idx % nv, c = idx / nv;
-    Vd[P[i] + c * nv] = i < rv ? (i == c ? 1. : 0.) : E[(i - rv) + (size_t)c * kv];
-  }
+  int* pinv = reinterpret_cast<int*>(sm);
+  for (int i = tid; i < nv; i += kThreads) pinv[P[i]] = i;
   __syncthreads();
   double* Vh = fact + nd.F + (size_t)nd.k * m;
   for (int idx = tid; idx < m * rv; idx += kThreads) {
     int i = idx % m, c = idx / m;
     double v = 0.;
-    if (i < ru0) for (int q = 0; q < rv0; q++) v += child_Vt1(fact, c0, i, q) * Vd[q + c * nv];
-    else for (int q = 0; q < rv1; q++) v += child_Vt1(fact, c1, i - ru0, q) * Vd[rv0 + q + c * nv];
+    const DNode& cc = i < ru0 ? c0 : c1;
+    const int a = i < ru0 ? i : i - ru0, qoff = i < ru0 ? 0 : rv0, nq = i < ru0 ? rv0 : rv1;
+    for (int q = 0; q < nq; q++) {
+      const int pi = pinv[qoff + q];
+      const double vd = pi < rv ? (pi == c ? 1. : 0.) : E[(pi - rv) + (size_t)c * kv];
+      v += child_Vt1(fact, cc, a, q) * vd;
+    }
     Vh[i + (size_t)c * m] = v;
   }
 }
@@ -363,12 +366,126 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
   }
 }
 
+// Trailing update of one 8-column slab C = A[j0:m, c0:c0+cw) with the block
+// reflector of the current panel:  C <- C - V (T^T (V^T C)).
+// V (mp x NB, explicit unit-lower trapezoid, zero padded to a multiple of 8
+// rows) and T (NB x NB upper) live in shared memory; C streams straight from
+// global/L2 into fp64 tensor-core fragments (no shared-memory staging) and is
+// read twice (second read hits L1), written once.  One warp per slab, no CTA
+// barrier: the 8 warps of a CTA work on different slabs asynchronously.
+//   phase 1  W^T[n][a]  = sum_i C[i][n] V[i][a]        (A = C^T, B = V)
+//   phase T  W2^T       = W^T T                         (A from accumulators
+//            via the K-slot permutation a = 8*at + 2t + e, B = T)
+//   phase 2  C[i][n]   -= sum_a V[i][a] W2[a][n]       (A = V, B = -W2)
+template <int NB>
+__device__ __forceinline__ void slab_update(double* __restrict__ Cg, int ldc, int mp,
+                                            int cw, const double* __restrict__ Vs,
+                                            int ldv, const double* __restrict__ Ts,
+                                            int ldt, int lane) {
+  constexpr int NT = NB / 8;
+  constexpr int U = 4;   // row tiles per prefetch group (8 loads in flight)
+  const int g = lane >> 2, t = lane & 3;
+  const int nit = (mp + 7) >> 3;
+  double wt[NT][2];
+#pragma unroll
+  for (int q = 0; q < NT; q++) wt[q][0] = wt[q][1] = 0.;
+  const bool gin = g < cw;
+  {
+    const double* Cn = Cg + (size_t)g * ldc + t;
+    const double* Vb = Vs + t + g * ldv;
+    for (int it0 = 0; it0 < nit; it0 += U) {
+      double a[U][2];
+#pragma unroll
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          const int i = (it0 + u) * 8 + ks * 4;
+          a[u][ks] = (gin && i + t < mp) ? Cn[i] : 0.;
+        }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int it = it0 + u;
+        if (it < nit) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++) {
+            const double* vb = Vb + it * 8 + ks * 4;
+#pragma unroll
+            for (int at = 0; at < NT; at++)
+              if (at <= it)   // V[i][a] = 0 for a > i
+                dmma(wt[at][0], wt[at][1], a[u][ks], vb[at * 8 * ldv]);
+          }
+        }
+      }
+    }
+  }
+  double w2[NT][2];
+#pragma unroll
+  for (int q = 0; q < NT; q++) w2[q][0] = w2[q][1] = 0.;
+#pragma unroll
+  for (int atp = 0; atp < NT; atp++)
+#pragma unroll
+    for (int at = 0; at < NT; at++)
+      if (at <= atp) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const double bb = Ts[(at * 8 + 2 * t + e) + (atp * 8 + g) * ldt];
+          dmma(w2[atp][0], w2[atp][1], wt[at][e], bb);
+        }
+      }
+  // accumulator layout -> B-fragment layout (natural K order), negated
+  double bneg[NB / 4];
+#pragma unroll
+  for (int s4 = 0; s4 < NB / 4; s4++) {
+    const int src = (g << 2) + ((s4 & 1) << 1) + (t >> 1);
+    const double v0 = __shfl_sync(0xffffffffu, w2[s4 >> 1][0], src);
+    const double v1 = __shfl_sync(0xffffffffu, w2[s4 >> 1][1], src);
+    bneg[s4] = -((t & 1) ? v1 : v0);
+  }
+  const bool c0in = 2 * t < cw, c1in = 2 * t + 1 < cw;
+  double* C0 = Cg + (size_t)(2 * t) * ldc + g;
+  double* C1 = C0 + ldc;
+  const double* Va = Vs + g + t * ldv;
+  for (int it0 = 0; it0 < nit; it0 += U) {
+    double acc[U][2];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int i = (it0 + u) * 8;
+      const bool iin = i + g < mp;
+      acc[u][0] = (iin && c0in) ? C0[i] : 0.;
+      acc[u][1] = (iin && c1in) ? C1[i] : 0.;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int it = it0 + u;
+      if (it < nit) {
+        const double* va = Va + it * 8;
+#pragma unroll
+        for (int s4 = 0; s4 < NB / 4; s4++)
+          if (s4 <= 2 * it + 1)   // V[i][a] = 0 for a > i
+            dmma(acc[u][0], acc[u][1], va[s4 * 4 * ldv], bneg[s4]);
+        const bool iin = it * 8 + g < mp;
+        if (iin && c0in) C0[it * 8] = acc[u][0];
+        if (iin && c1in) C1[it * 8] = acc[u][1];
+      }
+    }
+  }
+}
+
 // Blocked Householder QR of the first k columns of the m x naug factor block,
 // reflectors applied to all naug columns (right-looking, panel width NB).
-// One CTA per node.  All GEMM-shaped work (V^T C, T^T W, C -= V W, V^T V)
-// runs on the fp64 tensor pipe from shared memory.
+// One CTA per node, 2 CTAs per SM.
+//  * the panel (mp x NB) lives in shared memory and is factored in sub-panels
+//    of 8 columns: unblocked Householder inside a sub-panel with ONE barrier
+//    per column (norms are fused into the previous update, the scaling of a
+//    reflector is deferred, the warps that have no column to update compute
+//    the V^T v dot products that give the sub-panel's T factor for free);
+//    the rest of the panel is then updated on the fp64 tensor pipe
+//    (slab_update<8> on shared memory);
+//  * the NB x NB T factor is merged from the 8x8 ones (block dlarft);
+//  * the trailing matrix is updated slab by slab on the tensor pipe straight
+//    from L2 (slab_update<NB>), one warp per slab, no barrier.
 template <int NB>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
               double* __restrict__ fact, double* __restrict__ tfac, int ldv) {
   extern __shared__ double sm[];
@@ -378,80 +495,164 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
   double* Vs = sm;                       // ldv x NB
-  double* Cs = Vs + (size_t)ldv * NB;    // ldv x NB
-  double* Ws = Cs + (size_t)ldv * NB;    // LDW x NB
-  double* W2 = Ws + LDW * NB;            // LDW x NB
-  double* Ts = W2 + LDW * NB;            // LDW x NB
-  double* tau = Ts + LDW * NB;           // NB
-  double* red = tau + NB;                // 32
+  double* Ws = Vs + (size_t)ldv * NB;    // LDW x NB : S = V^T V blocks
+  double* Ts = Ws + LDW * NB;            // LDW x NB : T
+  double* Ys = Ts + LDW * NB;            // LDW x 8
+  double* tau = Ys + LDW * 8;            // NB
+  double* betas = tau + NB;              // NB
+  double* nrm2s = betas + NB;            // NB
+  double* zs = nrm2s + NB;               // 2 x 8
   double* A = fact + nd.F;
   double* Tg = tfac + nd.T;
   for (int j0 = 0; j0 < k; j0 += NB) {
     const int jb = min(NB, k - j0), mp = m - j0;
-    // ---- load panel
-    for (int idx = tid; idx < mp * jb; idx += kThreads) {
-      int i = idx % mp, c = idx / mp;
-      Vs[i + c * ldv] = A[(j0 + i) + (size_t)(j0 + c) * m];
+    const int mp8 = (mp + 7) & ~7;
+    // ---- load panel (zero padded to mp8 rows / NB columns), clear T
+    for (int idx = tid; idx < mp8 * NB; idx += kThreads) {
+      int i = idx % mp8, c = idx / mp8;
+      Vs[i + c * ldv] = (i < mp && c < jb) ? A[(j0 + i) + (size_t)(j0 + c) * m] : 0.;
     }
+    for (int idx = tid; idx < NB * NB; idx += kThreads) Ts[(idx % NB) + (idx / NB) * LDW] = 0.;
     __syncthreads();
-    // ---- unblocked Householder on the panel (dgeqr2)
-    for (int c = 0; c < jb; c++) {
-      double part = 0.;
-      for (int i = c + 1 + tid; i < mp; i += kThreads) {
-        double v = Vs[i + c * ldv];
-        part += v * v;
+    const int nsub = (jb + 7) >> 3;
+    for (int sp = 0; sp < nsub; sp++) {
+      const int cs = sp * 8, sbw = min(8, jb - cs);
+      if (warp == 0) {   // norm of the first pivot column of this sub-panel
+        const double* x = Vs + cs * ldv;
+        double nn = 0.;
+        for (int i = cs + 1 + lane; i < mp; i += 32) nn += x[i] * x[i];
+        nn = warp_sum(nn);
+        if (lane == 0) nrm2s[cs] = nn;
       }
-      const double xn2 = block_sum(part, red, tid);
-      const double alpha = Vs[c + c * ldv];
-      double tc = 0., scal = 0., beta = alpha;
-      if (xn2 > 0.) {
-        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-        tc = (beta - alpha) / beta;
-        scal = 1. / (alpha - beta);
-      }
-      __syncthreads();  // everyone has read alpha
-      if (xn2 > 0.)
-        for (int i = c + 1 + tid; i < mp; i += kThreads) Vs[i + c * ldv] *= scal;
-      if (tid == 0) { Vs[c + c * ldv] = beta; tau[c] = tc; }
       __syncthreads();
-      if (tc != 0.) {
-        for (int cc = c + 1 + warp; cc < jb; cc += kWarps) {
+      double scal_prev = 0.;
+      for (int cq = 0; cq < sbw; cq++) {
+        const int c = cs + cq;
+        const double* x = Vs + c * ldv;
+        const double alpha = x[c], xn2 = nrm2s[c];
+        double tc = 0., scal = 0., beta = alpha;
+        if (xn2 > 0.) {   // dlarfg
+          beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+          tc = (beta - alpha) / beta;
+          scal = 1. / (alpha - beta);
+        }
+        const int nupd = sbw - 1 - cq;
+        if (warp < nupd) {
+          // apply H_c to column cc (v = [1; scal * x]); the warp that owns the
+          // next pivot column also produces its norm
+          const int cc = c + 1 + warp;
           double* col = Vs + cc * ldv;
-          const double* v = Vs + c * ldv;
+          const double colc = col[c];
           double w = 0.;
-          for (int i = c + 1 + lane; i < mp; i += 32) w += v[i] * col[i];
+          for (int i = c + 1 + lane; i < mp; i += 32) w += x[i] * col[i];
           w = warp_sum(w);
-          w = tc * (w + col[c]);
-          for (int i = c + 1 + lane; i < mp; i += 32) col[i] -= w * v[i];
-          __syncwarp();
-          if (lane == 0) col[c] -= w;
+          w = tc * (colc + scal * w);
+          const double ws = w * scal;
+          double nn = 0.;
+          for (int i = c + 1 + lane; i < mp; i += 32) {
+            const double v = col[i] - ws * x[i];
+            col[i] = v;
+            if (i > c + 1) nn += v * v;
+          }
+          if (warp == 0) {
+            nn = warp_sum(nn);
+            if (lane == 0) nrm2s[c + 1] = nn;
+          }
+          if (lane == 0) col[c] = colc - w;
+        } else {
+          const int ww = warp - nupd;
+          if (ww < cq) {
+            // z_b = v_b^T v_c for an earlier reflector b of this sub-panel
+            const int bcol = cs + ww;
+            double* vb = Vs + bcol * ldv;
+            const bool unscaled = (bcol == c - 1);
+            double z = 0.;
+            for (int i = c + 1 + lane; i < mp; i += 32) z += vb[i] * x[i];
+            z = warp_sum(z);
+            double vbc = vb[c];
+            if (unscaled) { z *= scal_prev; vbc *= scal_prev; }
+            z = vbc + scal * z;
+            if (lane == 0) zs[(cq & 1) * 8 + ww] = z;
+            if (unscaled) {   // deferred scaling of the previous reflector
+              __syncwarp();
+              for (int i = bcol + 1 + lane; i < mp; i += 32) vb[i] *= scal_prev;
+            }
+          }
+        }
+        if (tid == 0) { betas[c] = beta; tau[c] = tc; }
+        scal_prev = scal;
+        __syncthreads();
+        if (warp == 7 && lane <= cq) {   // column cq of the 8x8 T (dlarft)
+          const int a = lane;
+          double val = tc;
+          if (a < cq) {
+            double acc = 0.;
+            for (int b = a; b < cq; b++)
+              acc += Ts[(cs + a) + (cs + b) * LDW] * zs[(cq & 1) * 8 + b];
+            val = -tc * acc;
+          }
+          Ts[(cs + a) + (cs + cq) * LDW] = val;
+        }
+      }
+      {  // scale the last reflector of the sub-panel
+        const int c = cs + sbw - 1;
+        for (int i = c + 1 + tid; i < mp; i += kThreads) Vs[i + c * ldv] *= scal_prev;
+      }
+      __syncthreads();
+      // ---- R entries of these columns to global; V explicit (unit diagonal)
+      for (int idx = tid; idx < jb * sbw; idx += kThreads) {
+        const int i = idx % jb, c = cs + idx / jb;
+        if (i <= c) {
+          A[(j0 + i) + (size_t)(j0 + c) * m] = (i == c) ? betas[c] : Vs[i + c * ldv];
+          Vs[i + c * ldv] = (i == c) ? 1. : 0.;
         }
       }
       __syncthreads();
-    }
-    // ---- R block to global, make V explicit (unit diagonal, zeros above)
-    for (int idx = tid; idx < jb * jb; idx += kThreads) {
-      int i = idx % jb, c = idx / jb;
-      if (i <= c) {
-        A[(j0 + i) + (size_t)(j0 + c) * m] = Vs[i + c * ldv];
-        Vs[i + c * ldv] = (i == c) ? 1. : 0.;
+      // ---- update the rest of the panel with this sub-panel's block reflector
+      const int nrest = jb - cs - 8;
+      if (nrest > 0) {
+        if (warp * 8 < nrest)
+          slab_update<8>(Vs + cs + (cs + 8 + warp * 8) * ldv, ldv, mp - cs,
+                         min(8, nrest - warp * 8), Vs + cs + cs * ldv, ldv,
+                         Ts + cs + cs * LDW, LDW, lane);
+        __syncthreads();
       }
     }
-    __syncthreads();
-    // ---- T factor (dlarft, forward/columnwise): S = V^T V, then per row
-    smem_gemm<true, false>(jb, jb, mp, 1., Vs, ldv, Vs, ldv, 0., Ws, LDW, warp, kWarps, lane);
-    for (int idx = tid; idx < NB * NB; idx += kThreads) Ts[(idx % NB) + (idx / NB) * LDW] = 0.;
-    __syncthreads();
-    if (warp == 0 && lane < jb) {
-      const int a = lane;
-      Ts[a + a * LDW] = tau[a];
-      for (int c = a + 1; c < jb; c++) {
-        double acc = 0.;
-        for (int b = a; b < c; b++) acc += Ts[a + b * LDW] * Ws[b + c * LDW];
-        Ts[a + c * LDW] = -tau[c] * acc;
+    // ---- merge the 8x8 T factors into the NB x NB one (block dlarft)
+    if (nsub > 1) {
+      {  // S(bi,bj) = V_bi^T V_bj for bi < bj, one 8x8 tile per warp
+        int tile = 0;
+        for (int bj = 1; bj < nsub; bj++)
+          for (int bi = 0; bi < bj; bi++, tile++)
+            if ((tile % kWarps) == warp) {
+              const int g = lane >> 2, t = lane & 3;
+              double c0 = 0., c1 = 0.;
+              const double* va = Vs + t + (bi * 8 + g) * ldv;
+              const double* vb = Vs + t + (bj * 8 + g) * ldv;
+              for (int i = bj * 8; i < mp8; i += 4) dmma(c0, c1, va[i], vb[i]);
+              Ws[(bi * 8 + g) + (bj * 8 + 2 * t) * LDW] = c0;
+              Ws[(bi * 8 + g) + (bj * 8 + 2 * t + 1) * LDW] = c1;
+            }
+      }
+      __syncthreads();
+      for (int bj = 1; bj < nsub; bj++) {
+        const int na = bj * 8, cw = min(8, jb - na);
+        for (int idx = tid; idx < na * cw; idx += kThreads) {
+          const int a = idx % na, cp = idx / na;
+          double acc = 0.;
+          for (int b = a; b < na; b++) acc += Ts[a + b * LDW] * Ws[b + (na + cp) * LDW];
+          Ys[a + cp * LDW] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < na * cw; idx += kThreads) {
+          const int a = idx % na, cp = idx / na;
+          double acc = 0.;
+          for (int d = 0; d <= cp; d++) acc += Ys[a + d * LDW] * Ts[(na + d) + (na + cp) * LDW];
+          Ts[a + (na + cp) * LDW] = -acc;
+        }
+        __syncthreads();
       }
     }
-    __syncthreads();
     for (int idx = tid; idx < jb * jb; idx += kThreads) {
       int a = idx % jb, c = idx / jb;
       Tg[a + (size_t)(j0 + c) * NB] = Ts[a + c * LDW];
@@ -461,25 +662,11 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
       int i = idx % mp, c = idx / mp;
       if (i > c) A[(j0 + i) + (size_t)(j0 + c) * m] = Vs[i + c * ldv];
     }
-    // ---- trailing update: C <- (I - V T^T V^T) C, NB columns at a time
-    for (int c0 = j0 + jb; c0 < naug; c0 += NB) {
-      const int nc = min(NB, naug - c0);
-      for (int idx = tid; idx < mp * nc; idx += kThreads) {
-        int i = idx % mp, c = idx / mp;
-        Cs[i + c * ldv] = A[(j0 + i) + (size_t)(c0 + c) * m];
-      }
-      __syncthreads();
-      smem_gemm<true, false>(jb, nc, mp, 1., Vs, ldv, Cs, ldv, 0., Ws, LDW, warp, kWarps, lane);
-      __syncthreads();
-      smem_gemm<true, false>(jb, nc, jb, 1., Ts, LDW, Ws, LDW, 0., W2, LDW, warp, kWarps, lane);
-      __syncthreads();
-      smem_gemm<false, false>(mp, nc, jb, -1., Vs, ldv, W2, LDW, 1., Cs, ldv, warp, kWarps, lane);
-      __syncthreads();
-      for (int idx = tid; idx < mp * nc; idx += kThreads) {
-        int i = idx % mp, c = idx / mp;
-        A[(j0 + i) + (size_t)(c0 + c) * m] = Cs[i + c * ldv];
-      }
-      __syncthreads();
+    // ---- trailing update: one warp per 8-column slab, no barrier inside
+    const int ntrail = naug - (j0 + jb);
+    for (int sl = warp; sl * 8 < ntrail; sl += kWarps) {
+      const int c0 = j0 + jb + sl * 8;
+      slab_update<NB>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0), Vs, ldv, Ts, LDW, lane);
     }
     __syncthreads();
   }
@@ -731,7 +918,7 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   if (nd.parent < 0) return;
   const DNode par = nodes[nd.parent];
   const int col = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m = nd.m, r = nd.u_rank, k = nd.k;
+  const int m = nd.m, k = nd.k;
   double* v = sm;        // m
   double* w = v + m;     // NB
   double* w2 = w + NB;   // NB
@@ -784,7 +971,25 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
 // ===========================================================================
 
 HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) { build_tables(); }
-HSSEngine::~HSSEngine() {}
+HSSEngine::~HSSEngine() {
+  for (auto& e : ev_) if (e) cudaEventDestroy(e);
+}
+
+void HSSEngine::set_profile(bool on) {
+  profile_ = on;
+  if (on && !ev_[0]) {
+    SB200_CUDA(cudaEventCreate(&ev_[0]));
+    SB200_CUDA(cudaEventCreate(&ev_[1]));
+  }
+}
+
+float HSSEngine::qr_leaf_ms() {
+  if (!ev_[0]) return 0.f;
+  float ms = 0.f;
+  SB200_CUDA(cudaEventSynchronize(ev_[1]));
+  SB200_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+  return ms;
+}
 
 void HSSEngine::build_tables() {
   const int N = int(H_.nodes.size());
@@ -798,7 +1003,7 @@ void HSSEngine::build_tables() {
     maxm = std::max(maxm, n.leaf() ? std::max(n.rows, n.cols)
                                    : H_.nodes[n.ch0].u_rank + H_.nodes[n.ch1].u_rank);
   }
-  nb_ = maxm <= 340 ? 32 : (maxm <= 800 ? 16 : 8);
+  nb_ = maxm <= 768 ? 32 : 16;
   if (maxm > 1600)
     throw std::invalid_argument("HSS block larger than 1600 not supported");
   for (int i = 0; i < N; i++) {
@@ -929,7 +1134,7 @@ void HSSEngine::sync_host_values() {
 
 template <int NB> static size_t qr_smem(int ldv) {
   constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
-  return sizeof(double) * ((size_t)2 * ldv * NB + 3 * LDW * NB + NB + 32);
+  return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 16);
 }
 
 void HSSEngine::factor(cudaStream_t st) {
@@ -968,8 +1173,7 @@ void HSSEngine::factor(cudaStream_t st) {
       ulv_vh_leaf_kernel<<<cnt, kThreads, 0, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p);
       launches_++;
     } else {
-      size_t smem = sizeof(double) * (size_t)mm * mm;  // Vd: v_rows x rv <= mm^2
-      smem = std::min(smem, sizeof(double) * (size_t)mm * std::max(H_.max_rank(), 1));
+      size_t smem = sizeof(int) * (size_t)(mm + 8);   // inverse permutation of V
       set_smem(ulv_build_inner_kernel, smem);
       ulv_build_inner_kernel<<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
       launches_++;
@@ -987,6 +1191,7 @@ void HSSEngine::factor(cudaStream_t st) {
     }
     launches_++;
     const int ldv = smem_ld(mm);
+    if (profile_ && h == 0) SB200_CUDA(cudaEventRecord(ev_[0], st));
     if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32>, smem);
       ulv_qr_kernel<32><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
     } else if (nb_ == 16) { size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16>, smem);
@@ -994,6 +1199,7 @@ void HSSEngine::factor(cudaStream_t st) {
     } else { size_t smem = qr_smem<8>(ldv); set_smem(ulv_qr_kernel<8>, smem);
       ulv_qr_kernel<8><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
     }
+    if (profile_ && h == 0) SB200_CUDA(cudaEventRecord(ev_[1], st));
     launches_++;
   }
   // root LU

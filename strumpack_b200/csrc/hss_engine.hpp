@@ -50,6 +50,10 @@ class HSSEngine {
 
   long long factor_nonzeros() const { return fact_nnz_; }
   long long launches() const { return launches_; }
+  // optional live timing of the dominant kernel (leaf-class QR) with CUDA
+  // events on the launching stream; ms of the last factor() call
+  void set_profile(bool on);
+  float qr_leaf_ms();
   // download the generator arena (after shift) for write_file / dense
   void sync_host_values();
 
@@ -81,6 +85,8 @@ class HSSEngine {
   bool factored_ = false;
   long long launches_ = 0;
   int nb_ = 32;
+  bool profile_ = false;
+  cudaEvent_t ev_[2] = {nullptr, nullptr};
 };
 
 }  // namespace sb200

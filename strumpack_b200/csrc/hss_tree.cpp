@@ -251,6 +251,34 @@ long long HSSHost::solve_flops_ref() const {
   return f;
 }
 
+long long HSSHost::qr_class_flops_ref(int h) const {
+  long long f = 0;
+  for (int q = hptr[h]; q < hptr[h + 1]; q++) {
+    const int i = by_height[q];
+    if (i == 0) continue;
+    auto& n = nodes[i];
+    long long m = n.leaf() ? n.rows : nodes[n.ch0].u_rank + nodes[n.ch1].u_rank;
+    long long r = n.u_rank, k = m - r;
+    if (k <= 0) continue;
+    f += ref_gelqf(k, m) + ref_xxglq(m, m, std::min(k, m));
+    f += 2 * ref_gemm(k, n.v_rank, m, 1., 0.) + ref_gemm(r, r, m, 1., 0.);
+  }
+  return f;
+}
+
+long long HSSHost::qr_class_flops_exec(int h) const {
+  long double f = 0;
+  for (int q = hptr[h]; q < hptr[h + 1]; q++) {
+    const int i = by_height[q];
+    if (i == 0) continue;
+    auto& n = nodes[i];
+    long long m = n.leaf() ? n.rows : nodes[n.ch0].u_rank + nodes[n.ch1].u_rank;
+    long long k = m - n.u_rank, na = m + n.v_rank;
+    for (long long j = 0; j < k; j++) f += 4.0L * (m - j) * (na - j - 1);
+  }
+  return (long long)f;
+}
+
 long long HSSHost::factor_flops_exec() const {
   // Householder QR of the m x k block applied to m x (k + r_v + r) columns,
   // no explicit Q: 2 * sum_j (m-j) * (cols right of j) * 2

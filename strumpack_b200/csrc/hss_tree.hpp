@@ -52,6 +52,11 @@ struct HSSHost {
   long long factor_flops_ref() const;  // params::ULV_factor_flops formula
   long long solve_flops_ref() const;   // params::hss_solve_flops, 1 rhs
   long long factor_flops_exec() const; // what the engine really executes
+  // The batched Householder-QR launch over height class h (the dominant
+  // kernel for h = 0): flops in the reference's accounting (LQ_flops + the
+  // three Q-GEMMs, factor.hpp:122-141) and as executed by the engine.
+  long long qr_class_flops_ref(int h) const;
+  long long qr_class_flops_exec(int h) const;
 
   // Reference dump format, HSSMatrix<double>::write/read
   // (reference src/HSS/HSSMatrix.cpp:438-510).
