@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace sb200 {
@@ -314,8 +315,14 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
 }
 
 // Elimination step: writes A = W0^T and W1^T into the factor block.
-// Dsrc = leaf ? D generator : Dfull scratch; tiles of TJ columns of Dsrc are
-// staged in smem so the row gather by P_u is a shared-memory gather.
+//   W0^T[j, i] = Dp[r+i, j] - sum_l E[i, l] Dp[l, j],   W1^T[j, l] = Dp[l, j],
+//   Dp = P_u^T D                                     (factor.hpp:109-121)
+// Dsrc = leaf ? D generator : Dfull scratch.  Tiles of TJ columns of Dsrc are
+// read coalesced into shared memory, so the row gather by P_u is a shared-
+// memory gather; the rank-r correction runs on the fp64 tensor pipe: each
+// warp owns 8-column slabs of the output, A fragments are gathered rows of the
+// tile, B fragments (E^T) stay in registers across the tile's row blocks.
+// HBM-bound: reads D once, writes the m x (k + r) block once.
 template <int TJ>
 __global__ void __launch_bounds__(kThreads)
 ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
@@ -326,42 +333,70 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0) return;
   const int m = nd.m, r = nd.u_rank, k = nd.k, rv = nd.v_rank, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const double* Dsrc = nd.leaf ? vals + nd.D : scratch + scratch_off[blockIdx.x];
   const int* P = perms + nd.Pu;
   const double* E = vals + nd.Eu;  // k x r
   double* A = fact + nd.F;
   double* W1t = A + (size_t)(k + rv) * m;
   constexpr int LD = TJ + 1;
-  double* Dn = sm;  // m x LD (row-major-ish: Dn[i*LD + jj])
+  constexpr int RT = TJ / 8;       // row tiles of the output per column tile
+  constexpr int KS = 16;           // k-steps held in registers (r <= 64 per pass)
+  double* Dn = sm;                 // m x LD : Dn[i*LD + jj] = Dsrc[i, j0+jj]
+  int* Ps = reinterpret_cast<int*>(Dn + (size_t)m * LD);   // m
+  for (int i = tid; i < m; i += kThreads) Ps[i] = P[i];
   for (int j0 = 0; j0 < m; j0 += TJ) {
     const int tj = min(TJ, m - j0);
     __syncthreads();
-    for (int idx = tid; idx < m * tj; idx += kThreads) {
+    for (int idx = tid; idx < m * TJ; idx += kThreads) {
       int i = idx % m, jj = idx / m;
-      Dn[i * LD + jj] = Dsrc[i + (size_t)(j0 + jj) * m];
+      Dn[i * LD + jj] = jj < tj ? Dsrc[i + (size_t)(j0 + jj) * m] : 0.;
     }
     __syncthreads();
     // W1^T[j, l] = Dp[l, j]
     for (int idx = tid; idx < r * tj; idx += kThreads) {
       int jj = idx % tj, l = idx / tj;
-      W1t[(j0 + jj) + (size_t)l * m] = Dn[P[l] * LD + jj];
+      W1t[(j0 + jj) + (size_t)l * m] = Dn[Ps[l] * LD + jj];
     }
-    // W0^T[j, i] = Dp[r+i, j] - sum_l E[i,l] Dp[l, j]
-    for (int i = tid; i < k; i += kThreads) {
-      double acc[TJ];
-      const double* src = Dn + P[r + i] * LD;
+    // W0^T tile (tj x k), 8-column slabs over the warps
+    for (int i0 = warp * 8; i0 < k; i0 += kWarps * 8) {
+      double acc[RT][2];
+      const int ia = i0 + 2 * t, ib = ia + 1;       // output columns of this lane
+      const double* ga = Dn + (ia < k ? Ps[r + ia] : 0) * LD + g;
+      const double* gb = Dn + (ib < k ? Ps[r + ib] : 0) * LD + g;
 #pragma unroll
-      for (int jj = 0; jj < TJ; jj++) acc[jj] = src[jj];
-      for (int l = 0; l < r; l++) {
-        const double e = E[i + (size_t)l * k];
-        const double* top = Dn + P[l] * LD;
+      for (int rt = 0; rt < RT; rt++) { acc[rt][0] = ga[rt * 8]; acc[rt][1] = gb[rt * 8]; }
+      for (int l0 = 0; l0 < r; l0 += 4 * KS) {
+        double bneg[KS];
+        int prow[KS];
 #pragma unroll
-        for (int jj = 0; jj < TJ; jj++) acc[jj] -= e * top[jj];
+        for (int s = 0; s < KS; s++) {
+          const int l = l0 + 4 * s + t;
+          // B[k=l][n=i] = -E[i, l]
+          bneg[s] = (l < r && i0 + g < k) ? -E[(i0 + g) + (size_t)l * k] : 0.;
+          prow[s] = (l < r ? Ps[l] : 0) * LD + g;
+        }
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+          if (l0 + 4 * s < r) {
+            const bool lin = l0 + 4 * s + t < r;
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {
+              // A[row=jj][k=l] = Dp[l, j] = Dn[P[l]][jj]
+              const double a = lin ? Dn[prow[s] + rt * 8] : 0.;
+              dmma(acc[rt][0], acc[rt][1], a, bneg[s]);
+            }
+          }
+        }
       }
-      double* dst = A + j0 + (size_t)i * m;
 #pragma unroll
-      for (int jj = 0; jj < TJ; jj++)
-        if (jj < tj) dst[jj] = acc[jj];
+      for (int rt = 0; rt < RT; rt++) {
+        const int jj = rt * 8 + g;
+        if (jj < tj) {
+          if (ia < k) A[(j0 + jj) + (size_t)ia * m] = acc[rt][0];
+          if (ib < k) A[(j0 + jj) + (size_t)ib * m] = acc[rt][1];
+        }
+      }
     }
   }
 }
@@ -386,9 +421,9 @@ __device__ __forceinline__ void slab_update(double* __restrict__ Cg, int ldc, in
   constexpr int U = 4;   // row tiles per prefetch group (8 loads in flight)
   const int g = lane >> 2, t = lane & 3;
   const int nit = (mp + 7) >> 3;
-  double wt[NT][2];
+  double wt[NT][2], wu[NT][2];   // two accumulator sets: shorter DMMA chains
 #pragma unroll
-  for (int q = 0; q < NT; q++) wt[q][0] = wt[q][1] = 0.;
+  for (int q = 0; q < NT; q++) wt[q][0] = wt[q][1] = wu[q][0] = wu[q][1] = 0.;
   const bool gin = g < cw;
   {
     const double* Cn = Cg + (size_t)g * ldc + t;
@@ -406,18 +441,19 @@ __device__ __forceinline__ void slab_update(double* __restrict__ Cg, int ldc, in
       for (int u = 0; u < U; u++) {
         const int it = it0 + u;
         if (it < nit) {
+          const double* vb = Vb + it * 8;
 #pragma unroll
-          for (int ks = 0; ks < 2; ks++) {
-            const double* vb = Vb + it * 8 + ks * 4;
-#pragma unroll
-            for (int at = 0; at < NT; at++)
-              if (at <= it)   // V[i][a] = 0 for a > i
-                dmma(wt[at][0], wt[at][1], a[u][ks], vb[at * 8 * ldv]);
-          }
+          for (int at = 0; at < NT; at++)
+            if (at <= it) {  // V[i][a] = 0 for a > i
+              dmma(wt[at][0], wt[at][1], a[u][0], vb[at * 8 * ldv]);
+              dmma(wu[at][0], wu[at][1], a[u][1], vb[4 + at * 8 * ldv]);
+            }
         }
       }
     }
   }
+#pragma unroll
+  for (int q = 0; q < NT; q++) { wt[q][0] += wu[q][0]; wt[q][1] += wu[q][1]; }
   double w2[NT][2];
 #pragma unroll
   for (int q = 0; q < NT; q++) w2[q][0] = w2[q][1] = 0.;
@@ -484,10 +520,11 @@ __device__ __forceinline__ void slab_update(double* __restrict__ Cg, int ldc, in
 //  * the NB x NB T factor is merged from the 8x8 ones (block dlarft);
 //  * the trailing matrix is updated slab by slab on the tensor pipe straight
 //    from L2 (slab_update<NB>), one warp per slab, no barrier.
-template <int NB>
+template <int NB, bool SMALL>
 __global__ void __launch_bounds__(kThreads, 2)
 ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
-              double* __restrict__ fact, double* __restrict__ tfac, int ldv) {
+              double* __restrict__ fact, double* __restrict__ tfac, int ldv,
+              int pmode, int pidx) {
   extern __shared__ double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0 || nd.k == 0) return;
@@ -501,113 +538,184 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   double* tau = Ys + LDW * 8;            // NB
   double* betas = tau + NB;              // NB
   double* nrm2s = betas + NB;            // NB
-  double* zs = nrm2s + NB;               // 2 x 8
+  double* scals = nrm2s;                 // NB (1/(alpha-beta) per column)
+  double* zs = nrm2s + NB;               // 2 x 16
   double* A = fact + nd.F;
   double* Tg = tfac + nd.T;
-  for (int j0 = 0; j0 < k; j0 += NB) {
+#ifdef SB200_QR_TIMING
+  long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#define QR_TICK(p) { long long now_ = clock64(); tph[p] += now_ - tlast; tlast = now_; }
+#else
+#define QR_TICK(p)
+#endif
+  // pmode 0: whole factorization in this launch (small classes);
+  // pmode 1: factor panel pidx only; pmode 2: trailing update with panel pidx
+  // only.  Splitting the leaf class into per-panel launches keeps the
+  // latency-bound Householder chains from sharing the fp64 pipe with the DMMA
+  // stream of a co-resident CTA and balances the slab updates.
+  for (int j0 = pmode ? pidx * NB : 0; j0 < k; j0 += NB) {
     const int jb = min(NB, k - j0), mp = m - j0;
     const int mp8 = (mp + 7) & ~7;
+    if (pmode == 2) {
+      // reload the explicit V (unit lower trapezoid) and T of this panel
+      for (int c = warp; c < NB; c += kWarps) {
+        const double* src = A + j0 + (size_t)(j0 + c) * m;
+        double* dst = Vs + c * ldv;
+        const bool cin = c < jb;
+        for (int i = lane; i < mp8; i += 32)
+          dst[i] = (cin && i < mp && i >= c) ? (i == c ? 1. : src[i]) : 0.;
+      }
+      for (int idx = tid; idx < NB * NB; idx += kThreads) {
+        const int a = idx % NB, c = idx / NB;
+        Ts[a + c * LDW] = (a < jb && c < jb && a <= c) ? Tg[a + (size_t)(j0 + c) * NB] : 0.;
+      }
+      __syncthreads();
+    } else {
     // ---- load panel (zero padded to mp8 rows / NB columns), clear T
-    for (int idx = tid; idx < mp8 * NB; idx += kThreads) {
-      int i = idx % mp8, c = idx / mp8;
-      Vs[i + c * ldv] = (i < mp && c < jb) ? A[(j0 + i) + (size_t)(j0 + c) * m] : 0.;
+    for (int c = warp; c < NB; c += kWarps) {
+      const double* src = A + j0 + (size_t)(j0 + c) * m;
+      double* dst = Vs + c * ldv;
+      const bool cin = c < jb;
+      for (int i = lane; i < mp8; i += 32) dst[i] = (cin && i < mp) ? src[i] : 0.;
     }
     for (int idx = tid; idx < NB * NB; idx += kThreads) Ts[(idx % NB) + (idx / NB) * LDW] = 0.;
     __syncthreads();
+    QR_TICK(0)
     const int nsub = (jb + 7) >> 3;
     for (int sp = 0; sp < nsub; sp++) {
       const int cs = sp * 8, sbw = min(8, jb - cs);
-      if (warp == 0) {   // norm of the first pivot column of this sub-panel
-        const double* x = Vs + cs * ldv;
-        double nn = 0.;
-        for (int i = cs + 1 + lane; i < mp; i += 32) nn += x[i] * x[i];
-        nn = warp_sum(nn);
-        if (lane == 0) nrm2s[cs] = nn;
-      }
-      __syncthreads();
-      double scal_prev = 0.;
       for (int cq = 0; cq < sbw; cq++) {
         const int c = cs + cq;
         const double* x = Vs + c * ldv;
-        const double alpha = x[c], xn2 = nrm2s[c];
-        double tc = 0., scal = 0., beta = alpha;
-        if (xn2 > 0.) {   // dlarfg
-          beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-          tc = (beta - alpha) / beta;
-          scal = 1. / (alpha - beta);
-        }
         const int nupd = sbw - 1 - cq;
-        if (warp < nupd) {
-          // apply H_c to column cc (v = [1; scal * x]); the warp that owns the
-          // next pivot column also produces its norm
-          const int cc = c + 1 + warp;
-          double* col = Vs + cc * ldv;
-          const double colc = col[c];
-          double w = 0.;
-          for (int i = c + 1 + lane; i < mp; i += 32) w += x[i] * col[i];
-          w = warp_sum(w);
-          w = tc * (colc + scal * w);
-          const double ws = w * scal;
-          double nn = 0.;
-          for (int i = c + 1 + lane; i < mp; i += 32) {
-            const double v = col[i] - ws * x[i];
-            col[i] = v;
-            if (i > c + 1) nn += v * v;
+        // role of this warp in step c:
+        //   lead (warp < nupd, or warp 7 when nothing is left to update):
+        //        norm of the pivot column + scalars (dlarfg) and, if warp <
+        //        nupd, apply H_c to column cc = c+1+warp
+        //   dot  (nupd <= warp, ww < cq): raw dot product v_b . x_c for the
+        //        earlier reflector b = cs+ww (gives the 8x8 T factor for free)
+        //   none: straight to the barrier
+        const int ww = warp - nupd;
+        const bool upd = warp < nupd, lead = upd || (nupd == 0 && warp == 7);
+        const bool dot = !lead && ww < cq;
+        const bool writer = nupd > 0 ? warp == 0 : warp == 7;
+        if (lead || dot) {
+          double* oth = upd ? Vs + (c + 1 + warp) * ldv : Vs + (cs + (dot ? ww : 0)) * ldv;
+          const bool use_oth = upd || dot;
+          double pn = 0., wr = 0.;
+          double xv[SMALL ? 8 : 1], ov[SMALL ? 8 : 1];
+          if (SMALL) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int i = lane + 32 * q;
+              const bool in = i > c && i < mp;
+              xv[q] = in ? x[i] : 0.;
+              ov[q] = (in && use_oth) ? oth[i] : 0.;
+            }
+            double p0 = 0., p1 = 0., w0 = 0., w1 = 0.;
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+              p0 += xv[q] * xv[q]; p1 += xv[q + 1] * xv[q + 1];
+              w0 += xv[q] * ov[q]; w1 += xv[q + 1] * ov[q + 1];
+            }
+            pn = p0 + p1; wr = w0 + w1;
+          } else {
+            double p0 = 0., p1 = 0., w0 = 0., w1 = 0.;
+            int i = c + 1 + lane;
+            for (; i + 32 < mp; i += 64) {
+              const double a0 = x[i], a1 = x[i + 32];
+              p0 += a0 * a0; p1 += a1 * a1;
+              if (use_oth) { w0 += a0 * oth[i]; w1 += a1 * oth[i + 32]; }
+            }
+            if (i < mp) { const double a0 = x[i]; p0 += a0 * a0; if (use_oth) w0 += a0 * oth[i]; }
+            pn = p0 + p1; wr = w0 + w1;
           }
-          if (warp == 0) {
-            nn = warp_sum(nn);
-            if (lane == 0) nrm2s[c + 1] = nn;
-          }
-          if (lane == 0) col[c] = colc - w;
-        } else {
-          const int ww = warp - nupd;
-          if (ww < cq) {
-            // z_b = v_b^T v_c for an earlier reflector b of this sub-panel
-            const int bcol = cs + ww;
-            double* vb = Vs + bcol * ldv;
-            const bool unscaled = (bcol == c - 1);
-            double z = 0.;
-            for (int i = c + 1 + lane; i < mp; i += 32) z += vb[i] * x[i];
-            z = warp_sum(z);
-            double vbc = vb[c];
-            if (unscaled) { z *= scal_prev; vbc *= scal_prev; }
-            z = vbc + scal * z;
-            if (lane == 0) zs[(cq & 1) * 8 + ww] = z;
-            if (unscaled) {   // deferred scaling of the previous reflector
+          QR_TICK(8)
+          if (lead) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              pn += __shfl_xor_sync(0xffffffffu, pn, o);
+              wr += __shfl_xor_sync(0xffffffffu, wr, o);
+            }
+            QR_TICK(9)
+            const double alpha = x[c];
+            double tc = 0., scal = 0., beta = alpha;
+            if (pn > 0.) {   // dlarfg
+              beta = -copysign(sqrt(alpha * alpha + pn), alpha);
+              const double d = alpha - beta;
+              scal = 1. / d;
+              tc = -d / beta;
+            }
+            QR_TICK(10)
+            if (upd) {
+              const double colc = oth[c];
+              const double w = tc * (colc + scal * wr);
+              const double ws = w * scal;
+              if (SMALL) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                  const int i = lane + 32 * q;
+                  if (i > c && i < mp) oth[i] = ov[q] - ws * xv[q];
+                }
+              } else {
+                for (int i = c + 1 + lane; i < mp; i += 32) oth[i] -= ws * x[i];
+              }
+              if (lane == 0) oth[c] = colc - w;
+            }
+            if (writer && lane == 0) { betas[c] = beta; tau[c] = tc; scals[c] = scal; }
+            QR_TICK(11)
+          } else {
+            // raw z_b = x_b[c+1:]^T x_c[c+1:] and x_b[c]; the scalings (the
+            // previous reflector is still unscaled) are applied by warp 7
+            wr = warp_sum(wr);
+            if (lane == 0) { zs[(cq & 1) * 16 + ww] = wr; zs[(cq & 1) * 16 + 8 + ww] = oth[c]; }
+            if (ww == cq - 1) {   // deferred scaling of the previous reflector
+              const double sp_ = scals[c - 1];
               __syncwarp();
-              for (int i = bcol + 1 + lane; i < mp; i += 32) vb[i] *= scal_prev;
+              for (int i = c + lane; i < mp; i += 32) oth[i] *= sp_;
             }
           }
         }
-        if (tid == 0) { betas[c] = beta; tau[c] = tc; }
-        scal_prev = scal;
+        QR_TICK(12)
         __syncthreads();
+        QR_TICK(13)
         if (warp == 7 && lane <= cq) {   // column cq of the 8x8 T (dlarft)
           const int a = lane;
+          const double tc = tau[c], sc = scals[c];
           double val = tc;
           if (a < cq) {
+            const double sprev = scals[c - 1];
             double acc = 0.;
-            for (int b = a; b < cq; b++)
-              acc += Ts[(cs + a) + (cs + b) * LDW] * zs[(cq & 1) * 8 + b];
+            for (int b = a; b < cq; b++) {
+              const double f = (b == cq - 1) ? sprev : 1.;   // v_b unscaled?
+              const double z = f * (zs[(cq & 1) * 16 + 8 + b] + sc * zs[(cq & 1) * 16 + b]);
+              acc += Ts[(cs + a) + (cs + b) * LDW] * z;
+            }
             val = -tc * acc;
           }
           Ts[(cs + a) + (cs + cq) * LDW] = val;
         }
+        QR_TICK(14)
       }
+      const double scal_prev = scals[cs + sbw - 1];
+      QR_TICK(1)
       {  // scale the last reflector of the sub-panel
         const int c = cs + sbw - 1;
         for (int i = c + 1 + tid; i < mp; i += kThreads) Vs[i + c * ldv] *= scal_prev;
       }
       __syncthreads();
       // ---- R entries of these columns to global; V explicit (unit diagonal)
-      for (int idx = tid; idx < jb * sbw; idx += kThreads) {
-        const int i = idx % jb, c = cs + idx / jb;
-        if (i <= c) {
-          A[(j0 + i) + (size_t)(j0 + c) * m] = (i == c) ? betas[c] : Vs[i + c * ldv];
+      if (warp < sbw) {
+        const int c = cs + warp;
+        double* dst = A + j0 + (size_t)(j0 + c) * m;
+        for (int i = lane; i <= c; i += 32) {
+          dst[i] = (i == c) ? betas[c] : Vs[i + c * ldv];
           Vs[i + c * ldv] = (i == c) ? 1. : 0.;
         }
       }
       __syncthreads();
+      QR_TICK(2)
       // ---- update the rest of the panel with this sub-panel's block reflector
       const int nrest = jb - cs - 8;
       if (nrest > 0) {
@@ -617,6 +725,7 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                          Ts + cs + cs * LDW, LDW, lane);
         __syncthreads();
       }
+      QR_TICK(3)
     }
     // ---- merge the 8x8 T factors into the NB x NB one (block dlarft)
     if (nsub > 1) {
@@ -653,23 +762,40 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
         __syncthreads();
       }
     }
-    for (int idx = tid; idx < jb * jb; idx += kThreads) {
-      int a = idx % jb, c = idx / jb;
-      Tg[a + (size_t)(j0 + c) * NB] = Ts[a + c * LDW];
+    QR_TICK(4)
+    for (int idx = tid; idx < NB * NB; idx += kThreads) {
+      const int a = idx % NB, c = idx / NB;
+      if (a < jb && c < jb) Tg[a + (size_t)(j0 + c) * NB] = Ts[a + c * LDW];
     }
     // ---- V (strictly lower part) back to global
-    for (int idx = tid; idx < mp * jb; idx += kThreads) {
-      int i = idx % mp, c = idx / mp;
-      if (i > c) A[(j0 + i) + (size_t)(j0 + c) * m] = Vs[i + c * ldv];
+    for (int c = warp; c < jb; c += kWarps) {
+      double* dst = A + j0 + (size_t)(j0 + c) * m;
+      const double* src = Vs + c * ldv;
+      for (int i = c + 1 + lane; i < mp; i += 32) dst[i] = src[i];
+    }
+    QR_TICK(5)
+    if (pmode == 1) break;
+    __syncthreads();
     }
     // ---- trailing update: one warp per 8-column slab, no barrier inside
     const int ntrail = naug - (j0 + jb);
-    for (int sl = warp; sl * 8 < ntrail; sl += kWarps) {
+    // (the warp that gets the extra slab rotates with the panel index)
+    for (int sl = (warp + (j0 / NB) * 3) % kWarps; sl * 8 < ntrail; sl += kWarps) {
       const int c0 = j0 + jb + sl * 8;
       slab_update<NB>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0), Vs, ldv, Ts, LDW, lane);
     }
+    QR_TICK(6)
+    if (pmode == 2) break;
     __syncthreads();
+    QR_TICK(7)
   }
+#ifdef SB200_QR_TIMING
+  if (lane == 0 && blockIdx.x < 4) {
+    printf("[qr timing] block %d warp %d m %d : load %lld steps %lld fin %lld inpanel %lld merge %lld wb %lld trail %lld wait %lld | pass %lld shfl %lld scalars %lld update %lld other %lld barrier %lld tcol %lld\n",
+           blockIdx.x, warp, m, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7],
+           tph[8], tph[9], tph[10], tph[11], tph[12], tph[13], tph[14]);
+  }
+#endif
 }
 
 // Root: Dfull (already assembled in the root factor block by
@@ -970,7 +1096,13 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
 //                                 HOST SIDE
 // ===========================================================================
 
-HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) { build_tables(); }
+HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
+  int dev = 0;
+  SB200_CUDA(cudaGetDevice(&dev));
+  SB200_CUDA(cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, dev));
+  if (const char* e = std::getenv("SB200_QR_SPLIT")) qr_split_ = std::atoi(e);
+  build_tables();
+}
 HSSEngine::~HSSEngine() {
   for (auto& e : ev_) if (e) cudaEventDestroy(e);
 }
@@ -1134,7 +1266,7 @@ void HSSEngine::sync_host_values() {
 
 template <int NB> static size_t qr_smem(int ldv) {
   constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
-  return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 16);
+  return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 32);
 }
 
 void HSSEngine::factor(cudaStream_t st) {
@@ -1181,23 +1313,35 @@ void HSSEngine::factor(cudaStream_t st) {
     if (h == nh - 1) break;  // root class: LU below
     // elimination
     if (mm <= 640) {
-      size_t smem = sizeof(double) * (size_t)mm * 33;
+      size_t smem = sizeof(double) * (size_t)mm * 33 + sizeof(int) * (size_t)(mm + 8);
       set_smem(ulv_eliminate_kernel<32>, smem);
       ulv_eliminate_kernel<32><<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
     } else {
-      size_t smem = sizeof(double) * (size_t)mm * 9;
+      size_t smem = sizeof(double) * (size_t)mm * 9 + sizeof(int) * (size_t)(mm + 8);
       set_smem(ulv_eliminate_kernel<8>, smem);
       ulv_eliminate_kernel<8><<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
     }
     launches_++;
     const int ldv = smem_ld(mm);
     if (profile_ && h == 0) SB200_CUDA(cudaEventRecord(ev_[0], st));
-    if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32>, smem);
-      ulv_qr_kernel<32><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
-    } else if (nb_ == 16) { size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16>, smem);
-      ulv_qr_kernel<16><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
-    } else { size_t smem = qr_smem<8>(ldv); set_smem(ulv_qr_kernel<8>, smem);
-      ulv_qr_kernel<8><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
+    {
+      // large classes: one launch per panel and phase; small ones: fused
+      int kmax = 0;
+      for (int q = hptr_[h]; q < hptr_[h + 1]; q++) kmax = std::max(kmax, hn_[H_.by_height[q]].k);
+      const bool split = qr_split_ && cnt >= 2 * nsm_ && kmax > nb_;
+      const int npan = split ? (kmax + nb_ - 1) / nb_ : 1;
+      for (int pp = 0; pp < npan; pp++)
+        for (int phase = split ? 1 : 0; phase <= (split ? 2 : 0); phase++) {
+          if (nb_ == 32 && mm <= 256) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true>, smem);
+            ulv_qr_kernel<32, true><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
+          } else if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, false>, smem);
+            ulv_qr_kernel<32, false><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
+          } else { size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, false>, smem);
+            ulv_qr_kernel<16, false><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
+          }
+          launches_++;
+        }
+      launches_--;
     }
     if (profile_ && h == 0) SB200_CUDA(cudaEventRecord(ev_[1], st));
     launches_++;
