@@ -135,6 +135,33 @@ int SB200_d_struct_factor_device(CSPStructMat S, void* stream);
 int SB200_d_struct_solve_device(const CSPStructMat S, int nrhs, double* dB,
                                 int ldB, void* stream);
 
+/* ---- subtree sharding over the GPUs of one node -------------
+ * Every rank holds a handle on the same matrix and calls
+ * SB200_d_hss_set_partition(S, nparts, part): it then owns the subtree of the
+ * part-th node at depth log2(nparts) (row range from SB200_d_hss_owned_range)
+ * while the nparts-1 nodes above the cut are replicated.  Each operation needs
+ * ONE small exchange, done by the caller between _begin and _end as an
+ * all-gather (NCCL) of `SB200_d_hss_dist_sizes(S, nrhs, out)[op]` doubles per
+ * rank: out[0] apply, out[1] factor, out[2] solve.  dSend/dRecv, dB/dC are
+ * device pointers; x/b/y are full-length vectors of which only the owned rows
+ * are read/written.  This replaces the reference's MPI/BLACS subtree mapping
+ * (src/HSS/HSSMatrixMPI.cpp:317-345, pgemr2d moves HSSMatrixMPI.factor.hpp:63-66). */
+int SB200_d_hss_set_partition(CSPStructMat S, int nparts, int part);
+int SB200_d_hss_owned_range(const CSPStructMat S, int* lo, int* hi);
+int SB200_d_hss_dist_sizes(const CSPStructMat S, int nrhs, long long int* out);
+int SB200_d_hss_dist_mult_begin(const CSPStructMat S, char trans, int m,
+                                const double* dB, int ldB, double* dSend,
+                                void* stream);
+int SB200_d_hss_dist_mult_end(const CSPStructMat S, char trans, int m,
+                              const double* dB, int ldB, double* dC, int ldC,
+                              const double* dRecv, void* stream);
+int SB200_d_hss_dist_factor_begin(CSPStructMat S, double* dSend, void* stream);
+int SB200_d_hss_dist_factor_end(CSPStructMat S, const double* dRecv, void* stream);
+int SB200_d_hss_dist_solve_begin(const CSPStructMat S, int nrhs, double* dB,
+                                 int ldB, double* dSend, void* stream);
+int SB200_d_hss_dist_solve_end(const CSPStructMat S, int nrhs, double* dB,
+                               int ldB, const double* dRecv, void* stream);
+
 /* Statistics (HSSMatrix::levels, factor_nonzeros; reference
  * HSSMatrix.cpp:326-332, HSSMatrixBase.cpp:74). */
 int SB200_d_struct_levels(const CSPStructMat S);

@@ -59,6 +59,15 @@ SYMBOLS = {
     "SB200_d_struct_mult_device": (_i, [_vp, C.c_char, _i, _vp, _i, _vp, _i, _vp]),
     "SB200_d_struct_factor_device": (_i, [_vp, _vp]),
     "SB200_d_struct_solve_device": (_i, [_vp, _i, _vp, _i, _vp]),
+    "SB200_d_hss_set_partition": (_i, [_vp, _i, _i]),
+    "SB200_d_hss_owned_range": (_i, [_vp, _vp, _vp]),
+    "SB200_d_hss_dist_sizes": (_i, [_vp, _i, _vp]),
+    "SB200_d_hss_dist_mult_begin": (_i, [_vp, C.c_char, _i, _vp, _i, _vp, _vp]),
+    "SB200_d_hss_dist_mult_end": (_i, [_vp, C.c_char, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "SB200_d_hss_dist_factor_begin": (_i, [_vp, _vp, _vp]),
+    "SB200_d_hss_dist_factor_end": (_i, [_vp, _vp, _vp]),
+    "SB200_d_hss_dist_solve_begin": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "SB200_d_hss_dist_solve_end": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "SB200_d_hss_file_info": (_i, [C.c_char_p, _vp]),
     "SB200_d_hss_file_copy": (_i, [C.c_char_p, C.c_char_p]),
     "SB200_d_struct_levels": (_i, [_vp]),

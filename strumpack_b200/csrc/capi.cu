@@ -248,6 +248,38 @@ int SB200_d_struct_solve_device(const CSPStructMat S, int nrhs, double* dB,
   });
 }
 
+int SB200_d_hss_set_partition(CSPStructMat S, int nparts, int part) {
+  return guarded([&] { hss(S).set_partition(nparts, part); });
+}
+int SB200_d_hss_owned_range(const CSPStructMat S, int* lo, int* hi) {
+  return guarded([&] { hss(S).owned_range(lo, hi); });
+}
+int SB200_d_hss_dist_sizes(const CSPStructMat S, int nrhs, long long int* out) {
+  return guarded([&] { hss(S).dist_sizes(nrhs, out); });
+}
+int SB200_d_hss_dist_mult_begin(const CSPStructMat S, char trans, int m,
+                                const double* dB, int ldB, double* dSend, void* stream) {
+  return guarded([&] { hss(S).dist_mult_begin(trans, m, dB, ldB, dSend, static_cast<cudaStream_t>(stream)); });
+}
+int SB200_d_hss_dist_mult_end(const CSPStructMat S, char trans, int m, const double* dB,
+                              int ldB, double* dC, int ldC, const double* dRecv, void* stream) {
+  return guarded([&] { hss(S).dist_mult_end(trans, m, dB, ldB, dC, ldC, dRecv, static_cast<cudaStream_t>(stream)); });
+}
+int SB200_d_hss_dist_factor_begin(CSPStructMat S, double* dSend, void* stream) {
+  return guarded([&] { hss(S).dist_factor_begin(dSend, static_cast<cudaStream_t>(stream)); });
+}
+int SB200_d_hss_dist_factor_end(CSPStructMat S, const double* dRecv, void* stream) {
+  return guarded([&] { hss(S).dist_factor_end(dRecv, static_cast<cudaStream_t>(stream)); });
+}
+int SB200_d_hss_dist_solve_begin(const CSPStructMat S, int nrhs, double* dB, int ldB,
+                                 double* dSend, void* stream) {
+  return guarded([&] { hss(S).dist_solve_begin(nrhs, dB, ldB, dSend, static_cast<cudaStream_t>(stream)); });
+}
+int SB200_d_hss_dist_solve_end(const CSPStructMat S, int nrhs, double* dB, int ldB,
+                               const double* dRecv, void* stream) {
+  return guarded([&] { hss(S).dist_solve_end(nrhs, dB, ldB, dRecv, static_cast<cudaStream_t>(stream)); });
+}
+
 int SB200_d_hss_file_info(const char* path, long long int* out) {
   return guarded([&] {
     HSSHost h = HSSHost::read_file(path);

@@ -1167,22 +1167,11 @@ void HSSEngine::build_tables() {
   ws_total_ = woff;
   tot_k_ = yoff; tot_rv_ = zoff; tot_ru_ = fo; tot_m_ = xo;
   fact_nnz_ = foff + toff;
-  hptr_ = H_.hptr;
-  const int nh = int(hptr_.size()) - 1;
-  cls_max_m_.assign(nh, 0);
-  cls_max_naug_.assign(nh, 0);
-  for (int h = 0; h < nh; h++)
-    for (int q = hptr_[h]; q < hptr_[h + 1]; q++) {
-      const DNode& d = hn_[H_.by_height[q]];
-      cls_max_m_[h] = std::max(cls_max_m_[h], std::max(d.m, std::max(d.rows * d.leaf, d.cols * d.leaf)));
-      cls_max_m_[h] = std::max(cls_max_m_[h], std::max(d.u_rows, d.v_rows));
-      cls_max_naug_[h] = std::max(cls_max_naug_[h], d.naug);
-    }
   dn_.upload(hn_.data(), hn_.size());
   vals_.upload(H_.vals.data(), H_.vals.size());
   perms_.upload(H_.perms.data(), H_.perms.size());
-  by_height_.upload(H_.by_height.data(), H_.by_height.size());
   SB200_CUDA(cudaStreamSynchronize(0));
+  set_partition(1, 0);
 }
 
 void HSSEngine::ensure_apply_ws(int s) {
@@ -1206,54 +1195,201 @@ template <typename K> static void set_smem(K kernel, size_t bytes) {
     SB200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
+__global__ void copy2d_kernel(double* __restrict__ dst, long long ldd,
+                              const double* __restrict__ src, long long lds,
+                              int rows, int cols) {
+  const long long tot = (long long)rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % rows), j = (int)(idx / rows);
+    dst[i + j * ldd] = src[i + j * lds];
+  }
+}
+
+static void copy2d(double* dst, long long ldd, const double* src, long long lds,
+                   int rows, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return;
+  const long long tot = (long long)rows * cols;
+  copy2d_kernel<<<(unsigned)std::min<long long>((tot + 255) / 256, 1024), 256, 0, st>>>(dst, ldd, src, lds, rows, cols);
+}
+
+// ---------------------------------------------------------------------------
+// node lists: the sweeps run over "owned" nodes (everything on one GPU; the
+// subtree of this rank's cut node when the tree is sharded) and over the "top"
+// nodes above the cut (replicated on every rank)
+// ---------------------------------------------------------------------------
+void HSSEngine::make_lists(NodeLists& L, const std::vector<int>& nodes) {
+  int maxh = 0;
+  for (int i : nodes) maxh = std::max(maxh, H_.nodes[i].height);
+  L.hptr.assign(nodes.empty() ? 1 : maxh + 2, 0);
+  for (int i : nodes) L.hptr[H_.nodes[i].height + 1]++;
+  for (size_t h = 0; h + 1 < L.hptr.size(); h++) L.hptr[h + 1] += L.hptr[h];
+  L.host.assign(nodes.size(), 0);
+  std::vector<int> pos(L.hptr.begin(), L.hptr.end());
+  for (int i : nodes) L.host[pos[H_.nodes[i].height]++] = i;   // `nodes` is in pre-order
+  const int nh = L.classes();
+  L.max_m.assign(nh, 0);
+  L.max_k.assign(nh, 0);
+  L.soff.assign(nodes.size(), 0);
+  L.smax = 0;
+  for (int h = 0; h < nh; h++) {
+    long long o = 0;
+    for (int q = L.hptr[h]; q < L.hptr[h + 1]; q++) {
+      const DNode& d = hn_[L.host[q]];
+      L.max_m[h] = std::max(L.max_m[h], std::max(d.m, std::max(d.rows * d.leaf, d.cols * d.leaf)));
+      L.max_m[h] = std::max(L.max_m[h], std::max(d.u_rows, d.v_rows));
+      L.max_k[h] = std::max(L.max_k[h], d.k);
+      L.soff[q] = o;
+      if (!d.leaf) o += (long long)d.m * d.m;
+    }
+    L.smax = std::max(L.smax, o);
+  }
+  L.list.upload(L.host.data(), L.host.size());
+  L.dsoff.upload(L.soff.data(), L.soff.size());
+  SB200_CUDA(cudaStreamSynchronize(0));
+}
+
+void HSSEngine::set_partition(int nparts, int part) {
+  const int N = int(H_.nodes.size());
+  std::vector<int> own, top;
+  cut_.clear();
+  if (nparts <= 1) {
+    nparts = 1; part = 0;
+    for (int i = 0; i < N; i++) own.push_back(i);
+  } else {
+    if (nparts & (nparts - 1)) throw std::invalid_argument("number of parts must be a power of two");
+    if (part < 0 || part >= nparts) throw std::invalid_argument("part out of range");
+    int depth = 0;
+    while ((1 << depth) < nparts) depth++;
+    for (int i = 0; i < N; i++) {
+      const auto& n = H_.nodes[i];
+      if (n.depth < depth) {
+        if (n.leaf()) throw std::invalid_argument("HSS tree too shallow for this many parts");
+        top.push_back(i);
+      } else if (n.depth == depth) cut_.push_back(i);   // pre-order = left to right
+    }
+    if ((int)cut_.size() != nparts) throw std::logic_error("cut size mismatch");
+    // subtree of cut_[part]: contiguous in pre-order
+    const int lo = cut_[part];
+    const int hi = (part + 1 < nparts) ? cut_[part + 1] : N;
+    for (int i = lo; i < hi; i++)
+      if (H_.nodes[i].depth >= depth) own.push_back(i);
+    // pre-order subtree of `lo` ends where depth returns to <= depth
+    own.clear();
+    own.push_back(lo);
+    for (int i = lo + 1; i < N && H_.nodes[i].depth > depth; i++) own.push_back(i);
+  }
+  nparts_ = nparts; part_ = part;
+  make_lists(own_, own);
+  make_lists(top_, top);
+  factored_ = false;
+}
+
+void HSSEngine::owned_range(int* lo, int* hi) const {
+  const auto& n = H_.nodes[nparts_ > 1 ? cut_[part_] : 0];
+  *lo = n.row_off;
+  *hi = n.row_off + n.rows;
+}
+
+void HSSEngine::dist_sizes(int s, long long* out) const {
+  long long a = 0, f = 0, v = 0;
+  for (int c : cut_) {
+    const DNode& d = hn_[c];
+    a = std::max<long long>(a, (long long)std::max(d.u_rank, d.v_rank) * s);
+    f = std::max<long long>(f, (long long)d.u_rank * (d.v_rank + d.u_rank));
+    v = std::max<long long>(v, (long long)(d.v_rank + d.u_rank) * s);
+  }
+  out[0] = std::max<long long>(a, 1); out[1] = std::max<long long>(f, 1); out[2] = std::max<long long>(v, 1);
+}
+
+// ------------------------------------------------------------------- apply
+void HSSEngine::run_up(const NodeLists& L, bool T, int s, const double* dB, int ldB, cudaStream_t st) {
+  for (int h = 0; h < L.classes(); h++) {
+    const int cnt = L.hptr[h + 1] - L.hptr[h];
+    if (!cnt) continue;
+    size_t smem = sizeof(double) * (size_t)std::max(L.max_m[h], 1);
+    dim3 grid(cnt, s);
+    const int* lst = L.list.p + L.hptr[h];
+    if (T) { set_smem(hss_up_kernel<true>, smem);
+      hss_up_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, dB, ldB, t1_.p, s);
+    } else { set_smem(hss_up_kernel<false>, smem);
+      hss_up_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, dB, ldB, t1_.p, s);
+    }
+    launches_++;
+  }
+}
+
+void HSSEngine::run_down(const NodeLists& L, bool T, int s, const double* dB, int ldB,
+                         double* dC, int ldC, bool leaves, cudaStream_t st) {
+  for (int h = L.classes() - 1; h >= 1; h--) {
+    const int cnt = L.hptr[h + 1] - L.hptr[h];
+    if (!cnt) continue;
+    size_t smem = sizeof(double) * (size_t)(2 * std::max(L.max_m[h], 1) + 8);
+    dim3 grid(cnt, s);
+    const int* lst = L.list.p + L.hptr[h];
+    if (T) { set_smem(hss_down_kernel<true>, smem);
+      hss_down_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, t1_.p, t2_.p, s);
+    } else { set_smem(hss_down_kernel<false>, smem);
+      hss_down_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, t1_.p, t2_.p, s);
+    }
+    launches_++;
+  }
+  if (leaves && L.classes() > 0 && L.hptr[1] > L.hptr[0]) {
+    const int cnt = L.hptr[1] - L.hptr[0];
+    size_t smem = sizeof(double) * (size_t)(3 * std::max(L.max_m[0], 1) + 8);
+    dim3 grid(cnt, s);
+    if (T) { set_smem(hss_leaf_kernel<true>, smem);
+      hss_leaf_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s);
+    } else { set_smem(hss_leaf_kernel<false>, smem);
+      hss_leaf_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s);
+    }
+    launches_++;
+  }
+}
+
 void HSSEngine::mult(char trans, int s, const double* dB, int ldB, double* dC,
                      int ldC, cudaStream_t st) {
+  if (nparts_ > 1) throw std::logic_error("sharded matrix: use the dist_* entry points");
   const bool T = !(trans == 'N' || trans == 'n');
   if (s <= 0) return;
   ensure_apply_ws(s);
-  const int nh = int(hptr_.size()) - 1;
-  const int* list = by_height_.p;
-  // up-sweep: classes 0 .. nh-2 (the root, alone in class nh-1, is skipped)
-  for (int h = 0; h < nh - 1; h++) {
-    const int cnt = hptr_[h + 1] - hptr_[h];
-    size_t smem = sizeof(double) * (size_t)std::max(cls_max_m_[h], 1);
-    dim3 grid(cnt, s);
-    if (T) { set_smem(hss_up_kernel<true>, smem);
-      hss_up_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, dB, ldB, t1_.p, s);
-    } else { set_smem(hss_up_kernel<false>, smem);
-      hss_up_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, dB, ldB, t1_.p, s);
-    }
-    launches_++;
+  run_up(own_, T, s, dB, ldB, st);
+  run_down(own_, T, s, dB, ldB, dC, ldC, true, st);
+  SB200_CUDA(cudaGetLastError());
+}
+
+// sharded apply: local up-sweep, export t1 of this rank's cut node ...
+void HSSEngine::dist_mult_begin(char trans, int s, const double* dB, int ldB,
+                                double* send, cudaStream_t st) {
+  const bool T = !(trans == 'N' || trans == 'n');
+  ensure_apply_ws(s);
+  run_up(own_, T, s, dB, ldB, st);
+  const DNode& d = hn_[cut_[part_]];
+  const int r = T ? d.u_rank : d.v_rank;
+  copy2d(send, r, t1_.p + (size_t)d.w_off * s, r, r, s, st);
+  SB200_CUDA(cudaGetLastError());
+}
+// ... import every cut node's t1, sweep the replicated top, finish locally
+void HSSEngine::dist_mult_end(char trans, int s, const double* dB, int ldB, double* dC,
+                              int ldC, const double* recv, cudaStream_t st) {
+  const bool T = !(trans == 'N' || trans == 'n');
+  long long sz[3];
+  dist_sizes(s, sz);
+  for (int c = 0; c < nparts_; c++) {
+    const DNode& d = hn_[cut_[c]];
+    const int r = T ? d.u_rank : d.v_rank;
+    copy2d(t1_.p + (size_t)d.w_off * s, r, recv + (size_t)c * sz[0], r, r, s, st);
   }
-  // down-sweep over inner nodes, top class first
-  for (int h = nh - 1; h >= 1; h--) {
-    const int cnt = hptr_[h + 1] - hptr_[h];
-    size_t smem = sizeof(double) * (size_t)(2 * std::max(cls_max_m_[h], 1) + 8);
-    dim3 grid(cnt, s);
-    if (T) { set_smem(hss_down_kernel<true>, smem);
-      hss_down_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, t1_.p, t2_.p, s);
-    } else { set_smem(hss_down_kernel<false>, smem);
-      hss_down_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, t1_.p, t2_.p, s);
-    }
-    launches_++;
-  }
-  {
-    const int cnt = hptr_[1] - hptr_[0];
-    size_t smem = sizeof(double) * (size_t)(3 * std::max(cls_max_m_[0], 1) + 8);
-    dim3 grid(cnt, s);
-    if (T) { set_smem(hss_leaf_kernel<true>, smem);
-      hss_leaf_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, list, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s);
-    } else { set_smem(hss_leaf_kernel<false>, smem);
-      hss_leaf_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, list, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s);
-    }
-    launches_++;
-  }
+  run_up(top_, T, s, dB, ldB, st);
+  run_down(top_, T, s, dB, ldB, dC, ldC, false, st);
+  run_down(own_, T, s, dB, ldB, dC, ldC, true, st);
+  // the cut node itself is an inner (or leaf) node of own_: its down kernel ran above
   SB200_CUDA(cudaGetLastError());
 }
 
 void HSSEngine::shift(double sigma, cudaStream_t st) {
-  const int cnt = hptr_[1] - hptr_[0];
-  hss_shift_kernel<<<cnt, 128, 0, st>>>(dn_.p, by_height_.p, vals_.p, sigma);
+  const int cnt = own_.classes() ? own_.hptr[1] - own_.hptr[0] : 0;
+  if (cnt) hss_shift_kernel<<<cnt, 128, 0, st>>>(dn_.p, own_.list.p, vals_.p, sigma);
   launches_++;
   SB200_CUDA(cudaGetLastError());
   factored_ = false;
@@ -1269,38 +1405,26 @@ template <int NB> static size_t qr_smem(int ldv) {
   return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 32);
 }
 
-void HSSEngine::factor(cudaStream_t st) {
+// ------------------------------------------------------------------ factor
+void HSSEngine::factor_prepare() {
   if (H_.rows() != H_.cols())
     throw std::invalid_argument("ULV factorization needs a square matrix");
   for (auto& n : H_.nodes)
     if (n.leaf() && n.rows != n.cols)
       throw std::invalid_argument("ULV factorization needs square diagonal blocks");
-  const int nh = int(hptr_.size()) - 1;
-  const int N = int(hn_.size());
   fact_.ensure((size_t)std::max<long long>(fact_nnz_, 1));
   tfac_.ensure((size_t)std::max<long long>((long long)nb_ * tot_k_, 1));
   rootpiv_.ensure(std::max(hn_[0].m, 1));
-  // scratch for the Dfull of inner nodes: one slab per class, reused
-  std::vector<long long> soff(N, 0);
-  long long smax = 0;
-  for (int h = 1; h < nh; h++) {
-    long long o = 0;
-    for (int q = hptr_[h]; q < hptr_[h + 1]; q++) {
-      const DNode& d = hn_[H_.by_height[q]];
-      soff[q] = o;
-      o += (long long)d.m * d.m;
-    }
-    smax = std::max(smax, o);
-  }
-  scratch_.ensure((size_t)std::max<long long>(smax, 1));
-  DevBuf<long long> dsoff;
-  dsoff.upload(soff.data(), soff.size(), st);
-  const int* list = by_height_.p;
-  for (int h = 0; h < nh; h++) {
-    const int cnt = hptr_[h + 1] - hptr_[h];
-    const int* lst = list + hptr_[h];
-    const long long* so = dsoff.p + hptr_[h];
-    const int mm = std::max(cls_max_m_[h], 1);
+  scratch_.ensure((size_t)std::max<long long>(std::max(own_.smax, top_.smax), 1));
+}
+
+void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t st) {
+  for (int h = 0; h < L.classes(); h++) {
+    const int cnt = L.hptr[h + 1] - L.hptr[h];
+    if (!cnt) continue;
+    const int* lst = L.list.p + L.hptr[h];
+    const long long* so = L.dsoff.p + L.hptr[h];
+    const int mm = std::max(L.max_m[h], 1);
     if (h == 0) {
       ulv_vh_leaf_kernel<<<cnt, kThreads, 0, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p);
       launches_++;
@@ -1310,7 +1434,15 @@ void HSSEngine::factor(cudaStream_t st) {
       ulv_build_inner_kernel<<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
       launches_++;
     }
-    if (h == nh - 1) break;  // root class: LU below
+    if (cnt == 1 && L.host[L.hptr[h]] == 0) {   // the root: LU
+      const DNode& root = hn_[0];
+      const long long n2 = (long long)root.m * root.m;
+      const double* src = root.leaf ? vals_.p + root.D : scratch_.p;  // slab offset 0 of its class
+      copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(src, fact_.p + root.F, n2);
+      ulv_root_lu_kernel<<<1, kThreads, 0, st>>>(fact_.p + root.F, root.m, rootpiv_.p);
+      launches_ += 2;
+      continue;
+    }
     // elimination
     if (mm <= 640) {
       size_t smem = sizeof(double) * (size_t)mm * 33 + sizeof(int) * (size_t)(mm + 8);
@@ -1323,11 +1455,11 @@ void HSSEngine::factor(cudaStream_t st) {
     }
     launches_++;
     const int ldv = smem_ld(mm);
-    if (profile_ && h == 0) SB200_CUDA(cudaEventRecord(ev_[0], st));
+    const bool timed = profile_ && time_leaf && h == 0;
+    if (timed) SB200_CUDA(cudaEventRecord(ev_[0], st));
     {
-      // large classes: one launch per panel and phase; small ones: fused
-      int kmax = 0;
-      for (int q = hptr_[h]; q < hptr_[h + 1]; q++) kmax = std::max(kmax, hn_[H_.by_height[q]].k);
+      // optional: one launch per panel and phase (SB200_QR_SPLIT=1); default fused
+      const int kmax = L.max_k[h];
       const bool split = qr_split_ && cnt >= 2 * nsm_ && kmax > nb_;
       const int npan = split ? (kmax + nb_ - 1) / nb_ : 1;
       for (int pp = 0; pp < npan; pp++)
@@ -1341,64 +1473,116 @@ void HSSEngine::factor(cudaStream_t st) {
           }
           launches_++;
         }
-      launches_--;
     }
-    if (profile_ && h == 0) SB200_CUDA(cudaEventRecord(ev_[1], st));
-    launches_++;
+    if (timed) SB200_CUDA(cudaEventRecord(ev_[1], st));
   }
-  // root LU
-  const DNode& root = hn_[0];
-  if (root.leaf) {
-    long long n2 = (long long)root.m * root.m;
-    copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(vals_.p + root.D, fact_.p + root.F, n2);
-  } else {
-    long long n2 = (long long)root.m * root.m;
-    // Dfull of the root was written to scratch slab offset 0 of its class
-    copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(scratch_.p, fact_.p + root.F, n2);
-  }
-  launches_++;
-  ulv_root_lu_kernel<<<1, kThreads, 0, st>>>(fact_.p + root.F, root.m, rootpiv_.p);
-  launches_++;
+}
+
+void HSSEngine::factor(cudaStream_t st) {
+  if (nparts_ > 1) throw std::logic_error("sharded matrix: use the dist_* entry points");
+  factor_prepare();
+  factor_classes(own_, true, st);
   SB200_CUDA(cudaGetLastError());
-  SB200_CUDA(cudaStreamSynchronize(st));  // dsoff lifetime
   factored_ = true;
 }
 
-void HSSEngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
-  if (!factored_) throw std::logic_error("solve called before factor");
-  if (s <= 0) return;
-  ensure_solve_ws(s);
-  const int nh = int(hptr_.size()) - 1;
-  const int* list = by_height_.p;
-  for (int h = 0; h < nh - 1; h++) {
-    const int cnt = hptr_[h + 1] - hptr_[h];
-    const int mm = std::max(cls_max_m_[h], 1);
+void HSSEngine::dist_factor_begin(double* send, cudaStream_t st) {
+  factor_prepare();
+  factor_classes(own_, true, st);
+  // export [Vt1 | Dt^T] of this rank's cut node: rows k..m, columns k..naug of F
+  const DNode& d = hn_[cut_[part_]];
+  copy2d(send, d.u_rank, fact_.p + d.F + d.k + (size_t)d.k * d.m, d.m, d.u_rank, d.v_rank + d.u_rank, st);
+  SB200_CUDA(cudaGetLastError());
+}
+
+void HSSEngine::dist_factor_end(const double* recv, cudaStream_t st) {
+  long long sz[3];
+  dist_sizes(1, sz);
+  for (int c = 0; c < nparts_; c++) {
+    const DNode& d = hn_[cut_[c]];
+    copy2d(fact_.p + d.F + d.k + (size_t)d.k * d.m, d.m, recv + (size_t)c * sz[1], d.u_rank,
+           d.u_rank, d.v_rank + d.u_rank, st);
+  }
+  factor_classes(top_, false, st);
+  SB200_CUDA(cudaGetLastError());
+  factored_ = true;
+}
+
+// ------------------------------------------------------------------- solve
+void HSSEngine::solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st) {
+  for (int h = 0; h < L.classes(); h++) {
+    const int cnt = L.hptr[h + 1] - L.hptr[h];
+    if (!cnt) continue;
+    const int mm = std::max(L.max_m[h], 1);
     size_t smem = sizeof(double) * (size_t)(3 * mm + 32 * 33 + 8);
     dim3 grid(cnt, s);
     set_smem(ulv_fwd_kernel<32>, smem);
-    ulv_fwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], vals_.p, perms_.p, fact_.p, dB, ldB, ysol_.p, zsol_.p, fsol_.p, s);
+    ulv_fwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p + L.hptr[h], vals_.p, perms_.p, fact_.p, dB, ldB, ysol_.p, zsol_.p, fsol_.p, s);
     launches_++;
   }
-  {
-    size_t smem = sizeof(double) * (size_t)std::max(hn_[0].m, 1);
-    set_smem(ulv_root_solve_kernel, smem);
-    ulv_root_solve_kernel<<<s, kThreads, smem, st>>>(dn_.p, vals_.p, fact_.p, rootpiv_.p, dB, ldB, zsol_.p, fsol_.p, xsol_.p, s);
-    launches_++;
-  }
-  for (int h = nh - 2; h >= 0; h--) {
-    const int cnt = hptr_[h + 1] - hptr_[h];
-    const int mm = std::max(cls_max_m_[h], 1);
+}
+
+void HSSEngine::solve_root(int s, double* dB, int ldB, cudaStream_t st) {
+  size_t smem = sizeof(double) * (size_t)std::max(hn_[0].m, 1);
+  set_smem(ulv_root_solve_kernel, smem);
+  ulv_root_solve_kernel<<<s, kThreads, smem, st>>>(dn_.p, vals_.p, fact_.p, rootpiv_.p, dB, ldB, zsol_.p, fsol_.p, xsol_.p, s);
+  launches_++;
+}
+
+void HSSEngine::solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st) {
+  for (int h = L.classes() - 1; h >= 0; h--) {
+    const int cnt = L.hptr[h + 1] - L.hptr[h];
+    if (!cnt) continue;
+    const int mm = std::max(L.max_m[h], 1);
     size_t smem = sizeof(double) * (size_t)(mm + 2 * 32 + 8);
     dim3 grid(cnt, s);
+    const int* lst = L.list.p + L.hptr[h];
     if (nb_ == 32) { set_smem(ulv_bwd_kernel<32>, smem);
-      ulv_bwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
-    } else if (nb_ == 16) { set_smem(ulv_bwd_kernel<16>, smem);
-      ulv_bwd_kernel<16><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
-    } else { set_smem(ulv_bwd_kernel<8>, smem);
-      ulv_bwd_kernel<8><<<grid, kThreads, smem, st>>>(dn_.p, list + hptr_[h], fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
+      ulv_bwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
+    } else { set_smem(ulv_bwd_kernel<16>, smem);
+      ulv_bwd_kernel<16><<<grid, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
     }
     launches_++;
   }
+}
+
+void HSSEngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
+  if (nparts_ > 1) throw std::logic_error("sharded matrix: use the dist_* entry points");
+  if (!factored_) throw std::logic_error("solve called before factor");
+  if (s <= 0) return;
+  ensure_solve_ws(s);
+  solve_fwd(own_, s, dB, ldB, st);     // the kernels skip the root
+  solve_root(s, dB, ldB, st);
+  solve_bwd(own_, s, dB, ldB, st);
+  SB200_CUDA(cudaGetLastError());
+}
+
+void HSSEngine::dist_solve_begin(int s, double* dB, int ldB, double* send, cudaStream_t st) {
+  if (!factored_) throw std::logic_error("solve called before factor");
+  ensure_solve_ws(s);
+  solve_fwd(own_, s, dB, ldB, st);
+  const DNode& d = hn_[cut_[part_]];
+  // export [z ; ft1] of the cut node, (r_v + r_u) x s
+  const int ld = d.v_rank + d.u_rank;
+  copy2d(send, ld, zsol_.p + (size_t)d.z_off * s, d.v_rank, d.v_rank, s, st);
+  copy2d(send + d.v_rank, ld, fsol_.p + (size_t)d.f_off * s, d.u_rank, d.u_rank, s, st);
+  SB200_CUDA(cudaGetLastError());
+}
+
+void HSSEngine::dist_solve_end(int s, double* dB, int ldB, const double* recv, cudaStream_t st) {
+  long long sz[3];
+  dist_sizes(s, sz);
+  for (int c = 0; c < nparts_; c++) {
+    const DNode& d = hn_[cut_[c]];
+    const int ld = d.v_rank + d.u_rank;
+    const double* src = recv + (size_t)c * sz[2];
+    copy2d(zsol_.p + (size_t)d.z_off * s, d.v_rank, src, ld, d.v_rank, s, st);
+    copy2d(fsol_.p + (size_t)d.f_off * s, d.u_rank, src + d.v_rank, ld, d.u_rank, s, st);
+  }
+  solve_fwd(top_, s, dB, ldB, st);
+  solve_root(s, dB, ldB, st);
+  solve_bwd(top_, s, dB, ldB, st);
+  solve_bwd(own_, s, dB, ldB, st);
   SB200_CUDA(cudaGetLastError());
 }
 

@@ -31,6 +31,17 @@ struct DNode {
   int y_off, z_off, f_off, x_off;  // solve workspace prefixes (k, v_rank, u_rank, m)
 };
 
+// node lists of one sweep domain, grouped into height classes
+struct NodeLists {
+  std::vector<int> host, hptr;          // nodes sorted by height; class h = [hptr[h], hptr[h+1])
+  std::vector<int> max_m, max_k;        // per class: launch configuration
+  std::vector<long long> soff;          // per entry: Dfull scratch offset (inner nodes)
+  long long smax = 0;
+  DevBuf<int> list;
+  DevBuf<long long> dsoff;
+  int classes() const { return hptr.empty() ? 0 : int(hptr.size()) - 1; }
+};
+
 class HSSEngine {
  public:
   explicit HSSEngine(HSSHost&& host);
@@ -48,6 +59,23 @@ class HSSEngine {
   void shift(double sigma, cudaStream_t st);
   bool factored() const { return factored_; }
 
+  // ---- subtree sharding over `nparts` GPUs: this rank owns the
+  // subtree of cut node `part` at depth log2(nparts); the nparts-1 nodes above
+  // the cut are replicated.  Each operation is split around the single small
+  // exchange it needs: *_begin fills `send` (dist_sizes doubles), the caller
+  // all-gathers send -> recv over NCCL, *_end consumes recv.
+  void set_partition(int nparts, int part);
+  int nparts() const { return nparts_; }
+  void owned_range(int* lo, int* hi) const;
+  void dist_sizes(int s, long long* out) const;   // apply, factor, solve (doubles per rank)
+  void dist_mult_begin(char trans, int s, const double* dB, int ldB, double* send, cudaStream_t st);
+  void dist_mult_end(char trans, int s, const double* dB, int ldB, double* dC, int ldC,
+                     const double* recv, cudaStream_t st);
+  void dist_factor_begin(double* send, cudaStream_t st);
+  void dist_factor_end(const double* recv, cudaStream_t st);
+  void dist_solve_begin(int s, double* dB, int ldB, double* send, cudaStream_t st);
+  void dist_solve_end(int s, double* dB, int ldB, const double* recv, cudaStream_t st);
+
   long long factor_nonzeros() const { return fact_nnz_; }
   long long launches() const { return launches_; }
   // optional live timing of the dominant kernel (leaf-class QR) with CUDA
@@ -61,16 +89,24 @@ class HSSEngine {
   void build_tables();
   void ensure_apply_ws(int s);
   void ensure_solve_ws(int s);
+  void make_lists(NodeLists& L, const std::vector<int>& nodes);
+  void run_up(const NodeLists& L, bool T, int s, const double* dB, int ldB, cudaStream_t st);
+  void run_down(const NodeLists& L, bool T, int s, const double* dB, int ldB, double* dC,
+                int ldC, bool leaves, cudaStream_t st);
+  void factor_prepare();
+  void factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t st);
+  void solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st);
+  void solve_root(int s, double* dB, int ldB, cudaStream_t st);
+  void solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st);
 
   HSSHost H_;
   std::vector<DNode> hn_;
   DevBuf<DNode> dn_;
   DevBuf<double> vals_;
   DevBuf<int32_t> perms_;
-  DevBuf<int> by_height_;
-  std::vector<int> hptr_;
-  // per height class: max sizes (launch configuration)
-  std::vector<int> cls_max_m_, cls_max_naug_;
+  NodeLists own_, top_;
+  std::vector<int> cut_;
+  int nparts_ = 1, part_ = 0;
   // apply workspace
   DevBuf<double> t1_, t2_;
   int ws_total_ = 0, apply_s_ = 0;
