@@ -1,9 +1,10 @@
 # development aid: per-phase clock64 timing of the QR kernel (built with -DSB200_QR_TIMING)
-import sys, os, shutil
+import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import strumpack_b200 as sb
-sb._SO = os.path.join(ROOT, "scripts", "libsb200_timing.so")
+variant = sys.argv[2] if len(sys.argv) > 2 else ""
+sb._SO = os.path.join(ROOT, "scripts", "libsb200_timing%s.so" % (("_" + variant) if variant else ""))
 import numpy as np
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 pts = np.random.default_rng(42).random((2, n))

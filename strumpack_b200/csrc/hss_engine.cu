@@ -585,124 +585,244 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
     const int nsub = (jb + 7) >> 3;
     for (int sp = 0; sp < nsub; sp++) {
       const int cs = sp * 8, sbw = min(8, jb - cs);
-      for (int cq = 0; cq < sbw; cq++) {
-        const int c = cs + cq;
-        const double* x = Vs + c * ldv;
-        const int nupd = sbw - 1 - cq;
-        // role of this warp in step c:
-        //   lead (warp < nupd, or warp 7 when nothing is left to update):
-        //        norm of the pivot column + scalars (dlarfg) and, if warp <
-        //        nupd, apply H_c to column cc = c+1+warp
-        //   dot  (nupd <= warp, ww < cq): raw dot product v_b . x_c for the
-        //        earlier reflector b = cs+ww (gives the 8x8 T factor for free)
-        //   none: straight to the barrier
-        const int ww = warp - nupd;
-        const bool upd = warp < nupd, lead = upd || (nupd == 0 && warp == 7);
-        const bool dot = !lead && ww < cq;
-        const bool writer = nupd > 0 ? warp == 0 : warp == 7;
-        if (lead || dot) {
-          double* oth = upd ? Vs + (c + 1 + warp) * ldv : Vs + (cs + (dot ? ww : 0)) * ldv;
-          const bool use_oth = upd || dot;
-          double pn = 0., wr = 0.;
-          double xv[SMALL ? 8 : 1], ov[SMALL ? 8 : 1];
-          if (SMALL) {
+      if (SMALL) {
+        // ---- register-resident sub-panel (mp <= 256): warps 0..3 hold the 8
+        // columns (2 x 32 rows per lane and warp) in registers, ONE fused
+        // 8-value shuffle reduction per column gives the pivot norm, the dot
+        // products with the columns still to update AND the v_b^T v_c products
+        // of the T factor; the 4 partial results are combined through shared
+        // memory behind a 128-thread named barrier.  Warps 4..7 wait at the
+        // CTA barrier below.  No per-column CTA barrier, no smem traffic for
+        // the column data.
+        if (warp < 4) {
+          double a[8][2];
+          const int r0 = warp * 64 + lane;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const int i = lane + 32 * q;
-              const bool in = i > c && i < mp;
-              xv[q] = in ? x[i] : 0.;
-              ov[q] = (in && use_oth) ? oth[i] : 0.;
-            }
-            double p0 = 0., p1 = 0., w0 = 0., w1 = 0.;
+          for (int q = 0; q < 8; q++)
 #pragma unroll
-            for (int q = 0; q < 8; q += 2) {
-              p0 += xv[q] * xv[q]; p1 += xv[q + 1] * xv[q + 1];
-              w0 += xv[q] * ov[q]; w1 += xv[q + 1] * ov[q + 1];
+            for (int rr = 0; rr < 2; rr++) {
+              const int i = r0 + 32 * rr;
+              a[q][rr] = i < mp ? Vs[i + (cs + q) * ldv] : 0.;
             }
-            pn = p0 + p1; wr = w0 + w1;
-          } else {
-            double p0 = 0., p1 = 0., w0 = 0., w1 = 0.;
-            int i = c + 1 + lane;
-            for (; i + 32 < mp; i += 64) {
-              const double a0 = x[i], a1 = x[i + 32];
-              p0 += a0 * a0; p1 += a1 * a1;
-              if (use_oth) { w0 += a0 * oth[i]; w1 += a1 * oth[i + 32]; }
-            }
-            if (i < mp) { const double a0 = x[i]; p0 += a0 * a0; if (use_oth) w0 += a0 * oth[i]; }
-            pn = p0 + p1; wr = w0 + w1;
-          }
-          QR_TICK(8)
-          if (lead) {
+          double tr[8];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              pn += __shfl_xor_sync(0xffffffffu, pn, o);
-              wr += __shfl_xor_sync(0xffffffffu, wr, o);
-            }
-            QR_TICK(9)
-            const double alpha = x[c];
-            double tc = 0., scal = 0., beta = alpha;
-            if (pn > 0.) {   // dlarfg
-              beta = -copysign(sqrt(alpha * alpha + pn), alpha);
-              const double d = alpha - beta;
-              scal = 1. / d;
-              tc = -d / beta;
-            }
-            QR_TICK(10)
-            if (upd) {
-              const double colc = oth[c];
-              const double w = tc * (colc + scal * wr);
-              const double ws = w * scal;
-              if (SMALL) {
+          for (int q = 0; q < 8; q++) tr[q] = 0.;
+          double* pair = zs;            // [2 parities][4 warps][8]
+          double* diag = Ws;            // [2 parities][8]   (Ws is free during the steps)
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                  const int i = lane + 32 * q;
-                  if (i > c && i < mp) oth[i] = ov[q] - ws * xv[q];
-                }
-              } else {
-                for (int i = c + 1 + lane; i < mp; i += 32) oth[i] -= ws * x[i];
+          for (int cq = 0; cq < 8; cq++) {
+            if (cq < sbw) {
+              const int c = cs + cq;   // diagonal row: c < 32, lives in warp 0, rr = 0, lane c
+              double p[8];
+#pragma unroll
+              for (int q = 0; q < 8; q++) p[q] = 0.;
+#pragma unroll
+              for (int rr = 0; rr < 2; rr++) {
+                const int i = r0 + 32 * rr;
+                const double xv = i > c ? a[cq][rr] : 0.;
+#pragma unroll
+                for (int q = 0; q < 8; q++) p[q] += xv * a[q][rr];
               }
-              if (lane == 0) oth[c] = colc - w;
-            }
-            if (writer && lane == 0) { betas[c] = beta; tau[c] = tc; scals[c] = scal; }
-            QR_TICK(11)
-          } else {
-            // raw z_b = x_b[c+1:]^T x_c[c+1:] and x_b[c]; the scalings (the
-            // previous reflector is still unscaled) are applied by warp 7
-            wr = warp_sum(wr);
-            if (lane == 0) { zs[(cq & 1) * 16 + ww] = wr; zs[(cq & 1) * 16 + 8 + ww] = oth[c]; }
-            if (ww == cq - 1) {   // deferred scaling of the previous reflector
-              const double sp_ = scals[c - 1];
-              __syncwarp();
-              for (int i = c + lane; i < mp; i += 32) oth[i] *= sp_;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < 8; q++) p[q] += __shfl_xor_sync(0xffffffffu, p[q], o);
+              double* pw = pair + (cq & 1) * 32 + warp * 8;
+              if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) pw[q] = p[q];
+              }
+              if (warp == 0 && lane == c) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) diag[(cq & 1) * 8 + q] = a[q][0];
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              const double* pp = pair + (cq & 1) * 32;
+              double sm_[8], dg[8];
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                sm_[q] = (pp[q] + pp[8 + q]) + (pp[16 + q] + pp[24 + q]);
+                dg[q] = diag[(cq & 1) * 8 + q];
+              }
+              const double pn = sm_[cq], alpha = dg[cq];
+              double tc = 0., scal = 0., beta = alpha;
+              if (pn > 0.) {   // dlarfg
+                beta = -copysign(sqrt(alpha * alpha + pn), alpha);
+                const double d = alpha - beta;
+                scal = 1. / d;
+                tc = -d / beta;
+              }
+              const bool isdiag = (warp == 0 && lane == c);
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                if (q > cq) {   // apply H_c to the columns to the right
+                  const double w = tc * (dg[q] + scal * sm_[q]);
+                  const double ws = w * scal;
+#pragma unroll
+                  for (int rr = 0; rr < 2; rr++)
+                    if (r0 + 32 * rr > c) a[q][rr] -= ws * a[cq][rr];
+                  if (isdiag) a[q][0] -= w;
+                }
+              }
+#pragma unroll
+              for (int rr = 0; rr < 2; rr++)
+                if (r0 + 32 * rr > c) a[cq][rr] *= scal;     // v_c
+              if (isdiag) a[cq][0] = beta;                    // R(c,c)
+              // column cq of the 8x8 T (dlarft): lane a (< 8, warp 0) keeps row a
+              {
+                double val = (lane == cq) ? tc : 0.;
+                double acc = 0.;
+#pragma unroll
+                for (int b = 0; b < 8; b++)
+                  if (b < cq) acc += (b >= lane ? tr[b] : 0.) * (dg[b] + scal * sm_[b]);
+                if (lane < cq) val = -tc * acc;
+                tr[cq] = val;
+              }
             }
           }
-        }
-        QR_TICK(12)
-        __syncthreads();
-        QR_TICK(13)
-        if (warp == 7 && lane <= cq) {   // column cq of the 8x8 T (dlarft)
-          const int a = lane;
-          const double tc = tau[c], sc = scals[c];
-          double val = tc;
-          if (a < cq) {
-            const double sprev = scals[c - 1];
-            double acc = 0.;
-            for (int b = a; b < cq; b++) {
-              const double f = (b == cq - 1) ? sprev : 1.;   // v_b unscaled?
-              const double z = f * (zs[(cq & 1) * 16 + 8 + b] + sc * zs[(cq & 1) * 16 + b]);
-              acc += Ts[(cs + a) + (cs + b) * LDW] * z;
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+              const int i = r0 + 32 * rr;
+              if (i < mp) Vs[i + (cs + q) * ldv] = a[q][rr];
             }
-            val = -tc * acc;
+          if (warp == 0 && lane < 8) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) Ts[(cs + lane) + (cs + q) * LDW] = (q >= lane) ? tr[q] : 0.;
           }
-          Ts[(cs + a) + (cs + cq) * LDW] = val;
         }
-        QR_TICK(14)
-      }
-      const double scal_prev = scals[cs + sbw - 1];
-      QR_TICK(1)
-      {  // scale the last reflector of the sub-panel
-        const int c = cs + sbw - 1;
-        for (int i = c + 1 + tid; i < mp; i += kThreads) Vs[i + c * ldv] *= scal_prev;
+        QR_TICK(1)
+      } else {
+      for (int cq = 0; cq < sbw; cq++) {
+          const int c = cs + cq;
+          const double* x = Vs + c * ldv;
+          const int nupd = sbw - 1 - cq;
+          // role of this warp in step c:
+          //   lead (warp < nupd, or warp 7 when nothing is left to update):
+          //        norm of the pivot column + scalars (dlarfg) and, if warp <
+          //        nupd, apply H_c to column cc = c+1+warp
+          //   dot  (nupd <= warp, ww < cq): raw dot product v_b . x_c for the
+          //        earlier reflector b = cs+ww (gives the 8x8 T factor for free)
+          //   none: straight to the barrier
+          const int ww = warp - nupd;
+          const bool upd = warp < nupd, lead = upd || (nupd == 0 && warp == 7);
+#ifdef SB200_EXP_NODOT
+          const bool dot = false;
+#else
+          const bool dot = !lead && ww < cq;
+#endif
+          const bool writer = nupd > 0 ? warp == 0 : warp == 7;
+          if (lead || dot) {
+            double* oth = upd ? Vs + (c + 1 + warp) * ldv : Vs + (cs + (dot ? ww : 0)) * ldv;
+            const bool use_oth = upd || dot;
+            double pn = 0., wr = 0.;
+            double xv[SMALL ? 8 : 1], ov[SMALL ? 8 : 1];
+            if (SMALL) {
+#pragma unroll
+              for (int q = 0; q < 8; q++) {
+                const int i = lane + 32 * q;
+                const bool in = i > c && i < mp;
+                xv[q] = in ? x[i] : 0.;
+                ov[q] = (in && use_oth) ? oth[i] : 0.;
+              }
+              double p0 = 0., p1 = 0., w0 = 0., w1 = 0.;
+#pragma unroll
+              for (int q = 0; q < 8; q += 2) {
+                p0 += xv[q] * xv[q]; p1 += xv[q + 1] * xv[q + 1];
+                w0 += xv[q] * ov[q]; w1 += xv[q + 1] * ov[q + 1];
+              }
+              pn = p0 + p1; wr = w0 + w1;
+            } else {
+              double p0 = 0., p1 = 0., w0 = 0., w1 = 0.;
+              int i = c + 1 + lane;
+              for (; i + 32 < mp; i += 64) {
+                const double a0 = x[i], a1 = x[i + 32];
+                p0 += a0 * a0; p1 += a1 * a1;
+                if (use_oth) { w0 += a0 * oth[i]; w1 += a1 * oth[i + 32]; }
+              }
+              if (i < mp) { const double a0 = x[i]; p0 += a0 * a0; if (use_oth) w0 += a0 * oth[i]; }
+              pn = p0 + p1; wr = w0 + w1;
+            }
+            QR_TICK(8)
+            if (lead) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                pn += __shfl_xor_sync(0xffffffffu, pn, o);
+                wr += __shfl_xor_sync(0xffffffffu, wr, o);
+              }
+              QR_TICK(9)
+              const double alpha = x[c];
+              double tc = 0., scal = 0., beta = alpha;
+#ifdef SB200_EXP_NOSQRT
+              if (pn > 0.) { beta = -copysign(alpha * alpha + pn, alpha); const double d = alpha - beta; scal = d * 0.5; tc = -d * beta; }
+#else
+              if (pn > 0.) {   // dlarfg
+                beta = -copysign(sqrt(alpha * alpha + pn), alpha);
+                const double d = alpha - beta;
+                scal = 1. / d;
+                tc = -d / beta;
+              }
+#endif
+              QR_TICK(10)
+              if (upd) {
+                const double colc = oth[c];
+                const double w = tc * (colc + scal * wr);
+                const double ws = w * scal;
+                if (SMALL) {
+#pragma unroll
+                  for (int q = 0; q < 8; q++) {
+                    const int i = lane + 32 * q;
+                    if (i > c && i < mp) oth[i] = ov[q] - ws * xv[q];
+                  }
+                } else {
+                  for (int i = c + 1 + lane; i < mp; i += 32) oth[i] -= ws * x[i];
+                }
+                if (lane == 0) oth[c] = colc - w;
+              }
+              if (writer && lane == 0) { betas[c] = beta; tau[c] = tc; scals[c] = scal; }
+              QR_TICK(11)
+            } else {
+              // raw z_b = x_b[c+1:]^T x_c[c+1:] and x_b[c]; the scalings (the
+              // previous reflector is still unscaled) are applied by warp 7
+              wr = warp_sum(wr);
+              if (lane == 0) { zs[(cq & 1) * 16 + ww] = wr; zs[(cq & 1) * 16 + 8 + ww] = oth[c]; }
+              if (ww == cq - 1) {   // deferred scaling of the previous reflector
+                const double sp_ = scals[c - 1];
+                __syncwarp();
+                for (int i = c + lane; i < mp; i += 32) oth[i] *= sp_;
+              }
+            }
+          }
+          QR_TICK(12)
+          __syncthreads();
+          QR_TICK(13)
+#ifndef SB200_EXP_NOTCOL
+          if (warp == 7 && lane <= cq) {   // column cq of the 8x8 T (dlarft)
+            const int a = lane;
+            const double tc = tau[c], sc = scals[c];
+            double val = tc;
+            if (a < cq) {
+              const double sprev = scals[c - 1];
+              double acc = 0.;
+              for (int b = a; b < cq; b++) {
+                const double f = (b == cq - 1) ? sprev : 1.;   // v_b unscaled?
+                const double z = f * (zs[(cq & 1) * 16 + 8 + b] + sc * zs[(cq & 1) * 16 + b]);
+                acc += Ts[(cs + a) + (cs + b) * LDW] * z;
+              }
+              val = -tc * acc;
+            }
+            Ts[(cs + a) + (cs + cq) * LDW] = val;
+          }
+#endif
+          QR_TICK(14)
+        }
+        const double scal_prev = scals[cs + sbw - 1];
+        QR_TICK(1)
+        {  // scale the last reflector of the sub-panel
+          const int c = cs + sbw - 1;
+          for (int i = c + 1 + tid; i < mp; i += kThreads) Vs[i + c * ldv] *= scal_prev;
+        }
       }
       __syncthreads();
       // ---- R entries of these columns to global; V explicit (unit diagonal)
@@ -710,7 +830,7 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
         const int c = cs + warp;
         double* dst = A + j0 + (size_t)(j0 + c) * m;
         for (int i = lane; i <= c; i += 32) {
-          dst[i] = (i == c) ? betas[c] : Vs[i + c * ldv];
+          dst[i] = (i == c && !SMALL) ? betas[c] : Vs[i + c * ldv];
           Vs[i + c * ldv] = (i == c) ? 1. : 0.;
         }
       }
@@ -1101,6 +1221,7 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   SB200_CUDA(cudaGetDevice(&dev));
   SB200_CUDA(cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, dev));
   if (const char* e = std::getenv("SB200_QR_SPLIT")) qr_split_ = std::atoi(e);
+  if (const char* e = std::getenv("SB200_QR_REGPANEL")) qr_regpanel_ = std::atoi(e);
   build_tables();
 }
 HSSEngine::~HSSEngine() {
@@ -1402,7 +1523,7 @@ void HSSEngine::sync_host_values() {
 
 template <int NB> static size_t qr_smem(int ldv) {
   constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
-  return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 32);
+  return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 64);
 }
 
 // ------------------------------------------------------------------ factor
@@ -1464,7 +1585,7 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       const int npan = split ? (kmax + nb_ - 1) / nb_ : 1;
       for (int pp = 0; pp < npan; pp++)
         for (int phase = split ? 1 : 0; phase <= (split ? 2 : 0); phase++) {
-          if (nb_ == 32 && mm <= 256) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true>, smem);
+          if (nb_ == 32 && mm <= 256 && qr_regpanel_) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true>, smem);
             ulv_qr_kernel<32, true><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
           } else if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, false>, smem);
             ulv_qr_kernel<32, false><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);

@@ -121,7 +121,7 @@ class HSSEngine {
   bool factored_ = false;
   long long launches_ = 0;
   int nb_ = 32;
-  int nsm_ = 148, qr_split_ = 0;
+  int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 0;   // experiment switches
   bool profile_ = false;
   cudaEvent_t ev_[2] = {nullptr, nullptr};
 };
