@@ -105,6 +105,18 @@ int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
                             int kernel_type, double h, double lambda,
                             const CSPOptions* opts, int* perm);
 
+/* BLRMatrix<double>::compress_and_factor(A, weak admissibility, opts)
+ * (reference src/BLR/BLRMatrix.cpp:113-241, RL variant; tiles from
+ * ClusterTree(n).refine(leaf_size) as in test/test_BLR_seq.cpp:136-145;
+ * pivot_threshold as BLROptions::pivot_threshold, DenseTile.cpp:111-117).
+ * The result supports SP_d_struct_solve (BLRMatrix::solve, BLRMatrix.hpp:118).
+ * A BLR matrix built by SP_d_struct_from_dense (compress only,
+ * StructuredMatrix.cpp:78-98) supports SP_d_struct_mult instead. */
+int SB200_d_blr_compress_and_factor(CSPStructMat* S, int n, const double* A,
+                                    int ldA, const CSPOptions* opts,
+                                    double pivot_threshold);
+int SB200_d_blr_tiles(const CSPStructMat S);
+
 /* Reads a reference HSS dump (HSSMatrix<double>::write, reference
  * HSSMatrix.cpp:438-486) and uploads its generators. */
 int SB200_d_hss_read(CSPStructMat* S, const char* path);

@@ -52,6 +52,8 @@ SYMBOLS = {
     "SP_d_struct_solve": (_i, [_vp, _i, _vp, _i]),
     "SP_d_struct_shift": (_i, [_vp, _d]),
     "SB200_d_hss_from_kernel": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp]),
+    "SB200_d_blr_compress_and_factor": (_i, [_pvp, _i, _vp, _i, _po, _d]),
+    "SB200_d_blr_tiles": (_i, [_vp]),
     "SB200_d_hss_read": (_i, [_pvp, C.c_char_p]),
     "SB200_d_hss_write": (_i, [_vp, C.c_char_p]),
     "SB200_d_hss_from_generators": (_i, [_pvp, _i, _vp, _vp, C.c_int64, _vp,
@@ -328,6 +330,27 @@ class StructuredMatrix:
             self.close()
         except Exception:
             pass
+
+
+class BLRMatrix(StructuredMatrix):
+    """Mirror of ``BLR::BLRMatrix<double>`` (reference src/BLR/BLRMatrix.hpp:68-291)."""
+
+    @classmethod
+    def compress_and_factor(cls, A, opts=None, pivot_threshold=-1.0):
+        """BLRMatrix::compress_and_factor with weak admissibility and tiles from
+        ClusterTree(n).refine(leaf) (reference BLRMatrix.cpp:113-241,
+        test/test_BLR_seq.cpp:136-156)."""
+        A = _fortran(A)
+        opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
+        h = C.c_void_p()
+        _check(lib().SB200_d_blr_compress_and_factor(
+            C.byref(h), A.shape[0], A.ctypes.data, A.shape[0], C.byref(opts),
+            float(pivot_threshold)), "compress_and_factor")
+        return cls(h.value)
+
+    @property
+    def tiles(self):
+        return lib().SB200_d_blr_tiles(self._h)
 
 
 class HSSMatrix(StructuredMatrix):

@@ -1,0 +1,684 @@
+// strumpack_b200 -- block low-rank (BLR) matrices on sm_100a:
+// tile compression, right-looking BLR LU, triangular solves, mat-vec.
+//
+// Replaces (reference):
+//   BLRMatrix::compress / compress_and_factor (RL)  src/BLR/BLRMatrix.cpp:91-241
+//   LRTile(RRQR) / DenseTile::LU                     src/BLR/LRTile.cpp:55-75, DenseTile.cpp:111-117
+//   trsm / laswp on tiles                            src/BLR/LRTile.cpp:296-311, BLRTileBLAS.hpp
+//   BLRMatrix::solve, trsm(L,L/U), gemv              src/BLR/BLRMatrix.hpp:118-122, .cpp:1667-1763
+// and the library-call GPU path construct_and_partial_factor_gpu
+// (src/BLR/BLRMatrix.GPU.cpp:70-262, src/BLR/BLRBatch.cpp) -- here every step
+// is a hand-written batched kernel over the tiles of a block row/column:
+//   K11 blr_copy_tiles + id_cpqr (sb200_cpqr.cuh) + blr_extract_lr : RRQR tiles
+//   K12 blr_getrf (+pivot threshold), blr_trsm_lower (L^{-1} P U_ij, U^{-T} V_ji^T)
+//   K13 blr_schur : C_kj -= U_ki (V_ki U_ij) V_ij, fused, fp64 tensor pipe
+//   K14 blr_lr_gemv / blr_trsm_lower on the right-hand side
+#include "blr_engine.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
+#include "sb200_cpqr.cuh"
+
+namespace sb200 {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+
+struct TileDesc {     // one off-diagonal tile of the current step
+  int i, j;           // tile coordinates
+  int ro, co, m, n;   // row/col offset and size in the matrix
+  long long lr;       // offset of [U (m x rc) | Vt (n x rc)] in the LR arena
+  int rc;             // rank capacity
+};
+
+// ---------------------------------------------------------------- diagonal LU
+// LU with partial pivoting of one diagonal tile, in place (ld = N), plus the
+// reference's small-pivot replacement (DenseTile::LU, DenseTile.cpp:111-117).
+// ipiv: LAPACK style (1-based, local); g: the same permutation as a gather.
+__global__ void __launch_bounds__(kThreads)
+blr_getrf_kernel(double* __restrict__ A, long long ld, int n, int* __restrict__ ipiv,
+                 int* __restrict__ g, double thresh) {
+  __shared__ double rv[kWarps];
+  __shared__ int ri[kWarps];
+  __shared__ int pivrow;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int j = 0; j < n; j++) {
+    double best = -1.;
+    int bi = j;
+    for (int i = j + tid; i < n; i += kThreads) {
+      double v = fabs(A[i + j * ld]);
+      if (v > best) { best = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { rv[warp] = best; ri[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = rv[0]; int p = ri[0];
+      for (int w = 1; w < kWarps; w++)
+        if (rv[w] > b || (rv[w] == b && ri[w] < p)) { b = rv[w]; p = ri[w]; }
+      pivrow = p;
+      ipiv[j] = p + 1;
+    }
+    __syncthreads();
+    const int p = pivrow;
+    if (p != j)
+      for (int c = tid; c < n; c += kThreads) {
+        double t = A[j + c * ld];
+        A[j + c * ld] = A[p + c * ld];
+        A[p + c * ld] = t;
+      }
+    __syncthreads();
+    const double d = A[j + j * ld];
+    const double inv = d != 0. ? 1. / d : 0.;
+    __syncthreads();
+    for (int i = j + 1 + tid; i < n; i += kThreads) A[i + j * ld] *= inv;
+    __syncthreads();
+    const int nt = n - j - 1;
+    for (int c = j + 1 + warp; c < n; c += kWarps) {
+      const double ujc = A[j + c * ld];
+      for (int i = j + 1 + lane; i < n; i += 32) A[i + c * ld] -= A[i + j * ld] * ujc;
+    }
+    (void)nt;
+    __syncthreads();
+  }
+  if (thresh > 0.)
+    for (int i = tid; i < n; i += kThreads) {
+      double d = A[i + i * ld];
+      if (fabs(d) < thresh) A[i + i * ld] = d < 0 ? -thresh : thresh;
+    }
+  if (tid == 0) {
+    for (int i = 0; i < n; i++) g[i] = i;
+    for (int i = 0; i < n; i++) {
+      int p = ipiv[i] - 1;
+      if (p != i) { int t = g[i]; g[i] = g[p]; g[p] = t; }
+    }
+  }
+}
+
+// UT = (upper triangle of A)^T, so that solves with U from the right become
+// solves with the lower triangular U^T from the left
+__global__ void blr_upper_transpose_kernel(const double* __restrict__ A, long long ld, int n,
+                                           double* __restrict__ UT) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+    int r = idx % n, c = idx / n;   // UT[r, c] = U[c, r] for c <= r
+    UT[r + (size_t)c * n] = (c <= r) ? A[c + r * ld] : 0.;
+  }
+}
+
+// ------------------------------------------------------------ tile compression
+__global__ void __launch_bounds__(kThreads)
+blr_copy_tiles_kernel(const double* __restrict__ A, long long ld, const TileDesc* __restrict__ tiles,
+                      double* __restrict__ scratch, long long stride) {
+  const TileDesc t = tiles[blockIdx.x];
+  double* dst = scratch + blockIdx.x * stride;
+  const double* src = A + t.ro + (size_t)t.co * ld;
+  for (int c = blockIdx.y * kWarps + (threadIdx.x >> 5); c < t.n; c += gridDim.y * kWarps)
+    for (int r = threadIdx.x & 31; r < t.m; r += 32) dst[r + (size_t)c * t.m] = src[r + c * ld];
+}
+
+// U = Q[:, pivots] (m x rank), Vt = R^T (n x rank)   (LRTile RRQR ctor, LRTile.cpp:55-65)
+__global__ void __launch_bounds__(kThreads)
+blr_extract_lr_kernel(const TileDesc* __restrict__ tiles, const double* __restrict__ scratch,
+                      long long stride, const double* __restrict__ R, long long rstride,
+                      const int* __restrict__ order, int ostride, const int* __restrict__ ranks_step,
+                      double* __restrict__ lr, int* __restrict__ rank_tab, int nb) {
+  const TileDesc t = tiles[blockIdx.x];
+  const int rank = ranks_step[blockIdx.x];
+  if (threadIdx.x == 0) rank_tab[t.i + t.j * nb] = rank;
+  if (rank <= 0) return;
+  const double* Q = scratch + blockIdx.x * stride;
+  const double* Rt = R + blockIdx.x * rstride;
+  const int* ord = order + (size_t)blockIdx.x * ostride;
+  double* U = lr + t.lr;
+  double* Vt = U + (size_t)t.m * t.rc;
+  for (int idx = threadIdx.x; idx < t.m * rank; idx += kThreads) {
+    int r = idx % t.m, a = idx / t.m;
+    U[r + (size_t)a * t.m] = Q[r + (size_t)ord[a] * t.m];
+  }
+  for (int idx = threadIdx.x; idx < t.n * rank; idx += kThreads) {
+    int c = idx % t.n, a = idx / t.n;
+    Vt[c + (size_t)a * t.n] = Rt[a + (size_t)c * t.rc];
+  }
+}
+
+// ------------------------------------------------------------ triangular solves
+// B <- L^{-1} B[g, :] for the columns of B, L lower triangular (unit or not),
+// one warp per column, blocked by 32 rows.  Used for
+//   U_ij <- L_ii^{-1} P_i U_ij         (laswp + trsm L,L,N,U; BLRMatrix.cpp:152-155)
+//   Vt_ji <- U_ii^{-T} Vt_ji           (trsm R,U,N,N on V;     BLRMatrix.cpp:165-166)
+//   and for the right-hand sides of the solve.
+__global__ void __launch_bounds__(kThreads)
+blr_trsm_lower_kernel(const double* __restrict__ L, long long ldl, int n, int unit,
+                      const int* __restrict__ g, const SolveTask* __restrict__ tasks,
+                      const int* __restrict__ ncols_dyn) {
+  extern __shared__ double sm[];
+  const SolveTask t = tasks[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncols = ncols_dyn ? ncols_dyn[blockIdx.x] : t.ncols;
+  const int col = blockIdx.y * kWarps + warp;
+  if (col >= ncols) return;
+  double* x = sm + (size_t)warp * n;
+  double* b = t.B + (size_t)col * t.ldb;
+  for (int i = lane; i < n; i += 32) x[i] = b[g ? g[i] : i];
+  __syncwarp();
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    double v = i < n ? x[i] : 0.;
+    if (i < n) {
+      double a0 = 0., a1 = 0.;
+      int j = 0;
+      for (; j + 2 <= i0; j += 2) {
+        a0 += L[i + j * ldl] * x[j];
+        a1 += L[i + (j + 1) * ldl] * x[j + 1];
+      }
+      v -= a0 + a1;
+    }
+    const int ib = min(32, n - i0);
+    for (int a = 0; a < ib; a++) {
+      if (!unit && lane == a) v /= L[(i0 + a) + (i0 + a) * ldl];
+      const double xa = __shfl_sync(0xffffffffu, v, a);
+      if (lane > a && i < n) v -= L[i + (i0 + a) * ldl] * xa;
+    }
+    if (i < n) x[i] = v;
+    __syncwarp();
+  }
+  for (int i = lane; i < n; i += 32) b[i] = x[i];
+}
+
+// B <- U^{-1} B (back substitution, U upper triangular non-unit), one warp per column
+__global__ void __launch_bounds__(kThreads)
+blr_trsm_upper_kernel(const double* __restrict__ U, long long ldu, int n, double* __restrict__ B,
+                      long long ldb, int ncols) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * kWarps + warp;
+  if (col >= ncols) return;
+  double* x = sm + (size_t)warp * n;
+  double* b = B + (size_t)col * ldb;
+  for (int i = lane; i < n; i += 32) x[i] = b[i];
+  __syncwarp();
+  const int nblk = (n + 31) / 32;
+  for (int bi = nblk - 1; bi >= 0; bi--) {
+    const int i0 = bi * 32, i = i0 + lane, ib = min(32, n - i0);
+    double v = i < n ? x[i] : 0.;
+    if (i < n) {
+      double a0 = 0.;
+      for (int j = i0 + ib; j < n; j++) a0 += U[i + j * ldu] * x[j];
+      v -= a0;
+    }
+    for (int a = ib - 1; a >= 0; a--) {
+      if (lane == a) v /= U[(i0 + a) + (i0 + a) * ldu];
+      const double xa = __shfl_sync(0xffffffffu, v, a);
+      if (lane < a) v -= U[i + (i0 + a) * ldu] * xa;
+    }
+    if (i < n) x[i] = v;
+    __syncwarp();
+  }
+  for (int i = lane; i < n; i += 32) b[i] = x[i];
+}
+
+// ranks of the tiles of one kind (0: slots with i<j, 1: slots with i>j) as the
+// dynamic column counts of the trsm launch
+__global__ void blr_select_kernel(const TileDesc* __restrict__ td, int cnt, int kind,
+                                  const int* __restrict__ rank_tab, int nb, int* __restrict__ sel) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= cnt) return;
+  const bool upper = td[q].i < td[q].j;
+  const int r = rank_tab[td[q].i + td[q].j * nb];
+  sel[q] = ((kind == 0) == upper && r > 0) ? r : 0;
+}
+
+// ------------------------------------------------------------------ Schur update
+// C_kj -= U_ki (Vt_ki^T U_ij) Vt_ij^T for every pair (k, j) of the trailing
+// matrix, one CTA per pair (RL update, BLRMatrix.cpp:170-185; the 3-stage
+// batched GEMM of BLRBatch.hpp:85-118 fused: the rank x rank core never leaves
+// shared memory).  Ranks above KC are processed in chunks of KC columns.
+template <int KC>
+__global__ void __launch_bounds__(kThreads)
+blr_schur_kernel(double* __restrict__ A, long long ld, const int* __restrict__ off, int nb, int istep,
+                 const double* __restrict__ lr, const long long* __restrict__ lroff,
+                 const int* __restrict__ rcap, const int* __restrict__ rank_tab, int ldp) {
+  extern __shared__ double sm[];
+  const int nrem = nb - istep - 1;
+  const int k = istep + 1 + blockIdx.x % nrem, j = istep + 1 + blockIdx.x / nrem;
+  const int ra = rank_tab[k + istep * nb], rb = rank_tab[istep + j * nb];
+  if (ra <= 0 || rb <= 0) return;    // zero tile: nothing to subtract
+  const int mk = off[k + 1] - off[k], mi = off[istep + 1] - off[istep], nj = off[j + 1] - off[j];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int LDM = KC + 4;
+  double* S1 = sm;                       // ldp x KC
+  double* S2 = S1 + (size_t)ldp * KC;    // ldp x KC
+  double* W = S2 + (size_t)ldp * KC;     // ldp x KC
+  double* Ms = W + (size_t)ldp * KC;     // LDM x KC
+  const double* Uki = lr + lroff[k + istep * nb];
+  const double* Vtki = Uki + (size_t)mk * rcap[k + istep * nb];
+  const double* Uij = lr + lroff[istep + j * nb];
+  const double* Vtij = Uij + (size_t)mi * rcap[istep + j * nb];
+  double* C = A + off[k] + (size_t)off[j] * ld;
+  for (int cb = 0; cb < rb; cb += KC) {
+    const int kb = min(KC, rb - cb);
+    for (int ca = 0; ca < ra; ca += KC) {
+      const int ka = min(KC, ra - ca);
+      __syncthreads();
+      for (int c = warp; c < ka; c += kWarps)
+        for (int r = lane; r < mi; r += 32) S1[r + c * ldp] = Vtki[r + (size_t)(ca + c) * mi];
+      for (int c = warp; c < kb; c += kWarps)
+        for (int r = lane; r < mi; r += 32) S2[r + c * ldp] = Uij[r + (size_t)(cb + c) * mi];
+      __syncthreads();
+      smem_gemm<true, false>(ka, kb, mi, 1., S1, ldp, S2, ldp, 0., Ms, LDM, warp, kWarps, lane);
+      __syncthreads();
+      for (int c = warp; c < ka; c += kWarps)
+        for (int r = lane; r < mk; r += 32) S1[r + c * ldp] = Uki[r + (size_t)(ca + c) * mk];
+      __syncthreads();
+      smem_gemm<false, false>(mk, kb, ka, 1., S1, ldp, Ms, LDM, ca ? 1. : 0., W, ldp, warp, kWarps, lane);
+    }
+    __syncthreads();
+    for (int c = warp; c < kb; c += kWarps)
+      for (int r = lane; r < nj; r += 32) S2[r + c * ldp] = Vtij[r + (size_t)(cb + c) * nj];
+    __syncthreads();
+    // C (mk x nj, global) -= W (mk x kb) * S2^T (kb x nj): 16x16 tiles over the warps
+    const int g = lane >> 2, t = lane & 3;
+    const int tm = (mk + 15) >> 4, tn = (nj + 15) >> 4;
+    for (int tile = warp; tile < tm * tn; tile += kWarps) {
+      const int i0 = (tile % tm) << 4, j0 = (tile / tm) << 4;
+      double c[2][2][2];
+#pragma unroll
+      for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+        for (int tj = 0; tj < 2; tj++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int ii = i0 + ti * 8 + g, jj = j0 + tj * 8 + 2 * t + e;
+            c[ti][tj][e] = (ii < mk && jj < nj) ? C[ii + (size_t)jj * ld] : 0.;
+          }
+      for (int k0 = 0; k0 < kb; k0 += 4) {
+        const int kk = k0 + t;
+        const bool kin = kk < kb;
+        const int ia0 = i0 + g, ia1 = ia0 + 8, jb0 = j0 + g, jb1 = jb0 + 8;
+        const double a0 = (kin && ia0 < mk) ? -W[ia0 + kk * ldp] : 0.;
+        const double a1 = (kin && ia1 < mk) ? -W[ia1 + kk * ldp] : 0.;
+        const double b0 = (kin && jb0 < nj) ? S2[jb0 + kk * ldp] : 0.;
+        const double b1 = (kin && jb1 < nj) ? S2[jb1 + kk * ldp] : 0.;
+        dmma(c[0][0][0], c[0][0][1], a0, b0);
+        dmma(c[0][1][0], c[0][1][1], a0, b1);
+        dmma(c[1][0][0], c[1][0][1], a1, b0);
+        dmma(c[1][1][0], c[1][1][1], a1, b1);
+      }
+#pragma unroll
+      for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+        for (int tj = 0; tj < 2; tj++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int ii = i0 + ti * 8 + g, jj = j0 + tj * 8 + 2 * t + e;
+            if (ii < mk && jj < nj) C[ii + (size_t)jj * ld] = c[ti][tj][e];
+          }
+    }
+  }
+}
+
+// ------------------------------------------------------------- vector kernels
+// y_k += alpha * T_kj x_j for a list of LR tiles (gemv_a, LRTile.cpp:313-327),
+// one CTA per tile, atomics into y (several tiles feed the same y block).
+struct GemvTask { int k, j; };
+
+__global__ void __launch_bounds__(kThreads)
+blr_lr_gemv_kernel(const GemvTask* __restrict__ tasks, const int* __restrict__ off, int nb,
+                   const double* __restrict__ lr, const long long* __restrict__ lroff,
+                   const int* __restrict__ rcap, const int* __restrict__ rank_tab,
+                   const double* __restrict__ x, long long ldx, double* __restrict__ y,
+                   long long ldy, double alpha) {
+  extern __shared__ double sm[];
+  const GemvTask tk = tasks[blockIdx.x];
+  const int col = blockIdx.y;
+  const int r = rank_tab[tk.k + tk.j * nb];
+  if (r <= 0) return;
+  const int m = off[tk.k + 1] - off[tk.k], n = off[tk.j + 1] - off[tk.j];
+  const double* U = lr + lroff[tk.k + tk.j * nb];
+  const double* Vt = U + (size_t)m * rcap[tk.k + tk.j * nb];
+  const double* xj = x + off[tk.j] + col * ldx;
+  double* yk = y + off[tk.k] + col * ldy;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double* tv = sm;   // r
+  for (int a = warp; a < r; a += kWarps) {
+    const double* va = Vt + (size_t)a * n;
+    double acc = 0.;
+    for (int i = lane; i < n; i += 32) acc += va[i] * xj[i];
+    acc = warp_sum(acc);
+    if (lane == 0) tv[a] = alpha * acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < m; i += kThreads) {
+    double acc = 0.;
+    for (int a = 0; a < r; a++) acc += U[i + (size_t)a * m] * tv[a];
+    atomicAdd(yk + i, acc);
+  }
+}
+
+// y_i += D_ii x_i (dense diagonal tiles of a compressed, unfactored matrix)
+__global__ void __launch_bounds__(kThreads)
+blr_diag_gemv_kernel(const double* __restrict__ A, long long ld, const int* __restrict__ off,
+                     const double* __restrict__ x, long long ldx, double* __restrict__ y,
+                     long long ldy, int trans) {
+  const int i = blockIdx.x, col = blockIdx.y;
+  const int m = off[i + 1] - off[i];
+  const double* D = A + off[i] + (size_t)off[i] * ld;
+  const double* xi = x + off[i] + col * ldx;
+  double* yi = y + off[i] + col * ldy;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (!trans) {
+    for (int r = threadIdx.x; r < m; r += kThreads) {
+      double acc = 0.;
+      for (int c = 0; c < m; c++) acc += D[r + c * ld] * xi[c];
+      atomicAdd(yi + r, acc);
+    }
+  } else {
+    for (int c = warp; c < m; c += kWarps) {
+      double acc = 0.;
+      for (int r = lane; r < m; r += 32) acc += D[r + c * ld] * xi[r];
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(yi + c, acc);
+    }
+  }
+}
+
+__global__ void blr_zero_kernel(double* y, long long ld, int n, int s) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)n * s;
+       idx += (long long)gridDim.x * blockDim.x)
+    y[(idx % n) + (idx / n) * ld] = 0.;
+}
+
+}  // namespace
+
+// ===========================================================================
+//                                 host side
+// ===========================================================================
+template <typename K> static void set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    SB200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+static void refine(std::vector<int>& tiles, int size, int leaf) {
+  // ClusterTree::refine (reference src/structured/ClusterTree.hpp:104-114)
+  if (size >= 2 * leaf) {
+    refine(tiles, size / 2, leaf);
+    refine(tiles, size - size / 2, leaf);
+  } else tiles.push_back(size);
+}
+
+BLREngine::BLREngine(int n, const double* hostA, int ldA, const BLROpts& o, bool do_factor)
+    : n_(n), opts_(o) {
+  if (n <= 0) throw std::invalid_argument("empty matrix");
+  std::vector<int> tiles;
+  refine(tiles, n, std::max(1, o.leaf_size));
+  nb_ = int(tiles.size());
+  off_.assign(nb_ + 1, 0);
+  for (int t = 0; t < nb_; t++) off_[t + 1] = off_[t] + tiles[t];
+  maxtile_ = *std::max_element(tiles.begin(), tiles.end());
+  if (maxtile_ > 1024) throw std::invalid_argument("BLR tiles larger than 1024 are not supported");
+  // LR arena: tile (i,j) gets [U m x rc | Vt n x rc], rc = min(m,n)/2 (a tile
+  // is kept low-rank only if rank*(m+n) <= m*n, BLRMatrix.cpp:563-570)
+  lroff_.assign((size_t)nb_ * nb_, -1);
+  rcap_.assign((size_t)nb_ * nb_, 0);
+  long long o_ = 0;
+  for (int j = 0; j < nb_; j++)
+    for (int i = 0; i < nb_; i++) {
+      if (i == j) continue;
+      const int m = tiles[i], nn = tiles[j];
+      const int rc = std::max(1, std::min(std::min(m, nn) / 2, o.max_rank));
+      lroff_[i + (size_t)j * nb_] = o_;
+      rcap_[i + (size_t)j * nb_] = rc;
+      o_ += (long long)(m + nn) * rc;
+    }
+  A_.alloc((size_t)n * n);
+  SB200_CUDA(cudaMemcpy2D(A_.p, sizeof(double) * n, hostA, sizeof(double) * ldA,
+                          sizeof(double) * n, n, cudaMemcpyHostToDevice));
+  lr_.alloc((size_t)std::max<long long>(o_, 1));
+  doff_.upload(off_.data(), off_.size());
+  dlroff_.upload(lroff_.data(), lroff_.size());
+  drcap_.upload(rcap_.data(), rcap_.size());
+  std::vector<int> rk((size_t)nb_ * nb_, 0);
+  drank_.upload(rk.data(), rk.size());
+  piv_.alloc(n);
+  gperm_.alloc(n);
+  SB200_CUDA(cudaStreamSynchronize(0));
+  run(do_factor);
+}
+
+void BLREngine::run(bool do_factor) {
+  cudaStream_t st = 0;
+  const int nb = nb_, n = n_;
+  const long long tstride = (long long)maxtile_ * maxtile_;
+  const int ntmax = 2 * (nb - 1);
+  DevBuf<double> scratch((size_t)std::max(ntmax, 1) * tstride), Rbuf((size_t)std::max(ntmax, 1) * tstride),
+      UT((size_t)tstride);
+  DevBuf<int> order((size_t)std::max(ntmax, 1) * maxtile_), ranks_step(std::max(ntmax, 1)),
+      sel(std::max(ntmax, 1));
+  SB200_CUDA(cudaMemsetAsync(Rbuf.p, 0, sizeof(double) * Rbuf.n, st));
+  // all per-step descriptors are built up front: no host sync inside the loop
+  std::vector<TileDesc> td;
+  std::vector<IDTask> idt;
+  std::vector<SolveTask> stL;
+  std::vector<int> step_ptr(nb + 1, 0);
+  auto add_tile = [&](int i, int j, int slot) {
+    TileDesc t;
+    t.i = i; t.j = j; t.ro = off_[i]; t.co = off_[j];
+    t.m = off_[i + 1] - off_[i]; t.n = off_[j + 1] - off_[j];
+    t.lr = lroff_[i + (size_t)j * nb]; t.rc = rcap_[i + (size_t)j * nb];
+    td.push_back(t);
+    IDTask q;
+    q.M = scratch.p + slot * tstride; q.R = Rbuf.p + slot * tstride;
+    q.ns = t.m; q.nc = t.n; q.rcap = t.rc;
+    q.order = order.p + (size_t)slot * maxtile_; q.rank = ranks_step.p + slot;
+    q.E = nullptr; q.strict = 1;
+    idt.push_back(q);
+  };
+  for (int i = 0; i < nb; i++) {
+    int slot = 0;
+    if (do_factor) {
+      for (int j = i + 1; j < nb; j++) { add_tile(i, j, slot++); add_tile(j, i, slot++); }
+    } else {
+      for (int j = 0; j < nb; j++) if (j != i) add_tile(i, j, slot++);   // compress only: row i
+    }
+    step_ptr[i + 1] = int(td.size());
+  }
+  // solve tasks: left: U of (i,j) ; right: Vt of (j,i)
+  for (size_t q = 0; q < td.size(); q++) {
+    const TileDesc& t = td[q];
+    SolveTask s;
+    if (t.i < t.j) { s.B = lr_.p + t.lr; s.ldb = t.m; }                          // U_ij, m x rank
+    else { s.B = lr_.p + t.lr + (long long)t.m * t.rc; s.ldb = t.n; }            // Vt_ji, n x rank
+    s.ncols = 0;
+    stL.push_back(s);
+  }
+  DevBuf<TileDesc> dtd; dtd.upload(td.data(), td.size(), st);
+  DevBuf<IDTask> didt; didt.upload(idt.data(), idt.size(), st);
+  DevBuf<SolveTask> dst; dst.upload(stL.data(), stL.size(), st);
+  const size_t cpqr_smem = (sizeof(double) + sizeof(int)) * (size_t)maxtile_ + 16;
+  set_smem(id_cpqr_kernel, cpqr_smem);
+  const int ldp = smem_ld(maxtile_);
+  const int KC = maxtile_ <= 256 ? 32 : 16;
+  for (int i = 0; i < nb; i++) {
+    const int m = off_[i + 1] - off_[i];
+    const int cnt = step_ptr[i + 1] - step_ptr[i];
+    double* Aii = A_.p + off_[i] + (size_t)off_[i] * n;
+    if (do_factor) {
+      blr_getrf_kernel<<<1, kThreads, 0, st>>>(Aii, n, m, piv_.p + off_[i], gperm_.p + off_[i],
+                                               opts_.pivot_threshold);
+      blr_upper_transpose_kernel<<<64, 256, 0, st>>>(Aii, n, m, UT.p);
+      launches_ += 2;
+    }
+    if (!cnt) continue;
+    const TileDesc* tds = dtd.p + step_ptr[i];
+    // K11: compress the tiles of block row / column i
+    blr_copy_tiles_kernel<<<dim3(cnt, 8), kThreads, 0, st>>>(A_.p, n, tds, scratch.p, tstride);
+    id_cpqr_kernel<<<cnt, kCpqrThreads, cpqr_smem, st>>>(didt.p + step_ptr[i], opts_.rel_tol,
+                                                         opts_.abs_tol, opts_.max_rank);
+    blr_extract_lr_kernel<<<cnt, kThreads, 0, st>>>(tds, scratch.p, tstride, Rbuf.p, tstride, order.p,
+                                                    maxtile_, ranks_step.p, lr_.p, drank_.p, nb);
+    SB200_CUDA(cudaMemsetAsync(Rbuf.p, 0, sizeof(double) * (size_t)cnt * tstride, st));
+    launches_ += 3;
+    if (!do_factor) continue;
+    // K12: U_ij <- L^{-1} P U_ij (even slots), Vt_ji <- U^{-T} Vt_ji (odd slots).
+    // Both lists are interleaved in one descriptor array; each launch covers
+    // all tiles and the kernel skips the ones of the other kind by ncols = 0.
+    {
+      const size_t smem = sizeof(double) * (size_t)kWarps * m;
+      set_smem(blr_trsm_lower_kernel, smem);
+      blr_select_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(tds, cnt, 0, drank_.p, nb, sel.p);
+      blr_trsm_lower_kernel<<<dim3(cnt, (maxtile_ / 2 + kWarps - 1) / kWarps), kThreads, smem, st>>>(
+          Aii, n, m, 1, gperm_.p + off_[i], dst.p + step_ptr[i], sel.p);
+      blr_select_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(tds, cnt, 1, drank_.p, nb, sel.p);
+      blr_trsm_lower_kernel<<<dim3(cnt, (maxtile_ / 2 + kWarps - 1) / kWarps), kThreads, smem, st>>>(
+          UT.p, m, m, 0, nullptr, dst.p + step_ptr[i], sel.p);
+      launches_ += 4;
+    }
+    // K13: trailing update
+    const int nrem = nb - i - 1;
+    if (nrem > 0) {
+      const size_t smem = sizeof(double) * ((size_t)3 * ldp * KC + (size_t)(KC + 4) * KC);
+      if (KC == 32) { set_smem(blr_schur_kernel<32>, smem);
+        blr_schur_kernel<32><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp);
+      } else { set_smem(blr_schur_kernel<16>, smem);
+        blr_schur_kernel<16><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp);
+      }
+      launches_++;
+    }
+  }
+  SB200_CUDA(cudaGetLastError());
+  SB200_CUDA(cudaStreamSynchronize(st));
+  hrank_.resize((size_t)nb * nb);
+  SB200_CUDA(cudaMemcpy(hrank_.data(), drank_.p, sizeof(int) * hrank_.size(), cudaMemcpyDeviceToHost));
+  for (int j = 0; j < nb; j++)
+    for (int i = 0; i < nb; i++)
+      if (i != j && hrank_[i + (size_t)j * nb] < 0)
+        throw std::runtime_error("BLR tile (" + std::to_string(i) + "," + std::to_string(j) +
+                                 ") is not compressible to rank <= min(m,n)/2: dense off-diagonal "
+                                 "tiles are not supported yet");
+  factored_ = do_factor;
+}
+
+
+// ------------------------------------------------------------------ solve
+// x <- A^{-1} x : laswp(piv), trsm(L, unit lower BLR), trsm(U, upper BLR)
+// (BLRMatrix::solve, BLRMatrix.hpp:118-122; left-looking block substitution,
+// BLRMatrix.cpp:1683-1707)
+void BLREngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
+  if (!factored_) throw std::logic_error("BLR solve called on an unfactored matrix");
+  const int nb = nb_, n = n_;
+  // task lists (k,j) for every block row, built once
+  if (!tasks_built_) {
+    std::vector<GemvTask> tl;
+    fwd_ptr_.assign(nb + 1, 0);
+    for (int i = 0; i < nb; i++) {
+      for (int j = 0; j < i; j++) tl.push_back({i, j});
+      fwd_ptr_[i + 1] = int(tl.size());
+    }
+    bwd_ptr_.assign(nb + 1, 0);
+    const int base = int(tl.size());
+    for (int i = 0; i < nb; i++) {
+      for (int j = i + 1; j < nb; j++) tl.push_back({i, j});
+      bwd_ptr_[i + 1] = int(tl.size()) - base;
+    }
+    bwd_base_ = base;
+    gtasks_.alloc(tl.size() * sizeof(GemvTask) / sizeof(int) + 2);
+    SB200_CUDA(cudaMemcpyAsync(gtasks_.p, tl.data(), tl.size() * sizeof(GemvTask), cudaMemcpyHostToDevice, st));
+    tasks_built_ = true;
+  }
+  const GemvTask* gt = reinterpret_cast<const GemvTask*>(gtasks_.p);
+  DevBuf<SolveTask>& sv = solve_task_;
+  if (!sv.p) {
+    std::vector<SolveTask> t(nb);
+    sv.alloc(nb);
+    solve_ldb_ = -1;
+  }
+  if (solve_ldb_ != ldB || solve_ptr_ != dB || solve_s_ != s) {
+    std::vector<SolveTask> t(nb);
+    for (int i = 0; i < nb; i++) { t[i].B = dB + off_[i]; t[i].ldb = ldB; t[i].ncols = s; }
+    SB200_CUDA(cudaMemcpyAsync(sv.p, t.data(), sizeof(SolveTask) * nb, cudaMemcpyHostToDevice, st));
+    SB200_CUDA(cudaStreamSynchronize(st));
+    solve_ldb_ = ldB; solve_ptr_ = dB; solve_s_ = s;
+  }
+  const size_t gsm = sizeof(double) * (size_t)(maxtile_ / 2 + 8);
+  for (int i = 0; i < nb; i++) {      // forward: x_i <- L_ii^{-1} P_i (x_i - sum_{j<i} T_ij x_j)
+    const int m = off_[i + 1] - off_[i], cnt = fwd_ptr_[i + 1] - fwd_ptr_[i];
+    if (cnt) {
+      blr_lr_gemv_kernel<<<dim3(cnt, s), kThreads, gsm, st>>>(gt + fwd_ptr_[i], doff_.p, nb, lr_.p, dlroff_.p,
+                                                             drcap_.p, drank_.p, dB, ldB, dB, ldB, -1.);
+      launches_++;
+    }
+    const size_t smem = sizeof(double) * (size_t)kWarps * m;
+    set_smem(blr_trsm_lower_kernel, smem);
+    blr_trsm_lower_kernel<<<dim3(1, (s + kWarps - 1) / kWarps), kThreads, smem, st>>>(
+        A_.p + off_[i] + (size_t)off_[i] * n, n, m, 1, gperm_.p + off_[i], sv.p + i, nullptr);
+    launches_++;
+  }
+  for (int i = nb - 1; i >= 0; i--) { // backward: x_i <- U_ii^{-1} (x_i - sum_{j>i} T_ij x_j)
+    const int m = off_[i + 1] - off_[i], cnt = bwd_ptr_[i + 1] - bwd_ptr_[i];
+    if (cnt) {
+      blr_lr_gemv_kernel<<<dim3(cnt, s), kThreads, gsm, st>>>(gt + bwd_base_ + bwd_ptr_[i], doff_.p, nb, lr_.p,
+                                                             dlroff_.p, drcap_.p, drank_.p, dB, ldB, dB, ldB, -1.);
+      launches_++;
+    }
+    const size_t smem = sizeof(double) * (size_t)kWarps * m;
+    set_smem(blr_trsm_upper_kernel, smem);
+    blr_trsm_upper_kernel<<<(s + kWarps - 1) / kWarps, kThreads, smem, st>>>(
+        A_.p + off_[i] + (size_t)off_[i] * n, n, m, dB + off_[i], ldB, s);
+    launches_++;
+  }
+  SB200_CUDA(cudaGetLastError());
+}
+
+// y = op(A) x on the compressed (unfactored) matrix  (BLRMatrix::mult ->
+// gemv, BLRMatrix.cpp:1742-1763)
+void BLREngine::mult(char trans, int s, const double* dB, int ldB, double* dC, int ldC,
+                     cudaStream_t st) {
+  if (factored_) throw std::logic_error("BLR mult: the tiles hold LU factors (use solve)");
+  const bool T = !(trans == 'N' || trans == 'n');
+  if (T) throw std::logic_error("BLR transposed mult is not implemented yet");
+  const int nb = nb_;
+  if (!mtasks_.p) {
+    std::vector<GemvTask> tl;
+    for (int i = 0; i < nb; i++)
+      for (int j = 0; j < nb; j++) if (i != j) tl.push_back({i, j});
+    nmt_ = int(tl.size());
+    mtasks_.alloc(tl.size() * sizeof(GemvTask) / sizeof(int) + 2);
+    SB200_CUDA(cudaMemcpy(mtasks_.p, tl.data(), tl.size() * sizeof(GemvTask), cudaMemcpyHostToDevice));
+  }
+  blr_zero_kernel<<<256, 256, 0, st>>>(dC, ldC, n_, s);
+  blr_diag_gemv_kernel<<<dim3(nb, s), kThreads, 0, st>>>(A_.p, n_, doff_.p, dB, ldB, dC, ldC, 0);
+  if (nmt_) {
+    const size_t gsm = sizeof(double) * (size_t)(maxtile_ / 2 + 8);
+    blr_lr_gemv_kernel<<<dim3(nmt_, s), kThreads, gsm, st>>>(reinterpret_cast<const GemvTask*>(mtasks_.p),
+                                                            doff_.p, nb, lr_.p, dlroff_.p, drcap_.p, drank_.p,
+                                                            dB, ldB, dC, ldC, 1.);
+  }
+  launches_ += 3;
+  SB200_CUDA(cudaGetLastError());
+}
+
+int BLREngine::max_rank() const {
+  int r = 0;
+  for (int v : hrank_) r = std::max(r, v);
+  return r;
+}
+
+long long BLREngine::nonzeros() const {
+  long long nnz = 0;
+  for (int j = 0; j < nb_; j++)
+    for (int i = 0; i < nb_; i++) {
+      const long long m = off_[i + 1] - off_[i], n = off_[j + 1] - off_[j];
+      nnz += (i == j) ? m * n : (long long)hrank_[i + (size_t)j * nb_] * (m + n);
+    }
+  return nnz;
+}
+
+}  // namespace sb200

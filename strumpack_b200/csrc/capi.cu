@@ -11,6 +11,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "blr_engine.hpp"
 #include "hss_compress.hpp"
 #include "hss_engine.hpp"
 #include "hss_tree.hpp"
@@ -22,6 +23,7 @@ namespace {
 struct Mat {
   SP_STRUCTURED_TYPE type = SP_TYPE_HSS;
   std::unique_ptr<HSSEngine> hss;
+  std::unique_ptr<BLREngine> blr;
   // staging buffers for the host-pointer entry points
   DevBuf<double> dB, dC;
 };
@@ -95,26 +97,45 @@ void SP_d_struct_destroy(CSPStructMat* S) {
   *S = nullptr;
 }
 
-int SP_d_struct_rows(const CSPStructMat S) { return S ? hss(S).rows() : 0; }
-int SP_d_struct_cols(const CSPStructMat S) { return S ? hss(S).cols() : 0; }
+int SP_d_struct_rows(const CSPStructMat S) {
+  if (!S) return 0;
+  return M(S)->blr ? M(S)->blr->rows() : hss(S).rows();
+}
+int SP_d_struct_cols(const CSPStructMat S) {
+  if (!S) return 0;
+  return M(S)->blr ? M(S)->blr->cols() : hss(S).cols();
+}
 long long int SP_d_struct_memory(const CSPStructMat S) {
-  return S ? hss(S).host().memory_bytes() : 0;
+  if (!S) return 0;
+  return M(S)->blr ? M(S)->blr->memory_bytes() : hss(S).host().memory_bytes();
 }
 long long int SP_d_struct_nonzeros(const CSPStructMat S) {
-  return S ? hss(S).host().nonzeros() : 0;
+  if (!S) return 0;
+  return M(S)->blr ? M(S)->blr->nonzeros() : hss(S).host().nonzeros();
 }
 int SP_d_struct_rank(const CSPStructMat S) {
-  return S ? hss(S).host().max_rank() : 0;
+  if (!S) return 0;
+  return M(S)->blr ? M(S)->blr->max_rank() : hss(S).host().max_rank();
 }
 
 int SP_d_struct_from_dense(CSPStructMat* S, int rows, int cols, const double* A,
                            int ldA, const CSPOptions* opts) {
   return guarded([&] {
     require_gpu();
-    if (opts->type != SP_TYPE_HSS)
-      throw std::invalid_argument("structured type not supported (HSS only)");
     auto m = std::make_unique<Mat>();
     m->type = opts->type;
+    if (opts->type == SP_TYPE_BLR) {
+      // construct_from_dense, Type::BLR: compress only (StructuredMatrix.cpp:78-98)
+      if (rows != cols) throw std::invalid_argument("BLR: only square matrices are supported");
+      BLROpts bo;
+      bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
+      bo.leaf_size = opts->leaf_size; bo.max_rank = opts->max_rank;
+      m->blr = std::make_unique<BLREngine>(rows, A, ldA, bo, false);
+      *S = m.release();
+      return;
+    }
+    if (opts->type != SP_TYPE_HSS)
+      throw std::invalid_argument("structured type not supported (HSS and BLR only)");
     CompressOptions co;
     co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
     co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
@@ -158,6 +179,25 @@ int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
   });
 }
 
+int SB200_d_blr_compress_and_factor(CSPStructMat* S, int n, const double* A, int ldA,
+                                    const CSPOptions* opts, double pivot_threshold) {
+  return guarded([&] {
+    require_gpu();
+    auto m = std::make_unique<Mat>();
+    m->type = SP_TYPE_BLR;
+    BLROpts bo;
+    bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
+    bo.leaf_size = opts->leaf_size; bo.max_rank = opts->max_rank;
+    bo.pivot_threshold = pivot_threshold;
+    m->blr = std::make_unique<BLREngine>(n, A, ldA, bo, true);
+    *S = m.release();
+  });
+}
+
+int SB200_d_blr_tiles(const CSPStructMat S) {
+  return (S && M(S)->blr) ? M(S)->blr->tiles() : 0;
+}
+
 int SB200_d_hss_read(CSPStructMat* S, const char* path) {
   return guarded([&] {
     require_gpu();
@@ -190,11 +230,20 @@ int SB200_d_hss_from_generators(CSPStructMat* S, int n_nodes,
 int SP_d_struct_mult(const CSPStructMat S, char trans, int m, const double* B,
                      int ldB, double* C, int ldC) {
   return guarded([&] {
-    auto& H = hss(S);
     Mat* mm = M(S);
+    cudaStream_t st = 0;
+    if (mm->blr) {
+      const int n = mm->blr->rows();
+      h2d(mm->dB, B, n, m, ldB, st);
+      mm->dC.ensure((size_t)n * m);
+      mm->blr->mult(trans, m, mm->dB.p, n, mm->dC.p, n, st);
+      d2h(C, mm->dC, n, m, ldC, st);
+      SB200_CUDA(cudaStreamSynchronize(st));
+      return;
+    }
+    auto& H = hss(S);
     const bool T = !(trans == 'N' || trans == 'n');
     const int nb = T ? H.rows() : H.cols(), nc = T ? H.cols() : H.rows();
-    cudaStream_t st = 0;
     h2d(mm->dB, B, nb, m, ldB, st);
     mm->dC.ensure((size_t)nc * m);
     H.mult(trans, m, mm->dB.p, nb, mm->dC.p, nc, st);
@@ -205,6 +254,9 @@ int SP_d_struct_mult(const CSPStructMat S, char trans, int m, const double* B,
 
 int SP_d_struct_factor(CSPStructMat S) {
   return guarded([&] {
+    if (M(S)->blr)   // as in the reference: BLRMatrix has no factor() (StructuredMatrix.cpp:1539-1589)
+      throw std::logic_error("factor() is not supported for a compressed BLR matrix; "
+                             "use SB200_d_blr_compress_and_factor");
     hss(S).factor(0);
     SB200_CUDA(cudaStreamSynchronize(0));
   });
@@ -212,9 +264,17 @@ int SP_d_struct_factor(CSPStructMat S) {
 
 int SP_d_struct_solve(const CSPStructMat S, int nrhs, double* B, int ldB) {
   return guarded([&] {
-    auto& H = hss(S);
     Mat* mm = M(S);
     cudaStream_t st = 0;
+    if (mm->blr) {
+      const int n = mm->blr->rows();
+      h2d(mm->dB, B, n, nrhs, ldB, st);
+      mm->blr->solve(nrhs, mm->dB.p, n, st);
+      d2h(B, mm->dB, n, nrhs, ldB, st);
+      SB200_CUDA(cudaStreamSynchronize(st));
+      return;
+    }
+    auto& H = hss(S);
     h2d(mm->dB, B, H.rows(), nrhs, ldB, st);
     H.solve(nrhs, mm->dB.p, H.rows(), st);
     d2h(B, mm->dB, H.rows(), nrhs, ldB, st);
@@ -322,7 +382,8 @@ double SB200_d_struct_kernel_ms(const CSPStructMat S, int which) {
   return ms;
 }
 long long int SB200_d_struct_launches(const CSPStructMat S) {
-  return S ? hss(S).launches() : 0;
+  if (!S) return 0;
+  return M(S)->blr ? M(S)->blr->launches() : hss(S).launches();
 }
 int SB200_d_struct_print_info(const CSPStructMat S) {
   return guarded([&] { hss(S).host().print_info(); });

@@ -33,13 +33,13 @@
 #include <stdexcept>
 
 #include "sb200_common.cuh"
+#include "sb200_cpqr.cuh"
 
 namespace sb200 {
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kWarps = 8;
 
 // ---- matrix element on the device ------------------------------------------
 struct ElemSrc {
@@ -97,109 +97,6 @@ eval_blocks_kernel(ElemSrc src, const BlockTask* __restrict__ tasks) {
       int j = (int)(idx % t.nc), i = (int)(idx / t.nc);
       t.out[j + (size_t)i * t.ld] = elem(src, t.rows[i], t.cols[j]);
     }
-  }
-}
-
-// ---- batched column-pivoted QR -> interpolative decomposition ----------------
-struct IDTask {
-  double* M;       // ns x nc, column-major, ld = ns (destroyed)
-  double* R;       // rcap x nc workspace, ld = rcap
-  int ns, nc, rcap;
-  int* order;      // nc: pivot order (output): order[0:rank] = skeleton columns
-  int* rank;       // 1
-  double* E;       // (nc - rank) x rank column-major (output), capacity (nc x rcap)
-};
-
-__global__ void __launch_bounds__(kThreads)
-id_cpqr_kernel(const IDTask* __restrict__ tasks, double rtol, double atol,
-               int max_rank) {
-  const IDTask t = tasks[blockIdx.x];
-  extern __shared__ double sm[];
-  double* nrm2 = sm;                 // nc
-  int* ord = (int*)(nrm2 + t.nc);    // nc
-  __shared__ double redv[kWarps];
-  __shared__ int redi[kWarps];
-  __shared__ int s_piv;
-  __shared__ double s_r00;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ns = t.ns, nc = t.nc;
-  for (int c = tid; c < nc; c += kThreads) ord[c] = c;
-  for (int c = warp; c < nc; c += kWarps) {
-    const double* col = t.M + (size_t)c * ns;
-    double a = 0.;
-    for (int i = lane; i < ns; i += 32) a += col[i] * col[i];
-    a = warp_sum(a);
-    if (lane == 0) nrm2[c] = a;
-  }
-  __syncthreads();
-  const int rmax = min(min(ns, nc), min(t.rcap, max_rank));
-  int rank = 0;
-  for (int j = 0; j < rmax; j++) {
-    // pivot = remaining column (position >= j) with the largest norm
-    double best = -1.;
-    int bp = j;
-    for (int p = j + tid; p < nc; p += kThreads) {
-      double v = nrm2[ord[p]];
-      if (v > best) { best = v; bp = p; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, best, o);
-      int op = __shfl_xor_sync(0xffffffffu, bp, o);
-      if (ov > best || (ov == best && op < bp)) { best = ov; bp = op; }
-    }
-    if (lane == 0) { redv[warp] = best; redi[warp] = bp; }
-    __syncthreads();
-    if (tid == 0) {
-      double b = redv[0]; int p = redi[0];
-      for (int w = 1; w < kWarps; w++)
-        if (redv[w] > b || (redv[w] == b && redi[w] < p)) { b = redv[w]; p = redi[w]; }
-      int tmp = ord[j]; ord[j] = ord[p]; ord[p] = tmp;
-      s_piv = ord[j];
-      if (j == 0) s_r00 = sqrt(fmax(b, 0.));
-    }
-    __syncthreads();
-    const int pc = s_piv;
-    const double rjj = sqrt(fmax(nrm2[pc], 0.));
-    // stopping rule of xGEQP3TOL: the new diagonal entry is tested first
-    if (rjj / s_r00 <= rtol || rjj <= atol || !(rjj > 0.)) break;
-    rank = j + 1;
-    double* q = t.M + (size_t)pc * ns;
-    const double inv = 1. / rjj;
-    for (int i = tid; i < ns; i += kThreads) q[i] *= inv;
-    if (tid == 0) t.R[j + (size_t)pc * t.rcap] = rjj;
-    __syncthreads();
-    // orthogonalise the remaining columns against q, refresh their norms
-    for (int p = j + 1 + warp; p < nc; p += kWarps) {
-      const int c = ord[p];
-      double* col = t.M + (size_t)c * ns;
-      double r = 0.;
-      for (int i = lane; i < ns; i += 32) r += q[i] * col[i];
-      r = warp_sum(r);
-      double a = 0.;
-      for (int i = lane; i < ns; i += 32) {
-        double v = col[i] - r * q[i];
-        col[i] = v;
-        a += v * v;
-      }
-      a = warp_sum(a);
-      if (lane == 0) { t.R[j + (size_t)c * t.rcap] = r; nrm2[c] = a; }
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  if (tid == 0) *t.rank = rank;
-  for (int c = tid; c < nc; c += kThreads) t.order[c] = ord[c];
-  // E^T = R11^{-1} R12 : back substitution, one thread per remaining column
-  const int k = nc - rank;
-  for (int p = tid; p < k; p += kThreads) {
-    const int c = ord[rank + p];
-    double* x = t.R + (size_t)c * t.rcap;   // in place in column c of R
-    for (int a = rank - 1; a >= 0; a--) {
-      double v = x[a];
-      for (int b = a + 1; b < rank; b++) v -= t.R[a + (size_t)ord[b] * t.rcap] * x[b];
-      x[a] = v / t.R[a + (size_t)ord[a] * t.rcap];
-    }
-    for (int a = 0; a < rank; a++) t.E[p + (size_t)a * k] = x[a];
   }
 }
 
@@ -468,7 +365,7 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
         //                col basis: M  [s,i] = A(J[s], I[i])  -> rows=J cols=I plain
         if (which == 0) bt[q] = {dI.p + oI, dJ.p + oJ, nc, ns, dM.p + oM, ns, 1};
         else            bt[q] = {dJ.p + oJ, dI.p + oI, ns, nc, dM.p + oM, ns, 0};
-        it[q] = {dM.p + oM, dR.p + oR, ns, nc, rcap[q], dOrder.p + oI, dRank.p + q, dE.p + oE};
+        it[q] = {dM.p + oM, dR.p + oR, ns, nc, rcap[q], dOrder.p + oI, dRank.p + q, dE.p + oE, 0};
         offI[q] = oI; offE[q] = oE;
         oI += nc; oJ += ns; oM += (size_t)ns * nc; oR += (size_t)rcap[q] * nc;
         oE += (size_t)nc * rcap[q];
