@@ -623,15 +623,34 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
 #pragma unroll
                 for (int q = 0; q < 8; q++) p[q] += xv * a[q][rr];
               }
+              // transpose-reduce: 9 shuffles instead of 40; lane L ends up with
+              // the warp total of value (L >> 2) & 7
+              double rsum;
+              {
+                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                double r1[4], r2[2];
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1)
+                for (int q = 0; q < 4; q++) {
+                  const double send = b4 ? p[q] : p[q + 4];
+                  const double keep = b4 ? p[q + 4] : p[q];
+                  r1[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
 #pragma unroll
-                for (int q = 0; q < 8; q++) p[q] += __shfl_xor_sync(0xffffffffu, p[q], o);
-              double* pw = pair + (cq & 1) * 32 + warp * 8;
-              if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < 8; q++) pw[q] = p[q];
+                for (int q = 0; q < 2; q++) {
+                  const double send = b3 ? r1[q] : r1[q + 2];
+                  const double keep = b3 ? r1[q + 2] : r1[q];
+                  r2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                {
+                  const double send = b2 ? r2[0] : r2[1];
+                  const double keep = b2 ? r2[1] : r2[0];
+                  rsum = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
+                rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
               }
+              double* pw = pair + (cq & 1) * 32 + warp * 8;
+              if ((lane & 3) == 0) pw[lane >> 2] = rsum;
               if (warp == 0 && lane == c) {
 #pragma unroll
                 for (int q = 0; q < 8; q++) diag[(cq & 1) * 8 + q] = a[q][0];
@@ -639,10 +658,16 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
               asm volatile("bar.sync 1, 128;" ::: "memory");
               const double* pp = pair + (cq & 1) * 32;
               double sm_[8], dg[8];
+              {
+                const double2* p2 = reinterpret_cast<const double2*>(pp);
+                const double2* d2 = reinterpret_cast<const double2*>(diag + (cq & 1) * 8);
 #pragma unroll
-              for (int q = 0; q < 8; q++) {
-                sm_[q] = (pp[q] + pp[8 + q]) + (pp[16 + q] + pp[24 + q]);
-                dg[q] = diag[(cq & 1) * 8 + q];
+                for (int q = 0; q < 4; q++) {
+                  const double2 a0 = p2[q], a1 = p2[4 + q], a2 = p2[8 + q], a3 = p2[12 + q], dd = d2[q];
+                  sm_[2 * q] = (a0.x + a1.x) + (a2.x + a3.x);
+                  sm_[2 * q + 1] = (a0.y + a1.y) + (a2.y + a3.y);
+                  dg[2 * q] = dd.x; dg[2 * q + 1] = dd.y;
+                }
               }
               const double pn = sm_[cq], alpha = dg[cq];
               double tc = 0., scal = 0., beta = alpha;
