@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kThreads)
 ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                        const double* __restrict__ vals, const int* __restrict__ perms,
                        double* __restrict__ fact, double* __restrict__ scratch,
-                       const long long* __restrict__ scratch_off) {
+                       const long long* __restrict__ scratch_off, int stage_vt1) {
   extern __shared__ double sm[];
   const int id = list[blockIdx.x];
   const DNode nd = nodes[id];
@@ -271,6 +271,25 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
   const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
   const int ru0 = c0.u_rank, ru1 = c1.u_rank, rv0 = c0.v_rank, rv1 = c1.v_rank;
   const int m = ru0 + ru1, tid = threadIdx.x;
+  const int rv = nd.v_rank, nv = rv0 + rv1, kv = nv - rv;
+  // the children's Vt1 blocks (ru x rv, strided inside their factor blocks) are
+  // staged in shared memory once: every entry is used O(m) times below
+  int* pinv = reinterpret_cast<int*>(sm);
+  const double* v0 = fact + c0.F + c0.k + (size_t)c0.k * c0.m;   // Vt1(c0)[a,j] = v0[a + j*ld0]
+  const double* v1 = fact + c1.F + c1.k + (size_t)c1.k * c1.m;
+  int ld0 = c0.m, ld1 = c1.m;
+  if (stage_vt1) {
+    double* s0 = sm + ((nv + 1) / 2 + 1);
+    double* s1 = s0 + ru0 * rv0;
+    for (int idx = tid; idx < ru0 * rv0; idx += kThreads) s0[idx] = v0[(idx % ru0) + (size_t)(idx / ru0) * ld0];
+    for (int idx = tid; idx < ru1 * rv1; idx += kThreads) s1[idx] = v1[(idx % ru1) + (size_t)(idx / ru1) * ld1];
+    v0 = s0; v1 = s1; ld0 = ru0; ld1 = ru1;
+  }
+  if (nd.parent >= 0) {
+    const int* P = perms + nd.Pv;
+    for (int i = tid; i < nv; i += kThreads) pinv[P[i]] = i;
+  }
+  __syncthreads();
   double* Df = scratch + scratch_off[blockIdx.x];
   const double* B01 = vals + nd.B01;
   const double* B10 = vals + nd.B10;
@@ -282,33 +301,30 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
     else if (i < ru0) {  // B01 * Vt1(c1)^H
       int b = j - ru0;
       v = 0.;
-      for (int q = 0; q < rv1; q++) v += B01[i + (size_t)q * ru0] * child_Vt1(fact, c1, b, q);
+      for (int q = 0; q < rv1; q++) v += B01[i + (size_t)q * ru0] * v1[b + q * ld1];
     } else {             // B10 * Vt1(c0)^H
       int a = i - ru0;
       v = 0.;
-      for (int q = 0; q < rv0; q++) v += B10[a + (size_t)q * ru1] * child_Vt1(fact, c0, j, q);
+      for (int q = 0; q < rv0; q++) v += B10[a + (size_t)q * ru1] * v0[j + q * ld0];
     }
     Df[i + (size_t)j * m] = v;
   }
   if (nd.parent < 0) return;
   // Vd = dense(V) = P_v [I; E_v] is never formed: row j of Vd is row
   // pinv[j] of [I; E_v]; only the inverse permutation sits in smem.
-  const int rv = nd.v_rank, nv = rv0 + rv1, kv = nv - rv;
-  const int* P = perms + nd.Pv;
   const double* E = vals + nd.Ev;
-  int* pinv = reinterpret_cast<int*>(sm);
-  for (int i = tid; i < nv; i += kThreads) pinv[P[i]] = i;
-  __syncthreads();
   double* Vh = fact + nd.F + (size_t)nd.k * m;
   for (int idx = tid; idx < m * rv; idx += kThreads) {
     int i = idx % m, c = idx / m;
     double v = 0.;
-    const DNode& cc = i < ru0 ? c0 : c1;
-    const int a = i < ru0 ? i : i - ru0, qoff = i < ru0 ? 0 : rv0, nq = i < ru0 ? rv0 : rv1;
+    const bool first = i < ru0;
+    const double* vv = first ? v0 : v1;
+    const int ldv_ = first ? ld0 : ld1;
+    const int a = first ? i : i - ru0, qoff = first ? 0 : rv0, nq = first ? rv0 : rv1;
     for (int q = 0; q < nq; q++) {
       const int pi = pinv[qoff + q];
       const double vd = pi < rv ? (pi == c ? 1. : 0.) : E[(pi - rv) + (size_t)c * kv];
-      v += child_Vt1(fact, cc, a, q) * vd;
+      v += vv[a + q * ldv_] * vd;
     }
     Vh[i + (size_t)c * m] = v;
   }
@@ -324,7 +340,7 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
 // tile, B fragments (E^T) stay in registers across the tile's row blocks.
 // HBM-bound: reads D once, writes the m x (k + r) block once.
 template <int TJ>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                      const double* __restrict__ vals, const int* __restrict__ perms,
                      double* __restrict__ fact, const double* __restrict__ scratch,
@@ -341,22 +357,23 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
   double* W1t = A + (size_t)(k + rv) * m;
   constexpr int LD = TJ + 1;
   constexpr int RT = TJ / 8;       // row tiles of the output per column tile
-  constexpr int KS = 16;           // k-steps held in registers (r <= 64 per pass)
+  constexpr int KS = 8;            // k-steps held in registers (r <= 32 per pass)
   double* Dn = sm;                 // m x LD : Dn[i*LD + jj] = Dsrc[i, j0+jj]
   int* Ps = reinterpret_cast<int*>(Dn + (size_t)m * LD);   // m
   for (int i = tid; i < m; i += kThreads) Ps[i] = P[i];
   for (int j0 = 0; j0 < m; j0 += TJ) {
     const int tj = min(TJ, m - j0);
     __syncthreads();
-    for (int idx = tid; idx < m * TJ; idx += kThreads) {
-      int i = idx % m, jj = idx / m;
-      Dn[i * LD + jj] = jj < tj ? Dsrc[i + (size_t)(j0 + jj) * m] : 0.;
+    for (int jj = warp; jj < TJ; jj += kWarps) {
+      const double* src = Dsrc + (size_t)(j0 + jj) * m;
+      const bool jin = jj < tj;
+      for (int i = lane; i < m; i += 32) Dn[i * LD + jj] = jin ? src[i] : 0.;
     }
     __syncthreads();
     // W1^T[j, l] = Dp[l, j]
-    for (int idx = tid; idx < r * tj; idx += kThreads) {
-      int jj = idx % tj, l = idx / tj;
-      W1t[(j0 + jj) + (size_t)l * m] = Dn[Ps[l] * LD + jj];
+    for (int l = warp; l < r; l += kWarps) {
+      const double* src = Dn + Ps[l] * LD;
+      for (int jj = lane; jj < tj; jj += 32) W1t[(j0 + jj) + (size_t)l * m] = src[jj];
     }
     // W0^T tile (tj x k), 8-column slabs over the warps
     for (int i0 = warp * 8; i0 < k; i0 += kWarps * 8) {
@@ -1575,9 +1592,12 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       ulv_vh_leaf_kernel<<<cnt, kThreads, 0, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p);
       launches_++;
     } else {
-      size_t smem = sizeof(int) * (size_t)(mm + 8);   // inverse permutation of V
+      // inverse permutation of V + (when it fits) the two children's Vt1 blocks
+      const size_t need = sizeof(double) * ((size_t)(mm + 1) / 2 + 2 + (size_t)mm * mm);
+      const int stage = need <= 160 * 1024;
+      size_t smem = stage ? need : sizeof(int) * (size_t)(mm + 8);
       set_smem(ulv_build_inner_kernel, smem);
-      ulv_build_inner_kernel<<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
+      ulv_build_inner_kernel<<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so, stage);
       launches_++;
     }
     if (cnt == 1 && L.host[L.hptr[h]] == 0) {   // the root: LU
