@@ -964,11 +964,19 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
 // ulv_build_inner_kernel, or D itself for a single-node tree) -> LU with
 // partial pivoting, in place.                       (factor.hpp:104-107)
 __global__ void __launch_bounds__(kThreads)
-ulv_root_lu_kernel(double* __restrict__ A, int n, int* __restrict__ piv) {
+ulv_root_lu_kernel(double* __restrict__ Ag, int n, int* __restrict__ piv, int use_smem) {
+  extern __shared__ double smA[];
   __shared__ double rv[kWarps];
   __shared__ int ri[kWarps];
   __shared__ int pivrow;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the reduced system at the root is small (sum of two ranks): factor it in
+  // shared memory when it fits, every step is a latency chain of barriers
+  double* A = use_smem ? smA : Ag;
+  if (use_smem) {
+    for (int idx = tid; idx < n * n; idx += kThreads) A[idx] = Ag[idx];
+    __syncthreads();
+  }
   for (int j = 0; j < n; j++) {
     // pivot search in column j
     double best = -1.;
@@ -1002,17 +1010,19 @@ ulv_root_lu_kernel(double* __restrict__ A, int n, int* __restrict__ piv) {
     __syncthreads();
     const double d = A[j + (size_t)j * n];
     const double inv = d != 0. ? 1. / d : 0.;
-    __syncthreads();
-    for (int i = j + 1 + tid; i < n; i += kThreads) A[i + (size_t)j * n] *= inv;
-    __syncthreads();
-    // rank-1 update of the trailing block
+    // scale the column and update the trailing block in one pass (each thread
+    // recomputes the multiplier it needs)
     const int nt = n - j - 1;
     for (int idx = tid; idx < nt * nt; idx += kThreads) {
       int i = j + 1 + idx % nt, c = j + 1 + idx / nt;
-      A[i + (size_t)c * n] -= A[i + (size_t)j * n] * A[j + (size_t)c * n];
+      A[i + (size_t)c * n] -= (A[i + (size_t)j * n] * inv) * A[j + (size_t)c * n];
     }
     __syncthreads();
+    for (int i = j + 1 + tid; i < n; i += kThreads) A[i + (size_t)j * n] *= inv;
+    __syncthreads();
   }
+  if (use_smem)
+    for (int idx = tid; idx < n * n; idx += kThreads) Ag[idx] = A[idx];
 }
 
 __global__ void copy_block_kernel(const double* __restrict__ src, double* __restrict__ dst, long long n) {
@@ -1138,12 +1148,16 @@ __global__ void __launch_bounds__(kThreads)
 ulv_root_solve_kernel(const DNode* __restrict__ nodes, const double* __restrict__ vals,
                       const double* __restrict__ fact, const int* __restrict__ piv,
                       double* __restrict__ b, int ldb, const double* __restrict__ zsol,
-                      const double* __restrict__ fsol, double* __restrict__ xsol, int s) {
+                      const double* __restrict__ fsol, double* __restrict__ xsol, int s,
+                      int use_smem) {
   extern __shared__ double sm[];
   const DNode nd = nodes[0];
   const int col = blockIdx.x, tid = threadIdx.x;
   const int n = nd.m;
   double* x = sm;
+  double* As = sm + ((n + 1) & ~1);   // LU factors staged in smem when they fit
+  if (use_smem)
+    for (int idx = tid; idx < n * n; idx += kThreads) As[idx] = fact[nd.F + idx];
   if (nd.leaf) {
     const double* bb = b + (size_t)col * ldb;
     for (int i = tid; i < n; i += kThreads) x[i] = bb[i];
@@ -1164,7 +1178,7 @@ ulv_root_solve_kernel(const DNode* __restrict__ nodes, const double* __restrict_
     }
   }
   __syncthreads();
-  const double* A = fact + nd.F;
+  const double* A = use_smem ? As : fact + nd.F;
   if (tid == 0)
     for (int j = 0; j < n; j++) {
       int p = piv[j];
@@ -1605,7 +1619,12 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       const long long n2 = (long long)root.m * root.m;
       const double* src = root.leaf ? vals_.p + root.D : scratch_.p;  // slab offset 0 of its class
       copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(src, fact_.p + root.F, n2);
-      ulv_root_lu_kernel<<<1, kThreads, 0, st>>>(fact_.p + root.F, root.m, rootpiv_.p);
+      {
+        const size_t bytes = sizeof(double) * (size_t)root.m * root.m;
+        const int use_smem = bytes <= 200 * 1024;
+        set_smem(ulv_root_lu_kernel, use_smem ? bytes : 0);
+        ulv_root_lu_kernel<<<1, kThreads, use_smem ? bytes : 0, st>>>(fact_.p + root.F, root.m, rootpiv_.p, use_smem);
+      }
       launches_ += 2;
       continue;
     }
@@ -1689,9 +1708,11 @@ void HSSEngine::solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaSt
 }
 
 void HSSEngine::solve_root(int s, double* dB, int ldB, cudaStream_t st) {
-  size_t smem = sizeof(double) * (size_t)std::max(hn_[0].m, 1);
+  const size_t nn = (size_t)std::max(hn_[0].m, 1);
+  const int use_smem = sizeof(double) * (nn * nn + nn + 2) <= 200 * 1024;
+  size_t smem = sizeof(double) * (use_smem ? nn * nn + nn + 2 : nn);
   set_smem(ulv_root_solve_kernel, smem);
-  ulv_root_solve_kernel<<<s, kThreads, smem, st>>>(dn_.p, vals_.p, fact_.p, rootpiv_.p, dB, ldB, zsol_.p, fsol_.p, xsol_.p, s);
+  ulv_root_solve_kernel<<<s, kThreads, smem, st>>>(dn_.p, vals_.p, fact_.p, rootpiv_.p, dB, ldB, zsol_.p, fsol_.p, xsol_.p, s, use_smem);
   launches_++;
 }
 
