@@ -115,6 +115,11 @@ int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
 int SB200_d_blr_compress_and_factor(CSPStructMat* S, int n, const double* A,
                                     int ldA, const CSPOptions* opts,
                                     double pivot_threshold);
+/* Same with the dense matrix already resident on the device (dA: device
+ * pointer); the engine keeps its own working copy. */
+int SB200_d_blr_compress_and_factor_device(CSPStructMat* S, int n, const double* dA,
+                                           int ldA, const CSPOptions* opts,
+                                           double pivot_threshold);
 int SB200_d_blr_tiles(const CSPStructMat S);
 
 /* Reads a reference HSS dump (HSSMatrix<double>::write, reference

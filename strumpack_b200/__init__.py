@@ -53,6 +53,7 @@ SYMBOLS = {
     "SP_d_struct_shift": (_i, [_vp, _d]),
     "SB200_d_hss_from_kernel": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp]),
     "SB200_d_blr_compress_and_factor": (_i, [_pvp, _i, _vp, _i, _po, _d]),
+    "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_tiles": (_i, [_vp]),
     "SB200_d_hss_read": (_i, [_pvp, C.c_char_p]),
     "SB200_d_hss_write": (_i, [_vp, C.c_char_p]),
@@ -346,6 +347,18 @@ class BLRMatrix(StructuredMatrix):
         _check(lib().SB200_d_blr_compress_and_factor(
             C.byref(h), A.shape[0], A.ctypes.data, A.shape[0], C.byref(opts),
             float(pivot_threshold)), "compress_and_factor")
+        return cls(h.value)
+
+    @classmethod
+    def compress_and_factor_device(cls, dA, opts=None, pivot_threshold=-1.0):
+        """dA: torch float64 CUDA tensor holding the column-major n x n matrix
+        (i.e. the transpose of a contiguous (n, n) row-major tensor)."""
+        n = dA.shape[0]
+        opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
+        h = C.c_void_p()
+        _check(lib().SB200_d_blr_compress_and_factor_device(
+            C.byref(h), n, C.c_void_p(dA.data_ptr()), n, C.byref(opts),
+            float(pivot_threshold)), "compress_and_factor_device")
         return cls(h.value)
 
     @property

@@ -36,57 +36,151 @@ struct TileDesc {     // one off-diagonal tile of the current step
 };
 
 // ---------------------------------------------------------------- diagonal LU
-// LU with partial pivoting of one diagonal tile, in place (ld = N), plus the
-// reference's small-pivot replacement (DenseTile::LU, DenseTile.cpp:111-117).
+// Blocked LU with partial pivoting of one diagonal tile, in place (ld = N), plus
+// the reference's small-pivot replacement (DenseTile::LU, DenseTile.cpp:111-117).
+// One CTA; the NB-column panel is factored in shared memory (one latency chain
+// per column), the row swaps are applied to the rest of the tile, U12 =
+// L11^{-1} A12 is formed in shared memory and the trailing block is updated on
+// the fp64 tensor pipe with L21 (smem) x U12 (smem), C streamed from global.
 // ipiv: LAPACK style (1-based, local); g: the same permutation as a gather.
+template <int NB>
 __global__ void __launch_bounds__(kThreads)
 blr_getrf_kernel(double* __restrict__ A, long long ld, int n, int* __restrict__ ipiv,
-                 int* __restrict__ g, double thresh) {
+                 int* __restrict__ g, double thresh, int ldp) {
+  extern __shared__ double sm[];
+  double* P = sm;                        // ldp x NB panel (rows j0..n)
+  double* U12 = P + (size_t)ldp * NB;    // NB x (n - j0 - NB), ld = NB + 4... stored [k + c*LDU]
+  constexpr int LDU = NB + 4;
   __shared__ double rv[kWarps];
   __shared__ int ri[kWarps];
   __shared__ int pivrow;
+  __shared__ int pl[NB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int j = 0; j < n; j++) {
-    double best = -1.;
-    int bi = j;
-    for (int i = j + tid; i < n; i += kThreads) {
-      double v = fabs(A[i + j * ld]);
-      if (v > best) { best = v; bi = i; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (lane == 0) { rv[warp] = best; ri[warp] = bi; }
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int jb = min(NB, n - j0), mp = n - j0;
+    for (int c = warp; c < jb; c += kWarps)
+      for (int i = lane; i < mp; i += 32) P[i + c * ldp] = A[(j0 + i) + (j0 + c) * ld];
     __syncthreads();
-    if (tid == 0) {
-      double b = rv[0]; int p = ri[0];
-      for (int w = 1; w < kWarps; w++)
-        if (rv[w] > b || (rv[w] == b && ri[w] < p)) { b = rv[w]; p = ri[w]; }
-      pivrow = p;
-      ipiv[j] = p + 1;
-    }
-    __syncthreads();
-    const int p = pivrow;
-    if (p != j)
-      for (int c = tid; c < n; c += kThreads) {
-        double t = A[j + c * ld];
-        A[j + c * ld] = A[p + c * ld];
-        A[p + c * ld] = t;
+    for (int c = 0; c < jb; c++) {
+      double best = -1.;
+      int bi = c;
+      for (int i = c + tid; i < mp; i += kThreads) {
+        double v = fabs(P[i + c * ldp]);
+        if (v > best) { best = v; bi = i; }
       }
-    __syncthreads();
-    const double d = A[j + j * ld];
-    const double inv = d != 0. ? 1. / d : 0.;
-    __syncthreads();
-    for (int i = j + 1 + tid; i < n; i += kThreads) A[i + j * ld] *= inv;
-    __syncthreads();
-    const int nt = n - j - 1;
-    for (int c = j + 1 + warp; c < n; c += kWarps) {
-      const double ujc = A[j + c * ld];
-      for (int i = j + 1 + lane; i < n; i += 32) A[i + c * ld] -= A[i + j * ld] * ujc;
+      for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) { rv[warp] = best; ri[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        double b = rv[0]; int p = ri[0];
+        for (int w = 1; w < kWarps; w++)
+          if (rv[w] > b || (rv[w] == b && ri[w] < p)) { b = rv[w]; p = ri[w]; }
+        pivrow = p;
+        pl[c] = p;
+        ipiv[j0 + c] = j0 + p + 1;
+      }
+      __syncthreads();
+      const int p = pivrow;
+      if (p != c && tid < jb) {
+        double t = P[c + tid * ldp];
+        P[c + tid * ldp] = P[p + tid * ldp];
+        P[p + tid * ldp] = t;
+      }
+      __syncthreads();
+      const double d = P[c + c * ldp];
+      const double inv = d != 0. ? 1. / d : 0.;
+      // rank-1 update of the remaining panel columns, one warp per column; the
+      // multipliers are recomputed on the fly and stored by the last warp pass
+      for (int cc = c + 1 + warp; cc < jb; cc += kWarps) {
+        const double u = P[c + cc * ldp];
+        for (int i = c + 1 + lane; i < mp; i += 32) P[i + cc * ldp] -= (P[i + c * ldp] * inv) * u;
+      }
+      __syncthreads();
+      for (int i = c + 1 + tid; i < mp; i += kThreads) P[i + c * ldp] *= inv;
+      __syncthreads();
     }
-    (void)nt;
+    // row swaps on the columns outside the panel
+    for (int col = tid; col < n; col += kThreads) {
+      if (col >= j0 && col < j0 + jb) continue;
+      double* a = A + col * ld + j0;
+      for (int c = 0; c < jb; c++) {
+        const int p = pl[c];
+        if (p != c) { double t = a[c]; a[c] = a[p]; a[p] = t; }
+      }
+    }
+    // panel back to global
+    for (int c = warp; c < jb; c += kWarps)
+      for (int i = lane; i < mp; i += 32) A[(j0 + i) + (j0 + c) * ld] = P[i + c * ldp];
+    __syncthreads();
+    const int nt = n - j0 - jb;        // trailing columns
+    if (nt <= 0) break;
+    // U12 = L11^{-1} A12, one thread per column, result to smem and global
+    for (int col = tid; col < nt; col += kThreads) {
+      double* a = A + (j0 + jb + col) * ld + j0;
+      double x[NB];
+#pragma unroll
+      for (int k = 0; k < NB; k++) x[k] = k < jb ? a[k] : 0.;
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+#pragma unroll
+        for (int i = 0; i < NB; i++)
+          if (i > k && i < jb) x[i] -= P[i + k * ldp] * x[k];
+      }
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        if (k < jb) a[k] = x[k];
+        U12[k + col * LDU] = x[k];
+      }
+    }
+    __syncthreads();
+    // A22 -= L21 U12 : 16x16 output tiles over the warps, K = jb
+    {
+      const int mr = mp - jb;
+      const int gq = lane >> 2, t = lane & 3;
+      const int tm = (mr + 15) >> 4, tn = (nt + 15) >> 4;
+      double* C = A + (j0 + jb) + (j0 + jb) * ld;
+      const double* L21 = P + jb;
+      for (int tile = warp; tile < tm * tn; tile += kWarps) {
+        const int i0 = (tile % tm) << 4, c0 = (tile / tm) << 4;
+        double c[2][2][2];
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+          for (int tj = 0; tj < 2; tj++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int ii = i0 + ti * 8 + gq, jj = c0 + tj * 8 + 2 * t + e;
+              c[ti][tj][e] = (ii < mr && jj < nt) ? C[ii + jj * ld] : 0.;
+            }
+#pragma unroll
+        for (int k0 = 0; k0 < NB; k0 += 4) {
+          const int kk = k0 + t;
+          const bool kin = kk < jb;
+          const int ia0 = i0 + gq, ia1 = ia0 + 8, jb0 = c0 + gq, jb1 = jb0 + 8;
+          const double a0 = (kin && ia0 < mr) ? -L21[ia0 + kk * ldp] : 0.;
+          const double a1 = (kin && ia1 < mr) ? -L21[ia1 + kk * ldp] : 0.;
+          const double b0 = (kin && jb0 < nt) ? U12[kk + jb0 * LDU] : 0.;
+          const double b1 = (kin && jb1 < nt) ? U12[kk + jb1 * LDU] : 0.;
+          dmma(c[0][0][0], c[0][0][1], a0, b0);
+          dmma(c[0][1][0], c[0][1][1], a0, b1);
+          dmma(c[1][0][0], c[1][0][1], a1, b0);
+          dmma(c[1][1][0], c[1][1][1], a1, b1);
+        }
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++)
+#pragma unroll
+          for (int tj = 0; tj < 2; tj++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int ii = i0 + ti * 8 + gq, jj = c0 + tj * 8 + 2 * t + e;
+              if (ii < mr && jj < nt) C[ii + jj * ld] = c[ti][tj][e];
+            }
+      }
+    }
     __syncthreads();
   }
   if (thresh > 0.)
@@ -94,6 +188,7 @@ blr_getrf_kernel(double* __restrict__ A, long long ld, int n, int* __restrict__ 
       double d = A[i + i * ld];
       if (fabs(d) < thresh) A[i + i * ld] = d < 0 ? -thresh : thresh;
     }
+  __syncthreads();
   if (tid == 0) {
     for (int i = 0; i < n; i++) g[i] = i;
     for (int i = 0; i < n; i++) {
@@ -414,7 +509,8 @@ static void refine(std::vector<int>& tiles, int size, int leaf) {
   } else tiles.push_back(size);
 }
 
-BLREngine::BLREngine(int n, const double* hostA, int ldA, const BLROpts& o, bool do_factor)
+BLREngine::BLREngine(int n, const double* hostA, int ldA, const BLROpts& o, bool do_factor,
+                     bool device_input)
     : n_(n), opts_(o) {
   if (n <= 0) throw std::invalid_argument("empty matrix");
   std::vector<int> tiles;
@@ -440,7 +536,8 @@ BLREngine::BLREngine(int n, const double* hostA, int ldA, const BLROpts& o, bool
     }
   A_.alloc((size_t)n * n);
   SB200_CUDA(cudaMemcpy2D(A_.p, sizeof(double) * n, hostA, sizeof(double) * ldA,
-                          sizeof(double) * n, n, cudaMemcpyHostToDevice));
+                          sizeof(double) * n, n,
+                          device_input ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
   lr_.alloc((size_t)std::max<long long>(o_, 1));
   doff_.upload(off_.data(), off_.size());
   dlroff_.upload(lroff_.data(), lroff_.size());
@@ -511,8 +608,20 @@ void BLREngine::run(bool do_factor) {
     const int cnt = step_ptr[i + 1] - step_ptr[i];
     double* Aii = A_.p + off_[i] + (size_t)off_[i] * n;
     if (do_factor) {
-      blr_getrf_kernel<<<1, kThreads, 0, st>>>(Aii, n, m, piv_.p + off_[i], gperm_.p + off_[i],
-                                               opts_.pivot_threshold);
+      {
+        const int lp = smem_ld(maxtile_);
+        if (maxtile_ <= 256) {
+          const size_t smem = sizeof(double) * ((size_t)lp * 32 + (size_t)36 * maxtile_);
+          set_smem(blr_getrf_kernel<32>, smem);
+          blr_getrf_kernel<32><<<1, kThreads, smem, st>>>(Aii, n, m, piv_.p + off_[i], gperm_.p + off_[i],
+                                                          opts_.pivot_threshold, lp);
+        } else {
+          const size_t smem = sizeof(double) * ((size_t)lp * 16 + (size_t)20 * maxtile_);
+          set_smem(blr_getrf_kernel<16>, smem);
+          blr_getrf_kernel<16><<<1, kThreads, smem, st>>>(Aii, n, m, piv_.p + off_[i], gperm_.p + off_[i],
+                                                          opts_.pivot_threshold, lp);
+        }
+      }
       blr_upper_transpose_kernel<<<64, 256, 0, st>>>(Aii, n, m, UT.p);
       launches_ += 2;
     }

@@ -20,7 +20,8 @@ class BLREngine {
  public:
   // do_factor = true : BLRMatrix::compress_and_factor(A, weak admissibility, RL)
   // do_factor = false: BLRMatrix::compress (all off-diagonal tiles low rank)
-  BLREngine(int n, const double* hostA, int ldA, const BLROpts& o, bool do_factor);
+  BLREngine(int n, const double* A, int ldA, const BLROpts& o, bool do_factor,
+            bool device_input = false);   // A: host pointer, or device pointer if device_input
   int rows() const { return n_; }
   int cols() const { return n_; }
   int tiles() const { return nb_; }

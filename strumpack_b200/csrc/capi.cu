@@ -194,6 +194,21 @@ int SB200_d_blr_compress_and_factor(CSPStructMat* S, int n, const double* A, int
   });
 }
 
+int SB200_d_blr_compress_and_factor_device(CSPStructMat* S, int n, const double* dA, int ldA,
+                                           const CSPOptions* opts, double pivot_threshold) {
+  return guarded([&] {
+    require_gpu();
+    auto m = std::make_unique<Mat>();
+    m->type = SP_TYPE_BLR;
+    BLROpts bo;
+    bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
+    bo.leaf_size = opts->leaf_size; bo.max_rank = opts->max_rank;
+    bo.pivot_threshold = pivot_threshold;
+    m->blr = std::make_unique<BLREngine>(n, dA, ldA, bo, true, true);
+    *S = m.release();
+  });
+}
+
 int SB200_d_blr_tiles(const CSPStructMat S) {
   return (S && M(S)->blr) ? M(S)->blr->tiles() : 0;
 }

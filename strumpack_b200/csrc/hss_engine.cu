@@ -545,6 +545,15 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   extern __shared__ double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0 || nd.k == 0) return;
+  if (pmode >= 16) {
+    // experiment (SB200_QR_SKEW): de-phase every other CTA so that co-resident
+    // equal-size nodes do not run their panel / trailing phases in lockstep
+    if ((blockIdx.x / 148) & 1) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)(pmode >> 4) * 1000) { }
+    }
+    pmode &= 15;
+  }
   const int m = nd.m, k = nd.k, naug = nd.naug, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
@@ -1278,6 +1287,7 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   SB200_CUDA(cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, dev));
   if (const char* e = std::getenv("SB200_QR_SPLIT")) qr_split_ = std::atoi(e);
   if (const char* e = std::getenv("SB200_QR_REGPANEL")) qr_regpanel_ = std::atoi(e);
+  if (const char* e = std::getenv("SB200_QR_SKEW")) qr_skew_ = std::atoi(e);   // in 1000 clk
   build_tables();
 }
 HSSEngine::~HSSEngine() {
@@ -1648,7 +1658,8 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       const bool split = qr_split_ && cnt >= 2 * nsm_ && kmax > nb_;
       const int npan = split ? (kmax + nb_ - 1) / nb_ : 1;
       for (int pp = 0; pp < npan; pp++)
-        for (int phase = split ? 1 : 0; phase <= (split ? 2 : 0); phase++) {
+        for (int phase0 = split ? 1 : 0; phase0 <= (split ? 2 : 0); phase0++) {
+          const int phase = phase0 + (h == 0 ? (qr_skew_ << 4) : 0);
           if (nb_ == 32 && mm <= 256 && qr_regpanel_) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true>, smem);
             ulv_qr_kernel<32, true><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
           } else if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, false>, smem);

@@ -121,7 +121,7 @@ class HSSEngine {
   bool factored_ = false;
   long long launches_ = 0;
   int nb_ = 32;
-  int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1;   // switches; env SB200_QR_*
+  int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0;   // switches; env SB200_QR_*
   bool profile_ = false;
   cudaEvent_t ev_[2] = {nullptr, nullptr};
 };
