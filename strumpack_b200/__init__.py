@@ -75,6 +75,7 @@ SYMBOLS = {
     "SB200_d_hss_file_copy": (_i, [C.c_char_p, C.c_char_p]),
     "SB200_d_struct_levels": (_i, [_vp]),
     "SB200_d_struct_factor_nonzeros": (_ll, [_vp]),
+    "SB200_d_struct_ulv_data": (_i, [_vp, _vp, _vp, _vp]),
     "SB200_d_struct_flops": (_ll, [_vp, _i]),
     "SB200_d_struct_set_profile": (_i, [_vp, _i]),
     "SB200_d_struct_kernel_ms": (_d, [_vp, _i]),
@@ -243,6 +244,15 @@ class StructuredMatrix:
     @property
     def factor_nonzeros(self):
         return lib().SB200_d_struct_factor_nonzeros(self._h)
+
+    def ulv_data(self):
+        """(factor arena, T arena) of the ULV factorization as numpy arrays
+        (reference accessor HSSMatrix::ULV(), HSSMatrix.hpp:497)."""
+        sz = np.zeros(2, dtype=np.int64)
+        _check(lib().SB200_d_struct_ulv_data(self._h, None, None, sz.ctypes.data), "ulv_data")
+        f = np.empty(int(sz[0])); t = np.empty(int(sz[1]))
+        _check(lib().SB200_d_struct_ulv_data(self._h, f.ctypes.data, t.ctypes.data, sz.ctypes.data), "ulv_data")
+        return f, t
 
     @property
     def launches(self):

@@ -375,6 +375,13 @@ int SB200_d_struct_levels(const CSPStructMat S) {
 long long int SB200_d_struct_factor_nonzeros(const CSPStructMat S) {
   return S ? hss(S).factor_nonzeros() : 0;
 }
+int SB200_d_struct_ulv_data(const CSPStructMat S, double* factors, double* tfactors,
+                            long long int* sizes) {
+  return guarded([&] {
+    if (!S) throw std::invalid_argument("null handle");
+    hss(S).export_ulv(factors, tfactors, sizes);
+  });
+}
 long long int SB200_d_struct_flops(const CSPStructMat S, int which) {
   if (!S) return 0;
   const auto& h = hss(S).host();

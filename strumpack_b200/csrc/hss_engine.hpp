@@ -78,6 +78,8 @@ class HSSEngine {
 
   long long factor_nonzeros() const { return fact_nnz_; }
   long long launches() const { return launches_; }
+  // ULV factors to host (HSSMatrix::ULV()); null pointers: sizes only
+  void export_ulv(double* factors, double* tfactors, long long* sizes);
   // optional live timing of the dominant kernel (leaf-class QR) with CUDA
   // events on the launching stream; ms of the last factor() call
   void set_profile(bool on);
@@ -121,7 +123,7 @@ class HSSEngine {
   bool factored_ = false;
   long long launches_ = 0;
   int nb_ = 32;
-  int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0;   // switches; env SB200_QR_*
+  int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0, qr_ll_ = 0;   // switches; env SB200_QR_*
   bool profile_ = false;
   cudaEvent_t ev_[2] = {nullptr, nullptr};
 };
