@@ -42,7 +42,7 @@ hss_up_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
               const double* __restrict__ vals, const int* __restrict__ perms,
               const double* __restrict__ x, int ldx, double* __restrict__ t1,
               int s) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   const int c = blockIdx.y, tid = threadIdx.x;
   const int r = TRANS ? nd.u_rank : nd.v_rank;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads)
 hss_down_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                 const double* __restrict__ vals, const int* __restrict__ perms,
                 const double* __restrict__ t1, double* __restrict__ t2, int s) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int id = list[blockIdx.x];
   const DNode nd = nodes[id];
   if (nd.leaf) return;
@@ -146,7 +146,7 @@ hss_leaf_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                 const double* __restrict__ vals, const int* __restrict__ perms,
                 const double* __restrict__ x, int ldx, const double* __restrict__ t2,
                 double* __restrict__ y, int ldy, int s) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   const int c = blockIdx.y, tid = threadIdx.x;
   const int nin = TRANS ? nd.rows : nd.cols;    // length of the x slice
@@ -264,7 +264,7 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
                        const double* __restrict__ vals, const int* __restrict__ perms,
                        double* __restrict__ fact, double* __restrict__ scratch,
                        const long long* __restrict__ scratch_off, int stage_vt1) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int id = list[blockIdx.x];
   const DNode nd = nodes[id];
   if (nd.leaf) return;
@@ -345,7 +345,7 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
                      const double* __restrict__ vals, const int* __restrict__ perms,
                      double* __restrict__ fact, const double* __restrict__ scratch,
                      const long long* __restrict__ scratch_off) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0) return;
   const int m = nd.m, r = nd.u_rank, k = nd.k, rv = nd.v_rank, tid = threadIdx.x;
@@ -429,13 +429,15 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
 //   phase T  W2^T       = W^T T                         (A from accumulators
 //            via the K-slot permutation a = 8*at + 2t + e, B = T)
 //   phase 2  C[i][n]   -= sum_a V[i][a] W2[a][n]       (A = V, B = -W2)
-template <int NB>
+// U = row tiles per prefetch group (2 U loads in flight per lane): the slab
+// comes from L2 at ~1-2 k clk under load, memory-level parallelism per warp is
+// what bounds the update when few warps are in this phase.
+template <int NB, int U = 4>
 __device__ __forceinline__ void slab_update(double* __restrict__ Cg, int ldc, int mp,
                                             int cw, const double* __restrict__ Vs,
                                             int ldv, const double* __restrict__ Ts,
                                             int ldt, int lane) {
   constexpr int NT = NB / 8;
-  constexpr int U = 4;   // row tiles per prefetch group (8 loads in flight)
   const int g = lane >> 2, t = lane & 3;
   const int nit = (mp + 7) >> 3;
   double wt[NT][2], wu[NT][2];   // two accumulator sets: shorter DMMA chains
@@ -524,6 +526,157 @@ __device__ __forceinline__ void slab_update(double* __restrict__ Cg, int ldc, in
   }
 }
 
+// K-slot / column permutation used by slab2_update inside every 8-wide tile:
+// sigma = (0,2,1,3,6,4,7,5).  sigma(2q+1) - sigma(2q) = 2 (mod 4) and
+// {sigma(2t+e) mod 4 : t} = {0,1,2,3} make both 128-bit fragment loads of V
+// from shared memory (ld = 4 mod 16 doubles) bank-conflict free.
+__device__ __forceinline__ int sig8(int j) { return (0x57463120u >> (4 * j)) & 7; }
+
+__device__ __forceinline__ double2 ld2(const double* p, bool pred) {
+  return pred ? *reinterpret_cast<const double2*>(p) : make_double2(0., 0.);
+}
+
+// Trailing update of TWO adjacent 8-column slabs by one warp (same math as
+// slab_update).  The LSU wavefront count, not the tensor pipe, bounds
+// slab_update (ncu: l1tex data pipe 54-63 % busy over the whole kernel, DMMA
+// 31 %): every DMMA takes a 64-bit V fragment from shared memory (2 wavefronts)
+// and the 8-byte C accesses touch 4-8 lines per instruction.  Here
+//  * every V fragment load is 128 bits wide and feeds 4 DMMAs (two k-steps or
+//    two row tiles, times two slabs);
+//  * C moves in 16-byte pieces: phase 1 takes rows (2t, 2t+1) of column g as
+//    the two k-steps of a tile (K-slot permutation), phase 2 works on 16-row
+//    blocks whose two DMMA row tiles are the even / odd rows, so a lane owns
+//    rows (2g, 2g+1) of two columns and an instruction covers whole 128-byte
+//    lines;
+//  * W^T T is chained through the accumulators with the column permutation
+//    sigma, W2 is already in B-fragment layout for phase 2 (no shuffles).
+// Needs 16-byte aligned columns: ldc even, Cg 16-byte aligned, mp even.
+template <int NB>
+__device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, int mp,
+                                             int cw0, int cw1,
+                                             const double* __restrict__ Vs, int ldv,
+                                             const double* __restrict__ Ts, int ldt,
+                                             int lane) {
+  constexpr int NT = NB / 8;
+  // row blocks per load group: with 16-column panels there are 4 CTAs of 4
+  // warps per SM and on average ~2 warps per scheduler in this phase, so each
+  // warp must keep more of the slab in flight to cover the L2 round trip
+  constexpr int U1 = NB <= 16 ? 8 : 4, U2 = NB <= 16 ? 4 : 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int sg = sig8(g), s0 = sig8(2 * t), s1 = sig8(2 * t + 1);
+  double wt[2][NT][2];
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int q = 0; q < NT; q++) wt[s][q][0] = wt[s][q][1] = 0.;
+  // ---- phase 1: W^T[n][a] = sum_i C[i][n] V[i][a]; k-steps (e) of row block
+  // i0 are rows i0 + 2t + e; B column g is reflector 8 at + sigma(g)
+  {
+    const int nb8 = (mp + 7) >> 3;
+    const bool in0 = g < cw0, in1 = g < cw1;
+    const double* C0 = Cg + (size_t)g * ldc + 2 * t;
+    const double* C1 = Cg + (size_t)(8 + g) * ldc + 2 * t;
+    const double* Vb = Vs + 2 * t + sg * ldv;
+    for (int ib0 = 0; ib0 < nb8; ib0 += U1) {
+      double2 c[U1][2];
+#pragma unroll
+      for (int u = 0; u < U1; u++) {
+        const int i0 = (ib0 + u) * 8;
+        const bool rin = i0 + 2 * t < mp;
+        c[u][0] = ld2(C0 + i0, rin && in0);
+        c[u][1] = ld2(C1 + i0, rin && in1);
+      }
+#pragma unroll
+      for (int u = 0; u < U1; u++) {
+        const int ib = ib0 + u;
+        if (ib < nb8) {
+#pragma unroll
+          for (int at = 0; at < NT; at++)
+            if (at <= ib) {   // V[i][a] = 0 for a > i
+              const double2 v = *reinterpret_cast<const double2*>(Vb + ib * 8 + at * 8 * ldv);
+              dmma(wt[0][at][0], wt[0][at][1], c[u][0].x, v.x);
+              dmma(wt[1][at][0], wt[1][at][1], c[u][1].x, v.x);
+              dmma(wt[0][at][0], wt[0][at][1], c[u][0].y, v.y);
+              dmma(wt[1][at][0], wt[1][at][1], c[u][1].y, v.y);
+            }
+        }
+      }
+    }
+  }
+  // ---- phase T: W2^T = W^T T.  wt[s][at][e] is the A fragment of k-step
+  // (at, e) with K slot t <-> reflector 8 at + sigma(2t+e); output column g <->
+  // reflector 8 atp + sigma(g), so w2[s][atp][e] = W2[8 atp + sigma(2t+e)][n = g]
+  double w2[2][NT][2];
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int q = 0; q < NT; q++) w2[s][q][0] = w2[s][q][1] = 0.;
+#pragma unroll
+  for (int atp = 0; atp < NT; atp++)
+#pragma unroll
+    for (int at = 0; at < NT; at++)
+      if (at <= atp) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const double bb = Ts[(at * 8 + (e ? s1 : s0)) + (atp * 8 + sg) * ldt];
+          dmma(w2[0][atp][0], w2[0][atp][1], wt[0][at][e], bb);
+          dmma(w2[1][atp][0], w2[1][atp][1], wt[1][at][e], bb);
+        }
+      }
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+#pragma unroll
+    for (int q = 0; q < NT; q++) { w2[s][q][0] = -w2[s][q][0]; w2[s][q][1] = -w2[s][q][1]; }
+  // ---- phase 2: C -= V W2 on 16-row blocks; DMMA row tile u holds rows
+  // r0 + 2g + u, so a lane owns rows (2g, 2g+1) of columns 2t and 2t+1
+  {
+    const int nb16 = (mp + 15) >> 4;
+    const bool k00 = 2 * t < cw0, k01 = 2 * t + 1 < cw0, k10 = 2 * t < cw1, k11 = 2 * t + 1 < cw1;
+    double* P00 = Cg + (size_t)(2 * t) * ldc + 2 * g;
+    double* P01 = P00 + ldc;
+    double* P10 = Cg + (size_t)(8 + 2 * t) * ldc + 2 * g;
+    double* P11 = P10 + ldc;
+    const double* Va0 = Vs + 2 * g + s0 * ldv;
+    const double* Va1 = Vs + 2 * g + s1 * ldv;
+    for (int ib0 = 0; ib0 < nb16; ib0 += U2) {
+      double2 a[U2][4];
+#pragma unroll
+      for (int u = 0; u < U2; u++) {
+        const int r0 = (ib0 + u) * 16;
+        const bool rin = r0 + 2 * g < mp;
+        a[u][0] = ld2(P00 + r0, rin && k00);
+        a[u][1] = ld2(P01 + r0, rin && k01);
+        a[u][2] = ld2(P10 + r0, rin && k10);
+        a[u][3] = ld2(P11 + r0, rin && k11);
+      }
+#pragma unroll
+      for (int u = 0; u < U2; u++) {
+        const int ib = ib0 + u;
+        if (ib < nb16) {
+          const int r0 = ib * 16;
+#pragma unroll
+          for (int atp = 0; atp < NT; atp++)
+            if (atp <= 2 * ib + 1) {   // V[i][a] = 0 for a > i
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                const double2 v = *reinterpret_cast<const double2*>((e ? Va1 : Va0) + r0 + atp * 8 * ldv);
+                dmma(a[u][0].x, a[u][1].x, v.x, w2[0][atp][e]);
+                dmma(a[u][2].x, a[u][3].x, v.x, w2[1][atp][e]);
+                dmma(a[u][0].y, a[u][1].y, v.y, w2[0][atp][e]);
+                dmma(a[u][2].y, a[u][3].y, v.y, w2[1][atp][e]);
+              }
+            }
+          const bool rin = r0 + 2 * g < mp;
+          if (rin && k00) *reinterpret_cast<double2*>(P00 + r0) = a[u][0];
+          if (rin && k01) *reinterpret_cast<double2*>(P01 + r0) = a[u][1];
+          if (rin && k10) *reinterpret_cast<double2*>(P10 + r0) = a[u][2];
+          if (rin && k11) *reinterpret_cast<double2*>(P11 + r0) = a[u][3];
+        }
+      }
+    }
+  }
+}
+
 // Blocked Householder QR of the first k columns of the m x naug factor block,
 // reflectors applied to all naug columns (right-looking, panel width NB).
 // One CTA per node, 2 CTAs per SM.
@@ -537,12 +690,17 @@ __device__ __forceinline__ void slab_update(double* __restrict__ Cg, int ldc, in
 //  * the NB x NB T factor is merged from the 8x8 ones (block dlarft);
 //  * the trailing matrix is updated slab by slab on the tensor pipe straight
 //    from L2 (slab_update<NB>), one warp per slab, no barrier.
-template <int NB, bool SMALL>
-__global__ void __launch_bounds__(kThreads, 2)
+//  NTH = 256: 2 CTAs per SM; NTH = 128 (register sub-panel only, NB = 16): 4
+//  CTAs per SM, i.e. four Householder column chains in flight per SM, so that
+//  the fp64 tensor pipe always finds a CTA in its trailing update.
+template <int NB, bool SMALL, int NTH, int MINB = (NTH == 128 ? 4 : 2)>
+__global__ void __launch_bounds__(NTH, MINB)
 ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
               double* __restrict__ fact, double* __restrict__ tfac, int ldv,
               int pmode, int pidx) {
-  extern __shared__ double sm[];
+  static_assert(NTH == 256 || SMALL, "the shared-memory sub-panel variant needs 8 warps");
+  constexpr int NWP = NTH / 32;
+  extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0 || nd.k == 0) return;
   if (pmode >= 16) {
@@ -568,6 +726,9 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   double* zs = nrm2s + NB;               // 2 x 16
   double* A = fact + nd.F;
   double* Tg = tfac + nd.T;
+  // every column of the factor block starts on a 16-byte boundary (even F, even m)
+  const bool wide = !(pmode & 8) && ((m & 1) == 0) && ((nd.F & 1) == 0);
+  pmode &= 7;
 #ifdef SB200_QR_TIMING
   long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -585,27 +746,31 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
     const int mp8 = (mp + 7) & ~7;
     if (pmode == 2) {
       // reload the explicit V (unit lower trapezoid) and T of this panel
-      for (int c = warp; c < NB; c += kWarps) {
+      for (int c = warp; c < NB; c += NWP) {
         const double* src = A + j0 + (size_t)(j0 + c) * m;
         double* dst = Vs + c * ldv;
         const bool cin = c < jb;
         for (int i = lane; i < mp8; i += 32)
           dst[i] = (cin && i < mp && i >= c) ? (i == c ? 1. : src[i]) : 0.;
       }
-      for (int idx = tid; idx < NB * NB; idx += kThreads) {
+      for (int idx = tid; idx < NB * NB; idx += NTH) {
         const int a = idx % NB, c = idx / NB;
         Ts[a + c * LDW] = (a < jb && c < jb && a <= c) ? Tg[a + (size_t)(j0 + c) * NB] : 0.;
       }
       __syncthreads();
     } else {
-    // ---- load panel (zero padded to mp8 rows / NB columns), clear T
-    for (int c = warp; c < NB; c += kWarps) {
+    // ---- load panel (zero padded to mp8 rows / NB columns), clear T.  The
+    // panel comes from L2 (it was just written by the trailing update): LDGSTS
+    // keeps every element of the panel in flight at once instead of one L2
+    // round trip per load -> store pair.
+    for (int c = warp; c < NB; c += NWP) {
       const double* src = A + j0 + (size_t)(j0 + c) * m;
       double* dst = Vs + c * ldv;
       const bool cin = c < jb;
-      for (int i = lane; i < mp8; i += 32) dst[i] = (cin && i < mp) ? src[i] : 0.;
+      for (int i = lane; i < mp8; i += 32) cp_async8(dst + i, src + i, cin && i < mp);
     }
-    for (int idx = tid; idx < NB * NB; idx += kThreads) Ts[(idx % NB) + (idx / NB) * LDW] = 0.;
+    cp_async_wait_all();
+    for (int idx = tid; idx < NB * NB; idx += NTH) Ts[(idx % NB) + (idx / NB) * LDW] = 0.;
     __syncthreads();
     QR_TICK(0)
     const int nsub = (jb + 7) >> 3;
@@ -872,13 +1037,13 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
         QR_TICK(1)
         {  // scale the last reflector of the sub-panel
           const int c = cs + sbw - 1;
-          for (int i = c + 1 + tid; i < mp; i += kThreads) Vs[i + c * ldv] *= scal_prev;
+          for (int i = c + 1 + tid; i < mp; i += NTH) Vs[i + c * ldv] *= scal_prev;
         }
       }
       __syncthreads();
       // ---- R entries of these columns to global; V explicit (unit diagonal)
-      if (warp < sbw) {
-        const int c = cs + warp;
+      for (int cw = warp; cw < sbw; cw += NWP) {
+        const int c = cs + cw;
         double* dst = A + j0 + (size_t)(j0 + c) * m;
         for (int i = lane; i <= c; i += 32) {
           dst[i] = (i == c && !SMALL) ? betas[c] : Vs[i + c * ldv];
@@ -904,7 +1069,7 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
         int tile = 0;
         for (int bj = 1; bj < nsub; bj++)
           for (int bi = 0; bi < bj; bi++, tile++)
-            if ((tile % kWarps) == warp) {
+            if ((tile % NWP) == warp) {
               const int g = lane >> 2, t = lane & 3;
               double c0 = 0., c1 = 0.;
               const double* va = Vs + t + (bi * 8 + g) * ldv;
@@ -917,14 +1082,14 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
       __syncthreads();
       for (int bj = 1; bj < nsub; bj++) {
         const int na = bj * 8, cw = min(8, jb - na);
-        for (int idx = tid; idx < na * cw; idx += kThreads) {
+        for (int idx = tid; idx < na * cw; idx += NTH) {
           const int a = idx % na, cp = idx / na;
           double acc = 0.;
           for (int b = a; b < na; b++) acc += Ts[a + b * LDW] * Ws[b + (na + cp) * LDW];
           Ys[a + cp * LDW] = acc;
         }
         __syncthreads();
-        for (int idx = tid; idx < na * cw; idx += kThreads) {
+        for (int idx = tid; idx < na * cw; idx += NTH) {
           const int a = idx % na, cp = idx / na;
           double acc = 0.;
           for (int d = 0; d <= cp; d++) acc += Ys[a + d * LDW] * Ts[(na + d) + (na + cp) * LDW];
@@ -934,12 +1099,12 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
       }
     }
     QR_TICK(4)
-    for (int idx = tid; idx < NB * NB; idx += kThreads) {
+    for (int idx = tid; idx < NB * NB; idx += NTH) {
       const int a = idx % NB, c = idx / NB;
       if (a < jb && c < jb) Tg[a + (size_t)(j0 + c) * NB] = Ts[a + c * LDW];
     }
     // ---- V (strictly lower part) back to global
-    for (int c = warp; c < jb; c += kWarps) {
+    for (int c = warp; c < jb; c += NWP) {
       double* dst = A + j0 + (size_t)(j0 + c) * m;
       const double* src = Vs + c * ldv;
       for (int i = c + 1 + lane; i < mp; i += 32) dst[i] = src[i];
@@ -951,9 +1116,19 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
     // ---- trailing update: one warp per 8-column slab, no barrier inside
     const int ntrail = naug - (j0 + jb);
     // (the warp that gets the extra slab rotates with the panel index)
-    for (int sl = (warp + (j0 / NB) * 3) % kWarps; sl * 8 < ntrail; sl += kWarps) {
-      const int c0 = j0 + jb + sl * 8;
-      slab_update<NB>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0), Vs, ldv, Ts, LDW, lane);
+    if (wide) {
+      // 16-byte aligned columns: two slabs per warp, 128-bit C and V accesses
+      const int npair = (ntrail + 15) >> 4;
+      for (int pr = (warp + (j0 / NB) * 3) % NWP; pr < npair; pr += NWP) {
+        const int c0 = j0 + jb + pr * 16;
+        slab2_update<NB>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0),
+                         max(0, min(8, naug - c0 - 8)), Vs, ldv, Ts, LDW, lane);
+      }
+    } else {
+      for (int sl = (warp + (j0 / NB) * 3) % NWP; sl * 8 < ntrail; sl += NWP) {
+        const int c0 = j0 + jb + sl * 8;
+        slab_update<NB, (NB == 16 ? 8 : 4)>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0), Vs, ldv, Ts, LDW, lane);
+      }
     }
     QR_TICK(6)
     if (pmode == 2) break;
@@ -1154,7 +1329,7 @@ __device__ __forceinline__ void ll_apply(double* Cp, int ldc, int m, int row0, i
 __global__ void __launch_bounds__(kLLThreads, 4)
 ulv_qr_ll_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                  double* fact, double* tfac, int ldc) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0 || nd.k == 0) return;
   const int m = nd.m, k = nd.k, naug = nd.naug, tid = threadIdx.x;
@@ -1555,7 +1730,7 @@ ulv_fwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                const double* __restrict__ fact, const double* __restrict__ b, int ldb,
                double* __restrict__ ysol, double* __restrict__ zsol,
                double* __restrict__ fsol, int s) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0) return;
   const int col = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1664,7 +1839,7 @@ ulv_root_solve_kernel(const DNode* __restrict__ nodes, const double* __restrict_
                       double* __restrict__ b, int ldb, const double* __restrict__ zsol,
                       const double* __restrict__ fsol, double* __restrict__ xsol, int s,
                       int use_smem) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[0];
   const int col = blockIdx.x, tid = threadIdx.x;
   const int n = nd.m;
@@ -1728,7 +1903,7 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                const double* __restrict__ fact, const double* __restrict__ tfac,
                double* __restrict__ b, int ldb, const double* __restrict__ ysol,
                double* __restrict__ xsol, int s) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int id = list[blockIdx.x];
   const DNode nd = nodes[id];
   if (nd.parent < 0) return;
@@ -1745,9 +1920,10 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   __syncthreads();
   const double* A = fact + nd.F;
   const double* Tg = tfac + nd.T;
-  const int nblk = (k + NB - 1) / NB;
+  const int nbq = nd.nbq;          // panel width the node was factored with (<= NB)
+  const int nblk = (k + nbq - 1) / nbq;
   for (int bi = nblk - 1; bi >= 0; bi--) {
-    const int j0 = bi * NB, jb = min(NB, k - j0);
+    const int j0 = bi * nbq, jb = min(nbq, k - j0);
     for (int a = warp; a < jb; a += kWarps) {
       const double* Va = A + (size_t)(j0 + a) * m;
       double acc = 0.;
@@ -1758,7 +1934,7 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
     __syncthreads();
     if (tid < jb) {
       double acc = 0.;
-      for (int c = tid; c < jb; c++) acc += Tg[tid + (size_t)(j0 + c) * NB] * w[c];
+      for (int c = tid; c < jb; c++) acc += Tg[tid + (size_t)(j0 + c) * nbq] * w[c];
       w2[tid] = acc;
     }
     __syncthreads();
@@ -1794,6 +1970,11 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   if (const char* e = std::getenv("SB200_QR_REGPANEL")) qr_regpanel_ = std::atoi(e);
   if (const char* e = std::getenv("SB200_QR_SKEW")) qr_skew_ = std::atoi(e);   // in 1000 clk
   if (const char* e = std::getenv("SB200_QR_LL")) qr_ll_ = std::atoi(e);       // 0 off, 1 leaf class, 2 all classes
+  // classes with m <= 256: 0 = 32-column panels, 256 threads, 2 CTAs/SM;
+  // 1 = 16-column panels, 128 threads, 4 CTAs/SM; 2 = 16-column panels, 256 threads
+  if (const char* e = std::getenv("SB200_QR_VARIANT")) qr_variant_ = std::atoi(e);
+  if (const char* e = std::getenv("SB200_QR_NOWIDE")) qr_nowide_ = std::atoi(e);   // 1: 64-bit one-slab trailing update
+  if (qr_split_) qr_variant_ = 0;   // the per-panel launch experiment assumes nb_-wide panels
   build_tables();
 }
 HSSEngine::~HSSEngine() {
@@ -1849,7 +2030,7 @@ void HSSEngine::build_tables() {
       d.naug = d.k + n.v_rank + n.u_rank;
     }
     d.F = foff;
-    foff += (long long)d.m * d.naug;
+    foff += ((long long)d.m * d.naug + 1) & ~1LL;   // even offsets: 16-byte aligned columns when m is even
     d.T = toff;
     toff += (long long)nb_ * d.k;
     d.y_off = yoff; yoff += d.k;
@@ -1936,10 +2117,18 @@ void HSSEngine::make_lists(NodeLists& L, const std::vector<int>& nodes) {
       if (!d.leaf) o += (long long)d.m * d.m;
     }
     L.smax = std::max(L.smax, o);
+    const int nbq = class_nb(h, std::max(L.max_m[h], 1));
+    for (int q = L.hptr[h]; q < L.hptr[h + 1]; q++) hn_[L.host[q]].nbq = nbq;
   }
   L.list.upload(L.host.data(), L.host.size());
   L.dsoff.upload(L.soff.data(), L.soff.size());
   SB200_CUDA(cudaStreamSynchronize(0));
+}
+
+int HSSEngine::class_nb(int h, int max_m) const {
+  if (nb_ != 32 || max_m > 256) return nb_;
+  if (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0)) return 32;   // the left-looking kernel writes 32-wide T
+  return (qr_regpanel_ && qr_variant_ >= 1) ? 16 : 32;
 }
 
 void HSSEngine::set_partition(int nparts, int part) {
@@ -1975,6 +2164,8 @@ void HSSEngine::set_partition(int nparts, int part) {
   nparts_ = nparts; part_ = part;
   make_lists(own_, own);
   make_lists(top_, top);
+  dn_.upload(hn_.data(), hn_.size());   // make_lists set the per-class panel widths
+  SB200_CUDA(cudaStreamSynchronize(0));
   factored_ = false;
 }
 
@@ -2174,7 +2365,7 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       const int npan = split ? (kmax + nb_ - 1) / nb_ : 1;
       for (int pp = 0; pp < npan; pp++)
         for (int phase0 = split ? 1 : 0; phase0 <= (split ? 2 : 0); phase0++) {
-          const int phase = phase0 + (h == 0 ? (qr_skew_ << 4) : 0);
+          const int phase = phase0 + (qr_nowide_ ? 8 : 0) + (h == 0 ? (qr_skew_ << 4) : 0);
           if (nb_ == 32 && mm <= 256 && !split && (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0))) {
             const size_t smem = qr_ll_smem(ldv);
             set_smem(ulv_qr_ll_kernel, smem);
@@ -2184,12 +2375,18 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
               std::fprintf(stderr, "[sb200] ulv_qr_ll_kernel: %d CTAs/SM (smem %zu B, class %d, %d nodes)\n", nbk, smem, h, cnt);
             }
             ulv_qr_ll_kernel<<<cnt, kLLThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
-          } else if (nb_ == 32 && mm <= 256 && qr_regpanel_) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true>, smem);
-            ulv_qr_kernel<32, true><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          } else if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, false>, smem);
-            ulv_qr_kernel<32, false><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          } else { size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, false>, smem);
-            ulv_qr_kernel<16, false><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
+          } else if (nb_ == 32 && mm <= 256 && qr_regpanel_ && qr_variant_ == 1) {
+            size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 128>, smem);
+            ulv_qr_kernel<16, true, 128><<<cnt, 128, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
+          } else if (nb_ == 32 && mm <= 256 && qr_regpanel_ && qr_variant_ == 2) {
+            size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 256>, smem);
+            ulv_qr_kernel<16, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
+          } else if (nb_ == 32 && mm <= 256 && qr_regpanel_) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true, 256>, smem);
+            ulv_qr_kernel<32, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
+          } else if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, false, 256>, smem);
+            ulv_qr_kernel<32, false, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
+          } else { size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, false, 256>, smem);
+            ulv_qr_kernel<16, false, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
           }
           launches_++;
         }
@@ -2259,11 +2456,8 @@ void HSSEngine::solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaSt
     size_t smem = sizeof(double) * (size_t)(mm + 2 * 32 + 8);
     dim3 grid(cnt, s);
     const int* lst = L.list.p + L.hptr[h];
-    if (nb_ == 32) { set_smem(ulv_bwd_kernel<32>, smem);
-      ulv_bwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
-    } else { set_smem(ulv_bwd_kernel<16>, smem);
-      ulv_bwd_kernel<16><<<grid, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
-    }
+    set_smem(ulv_bwd_kernel<32>, smem);   // the panel width (<= 32) is a per-node field
+    ulv_bwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
     launches_++;
   }
 }

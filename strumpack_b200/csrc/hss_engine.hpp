@@ -27,7 +27,8 @@ struct DNode {
   int m, k;            // reduced-system size, eliminated unknowns (m - u_rank)
   int naug;            // k + v_rank + u_rank columns of the factor block
   long long F;         // factor block m x naug (ld = m) in the factor arena
-  long long T;         // block-reflector T factors, NB x k (ld = NB)
+  long long T;         // block-reflector T factors, nbq x k (ld = nbq)
+  int nbq;             // panel width this node's QR runs with (its height class decides)
   int y_off, z_off, f_off, x_off;  // solve workspace prefixes (k, v_rank, u_rank, m)
 };
 
@@ -92,6 +93,7 @@ class HSSEngine {
   void ensure_apply_ws(int s);
   void ensure_solve_ws(int s);
   void make_lists(NodeLists& L, const std::vector<int>& nodes);
+  int class_nb(int h, int max_m) const;   // QR panel width of a height class
   void run_up(const NodeLists& L, bool T, int s, const double* dB, int ldB, cudaStream_t st);
   void run_down(const NodeLists& L, bool T, int s, const double* dB, int ldB, double* dC,
                 int ldC, bool leaves, cudaStream_t st);
@@ -123,7 +125,7 @@ class HSSEngine {
   bool factored_ = false;
   long long launches_ = 0;
   int nb_ = 32;
-  int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0, qr_ll_ = 0;   // switches; env SB200_QR_*
+  int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0, qr_ll_ = 0, qr_variant_ = 1, qr_nowide_ = 0;   // switches; env SB200_QR_*
   bool profile_ = false;
   cudaEvent_t ev_[2] = {nullptr, nullptr};
 };

@@ -65,6 +65,17 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
       : "d"(a), "d"(b));
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS); !pred zero-fills the
+// destination without touching global memory (src-size 0).
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc),
+               "r"(pred ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // Leading dimension for fp64 tiles in shared memory: ld % 16 == 4 makes both
 // "k along rows" and "k along columns" DMMA fragment loads conflict-free per
 // half-warp (an LDS.64 is two 128-byte wavefronts at best).
