@@ -121,6 +121,9 @@ int SB200_d_blr_compress_and_factor_device(CSPStructMat* S, int n, const double*
                                            int ldA, const CSPOptions* opts,
                                            double pivot_threshold);
 int SB200_d_blr_tiles(const CSPStructMat S);
+/* Number of off-diagonal tiles that did not compress to rank <= min(m,n)/2 and
+ * are kept dense (DenseTile in the reference, src/BLR/BLRMatrix.cpp:563-570). */
+int SB200_d_blr_dense_tiles(const CSPStructMat S);
 
 /* Reads a reference HSS dump (HSSMatrix<double>::write, reference
  * HSSMatrix.cpp:438-486) and uploads its generators. */

@@ -55,6 +55,7 @@ SYMBOLS = {
     "SB200_d_blr_compress_and_factor": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_tiles": (_i, [_vp]),
+    "SB200_d_blr_dense_tiles": (_i, [_vp]),
     "SB200_d_hss_read": (_i, [_pvp, C.c_char_p]),
     "SB200_d_hss_write": (_i, [_vp, C.c_char_p]),
     "SB200_d_hss_from_generators": (_i, [_pvp, _i, _vp, _vp, C.c_int64, _vp,
@@ -374,6 +375,11 @@ class BLRMatrix(StructuredMatrix):
     @property
     def tiles(self):
         return lib().SB200_d_blr_tiles(self._h)
+
+    @property
+    def dense_tiles(self):
+        """off-diagonal tiles kept dense (incompressible at the tolerance)"""
+        return lib().SB200_d_blr_dense_tiles(self._h)
 
 
 class HSSMatrix(StructuredMatrix):

@@ -322,13 +322,34 @@ blr_trsm_upper_kernel(const double* __restrict__ U, long long ldu, int n, double
 
 // ranks of the tiles of one kind (0: slots with i<j, 1: slots with i>j) as the
 // dynamic column counts of the trsm launch
+// kind 2: the dense (incompressible, rank_tab < 0) tiles with i<j: all their columns
 __global__ void blr_select_kernel(const TileDesc* __restrict__ td, int cnt, int kind,
                                   const int* __restrict__ rank_tab, int nb, int* __restrict__ sel) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= cnt) return;
   const bool upper = td[q].i < td[q].j;
   const int r = rank_tab[td[q].i + td[q].j * nb];
-  sel[q] = ((kind == 0) == upper && r > 0) ? r : 0;
+  if (kind == 2) sel[q] = (upper && r < 0) ? td[q].n : 0;
+  else sel[q] = ((kind == 0) == upper && r > 0) ? r : 0;
+}
+
+// Dense tiles below the diagonal: A_ji <- A_ji U_ii^{-1} (trsm R,U,N,N on a
+// DenseTile, reference BLRTileBLAS / DenseTile::trsm_b).  One CTA per tile of
+// the step, one thread per row; tiles that are low rank return at once.
+__global__ void __launch_bounds__(kThreads)
+blr_trsm_right_upper_dense_kernel(double* __restrict__ A, long long ld, const double* __restrict__ U,
+                                  int nu, const TileDesc* __restrict__ tiles,
+                                  const int* __restrict__ rank_tab, int nb) {
+  const TileDesc t = tiles[blockIdx.x];
+  if (t.i < t.j || rank_tab[t.i + t.j * nb] >= 0) return;
+  double* B = A + t.ro + (size_t)t.co * ld;   // t.m x nu
+  for (int r = threadIdx.x; r < t.m; r += kThreads) {
+    for (int c = 0; c < nu; c++) {
+      double v = B[r + (size_t)c * ld];
+      for (int a = 0; a < c; a++) v -= B[r + (size_t)a * ld] * U[a + (size_t)c * ld];
+      B[r + (size_t)c * ld] = v / U[c + (size_t)c * ld];
+    }
+  }
 }
 
 // ------------------------------------------------------------------ Schur update
@@ -338,14 +359,15 @@ __global__ void blr_select_kernel(const TileDesc* __restrict__ td, int cnt, int 
 // shared memory).  Ranks above KC are processed in chunks of KC columns.
 template <int KC>
 __global__ void __launch_bounds__(kThreads)
-blr_schur_kernel(double* __restrict__ A, long long ld, const int* __restrict__ off, int nb, int istep,
+blr_schur_kernel(double* A, long long ld, const int* __restrict__ off, int nb, int istep,
                  const double* __restrict__ lr, const long long* __restrict__ lroff,
-                 const int* __restrict__ rcap, const int* __restrict__ rank_tab, int ldp) {
+                 const int* __restrict__ rcap, const int* __restrict__ rank_tab, int ldp,
+                 const double* __restrict__ ident, int ldi) {
   extern __shared__ double sm[];
   const int nrem = nb - istep - 1;
   const int k = istep + 1 + blockIdx.x % nrem, j = istep + 1 + blockIdx.x / nrem;
-  const int ra = rank_tab[k + istep * nb], rb = rank_tab[istep + j * nb];
-  if (ra <= 0 || rb <= 0) return;    // zero tile: nothing to subtract
+  int ra = rank_tab[k + istep * nb], rb = rank_tab[istep + j * nb];
+  if (ra == 0 || rb == 0) return;    // zero tile: nothing to subtract
   const int mk = off[k + 1] - off[k], mi = off[istep + 1] - off[istep], nj = off[j + 1] - off[j];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int LDM = KC + 4;
@@ -353,10 +375,17 @@ blr_schur_kernel(double* __restrict__ A, long long ld, const int* __restrict__ o
   double* S2 = S1 + (size_t)ldp * KC;    // ldp x KC
   double* W = S2 + (size_t)ldp * KC;     // ldp x KC
   double* Ms = W + (size_t)ldp * KC;     // LDM x KC
+  // a tile is U Vt^T; a dense (incompressible) tile T is taken as T I^T with
+  // U = the tile itself inside A and Vt = the identity (DenseTile operands of
+  // the reference's gemm(LRTile/DenseTile, ...) overloads, BLRTileBLAS.hpp)
   const double* Uki = lr + lroff[k + istep * nb];
   const double* Vtki = Uki + (size_t)mk * rcap[k + istep * nb];
+  long long ldUki = mk, ldVki = mi;
+  if (ra < 0) { Uki = A + off[k] + (size_t)off[istep] * ld; ldUki = ld; Vtki = ident; ldVki = ldi; ra = mi; }
   const double* Uij = lr + lroff[istep + j * nb];
   const double* Vtij = Uij + (size_t)mi * rcap[istep + j * nb];
+  long long ldUij = mi, ldVij = nj;
+  if (rb < 0) { Uij = A + off[istep] + (size_t)off[j] * ld; ldUij = ld; Vtij = ident; ldVij = ldi; rb = nj; }
   double* C = A + off[k] + (size_t)off[j] * ld;
   for (int cb = 0; cb < rb; cb += KC) {
     const int kb = min(KC, rb - cb);
@@ -364,20 +393,20 @@ blr_schur_kernel(double* __restrict__ A, long long ld, const int* __restrict__ o
       const int ka = min(KC, ra - ca);
       __syncthreads();
       for (int c = warp; c < ka; c += kWarps)
-        for (int r = lane; r < mi; r += 32) S1[r + c * ldp] = Vtki[r + (size_t)(ca + c) * mi];
+        for (int r = lane; r < mi; r += 32) S1[r + c * ldp] = Vtki[r + (size_t)(ca + c) * ldVki];
       for (int c = warp; c < kb; c += kWarps)
-        for (int r = lane; r < mi; r += 32) S2[r + c * ldp] = Uij[r + (size_t)(cb + c) * mi];
+        for (int r = lane; r < mi; r += 32) S2[r + c * ldp] = Uij[r + (size_t)(cb + c) * ldUij];
       __syncthreads();
       smem_gemm<true, false>(ka, kb, mi, 1., S1, ldp, S2, ldp, 0., Ms, LDM, warp, kWarps, lane);
       __syncthreads();
       for (int c = warp; c < ka; c += kWarps)
-        for (int r = lane; r < mk; r += 32) S1[r + c * ldp] = Uki[r + (size_t)(ca + c) * mk];
+        for (int r = lane; r < mk; r += 32) S1[r + c * ldp] = Uki[r + (size_t)(ca + c) * ldUki];
       __syncthreads();
       smem_gemm<false, false>(mk, kb, ka, 1., S1, ldp, Ms, LDM, ca ? 1. : 0., W, ldp, warp, kWarps, lane);
     }
     __syncthreads();
     for (int c = warp; c < kb; c += kWarps)
-      for (int r = lane; r < nj; r += 32) S2[r + c * ldp] = Vtij[r + (size_t)(cb + c) * nj];
+      for (int r = lane; r < nj; r += 32) S2[r + c * ldp] = Vtij[r + (size_t)(cb + c) * ldVij];
     __syncthreads();
     // C (mk x nj, global) -= W (mk x kb) * S2^T (kb x nj): 16x16 tiles over the warps
     const int g = lane >> 2, t = lane & 3;
@@ -430,13 +459,24 @@ blr_lr_gemv_kernel(const GemvTask* __restrict__ tasks, const int* __restrict__ o
                    const double* __restrict__ lr, const long long* __restrict__ lroff,
                    const int* __restrict__ rcap, const int* __restrict__ rank_tab,
                    const double* __restrict__ x, long long ldx, double* __restrict__ y,
-                   long long ldy, double alpha) {
+                   long long ldy, double alpha, const double* __restrict__ A, long long ld) {
   extern __shared__ double sm[];
   const GemvTask tk = tasks[blockIdx.x];
   const int col = blockIdx.y;
   const int r = rank_tab[tk.k + tk.j * nb];
-  if (r <= 0) return;
+  if (r == 0) return;
   const int m = off[tk.k + 1] - off[tk.k], n = off[tk.j + 1] - off[tk.j];
+  if (r < 0) {   // dense tile, lives in A (DenseTile::gemv_a)
+    const double* D = A + off[tk.k] + (size_t)off[tk.j] * ld;
+    const double* xj = x + off[tk.j] + col * ldx;
+    double* yk = y + off[tk.k] + col * ldy;
+    for (int i = threadIdx.x; i < m; i += kThreads) {
+      double acc = 0.;
+      for (int c = 0; c < n; c++) acc += D[i + (size_t)c * ld] * xj[c];
+      atomicAdd(yk + i, alpha * acc);
+    }
+    return;
+  }
   const double* U = lr + lroff[tk.k + tk.j * nb];
   const double* Vt = U + (size_t)m * rcap[tk.k + tk.j * nb];
   const double* xj = x + off[tk.j] + col * ldx;
@@ -596,6 +636,17 @@ void BLREngine::run(bool do_factor) {
     s.ncols = 0;
     stL.push_back(s);
   }
+  // the same tiles kept dense (when they turn out incompressible): operands inside A
+  std::vector<SolveTask> stD;
+  for (const TileDesc& t : td) {
+    SolveTask s;
+    s.B = A_.p + t.ro + (size_t)t.co * n; s.ldb = n; s.ncols = 0;
+    stD.push_back(s);
+  }
+  DevBuf<SolveTask> dstD; dstD.upload(stD.data(), stD.size(), st);
+  std::vector<double> hid((size_t)maxtile_ * maxtile_, 0.);
+  for (int q = 0; q < maxtile_; q++) hid[q + (size_t)q * maxtile_] = 1.;
+  DevBuf<double> ident; ident.upload(hid.data(), hid.size(), st);
   DevBuf<TileDesc> dtd; dtd.upload(td.data(), td.size(), st);
   DevBuf<IDTask> didt; didt.upload(idt.data(), idt.size(), st);
   DevBuf<SolveTask> dst; dst.upload(stL.data(), stL.size(), st);
@@ -648,16 +699,21 @@ void BLREngine::run(bool do_factor) {
       blr_select_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(tds, cnt, 1, drank_.p, nb, sel.p);
       blr_trsm_lower_kernel<<<dim3(cnt, (maxtile_ / 2 + kWarps - 1) / kWarps), kThreads, smem, st>>>(
           UT.p, m, m, 0, nullptr, dst.p + step_ptr[i], sel.p);
-      launches_ += 4;
+      // dense off-diagonal tiles (DenseTile in the reference): A_ij <- L^{-1} P A_ij, A_ji <- A_ji U^{-1}
+      blr_select_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(tds, cnt, 2, drank_.p, nb, sel.p);
+      blr_trsm_lower_kernel<<<dim3(cnt, (maxtile_ + kWarps - 1) / kWarps), kThreads, smem, st>>>(
+          Aii, n, m, 1, gperm_.p + off_[i], dstD.p + step_ptr[i], sel.p);
+      blr_trsm_right_upper_dense_kernel<<<cnt, kThreads, 0, st>>>(A_.p, n, Aii, m, tds, drank_.p, nb);
+      launches_ += 7;
     }
     // K13: trailing update
     const int nrem = nb - i - 1;
     if (nrem > 0) {
       const size_t smem = sizeof(double) * ((size_t)3 * ldp * KC + (size_t)(KC + 4) * KC);
       if (KC == 32) { set_smem(blr_schur_kernel<32>, smem);
-        blr_schur_kernel<32><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp);
+        blr_schur_kernel<32><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp, ident.p, maxtile_);
       } else { set_smem(blr_schur_kernel<16>, smem);
-        blr_schur_kernel<16><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp);
+        blr_schur_kernel<16><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp, ident.p, maxtile_);
       }
       launches_++;
     }
@@ -666,12 +722,12 @@ void BLREngine::run(bool do_factor) {
   SB200_CUDA(cudaStreamSynchronize(st));
   hrank_.resize((size_t)nb * nb);
   SB200_CUDA(cudaMemcpy(hrank_.data(), drank_.p, sizeof(int) * hrank_.size(), cudaMemcpyDeviceToHost));
+  // rank -1 = a tile that does not compress to rank <= min(m,n)/2: kept dense
+  // inside A (DenseTile, reference BLRMatrix.cpp:563-570)
+  dense_tiles_ = 0;
   for (int j = 0; j < nb; j++)
     for (int i = 0; i < nb; i++)
-      if (i != j && hrank_[i + (size_t)j * nb] < 0)
-        throw std::runtime_error("BLR tile (" + std::to_string(i) + "," + std::to_string(j) +
-                                 ") is not compressible to rank <= min(m,n)/2: dense off-diagonal "
-                                 "tiles are not supported yet");
+      if (i != j && hrank_[i + (size_t)j * nb] < 0) dense_tiles_++;
   factored_ = do_factor;
 }
 
@@ -721,7 +777,7 @@ void BLREngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
     const int m = off_[i + 1] - off_[i], cnt = fwd_ptr_[i + 1] - fwd_ptr_[i];
     if (cnt) {
       blr_lr_gemv_kernel<<<dim3(cnt, s), kThreads, gsm, st>>>(gt + fwd_ptr_[i], doff_.p, nb, lr_.p, dlroff_.p,
-                                                             drcap_.p, drank_.p, dB, ldB, dB, ldB, -1.);
+                                                             drcap_.p, drank_.p, dB, ldB, dB, ldB, -1., A_.p, n);
       launches_++;
     }
     const size_t smem = sizeof(double) * (size_t)kWarps * m;
@@ -734,7 +790,7 @@ void BLREngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
     const int m = off_[i + 1] - off_[i], cnt = bwd_ptr_[i + 1] - bwd_ptr_[i];
     if (cnt) {
       blr_lr_gemv_kernel<<<dim3(cnt, s), kThreads, gsm, st>>>(gt + bwd_base_ + bwd_ptr_[i], doff_.p, nb, lr_.p,
-                                                             dlroff_.p, drcap_.p, drank_.p, dB, ldB, dB, ldB, -1.);
+                                                             dlroff_.p, drcap_.p, drank_.p, dB, ldB, dB, ldB, -1., A_.p, n);
       launches_++;
     }
     const size_t smem = sizeof(double) * (size_t)kWarps * m;
@@ -768,13 +824,15 @@ void BLREngine::mult(char trans, int s, const double* dB, int ldB, double* dC, i
     const size_t gsm = sizeof(double) * (size_t)(maxtile_ / 2 + 8);
     blr_lr_gemv_kernel<<<dim3(nmt_, s), kThreads, gsm, st>>>(reinterpret_cast<const GemvTask*>(mtasks_.p),
                                                             doff_.p, nb, lr_.p, dlroff_.p, drcap_.p, drank_.p,
-                                                            dB, ldB, dC, ldC, 1.);
+                                                            dB, ldB, dC, ldC, 1., A_.p, n_);
   }
   launches_ += 3;
   SB200_CUDA(cudaGetLastError());
 }
 
 int BLREngine::max_rank() const {
+  // BLRMatrix::rank() = max of BLRTile::maximum_rank(), which is 0 for a
+  // DenseTile (reference BLRMatrix.cpp:290-294, DenseTile.hpp:93)
   int r = 0;
   for (int v : hrank_) r = std::max(r, v);
   return r;
@@ -785,7 +843,8 @@ long long BLREngine::nonzeros() const {
   for (int j = 0; j < nb_; j++)
     for (int i = 0; i < nb_; i++) {
       const long long m = off_[i + 1] - off_[i], n = off_[j + 1] - off_[j];
-      nnz += (i == j) ? m * n : (long long)hrank_[i + (size_t)j * nb_] * (m + n);
+      const int r = hrank_[i + (size_t)j * nb_];
+      nnz += (i == j || r < 0) ? m * n : (long long)r * (m + n);
     }
   return nnz;
 }

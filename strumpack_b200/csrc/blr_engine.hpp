@@ -25,6 +25,7 @@ class BLREngine {
   int rows() const { return n_; }
   int cols() const { return n_; }
   int tiles() const { return nb_; }
+  int dense_tiles() const { return dense_tiles_; }   // off-diagonal tiles kept dense
   int max_rank() const;
   long long nonzeros() const;
   long long memory_bytes() const { return nonzeros() * (long long)sizeof(double); }
@@ -35,7 +36,7 @@ class BLREngine {
 
  private:
   void run(bool do_factor);
-  int n_ = 0, nb_ = 0, maxtile_ = 0;
+  int n_ = 0, nb_ = 0, maxtile_ = 0, dense_tiles_ = 0;
   BLROpts opts_;
   std::vector<int> off_, rcap_, hrank_;
   std::vector<long long> lroff_;

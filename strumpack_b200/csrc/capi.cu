@@ -213,6 +213,10 @@ int SB200_d_blr_tiles(const CSPStructMat S) {
   return (S && M(S)->blr) ? M(S)->blr->tiles() : 0;
 }
 
+int SB200_d_blr_dense_tiles(const CSPStructMat S) {
+  return (S && M(S)->blr) ? M(S)->blr->dense_tiles() : 0;
+}
+
 int SB200_d_hss_read(CSPStructMat* S, const char* path) {
   return guarded([&] {
     require_gpu();

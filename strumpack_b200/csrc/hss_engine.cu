@@ -13,6 +13,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr size_t kMaxSmem = 200 * 1024;   // dynamic shared memory we ask for at most
 
 // sum over the CTA; every thread gets the result. red: >= 32 doubles of smem.
 // Contains two __syncthreads().
@@ -205,6 +206,188 @@ hss_leaf_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
       acc = warp_sum(acc);
       if (lane == 0) yo[j] = u[j] + acc;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Multi-rhs (GEMM-shaped) apply: one CTA per (node, tile of kMS right-hand
+// sides).  The generators are read once per tile instead of once per column,
+// and the two large products (E^H * bot in the up-sweep, D * x at the leaves)
+// run on the fp64 tensor pipe (smem_gemm: A fragments straight from the
+// generator arena, B = the kMS vectors in shared memory).  Same math and
+// workspace layout as the single-column kernels above.
+// ---------------------------------------------------------------------------
+constexpr int kMS = 16;
+
+template <bool TRANS>
+__global__ void __launch_bounds__(kThreads)
+hss_up_mm_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                 const double* __restrict__ vals, const int* __restrict__ perms,
+                 const double* __restrict__ x, int ldx, double* t1, int s, int ldp) {
+  extern __shared__ __align__(16) double sm[];
+  const DNode nd = nodes[list[blockIdx.x]];
+  const int c0 = blockIdx.y * kMS, ns = min(kMS, s - c0), tid = threadIdx.x;
+  const int r = TRANS ? nd.u_rank : nd.v_rank;
+  const int n = TRANS ? nd.u_rows : nd.v_rows;
+  if (r == 0) return;
+  const int* P = perms + (TRANS ? nd.Pu : nd.Pv);
+  double* pb = sm;   // n x ns, ld = ldp
+  if (nd.leaf) {
+    const double* xin = x + (TRANS ? nd.row_off : nd.col_off) + (size_t)c0 * ldx;
+    for (int idx = tid; idx < n * ns; idx += kThreads) {
+      const int i = idx % n, c = idx / n;
+      pb[i + c * ldp] = xin[P[i] + (size_t)c * ldx];
+    }
+  } else {
+    const DNode ch0 = nodes[nd.ch0], ch1 = nodes[nd.ch1];
+    const int q0 = TRANS ? ch0.u_rank : ch0.v_rank;
+    const int q1 = TRANS ? ch1.u_rank : ch1.v_rank;
+    const double* a = t1 + (size_t)ch0.w_off * s + (size_t)c0 * q0;
+    const double* b = t1 + (size_t)ch1.w_off * s + (size_t)c0 * q1;
+    for (int idx = tid; idx < n * ns; idx += kThreads) {
+      const int i = idx % n, c = idx / n, p = P[i];
+      pb[i + c * ldp] = p < q0 ? a[p + (size_t)c * q0] : b[(p - q0) + (size_t)c * q1];
+    }
+  }
+  __syncthreads();
+  double* out = t1 + (size_t)nd.w_off * s + (size_t)c0 * r;   // r x ns, ld = r
+  for (int idx = tid; idx < r * ns; idx += kThreads) out[idx] = pb[(idx % r) + (idx / r) * ldp];
+  __syncthreads();
+  const int k = n - r;
+  if (k > 0)   // out += E^H * bot      (E is k x r)
+    smem_gemm<true, false>(r, ns, k, 1., vals + (TRANS ? nd.Eu : nd.Ev), k, pb + r, ldp, 1.,
+                           out, r, tid >> 5, kWarps, tid & 31);
+}
+
+// u(P[i], :) = [t2; E t2](i, :) for the kMS columns of this tile; `dst` is nout x ns
+// (ld = ldd).  One thread per row, the columns in registers: E is read once.
+template <bool TRANS>
+__device__ __forceinline__ void basis_expand_mm(const DNode& nd, const double* __restrict__ vals,
+                                                const int* __restrict__ perms,
+                                                const double* tin, int ldt, int nout, int rout,
+                                                int ns, double* dst, int ldd, int tid) {
+  const int* P = perms + (TRANS ? nd.Pv : nd.Pu);
+  const double* E = vals + (TRANS ? nd.Ev : nd.Eu);
+  const int k = nout - rout;
+  for (int i = tid; i < nout; i += kThreads) {
+    double acc[kMS];
+#pragma unroll
+    for (int c = 0; c < kMS; c++) acc[c] = 0.;
+    if (i < rout) {
+#pragma unroll
+      for (int c = 0; c < kMS; c++) if (c < ns) acc[c] = tin[i + c * ldt];
+    } else {
+      for (int l = 0; l < rout; l++) {
+        const double e = E[(i - rout) + (size_t)l * k];
+#pragma unroll
+        for (int c = 0; c < kMS; c++) acc[c] += e * tin[l + c * ldt];
+      }
+    }
+    const int p = P[i];
+#pragma unroll
+    for (int c = 0; c < kMS; c++) if (c < ns) dst[p + c * ldd] = acc[c];
+  }
+}
+
+template <bool TRANS>
+__global__ void __launch_bounds__(kThreads)
+hss_down_mm_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                   const double* __restrict__ vals, const int* __restrict__ perms,
+                   const double* __restrict__ t1, double* t2, int s, int ldp) {
+  extern __shared__ __align__(16) double sm[];
+  const int id = list[blockIdx.x];
+  const DNode nd = nodes[id];
+  if (nd.leaf) return;
+  const int c0 = blockIdx.y * kMS, ns = min(kMS, s - c0), tid = threadIdx.x;
+  const DNode ch0 = nodes[nd.ch0], ch1 = nodes[nd.ch1];
+  const int o0 = TRANS ? ch0.v_rank : ch0.u_rank, o1 = TRANS ? ch1.v_rank : ch1.u_rank;
+  const int q0 = TRANS ? ch0.u_rank : ch0.v_rank, q1 = TRANS ? ch1.u_rank : ch1.v_rank;
+  const int rout = TRANS ? nd.v_rank : nd.u_rank;
+  const int nout = o0 + o1;
+  double* u = sm;                 // nout x kMS, ld = ldp
+  double* tin = u + ldp * kMS;    // rout x kMS, ld = ldp
+  double* ta = tin + ldp * kMS;   // t1(c0): q0 x kMS, ld = ldp
+  double* tb = ta + ldp * kMS;    // t1(c1): q1 x kMS, ld = ldp
+  const bool has_u = (nd.parent >= 0) && rout > 0;
+  for (int idx = tid; idx < ldp * kMS * 4; idx += kThreads) sm[idx] = 0.;
+  __syncthreads();
+  if (has_u) {
+    const double* my = t2 + (size_t)nd.w_off * s + (size_t)c0 * rout;
+    for (int idx = tid; idx < rout * ns; idx += kThreads) tin[(idx % rout) + (idx / rout) * ldp] = my[idx];
+  }
+  {
+    const double* a = t1 + (size_t)ch0.w_off * s + (size_t)c0 * q0;
+    const double* b = t1 + (size_t)ch1.w_off * s + (size_t)c0 * q1;
+    for (int idx = tid; idx < q0 * ns; idx += kThreads) ta[(idx % q0) + (idx / q0) * ldp] = a[idx];
+    for (int idx = tid; idx < q1 * ns; idx += kThreads) tb[(idx % q1) + (idx / q1) * ldp] = b[idx];
+  }
+  __syncthreads();
+  if (has_u) basis_expand_mm<TRANS>(nd, vals, perms, tin, ldp, nout, rout, ns, u, ldp, tid);
+  __syncthreads();
+  double* oa = t2 + (size_t)ch0.w_off * s + (size_t)c0 * o0;
+  double* ob = t2 + (size_t)ch1.w_off * s + (size_t)c0 * o1;
+  const double* B01 = vals + nd.B01;  // u_rank(c0) x v_rank(c1)
+  const double* B10 = vals + nd.B10;  // u_rank(c1) x v_rank(c0)
+  for (int i = tid; i < nout; i += kThreads) {
+    double acc[kMS];
+#pragma unroll
+    for (int c = 0; c < kMS; c++) acc[c] = u[i + c * ldp];
+    const bool first = i < o0;
+    const int ii = first ? i : i - o0;
+    const int nq = first ? q1 : q0;
+    const double* tsrc = first ? tb : ta;
+    for (int j = 0; j < nq; j++) {
+      double bv;
+      if (!TRANS) bv = first ? B01[ii + (size_t)j * o0] : B10[ii + (size_t)j * o1];
+      else        bv = first ? B10[j + (size_t)ii * q1] : B01[j + (size_t)ii * q0];
+#pragma unroll
+      for (int c = 0; c < kMS; c++) acc[c] += bv * tsrc[j + c * ldp];
+    }
+    double* o = first ? oa : ob;
+    const int lo = first ? o0 : o1;
+#pragma unroll
+    for (int c = 0; c < kMS; c++) if (c < ns) o[ii + (size_t)c * lo] = acc[c];
+  }
+}
+
+template <bool TRANS>
+__global__ void __launch_bounds__(kThreads)
+hss_leaf_mm_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                   const double* __restrict__ vals, const int* __restrict__ perms,
+                   const double* __restrict__ x, int ldx, const double* __restrict__ t2,
+                   double* __restrict__ y, int ldy, int s, int ldp) {
+  extern __shared__ __align__(16) double sm[];
+  const DNode nd = nodes[list[blockIdx.x]];
+  const int c0 = blockIdx.y * kMS, ns = min(kMS, s - c0), tid = threadIdx.x;
+  const int nin = TRANS ? nd.rows : nd.cols;
+  const int nout = TRANS ? nd.cols : nd.rows;
+  const int rout = TRANS ? nd.v_rank : nd.u_rank;
+  double* xs = sm;                 // nin x kMS, ld = ldp
+  double* ys = xs + ldp * kMS;     // nout x kMS, ld = ldp
+  double* tin = ys + ldp * kMS;    // rout x kMS, ld = ldp
+  for (int idx = tid; idx < ldp * kMS * 3; idx += kThreads) sm[idx] = 0.;
+  __syncthreads();
+  const double* xin = x + (TRANS ? nd.row_off : nd.col_off) + (size_t)c0 * ldx;
+  for (int idx = tid; idx < nin * ns; idx += kThreads) {
+    const int i = idx % nin, c = idx / nin;
+    xs[i + c * ldp] = xin[i + (size_t)c * ldx];
+  }
+  const bool has_u = (nd.parent >= 0) && rout > 0;
+  if (has_u) {
+    const double* my = t2 + (size_t)nd.w_off * s + (size_t)c0 * rout;
+    for (int idx = tid; idx < rout * ns; idx += kThreads) tin[(idx % rout) + (idx / rout) * ldp] = my[idx];
+  }
+  __syncthreads();
+  if (has_u) basis_expand_mm<TRANS>(nd, vals, perms, tin, ldp, nout, rout, ns, ys, ldp, tid);
+  __syncthreads();
+  // ys += op(D) xs      (D is rows x cols, ld = rows)
+  smem_gemm<TRANS, false>(nout, ns, nin, 1., vals + nd.D, nd.rows, xs, ldp, 1., ys, ldp,
+                          tid >> 5, kWarps, tid & 31);
+  __syncthreads();
+  double* yo = y + (TRANS ? nd.col_off : nd.row_off) + (size_t)c0 * ldy;
+  for (int idx = tid; idx < nout * ns; idx += kThreads) {
+    const int i = idx % nout, c = idx / nout;
+    yo[i + (size_t)c * ldy] = ys[i + c * ldp];
   }
 }
 
@@ -1973,6 +2156,7 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   // classes with m <= 256: 0 = 32-column panels, 256 threads, 2 CTAs/SM;
   // 1 = 16-column panels, 128 threads, 4 CTAs/SM; 2 = 16-column panels, 256 threads
   if (const char* e = std::getenv("SB200_QR_VARIANT")) qr_variant_ = std::atoi(e);
+  if (const char* e = std::getenv("SB200_APPLY_MM_MIN")) mm_min_ = std::max(1, std::atoi(e));   // rhs count from which the GEMM-shaped apply kernels run
   if (const char* e = std::getenv("SB200_QR_NOWIDE")) qr_nowide_ = std::atoi(e);   // 1: 64-bit one-slab trailing update
   if (qr_split_) qr_variant_ = 0;   // the per-panel launch experiment assumes nb_-wide panels
   build_tables();
@@ -2191,9 +2375,21 @@ void HSSEngine::run_up(const NodeLists& L, bool T, int s, const double* dB, int 
   for (int h = 0; h < L.classes(); h++) {
     const int cnt = L.hptr[h + 1] - L.hptr[h];
     if (!cnt) continue;
+    const int* lst = L.list.p + L.hptr[h];
+    const int ldp = smem_ld(std::max(L.max_m[h], 1));
+    const size_t smem_mm = sizeof(double) * (size_t)ldp * kMS;
+    if (s >= mm_min_ && smem_mm <= kMaxSmem) {   // GEMM-shaped: kMS right-hand sides per CTA
+      dim3 grid(cnt, (s + kMS - 1) / kMS);
+      if (T) { set_smem(hss_up_mm_kernel<true>, smem_mm);
+        hss_up_mm_kernel<true><<<grid, kThreads, smem_mm, st>>>(dn_.p, lst, vals_.p, perms_.p, dB, ldB, t1_.p, s, ldp);
+      } else { set_smem(hss_up_mm_kernel<false>, smem_mm);
+        hss_up_mm_kernel<false><<<grid, kThreads, smem_mm, st>>>(dn_.p, lst, vals_.p, perms_.p, dB, ldB, t1_.p, s, ldp);
+      }
+      launches_++;
+      continue;
+    }
     size_t smem = sizeof(double) * (size_t)std::max(L.max_m[h], 1);
     dim3 grid(cnt, s);
-    const int* lst = L.list.p + L.hptr[h];
     if (T) { set_smem(hss_up_kernel<true>, smem);
       hss_up_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, dB, ldB, t1_.p, s);
     } else { set_smem(hss_up_kernel<false>, smem);
@@ -2208,9 +2404,21 @@ void HSSEngine::run_down(const NodeLists& L, bool T, int s, const double* dB, in
   for (int h = L.classes() - 1; h >= 1; h--) {
     const int cnt = L.hptr[h + 1] - L.hptr[h];
     if (!cnt) continue;
+    const int* lst = L.list.p + L.hptr[h];
+    const int ldp = smem_ld(std::max(L.max_m[h], 1));
+    const size_t smem_mm = sizeof(double) * (size_t)ldp * kMS * 4;
+    if (s >= mm_min_ && smem_mm <= kMaxSmem) {
+      dim3 grid(cnt, (s + kMS - 1) / kMS);
+      if (T) { set_smem(hss_down_mm_kernel<true>, smem_mm);
+        hss_down_mm_kernel<true><<<grid, kThreads, smem_mm, st>>>(dn_.p, lst, vals_.p, perms_.p, t1_.p, t2_.p, s, ldp);
+      } else { set_smem(hss_down_mm_kernel<false>, smem_mm);
+        hss_down_mm_kernel<false><<<grid, kThreads, smem_mm, st>>>(dn_.p, lst, vals_.p, perms_.p, t1_.p, t2_.p, s, ldp);
+      }
+      launches_++;
+      continue;
+    }
     size_t smem = sizeof(double) * (size_t)(2 * std::max(L.max_m[h], 1) + 8);
     dim3 grid(cnt, s);
-    const int* lst = L.list.p + L.hptr[h];
     if (T) { set_smem(hss_down_kernel<true>, smem);
       hss_down_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, t1_.p, t2_.p, s);
     } else { set_smem(hss_down_kernel<false>, smem);
@@ -2220,6 +2428,18 @@ void HSSEngine::run_down(const NodeLists& L, bool T, int s, const double* dB, in
   }
   if (leaves && L.classes() > 0 && L.hptr[1] > L.hptr[0]) {
     const int cnt = L.hptr[1] - L.hptr[0];
+    const int ldp = smem_ld(std::max(L.max_m[0], 1));
+    const size_t smem_mm = sizeof(double) * (size_t)ldp * kMS * 3;
+    if (s >= mm_min_ && smem_mm <= kMaxSmem) {
+      dim3 grid(cnt, (s + kMS - 1) / kMS);
+      if (T) { set_smem(hss_leaf_mm_kernel<true>, smem_mm);
+        hss_leaf_mm_kernel<true><<<grid, kThreads, smem_mm, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s, ldp);
+      } else { set_smem(hss_leaf_mm_kernel<false>, smem_mm);
+        hss_leaf_mm_kernel<false><<<grid, kThreads, smem_mm, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s, ldp);
+      }
+      launches_++;
+      return;
+    }
     size_t smem = sizeof(double) * (size_t)(3 * std::max(L.max_m[0], 1) + 8);
     dim3 grid(cnt, s);
     if (T) { set_smem(hss_leaf_kernel<true>, smem);

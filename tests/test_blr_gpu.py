@@ -77,3 +77,58 @@ def test_blr_upper_triangular_zero_tiles(built):
     B = sb.BLRMatrix.compress_and_factor(A, o)
     X = np.random.default_rng(3).standard_normal((n, 2))
     assert rel(B.solve(A @ X), X) <= 1e-4
+
+
+def _with_noise_tiles(n, leaf, blocks, seed=5):
+    """Toeplitz + full-rank noise in the listed off-diagonal tiles + a strong diagonal."""
+    A = toeplitz(n) + 4.0 * np.eye(n)
+    rng = np.random.default_rng(seed)
+    for (i, j) in blocks:
+        A[i * leaf:(i + 1) * leaf, j * leaf:(j + 1) * leaf] += 0.02 * rng.standard_normal((leaf, leaf))
+    return A
+
+
+@pytest.mark.parametrize("blocks", [[(0, 2)], [(3, 1)], [(0, 2), (3, 1), (1, 2), (2, 1), (3, 0)]])
+def test_blr_dense_offdiagonal_tiles(built, blocks):
+    """Tiles that do not compress to rank <= min(m,n)/2 stay dense (DenseTile,
+    reference BLRMatrix.cpp:563-570) and take part in trsm / Schur update / solve."""
+    sb = built
+    n, leaf, tol = 1024, 256, 1e-6
+    A = _with_noise_tiles(n, leaf, blocks)
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    B = sb.BLRMatrix.compress_and_factor(A, o)
+    assert B.dense_tiles >= len(blocks)       # fill-in may densify more tiles later in the LU
+    X = np.random.default_rng(0).standard_normal((n, 3))
+    assert rel(B.solve(A @ X), X) <= 1e2 * tol
+    assert 0 < B.rank < leaf // 2     # rank() only counts the low-rank tiles, as in the reference
+
+
+def test_blr_all_tiles_dense_matches_lapack(built):
+    sb = built
+    n, leaf = 768, 128
+    A = np.random.default_rng(7).standard_normal((n, n)) + n * np.eye(n) * 0.1
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=1e-8, abs_tol=1e-12, leaf_size=leaf)
+    B = sb.BLRMatrix.compress_and_factor(A, o)
+    assert B.dense_tiles == B.tiles * (B.tiles - 1)     # every off-diagonal tile
+    X = np.random.default_rng(1).standard_normal((n, 2))
+    Y = A @ X
+    assert rel(B.solve(Y), np.linalg.solve(A, Y)) <= 1e-10    # plain blocked LU, no compression error
+    C = sb.StructuredMatrix.from_dense(A, o)                   # compress only: mult through dense tiles
+    assert rel(C.mult(X), Y) <= 1e-12
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_blr_dense_tiles_match_reference(built):
+    from oracle import ref
+    sb = built
+    n, leaf, tol = 1024, 256, 1e-4
+    A = _with_noise_tiles(n, leaf, [(0, 1), (2, 0)])
+    R = ref.RefBLR(A, f"--blr_leaf_size {leaf} --blr_rel_tol {tol}")
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    B = sb.BLRMatrix.compress_and_factor(A, o)
+    X = np.random.default_rng(1).standard_normal((n, 4))
+    Y = A @ X
+    xr, xs = R.solve(Y), B.solve(Y)
+    assert rel(xs, X) <= 1e2 * tol and rel(xr, X) <= 1e2 * tol
+    assert B.dense_tiles >= 2
+    assert abs(B.rank - R.info()["rank"]) <= 3     # BLRMatrix::rank(): dense tiles count 0
