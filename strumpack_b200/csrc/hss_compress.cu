@@ -29,6 +29,7 @@
 #include <cstring>
 #include <functional>
 #include <numeric>
+#include <cstdlib>
 #include <random>
 #include <stdexcept>
 
@@ -82,6 +83,8 @@ struct BlockTask {
   double* out;       // device
   long long ld;
   int transpose;     // 1: out[j + i*ld] = A(rows[i], cols[j])
+  const double* wr;  // optional weights per row / per column position (nullptr: 1):
+  const double* wc;  //   a sampled index stands for `mass` points, weight = sqrt(mass)
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -92,10 +95,16 @@ eval_blocks_kernel(ElemSrc src, const BlockTask* __restrict__ tasks) {
        idx += (long long)gridDim.y * kThreads) {
     if (!t.transpose) {
       int i = (int)(idx % t.nr), j = (int)(idx / t.nr);
-      t.out[i + (size_t)j * t.ld] = elem(src, t.rows[i], t.cols[j]);
+      double v = elem(src, t.rows[i], t.cols[j]);
+      if (t.wr) v *= t.wr[i];
+      if (t.wc) v *= t.wc[j];
+      t.out[i + (size_t)j * t.ld] = v;
     } else {
       int j = (int)(idx % t.nc), i = (int)(idx / t.nc);
-      t.out[j + (size_t)i * t.ld] = elem(src, t.rows[i], t.cols[j]);
+      double v = elem(src, t.rows[i], t.cols[j]);
+      if (t.wr) v *= t.wr[i];
+      if (t.wc) v *= t.wc[j];
+      t.out[j + (size_t)i * t.ld] = v;
     }
   }
 }
@@ -175,6 +184,16 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
     for (int q = 0; q < d; q++) c[q] /= std::max(1, T[t].hi - T[t].lo);
   };
   std::vector<std::vector<int>> J(N);
+  // mass[t][q]: how many points of the complement the q-th sample of node t
+  // stands for.  The sampled block is a stratified sample of A(I_t, complement):
+  // scaling a sampled column by sqrt(mass) makes the pivoted QR's stopping rule
+  // an estimate of the Frobenius norm of the residual over the WHOLE complement
+  // (thousands of far columns with the same small residual add up; without the
+  // weights slowly decaying kernels such as 1/(1+|i-j|) lose 2-3 digits at large N)
+  std::vector<std::vector<double>> mass(N);
+  bool weighted = o.weighted_samples < 0 ? (P.type == 2 || P.type == 3) : o.weighted_samples != 0;
+  if (const char* e = std::getenv("SB200_COMPRESS_WEIGHTED")) weighted = std::atoi(e) != 0;
+  weighted = weighted && !P.full_complement;
   std::mt19937 rng(12345);
   if (P.full_complement) {
     for (int t = 1; t < N; t++) {
@@ -229,6 +248,9 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
     std::vector<double> c;
     std::vector<std::pair<double, int>> cand, heap, pq;
     std::vector<char> taken(n, 0);
+    std::vector<double> cmass;                      // mass of the candidates of strata (c)+(d), by point
+    std::vector<double> pmass(n, 0.);
+    std::vector<std::pair<int, double>> jm;
     for (int t = 1; t < N; t++) {  // pre-order: the parent's sample exists
       const int lo = T[t].lo, hi = T[t].hi;
       // ---- (a)+(b): best-first search of the Kc nearest outside points
@@ -263,13 +285,19 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
         }
       }
       std::sort(heap.begin(), heap.end());
-      auto take = [&](int i) { if (!taken[i]) { taken[i] = 1; J[t].push_back(i); } };
+      auto take = [&](int i, double ms) {
+        if (!taken[i]) { taken[i] = 1; J[t].push_back(i); mass[t].push_back(ms); }
+      };
       const int n1 = std::min<int>(K1, heap.size());
-      for (int i = 0; i < n1; i++) take(heap[i].second);
-      for (int i = 0; i < K2 && n1 + i < (int)heap.size(); i++) {
-        std::uniform_int_distribution<int> U(n1 + i, (int)heap.size() - 1);
-        std::swap(heap[n1 + i], heap[U(rng)]);
-        take(heap[n1 + i].second);
+      for (int i = 0; i < n1; i++) take(heap[i].second, 1.);
+      {
+        const int rest = (int)heap.size() - n1;
+        const double mb = rest > K2 ? double(rest) / K2 : 1.;
+        for (int i = 0; i < K2 && n1 + i < (int)heap.size(); i++) {
+          std::uniform_int_distribution<int> U(n1 + i, (int)heap.size() - 1);
+          std::swap(heap[n1 + i], heap[U(rng)]);
+          take(heap[n1 + i].second, mb);
+        }
       }
       // ---- (c)+(d): coarser scales through the sibling and the parent's sample
       const int p = T[t].parent;
@@ -285,20 +313,28 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
         }
         cand.emplace_back(r2, i);
       };
-      for (int i = T[s].lo; i < T[s].hi; i++) push(i);
-      for (int i : J[p]) if (i < lo || i >= hi) push(i);
+      for (int i = T[s].lo; i < T[s].hi; i++) { push(i); pmass[i] = 1.; }
+      for (size_t q = 0; q < J[p].size(); q++) {
+        const int i = J[p][q];
+        if (i < lo || i >= hi) { push(i); pmass[i] = mass[p][q]; }
+      }
       if ((int)cand.size() <= K3 + K4) {
-        for (auto& e : cand) take(e.second);
+        for (auto& e : cand) take(e.second, pmass[e.second]);
       } else {
         std::nth_element(cand.begin(), cand.begin() + K3, cand.end());
-        for (int i = 0; i < K3; i++) take(cand[i].second);
+        for (int i = 0; i < K3; i++) take(cand[i].second, pmass[cand[i].second]);
+        double mrest = 0.;
+        for (size_t i = K3; i < cand.size(); i++) mrest += pmass[cand[i].second];
         for (int i = 0; i < K4; i++) {
           std::uniform_int_distribution<int> U(K3 + i, (int)cand.size() - 1);
           std::swap(cand[K3 + i], cand[U(rng)]);
-          take(cand[K3 + i].second);
+          take(cand[K3 + i].second, mrest / K4);
         }
       }
-      std::sort(J[t].begin(), J[t].end());
+      jm.clear();
+      for (size_t q = 0; q < J[t].size(); q++) jm.emplace_back(J[t][q], mass[t][q]);
+      std::sort(jm.begin(), jm.end());
+      for (size_t q = 0; q < jm.size(); q++) { J[t][q] = jm[q].first; mass[t][q] = jm[q].second; }
       for (int i : J[t]) taken[i] = 0;
     }
   }
@@ -348,6 +384,8 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
         totR += (size_t)rcap[q] * nc; totE += (size_t)nc * rcap[q];
       }
       std::vector<int> hI(totI), hJ(totJ);
+      std::vector<double> hW(weighted ? totJ : 0);
+      DevBuf<double> dW(weighted && totJ ? totJ : 1);
       DevBuf<int> dI(totI ? totI : 1), dJ(totJ ? totJ : 1), dOrder(totI ? totI : 1), dRank(cnt);
       DevBuf<double> dM(totM ? totM : 1), dR(totR ? totR : 1), dE(totE ? totE : 1);
       SB200_CUDA(cudaMemset(dR.p, 0, sizeof(double) * (totR ? totR : 1)));
@@ -363,8 +401,10 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
         std::copy(J[t].begin(), J[t].end(), hJ.begin() + oJ);
         // M^T (ns x nc): row basis: M^T[s,i] = A(I[i], J[s])  -> rows=I cols=J transposed
         //                col basis: M  [s,i] = A(J[s], I[i])  -> rows=J cols=I plain
-        if (which == 0) bt[q] = {dI.p + oI, dJ.p + oJ, nc, ns, dM.p + oM, ns, 1};
-        else            bt[q] = {dJ.p + oJ, dI.p + oI, ns, nc, dM.p + oM, ns, 0};
+        const double* wq = weighted ? dW.p + oJ : nullptr;
+        if (weighted) for (int a = 0; a < ns; a++) hW[oJ + a] = std::sqrt(mass[t][a]);
+        if (which == 0) bt[q] = {dI.p + oI, dJ.p + oJ, nc, ns, dM.p + oM, ns, 1, nullptr, wq};
+        else            bt[q] = {dJ.p + oJ, dI.p + oI, ns, nc, dM.p + oM, ns, 0, wq, nullptr};
         it[q] = {dM.p + oM, dR.p + oR, ns, nc, rcap[q], dOrder.p + oI, dRank.p + q, dE.p + oE, 0};
         offI[q] = oI; offE[q] = oE;
         oI += nc; oJ += ns; oM += (size_t)ns * nc; oR += (size_t)rcap[q] * nc;
@@ -373,6 +413,7 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
       }
       dI.upload(hI.data(), totI);
       dJ.upload(hJ.data(), totJ);
+      if (weighted) dW.upload(hW.data(), totJ);
       DevBuf<BlockTask> dbt; dbt.upload(bt.data(), cnt);
       DevBuf<IDTask> dit; dit.upload(it.data(), cnt);
       eval_blocks_kernel<<<dim3(cnt, 16), kThreads>>>(src, dbt.p);

@@ -20,6 +20,14 @@ struct CompressOptions {
   // sampled-ID parameters: points per near-field / coarse-scale stratum
   // (the role HSSOptions::d0/ann_number play in the reference)
   int sample_near = 96, sample_far = 128;
+  // scale every sampled column by sqrt(number of complement points it stands
+  // for) before the interpolative decomposition.  -1 = automatic: on for
+  // algebraically decaying kernels (1/(1+|i-j|), sampled dense input), off for
+  // the exponentially decaying Gauss / Laplace kernels whose far field is
+  // numerically zero (there the weights only move the relative stopping
+  // threshold).  Measured: profiles/r1b_compress_accuracy.txt.
+  // env SB200_COMPRESS_WEIGHTED=0/1 overrides.
+  int weighted_samples = -1;
 };
 
 // A: host column-major rows x cols
