@@ -155,6 +155,32 @@ int SB200_d_struct_factor_device(CSPStructMat S, void* stream);
 int SB200_d_struct_solve_device(const CSPStructMat S, int nrhs, double* dB,
                                 int ldB, void* stream);
 
+/* apply_HSS(op, A, B, beta, C): C = op(S) B + beta C (reference
+ * src/HSS/HSSMatrix.cpp:419-435, free function HSSMatrix.hpp:705-713).  Host
+ * pointers; the _device form takes device pointers and a stream. */
+int SB200_d_hss_apply(const CSPStructMat S, char trans, int m, const double* B,
+                      int ldB, double beta, double* C, int ldC);
+int SB200_d_hss_apply_device(const CSPStructMat S, char trans, int m,
+                             const double* dB, int ldB, double beta, double* dC,
+                             int ldC, void* stream);
+/* HSSMatrix::extract(I, J) / extract_add(I, J, B) / get(i, j) (reference
+ * src/HSS/HSSMatrix.extract.hpp:8-188, test/test_HSS_seq.cpp:204-233): the
+ * nI x nJ sub-block H(I, J) for arbitrary 0-based index lists, written to
+ * (add = 0) or added to (add = 1) the host matrix B (column-major, ld ldB). */
+int SB200_d_hss_extract(const CSPStructMat S, int nI, const int* I, int nJ,
+                        const int* J, double* B, int ldB, int add);
+/* HSSMatrix::forward_solve / backward_solve (reference HSSMatrix.hpp:360-376,
+ * HSSMatrix.solve.hpp:52-66): solve = forward (bottom-up elimination of the
+ * right-hand side and the root solve) followed by backward (top-down
+ * reconstruction).  The state passed between the two (WorkSolve in the
+ * reference) is kept inside S.  forward reads B, backward writes X. */
+int SB200_d_hss_forward_solve(const CSPStructMat S, int nrhs, const double* B, int ldB);
+int SB200_d_hss_backward_solve(const CSPStructMat S, int nrhs, double* X, int ldX);
+int SB200_d_hss_forward_solve_device(const CSPStructMat S, int nrhs, double* dB,
+                                     int ldB, void* stream);
+int SB200_d_hss_backward_solve_device(const CSPStructMat S, int nrhs, double* dX,
+                                      int ldX, void* stream);
+
 /* ---- subtree sharding over the GPUs of one node -------------
  * Every rank holds a handle on the same matrix and calls
  * SB200_d_hss_set_partition(S, nparts, part): it then owns the subtree of the

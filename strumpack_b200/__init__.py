@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libstrumpack_b200.so")
+# SB200_LIB: development override (A/B builds of the engine); default = the in-tree library
+_SO = os.environ.get("SB200_LIB") or os.path.join(_HERE, "libstrumpack_b200.so")
 _lib = None
 
 SP_TYPE_HSS, SP_TYPE_BLR = 0, 1
@@ -63,6 +64,13 @@ SYMBOLS = {
     "SB200_d_struct_mult_device": (_i, [_vp, C.c_char, _i, _vp, _i, _vp, _i, _vp]),
     "SB200_d_struct_factor_device": (_i, [_vp, _vp]),
     "SB200_d_struct_solve_device": (_i, [_vp, _i, _vp, _i, _vp]),
+    "SB200_d_hss_apply": (_i, [_vp, C.c_char, _i, _vp, _i, _d, _vp, _i]),
+    "SB200_d_hss_apply_device": (_i, [_vp, C.c_char, _i, _vp, _i, _d, _vp, _i, _vp]),
+    "SB200_d_hss_extract": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i]),
+    "SB200_d_hss_forward_solve": (_i, [_vp, _i, _vp, _i]),
+    "SB200_d_hss_backward_solve": (_i, [_vp, _i, _vp, _i]),
+    "SB200_d_hss_forward_solve_device": (_i, [_vp, _i, _vp, _i, _vp]),
+    "SB200_d_hss_backward_solve_device": (_i, [_vp, _i, _vp, _i, _vp]),
     "SB200_d_hss_set_partition": (_i, [_vp, _i, _i]),
     "SB200_d_hss_owned_range": (_i, [_vp, _vp, _vp]),
     "SB200_d_hss_dist_sizes": (_i, [_vp, _i, _vp]),
@@ -394,6 +402,48 @@ class HSSMatrix(StructuredMatrix):
 
     def write(self, path):
         _check(lib().SB200_d_hss_write(self._h, str(path).encode()), "write")
+
+    def apply(self, b, beta=0.0, c=None, trans="N"):
+        """apply_HSS(op, H, B, beta, C): returns op(H) b + beta c
+        (reference HSSMatrix.cpp:419-435)."""
+        b = _fortran(b)
+        t = trans.upper() != "N"
+        ny = self.cols if t else self.rows
+        out = np.zeros((ny, b.shape[1]), order="F") if c is None else _fortran(c).copy(order="F")
+        _check(lib().SB200_d_hss_apply(self._h, trans.encode()[:1], b.shape[1], b.ctypes.data,
+                                       b.shape[0], float(beta), out.ctypes.data, ny), "apply")
+        return out
+
+    def extract(self, I, J, add_to=None):
+        """HSSMatrix::extract(I, J) (or extract_add when ``add_to`` is given):
+        the dense sub-block H(I, J) (reference HSSMatrix.extract.hpp:8-188)."""
+        I = np.ascontiguousarray(I, dtype=np.int32)
+        J = np.ascontiguousarray(J, dtype=np.int32)
+        B = (np.zeros((I.size, J.size), order="F") if add_to is None
+             else _fortran(add_to).copy(order="F"))
+        if I.size and J.size:
+            _check(lib().SB200_d_hss_extract(self._h, I.size, I.ctypes.data, J.size, J.ctypes.data,
+                                             B.ctypes.data, max(I.size, 1), int(add_to is not None)),
+                   "extract")
+        return B
+
+    def get(self, i, j):
+        """HSSMatrix::get(i, j) (reference HSSMatrix.extract.hpp:8-16)."""
+        return float(self.extract([i], [j])[0, 0])
+
+    def forward_solve(self, b):
+        """HSSMatrix::forward_solve (HSSMatrix.solve.hpp:52-58); state stays in the object."""
+        b = _fortran(b)
+        _check(lib().SB200_d_hss_forward_solve(self._h, b.shape[1], b.ctypes.data, b.shape[0]),
+               "forward_solve")
+        self._fwd_shape = b.shape
+
+    def backward_solve(self):
+        """HSSMatrix::backward_solve (HSSMatrix.solve.hpp:60-66): returns x."""
+        n, s = self._fwd_shape
+        x = np.zeros((n, s), order="F")
+        _check(lib().SB200_d_hss_backward_solve(self._h, s, x.ctypes.data, n), "backward_solve")
+        return x
 
     @classmethod
     def from_generators(cls, nodes):

@@ -327,6 +327,75 @@ int SB200_d_struct_solve_device(const CSPStructMat S, int nrhs, double* dB,
   });
 }
 
+int SB200_d_hss_apply(const CSPStructMat S, char trans, int m, const double* B,
+                      int ldB, double beta, double* C, int ldC) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    cudaStream_t st = 0;
+    const bool T = !(trans == 'N' || trans == 'n');
+    const int nb = T ? H.rows() : H.cols(), nc = T ? H.cols() : H.rows();
+    h2d(mm->dB, B, nb, m, ldB, st);
+    if (beta != 0.) h2d(mm->dC, C, nc, m, ldC, st);
+    else mm->dC.ensure((size_t)nc * m);
+    H.mult(trans, m, mm->dB.p, nb, mm->dC.p, nc, st, beta);
+    d2h(C, mm->dC, nc, m, ldC, st);
+    SB200_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int SB200_d_hss_apply_device(const CSPStructMat S, char trans, int m, const double* dB,
+                             int ldB, double beta, double* dC, int ldC, void* stream) {
+  return guarded([&] {
+    hss(S).mult(trans, m, dB, ldB, dC, ldC, static_cast<cudaStream_t>(stream), beta);
+  });
+}
+
+int SB200_d_hss_extract(const CSPStructMat S, int nI, const int* I, int nJ, const int* J,
+                        double* B, int ldB, int add) {
+  return guarded([&] {
+    if (nI <= 0 || nJ <= 0) return;
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    if (add) h2d(mm->dC, B, nI, nJ, ldB, 0);
+    else mm->dC.ensure((size_t)nI * nJ);
+    H.extract(nI, I, nJ, J, mm->dC.p, nI, add != 0, 0);
+    d2h(B, mm->dC, nI, nJ, ldB, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_hss_forward_solve(const CSPStructMat S, int nrhs, const double* B, int ldB) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    h2d(mm->dB, B, H.rows(), nrhs, ldB, 0);
+    H.forward_solve(nrhs, mm->dB.p, H.rows(), 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_hss_backward_solve(const CSPStructMat S, int nrhs, double* X, int ldX) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    mm->dB.ensure((size_t)H.rows() * nrhs);
+    H.backward_solve(nrhs, mm->dB.p, H.rows(), 0);
+    d2h(X, mm->dB, H.rows(), nrhs, ldX, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_hss_forward_solve_device(const CSPStructMat S, int nrhs, double* dB, int ldB,
+                                     void* stream) {
+  return guarded([&] { hss(S).forward_solve(nrhs, dB, ldB, static_cast<cudaStream_t>(stream)); });
+}
+
+int SB200_d_hss_backward_solve_device(const CSPStructMat S, int nrhs, double* dX, int ldX,
+                                      void* stream) {
+  return guarded([&] { hss(S).backward_solve(nrhs, dX, ldX, static_cast<cudaStream_t>(stream)); });
+}
+
 int SB200_d_hss_set_partition(CSPStructMat S, int nparts, int part) {
   return guarded([&] { hss(S).set_partition(nparts, part); });
 }

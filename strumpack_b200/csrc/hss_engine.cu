@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads)
 hss_leaf_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                 const double* __restrict__ vals, const int* __restrict__ perms,
                 const double* __restrict__ x, int ldx, const double* __restrict__ t2,
-                double* __restrict__ y, int ldy, int s) {
+                double* __restrict__ y, int ldy, int s, double beta) {
   extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   const int c = blockIdx.y, tid = threadIdx.x;
@@ -194,7 +194,8 @@ hss_leaf_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
         a3 += Di[(size_t)(j + 3) * m] * xs[j + 3];
       }
       for (; j < nin; j++) a0 += Di[(size_t)j * m] * xs[j];
-      yo[i] = (a0 + a1) + (a2 + a3);
+      const double v = (a0 + a1) + (a2 + a3);
+      yo[i] = beta == 0. ? v : v + beta * yo[i];   // apply_bwd: C = beta C + ... (apply.hpp:87-99)
     }
   } else {
     const int m = nd.rows;
@@ -204,7 +205,7 @@ hss_leaf_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
       double acc = 0.;
       for (int i = lane; i < m; i += 32) acc += Dj[i] * xs[i];
       acc = warp_sum(acc);
-      if (lane == 0) yo[j] = u[j] + acc;
+      if (lane == 0) yo[j] = beta == 0. ? u[j] + acc : u[j] + acc + beta * yo[j];
     }
   }
 }
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(kThreads)
 hss_leaf_mm_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                    const double* __restrict__ vals, const int* __restrict__ perms,
                    const double* __restrict__ x, int ldx, const double* __restrict__ t2,
-                   double* __restrict__ y, int ldy, int s, int ldp) {
+                   double* __restrict__ y, int ldy, int s, int ldp, double beta) {
   extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   const int c0 = blockIdx.y * kMS, ns = min(kMS, s - c0), tid = threadIdx.x;
@@ -387,7 +388,8 @@ hss_leaf_mm_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list
   double* yo = y + (TRANS ? nd.col_off : nd.row_off) + (size_t)c0 * ldy;
   for (int idx = tid; idx < nout * ns; idx += kThreads) {
     const int i = idx % nout, c = idx / nout;
-    yo[i + (size_t)c * ldy] = ys[i + c * ldp];
+    double* o = yo + i + (size_t)c * ldy;
+    *o = beta == 0. ? ys[i + c * ldp] : ys[i + c * ldp] + beta * *o;
   }
 }
 
@@ -399,6 +401,118 @@ __global__ void hss_shift_kernel(const DNode* __restrict__ nodes,
   double* D = vals + nd.D;
   const int n = min(nd.rows, nd.cols);
   for (int i = threadIdx.x; i < n; i += blockDim.x) D[i + (size_t)i * nd.rows] += sigma;
+}
+
+// ===========================================================================
+//                         ELEMENT EXTRACTION
+// ===========================================================================
+// H(I, J) for arbitrary index sets  (reference HSSMatrix::extract / extract_add /
+// get, HSSMatrix.extract.hpp:8-188, used by the sparse front assembly and
+// checked by test/test_HSS_seq.cpp:204-233).  The reference walks the tree
+// with per-node index sub-lists; here
+//  1. one CTA per requested row (column) index climbs from its leaf to the
+//     child of the root and records, for every node on the path, the row of
+//     the node's nested basis  U_big(node)[i, :]  (V_big(node)[j, :]);
+//  2. one thread per requested entry finds the level where the two paths part
+//     and evaluates  u^T B v  with the coupling block of their common parent
+//     (or reads D when both indices sit in the same leaf).
+// paths: for every index `maxd` node ids, top-down (depth 1 first), -1 padded.
+template <bool VSIDE>
+__global__ void __launch_bounds__(128)
+hss_basis_rows_kernel(const DNode* __restrict__ nodes, const double* __restrict__ vals,
+                      const int* __restrict__ perms, const int* __restrict__ idx,
+                      const int* __restrict__ paths, int maxd, int maxr,
+                      double* __restrict__ chain) {
+  extern __shared__ __align__(16) double sm[];
+  double* ua = sm;                  // maxr
+  double* ub = sm + maxr;           // maxr
+  int* pos = reinterpret_cast<int*>(ub + maxr);   // maxr
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int* path = paths + (size_t)q * maxd;
+  int dl = maxd - 1;
+  while (dl >= 0 && path[dl] < 0) dl--;
+  if (dl < 0) return;               // single-node tree: no basis
+  double* out = chain + (size_t)q * maxd * maxr;
+  // ---- leaf
+  {
+    const DNode nd = nodes[path[dl]];
+    const int li = idx[q] - (VSIDE ? nd.col_off : nd.row_off);
+    const int n = VSIDE ? nd.v_rows : nd.u_rows, r = VSIDE ? nd.v_rank : nd.u_rank;
+    const int* P = perms + (VSIDE ? nd.Pv : nd.Pu);
+    const double* E = vals + (VSIDE ? nd.Ev : nd.Eu);
+    for (int j = tid; j < n; j += 128) if (P[j] == li) pos[0] = j;
+    __syncthreads();
+    const int p = pos[0], k = n - r;
+    for (int c = tid; c < r; c += 128) ua[c] = p < r ? (p == c ? 1. : 0.) : E[(p - r) + (size_t)c * k];
+    __syncthreads();
+    for (int c = tid; c < r; c += 128) out[(size_t)dl * maxr + c] = ua[c];
+  }
+  // ---- ancestors
+  for (int d = dl - 1; d >= 0; d--) {
+    const DNode nd = nodes[path[d]];
+    const int child = path[d + 1];
+    const DNode c0 = nodes[nd.ch0];
+    const int r0 = VSIDE ? c0.v_rank : c0.u_rank;
+    const DNode cc = nodes[child];
+    const int rc = VSIDE ? cc.v_rank : cc.u_rank;
+    const int off = (child == nd.ch0) ? 0 : r0;
+    const int n = VSIDE ? nd.v_rows : nd.u_rows, r = VSIDE ? nd.v_rank : nd.u_rank;
+    const int* P = perms + (VSIDE ? nd.Pv : nd.Pu);
+    const double* E = vals + (VSIDE ? nd.Ev : nd.Eu);
+    __syncthreads();
+    for (int j = tid; j < n; j += 128) {
+      const int t = P[j] - off;
+      if (t >= 0 && t < rc) pos[t] = j;
+    }
+    __syncthreads();
+    const int k = n - r;
+    for (int c = tid; c < r; c += 128) {
+      double acc = 0.;
+      for (int t = 0; t < rc; t++) {
+        const int p = pos[t];
+        acc += ua[t] * (p < r ? (p == c ? 1. : 0.) : E[(p - r) + (size_t)c * k]);
+      }
+      ub[c] = acc;
+    }
+    __syncthreads();
+    for (int c = tid; c < r; c += 128) { ua[c] = ub[c]; out[(size_t)d * maxr + c] = ub[c]; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+hss_extract_kernel(const DNode* __restrict__ nodes, const double* __restrict__ vals,
+                   const int* __restrict__ I, const int* __restrict__ J, int nI, int nJ,
+                   const int* __restrict__ pI, const int* __restrict__ pJ, int maxd, int maxr,
+                   const double* __restrict__ cu, const double* __restrict__ cv,
+                   double* __restrict__ B, int ldb, int add) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)nI * nJ) return;
+  const int a = (int)(e % nI), b = (int)(e / nI);
+  const int* pa = pI + (size_t)a * maxd;
+  const int* pb = pJ + (size_t)b * maxd;
+  int d = 0;
+  while (d < maxd && pa[d] >= 0 && pa[d] == pb[d]) d++;
+  double v;
+  if (d == maxd || (pa[d] < 0 && pb[d] < 0)) {   // same leaf (the last common node)
+    const DNode nd = nodes[d == 0 ? 0 : pa[d - 1]];
+    v = vals[nd.D + (I[a] - nd.row_off) + (size_t)(J[b] - nd.col_off) * nd.rows];
+  } else {
+    const DNode par = nodes[d == 0 ? 0 : pa[d - 1]];
+    const DNode na = nodes[pa[d]], nb = nodes[pb[d]];
+    const bool first = pa[d] == par.ch0;          // row index below child 0: block B01
+    const double* Bk = vals + (first ? par.B01 : par.B10);
+    const int ru = na.u_rank, rv = nb.v_rank;
+    const double* u = cu + ((size_t)a * maxd + d) * maxr;
+    const double* w = cv + ((size_t)b * maxd + d) * maxr;
+    v = 0.;
+    for (int q = 0; q < rv; q++) {
+      double t = 0.;
+      for (int p = 0; p < ru; p++) t += u[p] * Bk[p + (size_t)q * ru];
+      v += t * w[q];
+    }
+  }
+  double* o = B + a + (size_t)b * ldb;
+  *o = add ? *o + v : v;
 }
 
 // ===========================================================================
@@ -2400,7 +2514,7 @@ void HSSEngine::run_up(const NodeLists& L, bool T, int s, const double* dB, int 
 }
 
 void HSSEngine::run_down(const NodeLists& L, bool T, int s, const double* dB, int ldB,
-                         double* dC, int ldC, bool leaves, cudaStream_t st) {
+                         double* dC, int ldC, bool leaves, cudaStream_t st, double beta) {
   for (int h = L.classes() - 1; h >= 1; h--) {
     const int cnt = L.hptr[h + 1] - L.hptr[h];
     if (!cnt) continue;
@@ -2433,9 +2547,9 @@ void HSSEngine::run_down(const NodeLists& L, bool T, int s, const double* dB, in
     if (s >= mm_min_ && smem_mm <= kMaxSmem) {
       dim3 grid(cnt, (s + kMS - 1) / kMS);
       if (T) { set_smem(hss_leaf_mm_kernel<true>, smem_mm);
-        hss_leaf_mm_kernel<true><<<grid, kThreads, smem_mm, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s, ldp);
+        hss_leaf_mm_kernel<true><<<grid, kThreads, smem_mm, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s, ldp, beta);
       } else { set_smem(hss_leaf_mm_kernel<false>, smem_mm);
-        hss_leaf_mm_kernel<false><<<grid, kThreads, smem_mm, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s, ldp);
+        hss_leaf_mm_kernel<false><<<grid, kThreads, smem_mm, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s, ldp, beta);
       }
       launches_++;
       return;
@@ -2443,22 +2557,22 @@ void HSSEngine::run_down(const NodeLists& L, bool T, int s, const double* dB, in
     size_t smem = sizeof(double) * (size_t)(3 * std::max(L.max_m[0], 1) + 8);
     dim3 grid(cnt, s);
     if (T) { set_smem(hss_leaf_kernel<true>, smem);
-      hss_leaf_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s);
+      hss_leaf_kernel<true><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s, beta);
     } else { set_smem(hss_leaf_kernel<false>, smem);
-      hss_leaf_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s);
+      hss_leaf_kernel<false><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p, vals_.p, perms_.p, dB, ldB, t2_.p, dC, ldC, s, beta);
     }
     launches_++;
   }
 }
 
 void HSSEngine::mult(char trans, int s, const double* dB, int ldB, double* dC,
-                     int ldC, cudaStream_t st) {
+                     int ldC, cudaStream_t st, double beta) {
   if (nparts_ > 1) throw std::logic_error("sharded matrix: use the dist_* entry points");
   const bool T = !(trans == 'N' || trans == 'n');
   if (s <= 0) return;
   ensure_apply_ws(s);
   run_up(own_, T, s, dB, ldB, st);
-  run_down(own_, T, s, dB, ldB, dC, ldC, true, st);
+  run_down(own_, T, s, dB, ldB, dC, ldC, true, st, beta);
   SB200_CUDA(cudaGetLastError());
 }
 
@@ -2516,6 +2630,53 @@ void HSSEngine::export_ulv(double* factors, double* tfactors, long long* sizes) 
 template <int NB> static size_t qr_smem(int ldv) {
   constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
   return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 64);
+}
+
+// ------------------------------------------------------------------ extract
+void HSSEngine::extract(int nI, const int* I, int nJ, const int* J, double* dB, int ldB,
+                        bool add, cudaStream_t st) {
+  if (nI <= 0 || nJ <= 0) return;
+  // leaves in index order (pre-order numbering = left to right)
+  if (leaf_ids_.empty()) {
+    for (int i = 0; i < (int)H_.nodes.size(); i++)
+      if (H_.nodes[i].leaf()) leaf_ids_.push_back(i);
+    max_depth_ = 0;
+    for (const auto& n : H_.nodes) max_depth_ = std::max(max_depth_, n.depth);
+  }
+  const int maxd = std::max(max_depth_, 1), maxr = std::max(H_.max_rank(), 1);
+  auto build_paths = [&](int cnt, const int* idx, bool cols, std::vector<int>& paths) {
+    paths.assign((size_t)cnt * maxd, -1);
+    for (int q = 0; q < cnt; q++) {
+      const int i = idx[q];
+      if (i < 0 || i >= (cols ? H_.cols() : H_.rows())) throw std::invalid_argument("extract: index out of range");
+      int lo = 0, hi = (int)leaf_ids_.size() - 1;     // last leaf with offset <= i
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        const auto& n = H_.nodes[leaf_ids_[mid]];
+        if ((cols ? n.col_off : n.row_off) <= i) lo = mid; else hi = mid - 1;
+      }
+      for (int t = leaf_ids_[lo]; t > 0; t = H_.nodes[t].parent)
+        paths[(size_t)q * maxd + H_.nodes[t].depth - 1] = t;
+    }
+  };
+  std::vector<int> pI, pJ;
+  build_paths(nI, I, false, pI);
+  build_paths(nJ, J, true, pJ);
+  DevBuf<int> dI, dJ, dpI, dpJ;
+  dI.upload(I, nI, st); dJ.upload(J, nJ, st);
+  dpI.upload(pI.data(), pI.size(), st); dpJ.upload(pJ.data(), pJ.size(), st);
+  DevBuf<double> cu((size_t)nI * maxd * maxr), cv((size_t)nJ * maxd * maxr);
+  const size_t smem = sizeof(double) * 2 * (size_t)maxr + sizeof(int) * (size_t)(maxr + 8);
+  set_smem(hss_basis_rows_kernel<false>, smem);
+  set_smem(hss_basis_rows_kernel<true>, smem);
+  hss_basis_rows_kernel<false><<<nI, 128, smem, st>>>(dn_.p, vals_.p, perms_.p, dI.p, dpI.p, maxd, maxr, cu.p);
+  hss_basis_rows_kernel<true><<<nJ, 128, smem, st>>>(dn_.p, vals_.p, perms_.p, dJ.p, dpJ.p, maxd, maxr, cv.p);
+  const long long tot = (long long)nI * nJ;
+  hss_extract_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dn_.p, vals_.p, dI.p, dJ.p, nI, nJ, dpI.p, dpJ.p,
+                                                                    maxd, maxr, cu.p, cv.p, dB, ldB, add ? 1 : 0);
+  launches_ += 3;
+  SB200_CUDA(cudaGetLastError());
+  SB200_CUDA(cudaStreamSynchronize(st));   // the index / path buffers are locals
 }
 
 // ------------------------------------------------------------------ factor
@@ -2689,6 +2850,26 @@ void HSSEngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
   ensure_solve_ws(s);
   solve_fwd(own_, s, dB, ldB, st);     // the kernels skip the root
   solve_root(s, dB, ldB, st);
+  solve_bwd(own_, s, dB, ldB, st);
+  SB200_CUDA(cudaGetLastError());
+}
+
+// forward_solve / backward_solve (reference HSSMatrix.solve.hpp:52-66): the
+// WorkSolve state between the two calls lives in the engine's workspaces.
+void HSSEngine::forward_solve(int s, double* dB, int ldB, cudaStream_t st) {
+  if (nparts_ > 1) throw std::logic_error("sharded matrix: use the dist_* entry points");
+  if (!factored_) throw std::logic_error("forward_solve called before factor");
+  if (s <= 0) return;
+  ensure_solve_ws(s);
+  solve_fwd(own_, s, dB, ldB, st);
+  solve_root(s, dB, ldB, st);
+  fwd_s_ = s;
+  SB200_CUDA(cudaGetLastError());
+}
+
+void HSSEngine::backward_solve(int s, double* dB, int ldB, cudaStream_t st) {
+  if (nparts_ > 1) throw std::logic_error("sharded matrix: use the dist_* entry points");
+  if (fwd_s_ != s || s <= 0) throw std::logic_error("backward_solve needs a forward_solve with the same number of right-hand sides");
   solve_bwd(own_, s, dB, ldB, st);
   SB200_CUDA(cudaGetLastError());
 }

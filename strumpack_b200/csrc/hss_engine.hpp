@@ -53,11 +53,20 @@ class HSSEngine {
   int cols() const { return H_.cols(); }
 
   // C = op(H) B ; dB, dC device pointers (column-major)
+  // beta != 0: C = op(H) B + beta C   (apply_HSS, reference HSSMatrix.cpp:419-435)
   void mult(char trans, int s, const double* dB, int ldB, double* dC, int ldC,
-            cudaStream_t st);
+            cudaStream_t st, double beta = 0.);
   void factor(cudaStream_t st);
   void solve(int s, double* dB, int ldB, cudaStream_t st);
+  // the two halves of solve (reference forward_solve / backward_solve): forward
+  // reads B (a single-node tree also overwrites it), backward writes x into B
+  void forward_solve(int s, double* dB, int ldB, cudaStream_t st);
+  void backward_solve(int s, double* dB, int ldB, cudaStream_t st);
   void shift(double sigma, cudaStream_t st);
+  // B (nI x nJ, device, ld ldB) = or += H(I, J); I, J host index lists
+  // (HSSMatrix::extract / extract_add, reference HSSMatrix.extract.hpp:8-188)
+  void extract(int nI, const int* I, int nJ, const int* J, double* dB, int ldB, bool add,
+               cudaStream_t st);
   bool factored() const { return factored_; }
 
   // ---- subtree sharding over `nparts` GPUs: this rank owns the
@@ -96,7 +105,7 @@ class HSSEngine {
   int class_nb(int h, int max_m) const;   // QR panel width of a height class
   void run_up(const NodeLists& L, bool T, int s, const double* dB, int ldB, cudaStream_t st);
   void run_down(const NodeLists& L, bool T, int s, const double* dB, int ldB, double* dC,
-                int ldC, bool leaves, cudaStream_t st);
+                int ldC, bool leaves, cudaStream_t st, double beta = 0.);
   void factor_prepare();
   void factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t st);
   void solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st);
@@ -104,6 +113,8 @@ class HSSEngine {
   void solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st);
 
   HSSHost H_;
+  std::vector<int> leaf_ids_;   // leaves in index order (extract)
+  int max_depth_ = 0;
   std::vector<DNode> hn_;
   DevBuf<DNode> dn_;
   DevBuf<double> vals_;
@@ -118,7 +129,7 @@ class HSSEngine {
   DevBuf<double> fact_, tfac_, scratch_;
   DevBuf<int> rootpiv_;
   DevBuf<double> ysol_, zsol_, fsol_, xsol_;
-  int solve_s_ = 0;
+  int solve_s_ = 0, fwd_s_ = 0;
   long long tot_k_ = 0, tot_rv_ = 0, tot_ru_ = 0, tot_m_ = 0;
   long long fact_nnz_ = 0;
   long long scratch_per_node_max_ = 0;

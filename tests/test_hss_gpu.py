@@ -159,3 +159,50 @@ def test_apply_many_rhs_gemm_path(sb, case, nrhs):
     # column by column through the single-rhs kernels
     y1 = np.hstack([H.mult(x[:, j]) for j in range(0, nrhs, 5)])
     assert rel(y[:, ::5], y1) < 1e-13
+
+
+@pytest.mark.parametrize("nrhs", [1, 3, 20])
+def test_apply_hss_with_beta_and_split_solve(sb, nrhs):
+    """apply_HSS(op, A, B, beta, C) (HSSMatrix.cpp:419-435) and the
+    forward_solve / backward_solve pair (HSSMatrix.solve.hpp:52-66)."""
+    case = CASES[2]
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    nodes, _ = hss_file.read_hss(os.path.join(GOLDEN, case + ".hss"))
+    H = sb.HSSMatrix.read(os.path.join(GOLDEN, case + ".hss"))
+    rng = np.random.default_rng(nrhs)
+    x = rng.standard_normal((H.rows, nrhs))
+    c = rng.standard_normal((H.rows, nrhs))
+    for tr in ("N", "T"):
+        ref = ho.apply(nodes, x, trans=(tr == "T")) - 0.75 * c
+        assert rel(H.apply(x, -0.75, c, tr), ref) < 1e-13
+    assert rel(H.apply(x), ho.apply(nodes, x)) < 1e-13
+    H.factor()
+    y = H.mult(x)
+    H.forward_solve(y)
+    xs = H.backward_solve()
+    assert rel(xs, H.solve(y)) < 1e-14       # same kernels, same order
+    assert rel(xs, x) < 1e-10
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_extract_sub_blocks(sb, case):
+    """extract / extract_add / get against dense(H) from the oracle, as
+    test/test_HSS_seq.cpp:204-233 does (random index sets, sorted and unsorted,
+    with repetitions, crossing every level of the tree)."""
+    nodes, _ = hss_file.read_hss(os.path.join(GOLDEN, case + ".hss"))
+    A = ho.to_dense(nodes)
+    H = sb.HSSMatrix.read(os.path.join(GOLDEN, case + ".hss"))
+    n = H.rows
+    rng = np.random.default_rng(11)
+    for nI, nJ in ((1, 1), (7, 5), (64, 80), (n, 3)):
+        I = rng.integers(0, n, nI) if nI < n else np.arange(n)
+        J = rng.integers(0, n, nJ)
+        B = H.extract(I, J)
+        ref = A[np.ix_(I, J)]
+        assert np.abs(B - ref).max() <= 1e-13 * max(1.0, np.abs(A).max())
+        C0 = rng.standard_normal((nI, nJ))
+        assert np.abs(H.extract(I, J, add_to=C0) - (C0 + ref)).max() <= 1e-12
+    assert abs(H.get(3, n - 2) - A[3, n - 2]) <= 1e-13
+    assert abs(H.get(5, 5) - A[5, 5]) <= 1e-13
+    with pytest.raises(RuntimeError):
+        H.extract([n], [0])
