@@ -181,6 +181,51 @@ int SB200_d_hss_forward_solve_device(const CSPStructMat S, int nrhs, double* dB,
 int SB200_d_hss_backward_solve_device(const CSPStructMat S, int nrhs, double* dX,
                                       int ldX, void* stream);
 
+/* ---- Schur complement of the (0,0) block: what the reference's HSS fronts
+ * use (src/sparse/fronts/FrontHSS.cpp:385-410 factor, :150-222 sampling,
+ * :452-462 / :487-495 solve).  With H = [H00 H01; H10 H11] split at the root's
+ * children (rows0 + rows1 = rows):
+ *   S = H11 - H10 H00^{-1} H01 = H11 - Theta Vhat^H Phi^H.
+ * partial_factor   HSSMatrix::partial_factor          (HSSMatrix.factor.hpp:44-50)
+ * schur_sizes      out[0..6] = rows1, cols1, r_v(child 0), m0, r_v(child 1),
+ *                  r_u(child 1), rows0; m0 = size of child 0's reduced block D0
+ * schur_update     HSSMatrix::Schur_update             (HSSMatrix.Schur.hpp:40-59)
+ *                  Theta rows1 x r_v0, DUB01 m0 x r_v1, Phi cols1 x m0 (host,
+ *                  any may be NULL; device copies are kept inside S)
+ * vhat             child(0)->ULV().Vhat(), m0 x r_v0   (HSSExtra.hpp:197-212)
+ * schur_product_direct    Sr = S R, Sc = S^H R, R rows1 x c
+ *                                                      (HSSMatrix.Schur.hpp:73-137)
+ *                  Theta / DUB01 / Phi = NULL: the ones of the last schur_update
+ * schur_product_indirect  Sr = Sr1 - H10 R0 - H10 H00^{-1} H01 R1 (and the
+ *                  transposed analogue for Sc) from Sr1 = (H [R0; R1])_1,
+ *                  Sc1 = (H^H [R0; R1])_1               (HSSMatrix.Schur.hpp:139-215)
+ * partial_forward_solve   child(0)->forward_solve(w, b0, partial = true): keeps
+ *                  x = D0^{-1} f inside S and returns reduced_rhs (r_v0 x nrhs)
+ *                                                      (HSSMatrix.solve.hpp:133-152)
+ * partial_x        get (set = 0) / overwrite (set = 1) that x (m0 x nrhs), as
+ *                  FrontHSS::bwd_solve_node updates it with Phi^H y_upd
+ * partial_backward_solve  child(0)->backward_solve(w, x0)
+ * The basis of the reduced space (hence Vhat, DUB01, Phi, x individually)
+ * depends on the orthogonal factors chosen by the ULV elimination; Theta,
+ * Vhat^H DUB01, Vhat^H Phi^H, reduced_rhs, Sr, Sc and x0 do not. */
+int SB200_d_hss_partial_factor(CSPStructMat S);
+int SB200_d_hss_schur_sizes(const CSPStructMat S, int* out);
+int SB200_d_hss_schur_update(const CSPStructMat S, double* Theta, int ldT, double* DUB01,
+                             int ldD, double* Phi, int ldP);
+int SB200_d_hss_vhat(const CSPStructMat S, double* Vhat, int ldV);
+int SB200_d_hss_schur_product_direct(const CSPStructMat S, const double* Theta, int ldT,
+                                     const double* DUB01, int ldD, const double* Phi, int ldP,
+                                     int c, const double* R, int ldR, double* Sr, int ldSr,
+                                     double* Sc, int ldSc);
+int SB200_d_hss_schur_product_indirect(const CSPStructMat S, const double* DUB01, int ldD, int c,
+                                       const double* R0, int ldR0, const double* R1, int ldR1,
+                                       const double* Sr1, int ldSr1, const double* Sc1, int ldSc1,
+                                       double* Sr, int ldSr, double* Sc, int ldSc);
+int SB200_d_hss_partial_forward_solve(const CSPStructMat S, int nrhs, const double* B0, int ldB,
+                                      double* reduced_rhs, int ldR);
+int SB200_d_hss_partial_x(const CSPStructMat S, int nrhs, double* X, int ldX, int set);
+int SB200_d_hss_partial_backward_solve(const CSPStructMat S, int nrhs, double* X0, int ldX);
+
 /* ---- subtree sharding over the GPUs of one node -------------
  * Every rank holds a handle on the same matrix and calls
  * SB200_d_hss_set_partition(S, nparts, part): it then owns the subtree of the

@@ -160,10 +160,12 @@ class ULV:
         self.flops = 0
 
 
-def _factor_node(nodes, f, i):
-    """One node of HSSMatrix::factor_recursive (HSSMatrix.factor.hpp:51-147)."""
+def _factor_node(nodes, f, i, root=0, partial=False):
+    """One node of HSSMatrix::factor_recursive (HSSMatrix.factor.hpp:51-147).
+    root/partial: partial_factor() runs the recursion on child(0) with
+    isroot = partial = true (factor.hpp:44-50)."""
     nd = nodes[i]
-    isroot = (i == 0)
+    isroot = (i == root)
 
     def gemm_flops(m, n, k):
         return 2 * m * n * k
@@ -178,7 +180,7 @@ def _factor_node(nodes, f, i):
         Df[r0:, :r0] = nd.B10 @ f.Vt1[c0].conj().T        # :76-77
         f.flops += gemm_flops(r0, r1, nd.B01.shape[1]) + \
             gemm_flops(r1, r0, nd.B10.shape[1])
-        if not isroot:
+        if not isroot or partial:                          # :81
             V = basis_dense(nd.Pv, nd.Ev)                  # :86
             rv0 = nodes[c0].V_rank
             Vh = np.vstack([f.Vt1[c0] @ V[:rv0, :], f.Vt1[c1] @ V[rv0:, :]])
@@ -186,11 +188,13 @@ def _factor_node(nodes, f, i):
                 gemm_flops(r1, V.shape[1], V.shape[0] - rv0)
     else:
         Df = nd.D.copy()
-        Vh = basis_dense(nd.Pv, nd.Ev) if not isroot else None
+        Vh = basis_dense(nd.Pv, nd.Ev) if (not isroot or partial) else None
     if isroot:
         f.lu = sla.lu_factor(Df)                           # :104-107
         n = Df.shape[0]
         f.flops += int(2 * n ** 3 / 3)
+        if partial:
+            f.Vhat = Vh                                    # :107
         return
     g = ipiv_to_gather(nd.Pu)
     Dp = Df[g, :]                                          # laswp fwd :109
@@ -222,6 +226,80 @@ def factor(nodes):
     for i in range(len(nodes) - 1, -1, -1):
         _factor_node(nodes, f, i)
     return f
+
+
+# ------------------------------------------- Schur complement (HSS fronts)
+def _subtree(nodes, i):
+    out, stack = [], [i]
+    while stack:
+        j = stack.pop()
+        out.append(j)
+        if not nodes[j].leaf:
+            stack.extend(nodes[j].ch)
+    return sorted(out)
+
+
+def partial_factor(nodes):
+    """HSSMatrix::partial_factor (HSSMatrix.factor.hpp:44-50): ULV of the
+    subtree of child(0) with child(0) as root; keeps Vhat = Vh(child 0)."""
+    f = ULV(len(nodes))
+    c0 = nodes[0].ch[0]
+    for i in reversed(_subtree(nodes, c0)):
+        _factor_node(nodes, f, i, root=c0, partial=True)
+    return f
+
+
+def _sub_apply(nodes, top, t2_top, x, trans):
+    """Down-sweep of the subtree of `top` started from t2(top) = t2_top with
+    the up-sweep results of `x` (None: x = 0, i.e. apply_UV_big,
+    HSSMatrix.Schur.hpp:248-320); returns (rows of the result that belong to
+    `top`, t1(top))."""
+    nd = nodes[top]
+    n = nodes[0].rows
+    s = t2_top.shape[1]
+    xin = np.zeros((n, s)) if x is None else x
+    st = _ApplyState(nodes, xin, trans)
+    sub = _subtree(nodes, top)
+    for i in reversed(sub):
+        st.fwd_node(i)
+    t1_top = st.tmp1[top]
+    st.tmp2[top] = t2_top
+    for i in sub:
+        st.bwd_node(i)
+    off = nd.col_off if trans else nd.row_off
+    cnt = nd.cols if trans else nd.rows
+    return st.y[off:off + cnt, :], t1_top
+
+
+def schur_update(nodes, f):
+    """HSSMatrix::Schur_update (HSSMatrix.Schur.hpp:40-59): Theta = U1big B10,
+    DUB01 = D0^{-1} U0 B01, Phi = V1big DUB01^H."""
+    root = nodes[0]
+    c0, c1 = root.ch
+    n0 = nodes[c0]
+    DUB01 = sla.lu_solve(f.lu, basis_apply(n0.Pu, n0.Eu, root.B01))
+    Theta, _ = _sub_apply(nodes, c1, root.B10, None, False)
+    Phi, _ = _sub_apply(nodes, c1, DUB01.conj().T.copy(), None, True)
+    return Theta, DUB01, Phi
+
+
+def schur_product_direct(nodes, f, Theta, DUB01, Phi, R):
+    """HSSMatrix::Schur_product_direct (HSSMatrix.Schur.hpp:73-137):
+    Sr = H11 R - Theta Vhat^H DUB01 (V1big^H R), Sc = H11^H R - Phi Vhat B10^H (U1big^H R)."""
+    root = nodes[0]
+    c1 = root.ch[1]
+    n1 = nodes[c1]
+    n = root.rows
+    s = R.shape[1]
+    Rf = np.zeros((n, s))
+    Rf[n1.col_off:n1.col_off + n1.cols, :] = R
+    Sr, t1r = _sub_apply(nodes, c1, np.zeros((n1.U_rank, s)), Rf, False)
+    Rf = np.zeros((n, s))
+    Rf[n1.row_off:n1.row_off + n1.rows, :] = R
+    Sc, t1c = _sub_apply(nodes, c1, np.zeros((n1.V_rank, s)), Rf, True)
+    Sr = Sr - Theta @ (f.Vhat.conj().T @ (DUB01 @ t1r))
+    Sc = Sc - Phi @ (f.Vhat @ (root.B10.conj().T @ t1c))
+    return Sr, Sc
 
 
 # ----------------------------------------------------------------- ULV solve

@@ -71,6 +71,14 @@ def lib():
         "ref_hss_dense_out": (None, [vp, dp, i]),
         "ref_hss_get": (d, [vp, i, i]),
         "ref_hss_destroy": (None, [vp]),
+        "ref_hss_partial_factor": (None, [vp]),
+        "ref_hss_schur_sizes": (None, [vp, lp]),
+        "ref_hss_schur_get": (None, [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "ref_hss_schur_product_direct": (None, [vp, i, dp, i, dp, i, dp, i]),
+        "ref_hss_partial_forward": (None, [vp, i, dp, i, dp]),
+        "ref_hss_partial_x_rows": (i, [vp]),
+        "ref_hss_partial_x": (None, [vp, dp, i]),
+        "ref_hss_partial_backward": (None, [vp, i, dp, i]),
         "ref_blr_factor_dense": (vp, [i, dp, i, cp, C.POINTER(i), C.c_void_p]),
         "ref_blr_solve": (None, [vp, i, dp, i]),
         "ref_blr_info": (None, [vp, lp]),
@@ -160,6 +168,50 @@ class RefHSS:
 
     def shift(self, sigma):
         lib().ref_hss_shift(self._h, float(sigma))
+
+    # -- Schur complement of the (0,0) block, as FrontHSS drives it ---------
+    def partial_factor(self):
+        """partial_factor + Schur_update (+ ThetaVhatC_or_VhatCPhiC); returns
+        dict(Theta, DUB01, Phi, Vhat)."""
+        L = lib()
+        L.ref_hss_partial_factor(self._h)
+        z = np.zeros(8, dtype=np.int64)
+        L.ref_hss_schur_sizes(self._h, z)
+        out = {k: np.zeros((int(z[2 * q]), int(z[2 * q + 1])), order="F")
+               for q, k in enumerate(("Theta", "DUB01", "Phi", "Vhat"))}
+        L.ref_hss_schur_get(self._h, *(out[k].ctypes.data for k in ("Theta", "DUB01", "Phi", "Vhat")))
+        return out
+
+    def schur_product_direct(self, R):
+        R = _f(R)
+        n1, c = R.shape
+        Sr = np.zeros((n1, c), order="F")
+        Sc = np.zeros((n1, c), order="F")
+        lib().ref_hss_schur_product_direct(self._h, c, R, n1, Sr, n1, Sc, n1)
+        return Sr, Sc
+
+    def partial_forward_solve(self, b0, rv0):
+        b0 = _f(b0)
+        red = np.zeros((rv0, b0.shape[1]), order="F")
+        lib().ref_hss_partial_forward(self._h, b0.shape[1], b0, b0.shape[0], red)
+        self._ps = b0.shape
+        return red
+
+    def partial_x(self, new=None):
+        m0 = lib().ref_hss_partial_x_rows(self._h)
+        if new is not None:
+            x = _f(new).copy(order="F")
+            lib().ref_hss_partial_x(self._h, x, 1)
+            return x
+        x = np.zeros((m0, self._ps[1]), order="F")
+        lib().ref_hss_partial_x(self._h, x, 0)
+        return x
+
+    def partial_backward_solve(self):
+        n0, s = self._ps
+        x0 = np.zeros((n0, s), order="F")
+        lib().ref_hss_partial_backward(self._h, s, x0, n0)
+        return x0
 
     def close(self):
         if self._h:

@@ -12,7 +12,11 @@
  *   - run mult / factor / solve     (reference src/HSS/HSSMatrix.apply.hpp:34,
  *                                    .factor.hpp:35, .solve.hpp:35),
  *   - read the reference's flop counters (src/StrumpackParameters.hpp:85-98),
- *   - run BLR compress_and_factor + solve (src/BLR/BLRMatrix.cpp:113, .hpp:118).
+ *   - run BLR compress_and_factor + solve (src/BLR/BLRMatrix.cpp:113, .hpp:118),
+ *   - run partial_factor / Schur_update / Schur_product_direct and the partial
+ *     forward / backward solves of child(0) the way FrontHSS does
+ *     (src/HSS/HSSMatrix.factor.hpp:44, HSSMatrix.Schur.hpp:40,73,
+ *      src/sparse/fronts/FrontHSS.cpp:385-410,452-462,487-495).
  * Nothing here restates an algorithm: every numeric result comes from the
  * reference code itself.
  */
@@ -41,7 +45,16 @@ using DenseW = DenseMatrixWrapper<double>;
 namespace {
   struct HSSHandle {
     std::unique_ptr<HSSMatrix<double>> H;
+    // state of a partial factorization, as FrontHSS keeps it
+    DenseD Theta, DUB01, Phi, TV;
+    std::unique_ptr<HSS::WorkSolve<double>> w;
   };
+  void copy_out(const DenseD& A, double* dst) {
+    if (!dst) return;
+    for (std::size_t j=0; j<A.cols(); j++)
+      for (std::size_t i=0; i<A.rows(); i++)
+        dst[i + j*A.rows()] = A(i, j);
+  }
   struct BLRHandle {
     std::unique_ptr<BLR::BLRMatrix<double>> B;
     int n = 0;
@@ -179,6 +192,94 @@ extern "C" {
   }
 
   void ref_hss_destroy(void* hv) { delete static_cast<HSSHandle*>(hv); }
+
+  /* ---- Schur complement of the (0,0) block, exactly the call sequence of
+   *      FrontHSS::multifrontal_factorization (FrontHSS.cpp:385-410) */
+  void ref_hss_partial_factor(void* hv) {
+    auto* h = static_cast<HSSHandle*>(hv);
+    auto& H = *h->H;
+    H.partial_factor();
+    H.Schur_update(h->Theta, h->DUB01, h->Phi);
+    const DenseD& Vhat = H.child(0)->ULV().Vhat();
+    if (h->Theta.cols() < h->Phi.cols()) {
+      h->TV = DenseD(Vhat.cols(), h->Phi.rows());
+      gemm(Trans::C, Trans::C, 1., Vhat, h->Phi, 0., h->TV);
+    } else {
+      h->TV = DenseD(h->Theta.rows(), Vhat.rows());
+      gemm(Trans::N, Trans::C, 1., h->Theta, Vhat, 0., h->TV);
+    }
+  }
+
+  /* out[0..7] = Theta rows, cols, DUB01 rows, cols, Phi rows, cols, Vhat rows, cols */
+  void ref_hss_schur_sizes(void* hv, long long* out) {
+    auto* h = static_cast<HSSHandle*>(hv);
+    const DenseD& Vhat = h->H->child(0)->ULV().Vhat();
+    out[0] = h->Theta.rows(); out[1] = h->Theta.cols();
+    out[2] = h->DUB01.rows(); out[3] = h->DUB01.cols();
+    out[4] = h->Phi.rows(); out[5] = h->Phi.cols();
+    out[6] = Vhat.rows(); out[7] = Vhat.cols();
+  }
+
+  /* packed column-major copies; any pointer may be null */
+  void ref_hss_schur_get(void* hv, double* Theta, double* DUB01, double* Phi,
+                         double* Vhat) {
+    auto* h = static_cast<HSSHandle*>(hv);
+    copy_out(h->Theta, Theta);
+    copy_out(h->DUB01, DUB01);
+    copy_out(h->Phi, Phi);
+    copy_out(h->H->child(0)->ULV().Vhat(), Vhat);
+  }
+
+  /* FrontHSS::sample_CB_direct (FrontHSS.cpp:211-221) */
+  void ref_hss_schur_product_direct(void* hv, int c, const double* R, int ldR,
+                                    double* Sr, int ldSr, double* Sc, int ldSc) {
+    auto* h = static_cast<HSSHandle*>(hv);
+    auto n1 = h->H->child(1)->rows();
+    DenseD Rd(n1, c, R, ldR), Srd(n1, c), Scd(n1, c);
+    h->H->Schur_product_direct(h->Theta, h->DUB01, h->Phi, h->TV, Rd, Srd, Scd);
+    for (int j=0; j<c; j++)
+      for (std::size_t i=0; i<n1; i++) {
+        Sr[i + std::size_t(j)*ldSr] = Srd(i, j);
+        Sc[i + std::size_t(j)*ldSc] = Scd(i, j);
+      }
+  }
+
+  /* FrontHSS::fwd_solve_node (FrontHSS.cpp:452-462): b0 is rows(child 0) x s;
+   * red receives reduced_rhs (V_rank(child 0) x s, packed) */
+  void ref_hss_partial_forward(void* hv, int s, const double* b0, int ldb,
+                               double* red) {
+    auto* h = static_cast<HSSHandle*>(hv);
+    auto n0 = h->H->child(0)->rows();
+    DenseD B(n0, s, b0, ldb);
+    h->w.reset(new HSS::WorkSolve<double>());
+    h->H->child(0)->forward_solve(*h->w, B, true);
+    copy_out(h->w->reduced_rhs, red);
+  }
+
+  /* w.x (rows = size of child 0's reduced block): get (set=0) or overwrite */
+  int ref_hss_partial_x_rows(void* hv) {
+    auto* h = static_cast<HSSHandle*>(hv);
+    return h->w ? int(h->w->x.rows()) : 0;
+  }
+  void ref_hss_partial_x(void* hv, double* x, int set) {
+    auto* h = static_cast<HSSHandle*>(hv);
+    auto& X = h->w->x;
+    for (std::size_t j=0; j<X.cols(); j++)
+      for (std::size_t i=0; i<X.rows(); i++)
+        if (set) X(i, j) = x[i + j*X.rows()];
+        else x[i + j*X.rows()] = X(i, j);
+  }
+
+  /* FrontHSS::bwd_solve_node (FrontHSS.cpp:487-495) */
+  void ref_hss_partial_backward(void* hv, int s, double* x0, int ldx) {
+    auto* h = static_cast<HSSHandle*>(hv);
+    auto n0 = h->H->child(0)->rows();
+    DenseD X(n0, s);
+    X.zero();
+    h->H->child(0)->backward_solve(*h->w, X);
+    for (int j=0; j<s; j++)
+      for (std::size_t i=0; i<n0; i++) x0[i + std::size_t(j)*ldx] = X(i, j);
+  }
 
   /* ---- BLR: compress_and_factor on a dense matrix, weak admissibility,
    *      tiles from ClusterTree(n).refine(leaf)   (test_BLR_seq.cpp:136-156) */

@@ -71,6 +71,17 @@ SYMBOLS = {
     "SB200_d_hss_backward_solve": (_i, [_vp, _i, _vp, _i]),
     "SB200_d_hss_forward_solve_device": (_i, [_vp, _i, _vp, _i, _vp]),
     "SB200_d_hss_backward_solve_device": (_i, [_vp, _i, _vp, _i, _vp]),
+    "SB200_d_hss_partial_factor": (_i, [_vp]),
+    "SB200_d_hss_schur_sizes": (_i, [_vp, _vp]),
+    "SB200_d_hss_schur_update": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i]),
+    "SB200_d_hss_vhat": (_i, [_vp, _vp, _i]),
+    "SB200_d_hss_schur_product_direct": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i,
+                                             _vp, _i, _vp, _i]),
+    "SB200_d_hss_schur_product_indirect": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i,
+                                               _vp, _i, _vp, _i, _vp, _i]),
+    "SB200_d_hss_partial_forward_solve": (_i, [_vp, _i, _vp, _i, _vp, _i]),
+    "SB200_d_hss_partial_x": (_i, [_vp, _i, _vp, _i, _i]),
+    "SB200_d_hss_partial_backward_solve": (_i, [_vp, _i, _vp, _i]),
     "SB200_d_hss_set_partition": (_i, [_vp, _i, _i]),
     "SB200_d_hss_owned_range": (_i, [_vp, _vp, _vp]),
     "SB200_d_hss_dist_sizes": (_i, [_vp, _i, _vp]),
@@ -444,6 +455,108 @@ class HSSMatrix(StructuredMatrix):
         x = np.zeros((n, s), order="F")
         _check(lib().SB200_d_hss_backward_solve(self._h, s, x.ctypes.data, n), "backward_solve")
         return x
+
+    # -- Schur complement of the (0,0) block (what FrontHSS uses) ------------
+    def partial_factor(self):
+        """HSSMatrix::partial_factor (reference HSSMatrix.factor.hpp:44-50)."""
+        _check(lib().SB200_d_hss_partial_factor(self._h), "partial_factor")
+
+    def schur_sizes(self):
+        out = np.zeros(7, dtype=np.int32)
+        _check(lib().SB200_d_hss_schur_sizes(self._h, out.ctypes.data), "schur_sizes")
+        keys = ("rows1", "cols1", "rv0", "m0", "rv1", "ru1", "rows0")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def schur_update(self):
+        """HSSMatrix::Schur_update (reference HSSMatrix.Schur.hpp:40-59):
+        returns (Theta, DUB01, Phi); S = H11 - Theta Vhat^H Phi^H."""
+        z = self.schur_sizes()
+        Theta = np.zeros((z["rows1"], z["rv0"]), order="F")
+        DUB01 = np.zeros((z["m0"], z["rv1"]), order="F")
+        Phi = np.zeros((z["cols1"], z["m0"]), order="F")
+        _check(lib().SB200_d_hss_schur_update(
+            self._h, Theta.ctypes.data, max(z["rows1"], 1), DUB01.ctypes.data, max(z["m0"], 1),
+            Phi.ctypes.data, max(z["cols1"], 1)), "Schur_update")
+        return Theta, DUB01, Phi
+
+    def vhat(self):
+        """child(0)->ULV().Vhat() (reference HSSExtra.hpp:197-212)."""
+        z = self.schur_sizes()
+        V = np.zeros((z["m0"], z["rv0"]), order="F")
+        _check(lib().SB200_d_hss_vhat(self._h, V.ctypes.data, max(z["m0"], 1)), "Vhat")
+        return V
+
+    def schur_product_direct(self, R, Theta=None, DUB01=None, Phi=None):
+        """HSSMatrix::Schur_product_direct (reference HSSMatrix.Schur.hpp:73-137):
+        returns (Sr, Sc) = (S R, S^H R).  Theta/DUB01/Phi default to the ones of
+        the last schur_update (kept on the device)."""
+        R = _fortran(R)
+        z = self.schur_sizes()
+        Sr = np.zeros((z["rows1"], R.shape[1]), order="F")
+        Sc = np.zeros((z["cols1"], R.shape[1]), order="F")
+
+        def arg(a):
+            if a is None:
+                return None, 1
+            a = _fortran(a)
+            keep.append(a)
+            return a.ctypes.data, max(a.shape[0], 1)
+        keep = []
+        (t, ldt), (d, ldd), (p_, ldp) = arg(Theta), arg(DUB01), arg(Phi)
+        _check(lib().SB200_d_hss_schur_product_direct(
+            self._h, t, ldt, d, ldd, p_, ldp, R.shape[1], R.ctypes.data, R.shape[0],
+            Sr.ctypes.data, max(z["rows1"], 1), Sc.ctypes.data, max(z["cols1"], 1)),
+            "Schur_product_direct")
+        return Sr, Sc
+
+    def schur_product_indirect(self, R0, R1, Sr1, Sc1, DUB01=None):
+        """HSSMatrix::Schur_product_indirect (reference HSSMatrix.Schur.hpp:139-215)."""
+        R0, R1, Sr1, Sc1 = (_fortran(a) for a in (R0, R1, Sr1, Sc1))
+        z = self.schur_sizes()
+        c = R1.shape[1]
+        Sr = np.zeros((z["rows1"], c), order="F")
+        Sc = np.zeros((z["cols1"], c), order="F")
+        d = None if DUB01 is None else _fortran(DUB01)
+        _check(lib().SB200_d_hss_schur_product_indirect(
+            self._h, None if d is None else d.ctypes.data, max(z["m0"], 1), c,
+            R0.ctypes.data, R0.shape[0], R1.ctypes.data, R1.shape[0],
+            Sr1.ctypes.data, Sr1.shape[0], Sc1.ctypes.data, Sc1.shape[0],
+            Sr.ctypes.data, max(z["rows1"], 1), Sc.ctypes.data, max(z["cols1"], 1)),
+            "Schur_product_indirect")
+        return Sr, Sc
+
+    def partial_forward_solve(self, b0):
+        """child(0)->forward_solve(w, b0, partial=True) (reference
+        HSSMatrix.solve.hpp:133-152): returns reduced_rhs (rv0 x s)."""
+        b0 = _fortran(b0)
+        z = self.schur_sizes()
+        red = np.zeros((z["rv0"], b0.shape[1]), order="F")
+        _check(lib().SB200_d_hss_partial_forward_solve(
+            self._h, b0.shape[1], b0.ctypes.data, b0.shape[0], red.ctypes.data, max(z["rv0"], 1)),
+            "partial forward_solve")
+        self._pfwd_s = b0.shape[1]
+        return red
+
+    def partial_x(self, new=None):
+        """The reduced solution x = D0^{-1} f (m0 x s) between the partial
+        forward and backward solves; ``new`` overwrites it."""
+        z = self.schur_sizes()
+        s = self._pfwd_s
+        if new is not None:
+            x = _fortran(new)
+            _check(lib().SB200_d_hss_partial_x(self._h, s, x.ctypes.data, max(z["m0"], 1), 1), "partial_x")
+            return x
+        x = np.zeros((z["m0"], s), order="F")
+        _check(lib().SB200_d_hss_partial_x(self._h, s, x.ctypes.data, max(z["m0"], 1), 0), "partial_x")
+        return x
+
+    def partial_backward_solve(self):
+        """child(0)->backward_solve(w, x0) (reference HSSMatrix.solve.hpp:62-66)."""
+        z = self.schur_sizes()
+        x0 = np.zeros((z["rows0"], self._pfwd_s), order="F")
+        _check(lib().SB200_d_hss_partial_backward_solve(
+            self._h, self._pfwd_s, x0.ctypes.data, max(z["rows0"], 1)), "partial backward_solve")
+        return x0
 
     @classmethod
     def from_generators(cls, nodes):

@@ -555,29 +555,61 @@ BLREngine::BLREngine(int n, const double* hostA, int ldA, const BLROpts& o, bool
   if (n <= 0) throw std::invalid_argument("empty matrix");
   std::vector<int> tiles;
   refine(tiles, n, std::max(1, o.leaf_size));
+  n1_ = n;
+  nsteps_ = int(tiles.size());
+  setup(tiles, do_factor);
+  SB200_CUDA(cudaMemcpy2D(A_.p, sizeof(double) * n, hostA, sizeof(double) * ldA,
+                          sizeof(double) * n, n,
+                          device_input ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  run(do_factor);
+}
+
+BLREngine::BLREngine(int n1, int n2, const double* A11, int ld11, const double* A12, int ld12,
+                     const double* A21, int ld21, const double* A22, int ld22, const BLROpts& o,
+                     bool device_input)
+    : n_(n1 + n2), opts_(o) {
+  if (n1 <= 0 || n2 < 0) throw std::invalid_argument("partial factorization needs n1 > 0, n2 >= 0");
+  std::vector<int> tiles;
+  refine(tiles, n1, std::max(1, o.leaf_size));
+  n1_ = n1;
+  nsteps_ = int(tiles.size());
+  if (n2 > 0) refine(tiles, n2, std::max(1, o.leaf_size));
+  setup(tiles, true);
+  const cudaMemcpyKind kind = device_input ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const size_t n = (size_t)n_, w = sizeof(double);
+  SB200_CUDA(cudaMemcpy2D(A_.p, w * n, A11, w * ld11, w * n1, n1, kind));
+  if (n2 > 0) {
+    SB200_CUDA(cudaMemcpy2D(A_.p + (size_t)n1 * n, w * n, A12, w * ld12, w * n1, n2, kind));
+    SB200_CUDA(cudaMemcpy2D(A_.p + n1, w * n, A21, w * ld21, w * n2, n1, kind));
+    SB200_CUDA(cudaMemcpy2D(A_.p + n1 + (size_t)n1 * n, w * n, A22, w * ld22, w * n2, n2, kind));
+  }
+  run(true);
+}
+
+void BLREngine::setup(const std::vector<int>& tiles, bool do_factor) {
+  const int n = n_;
   nb_ = int(tiles.size());
   off_.assign(nb_ + 1, 0);
   for (int t = 0; t < nb_; t++) off_[t + 1] = off_[t] + tiles[t];
   maxtile_ = *std::max_element(tiles.begin(), tiles.end());
   if (maxtile_ > 1024) throw std::invalid_argument("BLR tiles larger than 1024 are not supported");
   // LR arena: tile (i,j) gets [U m x rc | Vt n x rc], rc = min(m,n)/2 (a tile
-  // is kept low-rank only if rank*(m+n) <= m*n, BLRMatrix.cpp:563-570)
+  // is kept low-rank only if rank*(m+n) <= m*n, BLRMatrix.cpp:563-570).  In a
+  // partial factorization the tiles of the trailing (2,2) block stay dense.
   lroff_.assign((size_t)nb_ * nb_, -1);
   rcap_.assign((size_t)nb_ * nb_, 0);
   long long o_ = 0;
   for (int j = 0; j < nb_; j++)
     for (int i = 0; i < nb_; i++) {
       if (i == j) continue;
+      if (do_factor && std::min(i, j) >= nsteps_) continue;
       const int m = tiles[i], nn = tiles[j];
-      const int rc = std::max(1, std::min(std::min(m, nn) / 2, o.max_rank));
+      const int rc = std::max(1, std::min(std::min(m, nn) / 2, opts_.max_rank));
       lroff_[i + (size_t)j * nb_] = o_;
       rcap_[i + (size_t)j * nb_] = rc;
       o_ += (long long)(m + nn) * rc;
     }
   A_.alloc((size_t)n * n);
-  SB200_CUDA(cudaMemcpy2D(A_.p, sizeof(double) * n, hostA, sizeof(double) * ldA,
-                          sizeof(double) * n, n,
-                          device_input ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
   lr_.alloc((size_t)std::max<long long>(o_, 1));
   doff_.upload(off_.data(), off_.size());
   dlroff_.upload(lroff_.data(), lroff_.size());
@@ -587,7 +619,6 @@ BLREngine::BLREngine(int n, const double* hostA, int ldA, const BLROpts& o, bool
   piv_.alloc(n);
   gperm_.alloc(n);
   SB200_CUDA(cudaStreamSynchronize(0));
-  run(do_factor);
 }
 
 void BLREngine::run(bool do_factor) {
@@ -618,7 +649,8 @@ void BLREngine::run(bool do_factor) {
     q.E = nullptr; q.strict = 1;
     idt.push_back(q);
   };
-  for (int i = 0; i < nb; i++) {
+  const int nsteps = do_factor ? nsteps_ : nb;   // partial factorization: the tiles of A11 only
+  for (int i = 0; i < nsteps; i++) {
     int slot = 0;
     if (do_factor) {
       for (int j = i + 1; j < nb; j++) { add_tile(i, j, slot++); add_tile(j, i, slot++); }
@@ -654,7 +686,7 @@ void BLREngine::run(bool do_factor) {
   set_smem(id_cpqr_kernel, cpqr_smem);
   const int ldp = smem_ld(maxtile_);
   const int KC = maxtile_ <= 256 ? 32 : 16;
-  for (int i = 0; i < nb; i++) {
+  for (int i = 0; i < nsteps; i++) {
     const int m = off_[i + 1] - off_[i];
     const int cnt = step_ptr[i + 1] - step_ptr[i];
     double* Aii = A_.p + off_[i] + (size_t)off_[i] * n;

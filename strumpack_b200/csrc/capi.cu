@@ -4,6 +4,7 @@
 // stderr and return code 1 on error.
 #include "../../include/sb200_structured.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -26,6 +27,9 @@ struct Mat {
   std::unique_ptr<BLREngine> blr;
   // staging buffers for the host-pointer entry points
   DevBuf<double> dB, dC;
+  // device copies of Theta / DUB01 / Phi of the last Schur_update and staging
+  // for the Schur products
+  DevBuf<double> dTheta, dDUB01, dPhi, dS[6];
 };
 
 void require_gpu() {
@@ -394,6 +398,154 @@ int SB200_d_hss_forward_solve_device(const CSPStructMat S, int nrhs, double* dB,
 int SB200_d_hss_backward_solve_device(const CSPStructMat S, int nrhs, double* dX, int ldX,
                                       void* stream) {
   return guarded([&] { hss(S).backward_solve(nrhs, dX, ldX, static_cast<cudaStream_t>(stream)); });
+}
+
+/* ---- Schur complement of the (0,0) block (HSS fronts) --------------------- */
+int SB200_d_hss_partial_factor(CSPStructMat S) {
+  return guarded([&] {
+    hss(S).partial_factor(0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_hss_schur_sizes(const CSPStructMat S, int* out) {
+  return guarded([&] { hss(S).schur_sizes(out); });
+}
+
+int SB200_d_hss_schur_update(const CSPStructMat S, double* Theta, int ldT, double* DUB01,
+                             int ldD, double* Phi, int ldP) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    int z[7];
+    H.schur_sizes(z);
+    const int rows1 = z[0], cols1 = z[1], rv0 = z[2], m0 = z[3], rv1 = z[4];
+    mm->dTheta.ensure((size_t)std::max(rows1, 1) * std::max(rv0, 1));
+    mm->dDUB01.ensure((size_t)std::max(m0, 1) * std::max(rv1, 1));
+    mm->dPhi.ensure((size_t)std::max(cols1, 1) * std::max(m0, 1));
+    H.schur_update(mm->dTheta.p, std::max(rows1, 1), mm->dDUB01.p, std::max(m0, 1), mm->dPhi.p,
+                   std::max(cols1, 1), 0);
+    if (Theta && rows1 && rv0) d2h(Theta, mm->dTheta, rows1, rv0, ldT, 0);
+    if (DUB01 && m0 && rv1) d2h(DUB01, mm->dDUB01, m0, rv1, ldD, 0);
+    if (Phi && cols1 && m0) d2h(Phi, mm->dPhi, cols1, m0, ldP, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_hss_vhat(const CSPStructMat S, double* Vhat, int ldV) {
+  return guarded([&] {
+    auto& H = hss(S);
+    if (!H.partially_factored()) throw std::logic_error("Vhat requested before partial_factor");
+    int z[7];
+    H.schur_sizes(z);
+    if (z[3] && z[2])
+      SB200_CUDA(cudaMemcpy2D(Vhat, sizeof(double) * ldV, H.vhat(), sizeof(double) * z[3],
+                              sizeof(double) * z[3], z[2], cudaMemcpyDeviceToHost));
+  });
+}
+
+int SB200_d_hss_schur_product_direct(const CSPStructMat S, const double* Theta, int ldT,
+                                     const double* DUB01, int ldD, const double* Phi, int ldP,
+                                     int c, const double* R, int ldR, double* Sr, int ldSr,
+                                     double* Sc, int ldSc) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    int z[7];
+    H.schur_sizes(z);
+    const int rows1 = z[0], cols1 = z[1], rv0 = z[2], m0 = z[3], rv1 = z[4];
+    if (c <= 0) return;
+    // NULL: use the device copies kept by the last SB200_d_hss_schur_update
+    if (Theta && rows1 && rv0) h2d(mm->dTheta, Theta, rows1, rv0, ldT, 0);
+    if (DUB01 && m0 && rv1) h2d(mm->dDUB01, DUB01, m0, rv1, ldD, 0);
+    if (Phi && cols1 && m0) h2d(mm->dPhi, Phi, cols1, m0, ldP, 0);
+    if (!mm->dTheta.p || !mm->dDUB01.p || !mm->dPhi.p)
+      throw std::logic_error("Schur_product_direct: no Theta / DUB01 / Phi (call Schur_update first)");
+    h2d(mm->dS[0], R, rows1, c, ldR, 0);
+    mm->dS[1].ensure((size_t)rows1 * c);
+    mm->dS[2].ensure((size_t)cols1 * c);
+    H.schur_product_direct(mm->dTheta.p, std::max(rows1, 1), mm->dDUB01.p, std::max(m0, 1),
+                           mm->dPhi.p, std::max(cols1, 1), c, mm->dS[0].p, rows1, mm->dS[1].p,
+                           rows1, mm->dS[2].p, cols1, 0);
+    d2h(Sr, mm->dS[1], rows1, c, ldSr, 0);
+    d2h(Sc, mm->dS[2], cols1, c, ldSc, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_hss_schur_product_indirect(const CSPStructMat S, const double* DUB01, int ldD, int c,
+                                       const double* R0, int ldR0, const double* R1, int ldR1,
+                                       const double* Sr1, int ldSr1, const double* Sc1, int ldSc1,
+                                       double* Sr, int ldSr, double* Sc, int ldSc) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    int z[7];
+    H.schur_sizes(z);
+    const int rows1 = z[0], cols1 = z[1], m0 = z[3], rv1 = z[4], rows0 = z[6];
+    if (c <= 0) return;
+    if (DUB01 && m0 && rv1) h2d(mm->dDUB01, DUB01, m0, rv1, ldD, 0);
+    if (!mm->dDUB01.p) throw std::logic_error("Schur_product_indirect: no DUB01 (call Schur_update first)");
+    h2d(mm->dS[0], R0, rows0, c, ldR0, 0);
+    h2d(mm->dS[3], R1, rows1, c, ldR1, 0);
+    h2d(mm->dS[1], Sr1, rows1, c, ldSr1, 0);
+    h2d(mm->dS[2], Sc1, cols1, c, ldSc1, 0);
+    H.schur_product_indirect(mm->dDUB01.p, std::max(m0, 1), c, mm->dS[0].p, rows0, mm->dS[3].p, rows1,
+                             mm->dS[1].p, rows1, mm->dS[2].p, cols1, mm->dS[1].p, rows1,
+                             mm->dS[2].p, cols1, 0);
+    d2h(Sr, mm->dS[1], rows1, c, ldSr, 0);
+    d2h(Sc, mm->dS[2], cols1, c, ldSc, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_hss_partial_forward_solve(const CSPStructMat S, int nrhs, const double* B0, int ldB,
+                                      double* reduced_rhs, int ldR) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    int z[7];
+    H.schur_sizes(z);
+    const int rv0 = z[2], rows0 = z[6];
+    if (nrhs <= 0) return;
+    h2d(mm->dS[4], B0, rows0, nrhs, ldB, 0);
+    mm->dS[5].ensure((size_t)std::max(rv0, 1) * nrhs);
+    H.partial_forward_solve(nrhs, mm->dS[4].p, rows0, mm->dS[5].p, std::max(rv0, 1), 0);
+    if (rv0 && reduced_rhs) d2h(reduced_rhs, mm->dS[5], rv0, nrhs, ldR, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_hss_partial_x(const CSPStructMat S, int nrhs, double* X, int ldX, int set) {
+  return guarded([&] {
+    auto& H = hss(S);
+    int z[7];
+    H.schur_sizes(z);
+    const int m0 = z[3];
+    double* dx = H.partial_x(nrhs);
+    if (!m0) return;
+    if (set)
+      SB200_CUDA(cudaMemcpy2D(dx, sizeof(double) * m0, X, sizeof(double) * ldX, sizeof(double) * m0,
+                              nrhs, cudaMemcpyHostToDevice));
+    else
+      SB200_CUDA(cudaMemcpy2D(X, sizeof(double) * ldX, dx, sizeof(double) * m0, sizeof(double) * m0,
+                              nrhs, cudaMemcpyDeviceToHost));
+  });
+}
+
+int SB200_d_hss_partial_backward_solve(const CSPStructMat S, int nrhs, double* X0, int ldX) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    auto& H = hss(S);
+    int z[7];
+    H.schur_sizes(z);
+    const int rows0 = z[6];
+    if (nrhs <= 0) return;
+    mm->dS[4].ensure((size_t)rows0 * nrhs);
+    H.partial_backward_solve(nrhs, mm->dS[4].p, rows0, 0);
+    d2h(X0, mm->dS[4], rows0, nrhs, ldX, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
 }
 
 int SB200_d_hss_set_partition(CSPStructMat S, int nparts, int part) {

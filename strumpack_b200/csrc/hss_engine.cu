@@ -2130,22 +2130,25 @@ ulv_fwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
 
 // Root: f = [ft1(c0) - B01 z(c1); ft1(c1) - B10 z(c0)], x = LU^{-1} f
 //                                                   (solve.hpp:88-135)
+// `node` = 0 with lu = the root's factor block; for a partial factorization
+// (partial_forward_solve) node = child 0 of the root and lu = its separate LU
+// buffer, and x always goes to the solve workspace.
 __global__ void __launch_bounds__(kThreads)
-ulv_root_solve_kernel(const DNode* __restrict__ nodes, const double* __restrict__ vals,
-                      const double* __restrict__ fact, const int* __restrict__ piv,
+ulv_root_solve_kernel(const DNode* __restrict__ nodes, int node, const double* __restrict__ vals,
+                      const double* __restrict__ lu, const int* __restrict__ piv,
                       double* __restrict__ b, int ldb, const double* __restrict__ zsol,
                       const double* __restrict__ fsol, double* __restrict__ xsol, int s,
                       int use_smem) {
   extern __shared__ __align__(16) double sm[];
-  const DNode nd = nodes[0];
+  const DNode nd = nodes[node];
   const int col = blockIdx.x, tid = threadIdx.x;
   const int n = nd.m;
   double* x = sm;
   double* As = sm + ((n + 1) & ~1);   // LU factors staged in smem when they fit
   if (use_smem)
-    for (int idx = tid; idx < n * n; idx += kThreads) As[idx] = fact[nd.F + idx];
+    for (int idx = tid; idx < n * n; idx += kThreads) As[idx] = lu[idx];
   if (nd.leaf) {
-    const double* bb = b + (size_t)col * ldb;
+    const double* bb = b + nd.row_off + (size_t)col * ldb;
     for (int i = tid; i < n; i += kThreads) x[i] = bb[i];
   } else {
     const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
@@ -2164,7 +2167,7 @@ ulv_root_solve_kernel(const DNode* __restrict__ nodes, const double* __restrict_
     }
   }
   __syncthreads();
-  const double* A = use_smem ? As : fact + nd.F;
+  const double* A = use_smem ? As : lu;
   if (tid == 0)
     for (int j = 0; j < n; j++) {
       int p = piv[j];
@@ -2183,7 +2186,7 @@ ulv_root_solve_kernel(const DNode* __restrict__ nodes, const double* __restrict_
     for (int i = tid; i < j; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
     __syncthreads();
   }
-  if (nd.leaf) {
+  if (nd.leaf && node == 0) {
     double* bb = b + (size_t)col * ldb;
     for (int i = tid; i < n; i += kThreads) bb[i] = x[i];
   } else {
@@ -2253,6 +2256,134 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   }
 }
 
+// ===========================================================================
+//            SCHUR COMPLEMENT OF THE (0,0) BLOCK / PARTIAL FACTORIZATION
+// ===========================================================================
+// Building blocks of partial_factor / Schur_update / Schur_product_* (reference
+// HSSMatrix.factor.hpp:44-50, HSSMatrix.Schur.hpp:35-215): the tree sweeps are
+// the apply / ULV kernels above run over the node lists of the two subtrees;
+// what is left are small dense products with the reduced blocks.
+
+// C = alpha op(A) op(B) + beta C, column-major, any sizes: one CTA per 128 x 64
+// tile of C on the fp64 tensor pipe (smem_gemm reads its operands through
+// predicated loads, so they may live in global memory).
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(kThreads)
+dense_gemm_kernel(int M, int N, int K, double alpha, const double* A, int lda,
+                  const double* B, int ldb, double beta, double* C, int ldc) {
+  const int i0 = blockIdx.x * 128, j0 = blockIdx.y * 64;
+  const int mm = min(128, M - i0), nn = min(64, N - j0);
+  const double* Ab = TA ? A + (size_t)i0 * lda : A + i0;
+  const double* Bb = TB ? B + j0 : B + (size_t)j0 * ldb;
+  smem_gemm<TA, TB>(mm, nn, K, alpha, Ab, lda, Bb, ldb, beta, C + i0 + (size_t)j0 * ldc, ldc,
+                    threadIdx.x >> 5, kWarps, threadIdx.x & 31);
+}
+
+// Y = U X with U = P_u [I; E_u] of `node` (u_rows x u_rank), X u_rank x ncols
+//                                       (HSSBasisID::apply, HSSBasisID.hpp:155-169)
+__global__ void __launch_bounds__(kThreads)
+basis_apply_kernel(const DNode* __restrict__ nodes, int node, const double* __restrict__ vals,
+                   const int* __restrict__ perms, const double* __restrict__ X, int ldx,
+                   int ncols, double* __restrict__ Y, int ldy) {
+  const DNode nd = nodes[node];
+  const int n = nd.u_rows, r = nd.u_rank, k = n - r;
+  const int* P = perms + nd.Pu;
+  const double* E = vals + nd.Eu;
+  const long long tot = (long long)n * ncols;
+  for (long long idx = blockIdx.x * (long long)kThreads + threadIdx.x; idx < tot;
+       idx += (long long)gridDim.x * kThreads) {
+    const int i = (int)(idx % n), c = (int)(idx / n);
+    const double* x = X + (size_t)c * ldx;
+    double v;
+    if (i < r) v = x[i];
+    else {
+      v = 0.;
+      for (int l = 0; l < r; l++) v += E[(i - r) + (size_t)l * k] * x[l];
+    }
+    Y[P[i] + (size_t)c * ldy] = v;
+  }
+}
+
+// X <- (LU)^{-1} X, one CTA per column     (DenseMatrix::solve, DenseMatrix.cpp:625-640)
+__global__ void __launch_bounds__(kThreads)
+lu_solve_kernel(const double* __restrict__ A, int n, const int* __restrict__ piv,
+                double* __restrict__ X, int ldx) {
+  extern __shared__ __align__(16) double sm[];
+  double* x = sm;
+  const int tid = threadIdx.x;
+  double* xg = X + (size_t)blockIdx.x * ldx;
+  for (int i = tid; i < n; i += kThreads) x[i] = xg[i];
+  __syncthreads();
+  if (tid == 0)
+    for (int j = 0; j < n; j++) {
+      const int p = piv[j];
+      if (p != j) { const double t = x[j]; x[j] = x[p]; x[p] = t; }
+    }
+  __syncthreads();
+  for (int j = 0; j < n; j++) {   // unit lower
+    const double xj = x[j];
+    for (int i = j + 1 + tid; i < n; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; j--) {  // upper
+    if (tid == 0) x[j] /= A[j + (size_t)j * n];
+    __syncthreads();
+    const double xj = x[j];
+    for (int i = tid; i < j; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += kThreads) xg[i] = x[i];
+}
+
+// dst (cols x rows, ld ldd) = src^T (src rows x cols, ld lds)
+__global__ void transpose_kernel(const double* __restrict__ src, int lds, int rows, int cols,
+                                 double* __restrict__ dst, int ldd) {
+  const long long tot = (long long)rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % rows), j = (int)(idx / rows);
+    dst[j + (size_t)i * ldd] = src[i + (size_t)j * lds];
+  }
+}
+
+// reduced_rhs = Vhat^H x + V^H [z(c0); z(c1)] at the sub-root of a partial
+// factorization                                     (solve.hpp:136-152)
+__global__ void __launch_bounds__(kThreads)
+partial_reduced_rhs_kernel(const DNode* __restrict__ nodes, int node,
+                           const double* __restrict__ vals, const int* __restrict__ perms,
+                           const double* __restrict__ vhat, const double* __restrict__ xsol,
+                           const double* __restrict__ zsol, double* __restrict__ red, int ldred,
+                           int s) {
+  extern __shared__ __align__(16) double sm[];
+  double* zc = sm;
+  const DNode nd = nodes[node];
+  const int col = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = nd.m, rv = nd.v_rank;
+  const double* x = xsol + (size_t)nd.x_off * s + (size_t)col * m;
+  if (!nd.leaf) {
+    const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
+    const int rv0 = c0.v_rank, rv1 = c1.v_rank;
+    const double* z0 = zsol + (size_t)c0.z_off * s + (size_t)col * rv0;
+    const double* z1 = zsol + (size_t)c1.z_off * s + (size_t)col * rv1;
+    for (int i = tid; i < rv0 + rv1; i += kThreads) zc[i] = i < rv0 ? z0[i] : z1[i - rv0];
+  }
+  __syncthreads();
+  const int* Pv = perms + nd.Pv;
+  const double* Ev = vals + nd.Ev;
+  const int kv = nd.v_rows - rv;
+  for (int c = warp; c < rv; c += kWarps) {
+    double acc = 0.;
+    const double* vc = vhat + (size_t)c * m;
+    for (int i = lane; i < m; i += 32) acc += vc[i] * x[i];
+    if (!nd.leaf) {
+      for (int i = lane; i < kv; i += 32) acc += Ev[i + (size_t)c * kv] * zc[Pv[rv + i]];
+      if (lane == 0) acc += zc[Pv[c]];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[c + (size_t)col * ldred] = acc;
+  }
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -2308,6 +2439,14 @@ void HSSEngine::build_tables() {
                                    : H_.nodes[n.ch0].u_rank + H_.nodes[n.ch1].u_rank);
   }
   nb_ = maxm <= 768 ? 32 : 16;
+  class_gmm_.assign(H_.hptr.size(), 0);
+  for (int i = 0; i < N; i++) {
+    const auto& n = H_.nodes[i];
+    const int mi = n.leaf() ? std::max(n.rows, n.cols)
+                            : H_.nodes[n.ch0].u_rank + H_.nodes[n.ch1].u_rank;
+    int& g = class_gmm_[n.height];
+    g = std::max(g, std::max(mi, std::max(n.u_rows, n.v_rows)));
+  }
   if (maxm > 1600)
     throw std::invalid_argument("HSS block larger than 1600 not supported");
   for (int i = 0; i < N; i++) {
@@ -2415,7 +2554,9 @@ void HSSEngine::make_lists(NodeLists& L, const std::vector<int>& nodes) {
       if (!d.leaf) o += (long long)d.m * d.m;
     }
     L.smax = std::max(L.smax, o);
-    const int nbq = class_nb(h, std::max(L.max_m[h], 1));
+    // panel width by the class maximum over the WHOLE tree, so that every list a
+    // node appears in (owned / top / Schur subtrees) factors it the same way
+    const int nbq = class_nb(h, std::max(class_gmm_[h], 1));
     for (int q = L.hptr[h]; q < L.hptr[h + 1]; q++) hn_[L.host[q]].nbq = nbq;
   }
   L.list.upload(L.host.data(), L.host.size());
@@ -2680,19 +2821,22 @@ void HSSEngine::extract(int nI, const int* I, int nJ, const int* J, double* dB, 
 }
 
 // ------------------------------------------------------------------ factor
-void HSSEngine::factor_prepare() {
-  if (H_.rows() != H_.cols())
-    throw std::invalid_argument("ULV factorization needs a square matrix");
-  for (auto& n : H_.nodes)
-    if (n.leaf() && n.rows != n.cols)
-      throw std::invalid_argument("ULV factorization needs square diagonal blocks");
+void HSSEngine::factor_prepare(bool whole) {
+  if (whole) {
+    if (H_.rows() != H_.cols())
+      throw std::invalid_argument("ULV factorization needs a square matrix");
+    for (auto& n : H_.nodes)
+      if (n.leaf() && n.rows != n.cols)
+        throw std::invalid_argument("ULV factorization needs square diagonal blocks");
+  }
   fact_.ensure((size_t)std::max<long long>(fact_nnz_, 1));
   tfac_.ensure((size_t)std::max<long long>((long long)nb_ * tot_k_, 1));
   rootpiv_.ensure(std::max(hn_[0].m, 1));
-  scratch_.ensure((size_t)std::max<long long>(std::max(own_.smax, top_.smax), 1));
+  scratch_.ensure((size_t)std::max<long long>(std::max(std::max(own_.smax, top_.smax), sub0_.smax), 1));
 }
 
-void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t st) {
+void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t st, int lu_node,
+                               double* lu_dst, int* lu_piv) {
   for (int h = 0; h < L.classes(); h++) {
     const int cnt = L.hptr[h + 1] - L.hptr[h];
     if (!cnt) continue;
@@ -2711,16 +2855,17 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       ulv_build_inner_kernel<<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so, stage);
       launches_++;
     }
-    if (cnt == 1 && L.host[L.hptr[h]] == 0) {   // the root: LU
-      const DNode& root = hn_[0];
+    if (cnt == 1 && L.host[L.hptr[h]] == lu_node) {   // the root (of the factored subtree): LU
+      const DNode& root = hn_[lu_node];
       const long long n2 = (long long)root.m * root.m;
       const double* src = root.leaf ? vals_.p + root.D : scratch_.p;  // slab offset 0 of its class
-      copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(src, fact_.p + root.F, n2);
+      double* dst = lu_dst ? lu_dst : fact_.p + root.F;
+      if (n2 > 0) copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(src, dst, n2);
       {
         const size_t bytes = sizeof(double) * (size_t)root.m * root.m;
         const int use_smem = bytes <= 200 * 1024;
         set_smem(ulv_root_lu_kernel, use_smem ? bytes : 0);
-        ulv_root_lu_kernel<<<1, kThreads, use_smem ? bytes : 0, st>>>(fact_.p + root.F, root.m, rootpiv_.p, use_smem);
+        ulv_root_lu_kernel<<<1, kThreads, use_smem ? bytes : 0, st>>>(dst, root.m, lu_piv ? lu_piv : rootpiv_.p, use_smem);
       }
       launches_ += 2;
       continue;
@@ -2737,6 +2882,7 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
     }
     launches_++;
     const int ldv = smem_ld(mm);
+    const int gmm = std::max(class_gmm_[h], mm);   // kernel variant by the tree-wide class maximum (see make_lists)
     const bool timed = profile_ && time_leaf && h == 0;
     if (timed) SB200_CUDA(cudaEventRecord(ev_[0], st));
     {
@@ -2747,7 +2893,7 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       for (int pp = 0; pp < npan; pp++)
         for (int phase0 = split ? 1 : 0; phase0 <= (split ? 2 : 0); phase0++) {
           const int phase = phase0 + (qr_nowide_ ? 8 : 0) + (h == 0 ? (qr_skew_ << 4) : 0);
-          if (nb_ == 32 && mm <= 256 && !split && (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0))) {
+          if (nb_ == 32 && gmm <= 256 && !split && (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0))) {
             const size_t smem = qr_ll_smem(ldv);
             set_smem(ulv_qr_ll_kernel, smem);
             if (std::getenv("SB200_DEBUG_OCC")) {
@@ -2756,13 +2902,13 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
               std::fprintf(stderr, "[sb200] ulv_qr_ll_kernel: %d CTAs/SM (smem %zu B, class %d, %d nodes)\n", nbk, smem, h, cnt);
             }
             ulv_qr_ll_kernel<<<cnt, kLLThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
-          } else if (nb_ == 32 && mm <= 256 && qr_regpanel_ && qr_variant_ == 1) {
+          } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 1) {
             size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 128>, smem);
             ulv_qr_kernel<16, true, 128><<<cnt, 128, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          } else if (nb_ == 32 && mm <= 256 && qr_regpanel_ && qr_variant_ == 2) {
+          } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 2) {
             size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 256>, smem);
             ulv_qr_kernel<16, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          } else if (nb_ == 32 && mm <= 256 && qr_regpanel_) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true, 256>, smem);
+          } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true, 256>, smem);
             ulv_qr_kernel<32, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
           } else if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, false, 256>, smem);
             ulv_qr_kernel<32, false, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
@@ -2782,6 +2928,7 @@ void HSSEngine::factor(cudaStream_t st) {
   factor_classes(own_, true, st);
   SB200_CUDA(cudaGetLastError());
   factored_ = true;
+  pf_ok_ = false;   // the factor arena now holds the full factorization
 }
 
 void HSSEngine::dist_factor_begin(double* send, cudaStream_t st) {
@@ -2806,9 +2953,250 @@ void HSSEngine::dist_factor_end(const double* recv, cudaStream_t st) {
   factored_ = true;
 }
 
+
+// ---------------------------------------------------------------------------
+// Schur complement of the (0,0) block (HSS fronts)
+// ---------------------------------------------------------------------------
+static void dgemm(bool ta, bool tb, int M, int N, int K, double alpha, const double* A, int lda,
+                  const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return;
+  dim3 grid((M + 127) / 128, (N + 63) / 64);
+  if (!ta && !tb) dense_gemm_kernel<false, false><<<grid, kThreads, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (ta && !tb) dense_gemm_kernel<true, false><<<grid, kThreads, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (!ta && tb) dense_gemm_kernel<false, true><<<grid, kThreads, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else dense_gemm_kernel<true, true><<<grid, kThreads, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+void HSSEngine::schur_lists() {
+  if (nparts_ > 1) throw std::logic_error("sharded matrix: Schur operations need the whole tree on one GPU");
+  if (sub_ok_) return;
+  const auto& root = H_.nodes[0];
+  if (root.leaf()) throw std::logic_error("Schur complement needs a root with two children");
+  const int N = int(H_.nodes.size());
+  std::vector<int> s0, s1;   // pre-order: subtree(ch0) = [ch0, ch1), subtree(ch1) = [ch1, N)
+  for (int i = root.ch0; i < root.ch1; i++) s0.push_back(i);
+  for (int i = root.ch1; i < N; i++) s1.push_back(i);
+  make_lists(sub0_, s0);
+  make_lists(sub1_, s1);
+  dn_.upload(hn_.data(), hn_.size());
+  const size_t nz = (size_t)std::max(std::max(H_.rows(), H_.cols()), 1);
+  zeros_.alloc(nz);
+  SB200_CUDA(cudaMemset(zeros_.p, 0, nz * sizeof(double)));
+  SB200_CUDA(cudaStreamSynchronize(0));
+  sub_ok_ = true;
+}
+
+void HSSEngine::schur_sizes(int* out) const {
+  const DNode& r = hn_[0];
+  if (r.leaf) throw std::logic_error("Schur complement needs a root with two children");
+  const DNode &c0 = hn_[r.ch0], &c1 = hn_[r.ch1];
+  out[0] = c1.rows; out[1] = c1.cols; out[2] = c0.v_rank; out[3] = c0.m;
+  out[4] = c1.v_rank; out[5] = c1.u_rank; out[6] = c0.rows;
+}
+
+// partial_factor: ULV-factor the subtree of child 0 with child 0 as its root (LU
+// of its reduced block D0) and keep Vhat = Vh(child 0)      (factor.hpp:44-50)
+void HSSEngine::partial_factor(cudaStream_t st) {
+  schur_lists();
+  const int ch0 = hn_[0].ch0;
+  const DNode& c0 = hn_[ch0];
+  if (c0.rows != c0.cols) throw std::invalid_argument("partial_factor needs a square (0,0) block");
+  for (int i : sub0_.host)
+    if (H_.nodes[i].leaf() && H_.nodes[i].rows != H_.nodes[i].cols)
+      throw std::invalid_argument("ULV factorization needs square diagonal blocks");
+  factor_prepare(false);
+  const int m0 = c0.m, rv0 = c0.v_rank;
+  pf_lu_.ensure((size_t)std::max(m0 * m0, 1));
+  pf_piv_.ensure((size_t)std::max(m0, 1));
+  vhat_.ensure((size_t)std::max(m0 * rv0, 1));
+  factor_classes(sub0_, false, st, ch0, pf_lu_.p, pf_piv_.p);
+  copy2d(vhat_.p, m0, fact_.p + c0.F + (size_t)c0.k * c0.m, c0.m, m0, rv0, st);
+  launches_++;
+  SB200_CUDA(cudaGetLastError());
+  factored_ = false;
+  pf_ok_ = true;
+  pfwd_s_ = 0;
+}
+
+// Schur_update: Theta = U1big B10, DUB01 = D0^{-1} U0 B01, Phi = V1big DUB01^H
+//                                                   (HSSMatrix.Schur.hpp:40-59)
+void HSSEngine::schur_update(double* dTheta, int ldT, double* dDUB01, int ldD, double* dPhi,
+                             int ldP, cudaStream_t st) {
+  if (!pf_ok_) throw std::logic_error("Schur_update called before partial_factor");
+  const DNode& r = hn_[0];
+  const int ch0 = r.ch0;
+  const DNode &c0 = hn_[ch0], &c1 = hn_[r.ch1];
+  const int m0 = c0.m, ru0 = c0.u_rank, rv0 = c0.v_rank, ru1 = c1.u_rank, rv1 = c1.v_rank;
+  if (m0 > 0 && rv1 > 0) {
+    if (ru0 > 0) {
+      const long long tot = (long long)m0 * rv1;
+      basis_apply_kernel<<<(unsigned)std::min<long long>((tot + kThreads - 1) / kThreads, 1024), kThreads, 0, st>>>(
+          dn_.p, ch0, vals_.p, perms_.p, vals_.p + r.B01, ru0, rv1, dDUB01, ldD);
+    } else {
+      SB200_CUDA(cudaMemset2DAsync(dDUB01, sizeof(double) * ldD, 0, sizeof(double) * m0, rv1, st));
+    }
+    lu_solve_kernel<<<rv1, kThreads, sizeof(double) * (size_t)m0, st>>>(pf_lu_.p, m0, pf_piv_.p, dDUB01, ldD);
+    launches_ += 2;
+  }
+  const int smax = std::max(std::max(rv0, m0), 1);
+  ensure_apply_ws(smax);
+  SB200_CUDA(cudaMemsetAsync(t1_.p, 0, t1_.n * sizeof(double), st));
+  if (rv0 > 0 && c1.rows > 0) {      // Theta: down-sweep of child 1 started from t2(ch1) = B10
+    const int s = rv0;
+    if (ru1 > 0)
+      SB200_CUDA(cudaMemcpyAsync(t2_.p + (size_t)c1.w_off * s, vals_.p + r.B10,
+                                 sizeof(double) * (size_t)ru1 * rv0, cudaMemcpyDeviceToDevice, st));
+    run_down(sub1_, false, s, zeros_.p, 0, dTheta - c1.row_off, ldT, true, st);
+  }
+  if (m0 > 0 && c1.cols > 0) {       // Phi: transposed down-sweep from t2(ch1) = DUB01^H
+    const int s = m0;
+    if (rv1 > 0) {
+      const long long tot = (long long)m0 * rv1;
+      transpose_kernel<<<(unsigned)std::min<long long>((tot + 255) / 256, 1024), 256, 0, st>>>(
+          dDUB01, ldD, m0, rv1, t2_.p + (size_t)c1.w_off * s, rv1);
+      launches_++;
+    }
+    run_down(sub1_, true, s, zeros_.p, 0, dPhi - c1.col_off, ldP, true, st);
+  }
+  SB200_CUDA(cudaGetLastError());
+}
+
+// Schur_product_direct                              (HSSMatrix.Schur.hpp:73-137)
+//   Sr = H11 R   - Theta Vhat^H DUB01 (V1big^H R)
+//   Sc = H11^H R - Phi Vhat B10^H (U1big^H R)
+// V1big^H R / U1big^H R are the up-sweeps of the two products with H11, reused.
+void HSSEngine::schur_product_direct(const double* dTheta, int ldT, const double* dDUB01, int ldD,
+                                     const double* dPhi, int ldP, int c, const double* dR, int ldR,
+                                     double* dSr, int ldSr, double* dSc, int ldSc,
+                                     cudaStream_t st) {
+  if (!pf_ok_) throw std::logic_error("Schur_product_direct called before partial_factor");
+  if (c <= 0) return;
+  const DNode& r = hn_[0];
+  const DNode &c0 = hn_[r.ch0], &c1 = hn_[r.ch1];
+  if (c1.rows != c1.cols) throw std::invalid_argument("Schur_product_direct needs a square (1,1) block");
+  const int m0 = c0.m, rv0 = c0.v_rank, ru1 = c1.u_rank, rv1 = c1.v_rank;
+  ensure_apply_ws(c);
+  stmp_[0].ensure((size_t)std::max(m0, 1) * c);
+  stmp_[1].ensure((size_t)std::max(rv0, 1) * c);
+  double* tA = stmp_[0].p;   // m0 x c
+  double* tB = stmp_[1].p;   // rv0 x c
+  double* t1c1 = t1_.p + (size_t)c1.w_off * c;
+  double* t2c1 = t2_.p + (size_t)c1.w_off * c;
+  // ---- Sr
+  run_up(sub1_, false, c, dR - c1.col_off, ldR, st);
+  SB200_CUDA(cudaMemsetAsync(t2c1, 0, sizeof(double) * (size_t)std::max(ru1, 1) * c, st));
+  run_down(sub1_, false, c, dR - c1.col_off, ldR, dSr - c1.row_off, ldSr, true, st);
+  dgemm(false, false, m0, c, rv1, 1., dDUB01, ldD, t1c1, std::max(rv1, 1), 0., tA, std::max(m0, 1), st);
+  dgemm(true, false, rv0, c, m0, 1., vhat_.p, std::max(m0, 1), tA, std::max(m0, 1), 0., tB, std::max(rv0, 1), st);
+  dgemm(false, false, c1.rows, c, rv0, -1., dTheta, ldT, tB, std::max(rv0, 1), 1., dSr, ldSr, st);
+  // ---- Sc
+  run_up(sub1_, true, c, dR - c1.row_off, ldR, st);
+  SB200_CUDA(cudaMemsetAsync(t2c1, 0, sizeof(double) * (size_t)std::max(rv1, 1) * c, st));
+  run_down(sub1_, true, c, dR - c1.row_off, ldR, dSc - c1.col_off, ldSc, true, st);
+  dgemm(true, false, rv0, c, ru1, 1., vals_.p + r.B10, std::max(ru1, 1), t1c1, std::max(ru1, 1), 0., tB, std::max(rv0, 1), st);
+  dgemm(false, false, m0, c, rv0, 1., vhat_.p, std::max(m0, 1), tB, std::max(rv0, 1), 0., tA, std::max(m0, 1), st);
+  dgemm(false, false, c1.cols, c, m0, -1., dPhi, ldP, tA, std::max(m0, 1), 1., dSc, ldSc, st);
+  launches_ += 6;
+  SB200_CUDA(cudaGetLastError());
+}
+
+// Schur_product_indirect                            (HSSMatrix.Schur.hpp:139-215)
+// with W = B10 Vhat^H DUB01 (ru1 x rv1):
+//   Sr = Sr1 - U1big (B10 (V0big^H R0) + W (V1big^H R1))
+//   Sc = Sc1 - V1big (B01^H (U0big^H R0) + W^H (U1big^H R1))
+// (Sr1, Sc1: rows of H [R0; R1] / H^H [R0; R1] that belong to block 1)
+void HSSEngine::schur_product_indirect(const double* dDUB01, int ldD, int c, const double* dR0,
+                                       int ldR0, const double* dR1, int ldR1, const double* dSr1,
+                                       int ldSr1, const double* dSc1, int ldSc1, double* dSr,
+                                       int ldSr, double* dSc, int ldSc, cudaStream_t st) {
+  if (!pf_ok_) throw std::logic_error("Schur_product_indirect called before partial_factor");
+  if (c <= 0) return;
+  const DNode& r = hn_[0];
+  const DNode &c0 = hn_[r.ch0], &c1 = hn_[r.ch1];
+  const int m0 = c0.m, ru0 = c0.u_rank, rv0 = c0.v_rank, ru1 = c1.u_rank, rv1 = c1.v_rank;
+  ensure_apply_ws(c);
+  auto pad = [](long long n) { return (size_t)std::max<long long>(n, 1); };
+  const size_t nV0 = pad((long long)rv0 * c), nU0 = pad((long long)ru0 * c), nV1 = pad((long long)rv1 * c),
+               nU1 = pad((long long)ru1 * c), nVtD = pad((long long)rv0 * rv1), nW = pad((long long)ru1 * rv1);
+  stmp_[2].ensure(nV0 + nU0 + nV1 + nU1 + nVtD + nW);
+  double* V0tR0 = stmp_[2].p;
+  double* U0tR0 = V0tR0 + nV0;
+  double* V1tR1 = U0tR0 + nU0;
+  double* U1tR1 = V1tR1 + nV1;
+  double* VtD = U1tR1 + nU1;
+  double* W = VtD + nVtD;
+  double* t1c0 = t1_.p + (size_t)c0.w_off * c;
+  double* t1c1 = t1_.p + (size_t)c1.w_off * c;
+  double* t2c1 = t2_.p + (size_t)c1.w_off * c;
+  // apply_UtVt_big on both subtrees = the four up-sweeps
+  run_up(sub0_, false, c, dR0 - c0.col_off, ldR0, st);
+  copy2d(V0tR0, std::max(rv0, 1), t1c0, std::max(rv0, 1), rv0, c, st);
+  run_up(sub0_, true, c, dR0 - c0.row_off, ldR0, st);
+  copy2d(U0tR0, std::max(ru0, 1), t1c0, std::max(ru0, 1), ru0, c, st);
+  run_up(sub1_, false, c, dR1 - c1.col_off, ldR1, st);
+  copy2d(V1tR1, std::max(rv1, 1), t1c1, std::max(rv1, 1), rv1, c, st);
+  run_up(sub1_, true, c, dR1 - c1.row_off, ldR1, st);
+  copy2d(U1tR1, std::max(ru1, 1), t1c1, std::max(ru1, 1), ru1, c, st);
+  // W = B10 (Vhat^H DUB01)
+  dgemm(true, false, rv0, rv1, m0, 1., vhat_.p, std::max(m0, 1), dDUB01, ldD, 0., VtD, std::max(rv0, 1), st);
+  dgemm(false, false, ru1, rv1, rv0, 1., vals_.p + r.B10, std::max(ru1, 1), VtD, std::max(rv0, 1), 0., W, std::max(ru1, 1), st);
+  SB200_CUDA(cudaMemsetAsync(t1_.p, 0, t1_.n * sizeof(double), st));
+  // ---- Sr = Sr1 + U1big t2,  t2(ch1) = -(B10 V0tR0 + W V1tR1)
+  dgemm(false, false, ru1, c, rv0, -1., vals_.p + r.B10, std::max(ru1, 1), V0tR0, std::max(rv0, 1), 0., t2c1, std::max(ru1, 1), st);
+  dgemm(false, false, ru1, c, rv1, -1., W, std::max(ru1, 1), V1tR1, std::max(rv1, 1), 1., t2c1, std::max(ru1, 1), st);
+  if (dSr != dSr1) copy2d(dSr, ldSr, dSr1, ldSr1, c1.rows, c, st);
+  run_down(sub1_, false, c, zeros_.p, 0, dSr - c1.row_off, ldSr, true, st, 1.);
+  // ---- Sc = Sc1 + V1big t2,  t2(ch1) = -(B01^H U0tR0 + W^H U1tR1)
+  dgemm(true, false, rv1, c, ru0, -1., vals_.p + r.B01, std::max(ru0, 1), U0tR0, std::max(ru0, 1), 0., t2c1, std::max(rv1, 1), st);
+  dgemm(true, false, rv1, c, ru1, -1., W, std::max(ru1, 1), U1tR1, std::max(ru1, 1), 1., t2c1, std::max(rv1, 1), st);
+  if (dSc != dSc1) copy2d(dSc, ldSc, dSc1, ldSc1, c1.cols, c, st);
+  run_down(sub1_, true, c, zeros_.p, 0, dSc - c1.col_off, ldSc, true, st, 1.);
+  launches_ += 12;
+  SB200_CUDA(cudaGetLastError());
+}
+
+// child(0)->forward_solve(w, b, partial = true)      (solve.hpp:52-60,133-152)
+void HSSEngine::partial_forward_solve(int s, double* dB0, int ldB, double* dRed, int ldRed,
+                                      cudaStream_t st) {
+  if (!pf_ok_) throw std::logic_error("partial forward_solve called before partial_factor");
+  if (s <= 0) return;
+  ensure_solve_ws(s);
+  const int ch0 = hn_[0].ch0;
+  const DNode& c0 = hn_[ch0];
+  const int h0 = H_.nodes[ch0].height;
+  solve_fwd(sub0_, s, dB0, ldB, st, h0);       // the classes below child 0
+  solve_root(s, dB0, ldB, st, ch0, pf_lu_.p, pf_piv_.p);
+  if (c0.v_rank > 0) {
+    const size_t smem = sizeof(double) * (size_t)std::max(c0.v_rows, 1);
+    set_smem(partial_reduced_rhs_kernel, smem);
+    partial_reduced_rhs_kernel<<<s, kThreads, smem, st>>>(dn_.p, ch0, vals_.p, perms_.p, vhat_.p, xsol_.p,
+                                                          zsol_.p, dRed, ldRed, s);
+    launches_++;
+  }
+  pfwd_s_ = s;
+  SB200_CUDA(cudaGetLastError());
+}
+
+double* HSSEngine::partial_x(int s) {
+  if (pfwd_s_ != s || s <= 0) throw std::logic_error("no partial forward_solve with this number of right-hand sides");
+  return xsol_.p + (size_t)hn_[hn_[0].ch0].x_off * s;
+}
+
+// child(0)->backward_solve(w, x)                    (solve.hpp:62-66,199-238)
+void HSSEngine::partial_backward_solve(int s, double* dX0, int ldX, cudaStream_t st) {
+  double* x = partial_x(s);
+  const int ch0 = hn_[0].ch0;
+  const DNode& c0 = hn_[ch0];
+  if (c0.leaf) copy2d(dX0, ldX, x, c0.m, c0.m, s, st);
+  else solve_bwd(sub0_, s, dX0, ldX, st, H_.nodes[ch0].height);
+  launches_++;
+  SB200_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------- solve
-void HSSEngine::solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st) {
-  for (int h = 0; h < L.classes(); h++) {
+void HSSEngine::solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st, int nclass) {
+  const int nh = nclass < 0 ? L.classes() : std::min(nclass, L.classes());
+  for (int h = 0; h < nh; h++) {
     const int cnt = L.hptr[h + 1] - L.hptr[h];
     if (!cnt) continue;
     const int mm = std::max(L.max_m[h], 1);
@@ -2820,17 +3208,21 @@ void HSSEngine::solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaSt
   }
 }
 
-void HSSEngine::solve_root(int s, double* dB, int ldB, cudaStream_t st) {
-  const size_t nn = (size_t)std::max(hn_[0].m, 1);
+void HSSEngine::solve_root(int s, double* dB, int ldB, cudaStream_t st, int node,
+                           const double* lu, const int* piv) {
+  const size_t nn = (size_t)std::max(hn_[node].m, 1);
   const int use_smem = sizeof(double) * (nn * nn + nn + 2) <= 200 * 1024;
   size_t smem = sizeof(double) * (use_smem ? nn * nn + nn + 2 : nn);
   set_smem(ulv_root_solve_kernel, smem);
-  ulv_root_solve_kernel<<<s, kThreads, smem, st>>>(dn_.p, vals_.p, fact_.p, rootpiv_.p, dB, ldB, zsol_.p, fsol_.p, xsol_.p, s, use_smem);
+  ulv_root_solve_kernel<<<s, kThreads, smem, st>>>(dn_.p, node, vals_.p, lu ? lu : fact_.p + hn_[node].F,
+                                                   piv ? piv : rootpiv_.p, dB, ldB, zsol_.p, fsol_.p,
+                                                   xsol_.p, s, use_smem);
   launches_++;
 }
 
-void HSSEngine::solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st) {
-  for (int h = L.classes() - 1; h >= 0; h--) {
+void HSSEngine::solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st, int nclass) {
+  const int nh = nclass < 0 ? L.classes() : std::min(nclass, L.classes());
+  for (int h = nh - 1; h >= 0; h--) {
     const int cnt = L.hptr[h + 1] - L.hptr[h];
     if (!cnt) continue;
     const int mm = std::max(L.max_m[h], 1);

@@ -86,6 +86,42 @@ class HSSEngine {
   void dist_solve_begin(int s, double* dB, int ldB, double* send, cudaStream_t st);
   void dist_solve_end(int s, double* dB, int ldB, const double* recv, cudaStream_t st);
 
+  // ---- Schur complement of the (0,0) block of H = [H00 H01; H10 H11] (root's
+  // children), what the reference's HSS fronts use (reference
+  // HSSMatrix.factor.hpp:44-50 partial_factor, HSSMatrix.Schur.hpp:35-215,
+  // caller src/sparse/fronts/FrontHSS.cpp:385-410,150-222,440-500):
+  //   S = H11 - Theta Vhat^H Phi^H,  Theta = U1big B10 (rows1 x rv0),
+  //   DUB01 = D0^{-1} U0 B01 (m0 x rv1),  Phi = V1big DUB01^H (cols1 x m0),
+  //   Vhat = Vh of child 0 (m0 x rv0), m0 = reduced size of child 0.
+  // All matrix arguments are DEVICE pointers, column-major.
+  void partial_factor(cudaStream_t st);
+  bool partially_factored() const { return pf_ok_; }
+  // out[0..6] = rows(ch1), cols(ch1), v_rank(ch0), m0, v_rank(ch1), u_rank(ch1), rows(ch0)
+  void schur_sizes(int* out) const;
+  void schur_update(double* dTheta, int ldT, double* dDUB01, int ldD, double* dPhi, int ldP,
+                    cudaStream_t st);
+  const double* vhat() const { return vhat_.p; }   // m0 x v_rank(ch0), ld = m0
+  // Sr = S R, Sc = S^H R for R (rows1 x c)     (Schur_product_direct)
+  void schur_product_direct(const double* dTheta, int ldT, const double* dDUB01, int ldD,
+                            const double* dPhi, int ldP, int c, const double* dR, int ldR,
+                            double* dSr, int ldSr, double* dSc, int ldSc, cudaStream_t st);
+  // Sr = Sr1 - U1big (B10 V0big^H R0 + B10 Vhat^H DUB01 V1big^H R1),
+  // Sc = Sc1 - V1big (B01^H U0big^H R0 + (B10 Vhat^H DUB01)^H U1big^H R1)
+  //                                             (Schur_product_indirect)
+  void schur_product_indirect(const double* dDUB01, int ldD, int c, const double* dR0, int ldR0,
+                              const double* dR1, int ldR1, const double* dSr1, int ldSr1,
+                              const double* dSc1, int ldSc1, double* dSr, int ldSr,
+                              double* dSc, int ldSc, cudaStream_t st);
+  // child(0)->forward_solve(w, b, partial = true) / child(0)->backward_solve(w, x)
+  // (reference HSSMatrix.solve.hpp:52-66,133-152; FrontHSS.cpp:452-462,487-495):
+  // forward eliminates b0 (rows0 x s, overwritten) in the subtree of child 0,
+  // solves with D0 and returns reduced_rhs = Vhat^H x + V0^H [z0; z1] (rv0 x s);
+  // the reduced solution x (m0 x s, kept inside the engine) can be updated in
+  // place (partial_x) before backward expands it into x0 (rows0 x s).
+  void partial_forward_solve(int s, double* dB0, int ldB, double* dRed, int ldRed, cudaStream_t st);
+  double* partial_x(int s);   // device, m0 x s, ld = m0
+  void partial_backward_solve(int s, double* dX0, int ldX, cudaStream_t st);
+
   long long factor_nonzeros() const { return fact_nnz_; }
   long long launches() const { return launches_; }
   // ULV factors to host (HSSMatrix::ULV()); null pointers: sizes only
@@ -106,14 +142,21 @@ class HSSEngine {
   void run_up(const NodeLists& L, bool T, int s, const double* dB, int ldB, cudaStream_t st);
   void run_down(const NodeLists& L, bool T, int s, const double* dB, int ldB, double* dC,
                 int ldC, bool leaves, cudaStream_t st, double beta = 0.);
-  void factor_prepare();
-  void factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t st);
-  void solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st);
-  void solve_root(int s, double* dB, int ldB, cudaStream_t st);
-  void solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st);
+  void factor_prepare(bool whole = true);
+  // lu_node: the node that is LU-factored instead of eliminated (the root; child
+  // 0 for partial_factor, whose LU goes to lu_dst / lu_piv)
+  void factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t st, int lu_node = 0,
+                      double* lu_dst = nullptr, int* lu_piv = nullptr);
+  void schur_lists();
+  // nclass >= 0: only the lowest nclass height classes of the list
+  void solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st, int nclass = -1);
+  void solve_root(int s, double* dB, int ldB, cudaStream_t st, int node = 0,
+                  const double* lu = nullptr, const int* piv = nullptr);
+  void solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaStream_t st, int nclass = -1);
 
   HSSHost H_;
   std::vector<int> leaf_ids_;   // leaves in index order (extract)
+  std::vector<int> class_gmm_;  // per height class: largest block of the whole tree
   int max_depth_ = 0;
   std::vector<DNode> hn_;
   DevBuf<DNode> dn_;
@@ -135,6 +178,12 @@ class HSSEngine {
   long long scratch_per_node_max_ = 0;
   bool factored_ = false;
   long long launches_ = 0;
+  // Schur / partial factorization state
+  NodeLists sub0_, sub1_;        // subtrees of the root's children (cut nodes included)
+  bool sub_ok_ = false, pf_ok_ = false;
+  int pfwd_s_ = 0;
+  DevBuf<double> pf_lu_, vhat_, zeros_, stmp_[4];
+  DevBuf<int> pf_piv_;
   int nb_ = 32;
   int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0, qr_ll_ = 0, qr_variant_ = 1, qr_nowide_ = 0;   // switches; env SB200_QR_*
   int mm_min_ = 4;      // >= this many right-hand sides: GEMM-shaped (tensor pipe) apply kernels

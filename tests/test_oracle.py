@@ -84,3 +84,31 @@ def test_reference_selftests_pass():
     out = subprocess.run([os.path.join(d, "test_BLR_seq"), "512"],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-500:]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_schur_restatement_matches_reference_golden(case):
+    """partial_factor / Schur_update / Schur_product_direct: the
+    numpy restatement reproduces what the reference computed through the call
+    sequence of FrontHSS (tests/golden/make_golden_schur.py).  Compared on the
+    quantities that do not depend on the ULV's orthogonal basis."""
+    def rel(a, b):   # the upper-triangular case has Theta = 0 exactly
+        return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    nodes, _ = hss_file.read_hss(os.path.join(GOLDEN, case + ".hss"))
+    g = np.load(os.path.join(GOLDEN, case + "_schur.npz"))
+    f = ho.partial_factor(nodes)
+    Theta, DUB01, Phi = ho.schur_update(nodes, f)
+    assert [list(a.shape) for a in (Theta, DUB01, Phi, f.Vhat)] == g["sizes"].tolist()
+    assert rel(Theta, g["Theta"]) < 1e-13
+    assert rel(f.Vhat.T @ DUB01, g["VtD"]) < 1e-12
+    assert rel(f.Vhat.T @ Phi.T, g["VtPhiT"]) < 1e-12
+    Sr, Sc = ho.schur_product_direct(nodes, f, Theta, DUB01, Phi, g["R"])
+    assert rel(Sr, g["Sr"]) < 1e-13 and rel(Sc, g["Sc"]) < 1e-13
+    # and the identity the fronts rely on: S = H11 - H10 H00^{-1} H01
+    A = ho.to_dense(nodes)
+    n0 = A.shape[0] - Theta.shape[0]
+    S = A[n0:, n0:] - A[n0:, :n0] @ np.linalg.solve(A[:n0, :n0], A[:n0, n0:])
+    assert rel(A[n0:, n0:] - Theta @ f.Vhat.T @ Phi.T, S) < 1e-12
+    assert rel(g["Sr"], S @ g["R"]) < 1e-12 and rel(g["Sc"], S.T @ g["R"]) < 1e-12
+    assert rel(g["Theta"] @ g["red"], A[n0:, :n0] @ g["x0"]) < 1e-12
+    assert rel(g["x0"], np.linalg.solve(A[:n0, :n0], g["b0"])) < 1e-12
