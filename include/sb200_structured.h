@@ -120,6 +120,34 @@ int SB200_d_blr_compress_and_factor(CSPStructMat* S, int n, const double* A,
 int SB200_d_blr_compress_and_factor_device(CSPStructMat* S, int n, const double* dA,
                                            int ldA, const CSPOptions* opts,
                                            double pivot_threshold);
+/* BLRMatrix<double>::construct_and_partial_factor(A11, A12, A21, A22, B11, B12,
+ * B21, tiles1, tiles2, admissible, opts) (reference src/BLR/BLRMatrix.cpp:739-1037,
+ * RL variant, weak admissibility; caller src/sparse/fronts/FrontBLR.cpp:429-433):
+ * the front [A11 A12; A21 A22] (n1 + n2 rows, tiles ClusterTree(n1).refine(leaf)
+ * and ClusterTree(n2).refine(leaf)) is eliminated over the tiles of A11 only.
+ * S then holds F11 = LU(A11) in BLR form and the compressed F12 = L^{-1} P A12,
+ * F21 = A21 U^{-1}; A22 is overwritten IN PLACE with the dense Schur complement
+ * A22 - A21 A11^{-1} A12 (what extend_add passes to the parent front).  Host
+ * pointers; the _device form takes device pointers. */
+int SB200_d_blr_partial_factor(CSPStructMat* S, int n1, int n2, const double* A11, int ld11,
+                               const double* A12, int ld12, const double* A21, int ld21,
+                               double* A22, int ld22, const CSPOptions* opts,
+                               double pivot_threshold);
+int SB200_d_blr_partial_factor_device(CSPStructMat* S, int n1, int n2, const double* dA11, int ld11,
+                                      const double* dA12, int ld12, const double* dA21, int ld21,
+                                      double* dA22, int ld22, const CSPOptions* opts,
+                                      double pivot_threshold);
+/* n1 of a partially factored front (rows of S otherwise). */
+int SB200_d_blr_sep_rows(const CSPStructMat S);
+/* The two halves of the front solve (FrontBLR::fwd_solve_node / bwd_solve_node,
+ * FrontBLR.cpp:525-568) on B = [b_sep; b_upd] ((n1 + n2) x nrhs, host, in place):
+ * forward:  b_sep <- L11^{-1} P b_sep,  b_upd <- b_upd - F21 b_sep
+ *           (laswp + BLRMatrix::trsmLNU_gemm, BLRMatrix.cpp:1552-1608)
+ * backward: b_sep <- U11^{-1} (b_sep - F12 b_upd)
+ *           (BLRMatrix::gemm_trsmUNN, BLRMatrix.cpp:1610-1665)
+ * (b_upd is not touched by backward; the caller solves the Schur system in between). */
+int SB200_d_blr_partial_forward_solve(const CSPStructMat S, int nrhs, double* B, int ldB);
+int SB200_d_blr_partial_backward_solve(const CSPStructMat S, int nrhs, double* Y, int ldY);
 int SB200_d_blr_tiles(const CSPStructMat S);
 /* Number of off-diagonal tiles that did not compress to rank <= min(m,n)/2 and
  * are kept dense (DenseTile in the reference, src/BLR/BLRMatrix.cpp:563-570). */

@@ -83,6 +83,10 @@ def lib():
         "ref_blr_solve": (None, [vp, i, dp, i]),
         "ref_blr_info": (None, [vp, lp]),
         "ref_blr_destroy": (None, [vp]),
+        "ref_blr_partial_factor": (vp, [i, i, dp, i, dp, i, dp, i, dp, i, cp]),
+        "ref_blr_partial_info": (None, [vp, lp]),
+        "ref_blr_partial_forward": (None, [vp, i, dp, i]),
+        "ref_blr_partial_backward": (None, [vp, i, dp, i]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -248,6 +252,46 @@ class RefBLR:
     def solve(self, b):
         x = _f(b).copy(order="F")
         lib().ref_blr_solve(self._h, x.shape[1], x, x.shape[0])
+        return x
+
+    def close(self):
+        if self._h:
+            lib().ref_blr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RefBLRFront:
+    """Reference ``BLRMatrix<double>::construct_and_partial_factor`` on a front
+    [A11 A12; A21 A22] (weak admissibility, ClusterTree tiles); ``.S`` is the
+    Schur complement the reference leaves in A22."""
+
+    def __init__(self, A11, A12, A21, A22, args=""):
+        A11, A12, A21 = _f(A11), _f(A12), _f(A21)
+        self.S = _f(A22).copy(order="F")
+        self.n1, self.n2 = A11.shape[0], self.S.shape[0]
+        self._h = lib().ref_blr_partial_factor(
+            self.n1, self.n2, A11, self.n1, A12, self.n1, A21, self.n2,
+            self.S, self.n2, args.encode())
+
+    def ranks(self):
+        out = np.zeros(3, dtype=np.int64)
+        lib().ref_blr_partial_info(self._h, out)
+        return tuple(int(v) for v in out)
+
+    def partial_forward_solve(self, b):
+        x = _f(b).copy(order="F")
+        lib().ref_blr_partial_forward(self._h, x.shape[1], x, x.shape[0])
+        return x
+
+    def partial_backward_solve(self, y):
+        x = _f(y).copy(order="F")
+        lib().ref_blr_partial_backward(self._h, x.shape[1], x, x.shape[0])
         return x
 
     def close(self):

@@ -58,6 +58,9 @@ namespace {
   struct BLRHandle {
     std::unique_ptr<BLR::BLRMatrix<double>> B;
     int n = 0;
+    // partially factored front (construct_and_partial_factor)
+    BLR::BLRMatrix<double> B11, B12, B21;
+    int n1 = 0, n2 = 0;
   };
 
   // "--hss_leaf_size 128 --hss_rel_tol 1e-4" -> argc/argv for the reference's
@@ -320,4 +323,56 @@ extern "C" {
   }
 
   void ref_blr_destroy(void* hv) { delete static_cast<BLRHandle*>(hv); }
+
+  /* ---- BLRMatrix::construct_and_partial_factor on the front [A11 A12; A21 A22]
+   *      (BLRMatrix.cpp:739-1037; caller FrontBLR.cpp:429-433), weak
+   *      admissibility, tiles from ClusterTree(n1/n2).refine(leaf).  A22 (n2 x n2,
+   *      ld22) is overwritten with the Schur complement, as in the reference. */
+  void* ref_blr_partial_factor(int n1, int n2, const double* A11, int ld11,
+                               const double* A12, int ld12, const double* A21,
+                               int ld21, double* A22, int ld22,
+                               const char* blr_args) {
+    DenseD a11(n1, n1, A11, ld11), a12(n1, n2, A12, ld12),
+      a21(n2, n1, A21, ld21), a22(n2, n2, A22, ld22);
+    BLR::BLROptions<double> opts;
+    opts.set_verbose(false);
+    parse(opts, blr_args);
+    structured::ClusterTree t1(n1), t2(n2);
+    t1.refine(opts.leaf_size());
+    t2.refine(opts.leaf_size());
+    auto tiles1 = t1.template leaf_sizes<std::size_t>();
+    auto tiles2 = t2.template leaf_sizes<std::size_t>();
+    int nt = tiles1.size();
+    DenseMatrix<bool> adm(nt, nt);
+    adm.fill(true);
+    for (int t=0; t<nt; t++) adm(t, t) = false;
+    auto h = new BLRHandle;
+    h->n = n1 + n2; h->n1 = n1; h->n2 = n2;
+    BLR::BLRMatrix<double>::construct_and_partial_factor
+      (a11, a12, a21, a22, h->B11, h->B12, h->B21, tiles1, tiles2, adm, opts);
+    for (int j=0; j<n2; j++)
+      for (int i=0; i<n2; i++) A22[i + std::size_t(j)*ld22] = a22(i, j);
+    return h;
+  }
+
+  /* out[0..2] = rank(F11), rank(F12), rank(F21) */
+  void ref_blr_partial_info(void* hv, long long* out) {
+    auto* h = static_cast<BLRHandle*>(hv);
+    out[0] = h->B11.rank(); out[1] = h->B12.rank(); out[2] = h->B21.rank();
+  }
+
+  /* FrontBLR::fwd_solve_phase2 (FrontBLR.cpp:525-531) on b = [bloc; bupd] */
+  void ref_blr_partial_forward(void* hv, int s, double* b, int ldb) {
+    auto* h = static_cast<BLRHandle*>(hv);
+    DenseW bloc(h->n1, s, b, ldb), bupd(h->n2, s, b + h->n1, ldb);
+    bloc.laswp(h->B11.piv(), true);
+    BLR::BLRMatrix<double>::trsmLNU_gemm(h->B11, h->B21, bloc, bupd, 0);
+  }
+
+  /* FrontBLR::bwd_solve_phase1 (FrontBLR.cpp:551-555) on y = [yloc; yupd] */
+  void ref_blr_partial_backward(void* hv, int s, double* y, int ldy) {
+    auto* h = static_cast<BLRHandle*>(hv);
+    DenseW yloc(h->n1, s, y, ldy), yupd(h->n2, s, y + h->n1, ldy);
+    BLR::BLRMatrix<double>::gemm_trsmUNN(h->B11, h->B12, yloc, yupd, 0);
+  }
 }

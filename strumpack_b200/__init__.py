@@ -55,6 +55,11 @@ SYMBOLS = {
     "SB200_d_hss_from_kernel": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp]),
     "SB200_d_blr_compress_and_factor": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),
+    "SB200_d_blr_partial_factor": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d]),
+    "SB200_d_blr_partial_factor_device": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d]),
+    "SB200_d_blr_sep_rows": (_i, [_vp]),
+    "SB200_d_blr_partial_forward_solve": (_i, [_vp, _i, _vp, _i]),
+    "SB200_d_blr_partial_backward_solve": (_i, [_vp, _i, _vp, _i]),
     "SB200_d_blr_tiles": (_i, [_vp]),
     "SB200_d_blr_dense_tiles": (_i, [_vp]),
     "SB200_d_hss_read": (_i, [_pvp, C.c_char_p]),
@@ -390,6 +395,43 @@ class BLRMatrix(StructuredMatrix):
             C.byref(h), n, C.c_void_p(dA.data_ptr()), n, C.byref(opts),
             float(pivot_threshold)), "compress_and_factor_device")
         return cls(h.value)
+
+    @classmethod
+    def construct_and_partial_factor(cls, A11, A12, A21, A22, opts=None, pivot_threshold=-1.0):
+        """BLRMatrix::construct_and_partial_factor (reference BLRMatrix.cpp:739-1037,
+        RL, weak admissibility, tiles from ClusterTree(n1/n2).refine(leaf)).
+        Returns (F, S): F holds F11 = LU(A11), F12, F21 in BLR form, S is the dense
+        Schur complement A22 - A21 A11^{-1} A12 (the reference updates A22 in place)."""
+        A11, A12, A21 = _fortran(A11), _fortran(A12), _fortran(A21)
+        S = _fortran(A22).copy(order="F")
+        n1, n2 = A11.shape[0], S.shape[0]
+        opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
+        h = C.c_void_p()
+        _check(lib().SB200_d_blr_partial_factor(
+            C.byref(h), n1, n2, A11.ctypes.data, n1, A12.ctypes.data, max(n1, 1),
+            A21.ctypes.data, max(n2, 1), S.ctypes.data, max(n2, 1), C.byref(opts),
+            float(pivot_threshold)), "construct_and_partial_factor")
+        return cls(h.value), S
+
+    @property
+    def sep_rows(self):
+        return lib().SB200_d_blr_sep_rows(self._h)
+
+    def partial_forward_solve(self, b):
+        """[b_sep; b_upd] -> [L11^{-1} P b_sep; b_upd - F21 b_sep] (laswp + trsmLNU_gemm,
+        reference BLRMatrix.cpp:1552-1608, FrontBLR.cpp:529-531)."""
+        x = _fortran(b).copy(order="F")
+        _check(lib().SB200_d_blr_partial_forward_solve(self._h, x.shape[1], x.ctypes.data, x.shape[0]),
+               "partial_forward_solve")
+        return x
+
+    def partial_backward_solve(self, y):
+        """[y_sep; y_upd] -> [U11^{-1} (y_sep - F12 y_upd); y_upd] (gemm_trsmUNN,
+        reference BLRMatrix.cpp:1610-1665, FrontBLR.cpp:555)."""
+        x = _fortran(y).copy(order="F")
+        _check(lib().SB200_d_blr_partial_backward_solve(self._h, x.shape[1], x.ctypes.data, x.shape[0]),
+               "partial_backward_solve")
+        return x
 
     @property
     def tiles(self):

@@ -768,15 +768,16 @@ void BLREngine::run(bool do_factor) {
 // x <- A^{-1} x : laswp(piv), trsm(L, unit lower BLR), trsm(U, upper BLR)
 // (BLRMatrix::solve, BLRMatrix.hpp:118-122; left-looking block substitution,
 // BLRMatrix.cpp:1683-1707)
-void BLREngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
-  if (!factored_) throw std::logic_error("BLR solve called on an unfactored matrix");
-  const int nb = nb_, n = n_;
-  // task lists (k,j) for every block row, built once
+void BLREngine::build_solve_tasks(int s, double* dB, int ldB, cudaStream_t st) {
+  const int nb = nb_;
+  // task lists (k,j) for every block row, built once.  Forward: the tiles left
+  // of the diagonal that belong to eliminated block columns (all of them unless
+  // the factorization is partial); backward: the tiles right of the diagonal.
   if (!tasks_built_) {
     std::vector<GemvTask> tl;
     fwd_ptr_.assign(nb + 1, 0);
     for (int i = 0; i < nb; i++) {
-      for (int j = 0; j < i; j++) tl.push_back({i, j});
+      for (int j = 0; j < std::min(i, nsteps_); j++) tl.push_back({i, j});
       fwd_ptr_[i + 1] = int(tl.size());
     }
     bwd_ptr_.assign(nb + 1, 0);
@@ -790,10 +791,8 @@ void BLREngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
     SB200_CUDA(cudaMemcpyAsync(gtasks_.p, tl.data(), tl.size() * sizeof(GemvTask), cudaMemcpyHostToDevice, st));
     tasks_built_ = true;
   }
-  const GemvTask* gt = reinterpret_cast<const GemvTask*>(gtasks_.p);
   DevBuf<SolveTask>& sv = solve_task_;
   if (!sv.p) {
-    std::vector<SolveTask> t(nb);
     sv.alloc(nb);
     solve_ldb_ = -1;
   }
@@ -804,21 +803,39 @@ void BLREngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
     SB200_CUDA(cudaStreamSynchronize(st));
     solve_ldb_ = ldB; solve_ptr_ = dB; solve_s_ = s;
   }
+}
+
+// forward: x_i <- L_ii^{-1} P_i (x_i - sum_{j<i} T_ij x_j) for the eliminated
+// block rows; the remaining rows (partial factorization) only receive the
+// update  x_i -= sum_j F21_ij x_j   (trsmLNU_gemm, BLRMatrix.cpp:1552-1608)
+void BLREngine::forward_rows(int s, double* dB, int ldB, cudaStream_t st) {
+  const int nb = nb_, n = n_;
+  const GemvTask* gt = reinterpret_cast<const GemvTask*>(gtasks_.p);
   const size_t gsm = sizeof(double) * (size_t)(maxtile_ / 2 + 8);
-  for (int i = 0; i < nb; i++) {      // forward: x_i <- L_ii^{-1} P_i (x_i - sum_{j<i} T_ij x_j)
+  for (int i = 0; i < nb; i++) {
     const int m = off_[i + 1] - off_[i], cnt = fwd_ptr_[i + 1] - fwd_ptr_[i];
     if (cnt) {
       blr_lr_gemv_kernel<<<dim3(cnt, s), kThreads, gsm, st>>>(gt + fwd_ptr_[i], doff_.p, nb, lr_.p, dlroff_.p,
                                                              drcap_.p, drank_.p, dB, ldB, dB, ldB, -1., A_.p, n);
       launches_++;
     }
+    if (i >= nsteps_) continue;
     const size_t smem = sizeof(double) * (size_t)kWarps * m;
     set_smem(blr_trsm_lower_kernel, smem);
     blr_trsm_lower_kernel<<<dim3(1, (s + kWarps - 1) / kWarps), kThreads, smem, st>>>(
-        A_.p + off_[i] + (size_t)off_[i] * n, n, m, 1, gperm_.p + off_[i], sv.p + i, nullptr);
+        A_.p + off_[i] + (size_t)off_[i] * n, n, m, 1, gperm_.p + off_[i], solve_task_.p + i, nullptr);
     launches_++;
   }
-  for (int i = nb - 1; i >= 0; i--) { // backward: x_i <- U_ii^{-1} (x_i - sum_{j>i} T_ij x_j)
+}
+
+// backward: x_i <- U_ii^{-1} (x_i - sum_{j>i} T_ij x_j) over the eliminated
+// block rows; with a partial factorization the tiles j of the trailing block
+// are F12, i.e. gemm_trsmUNN (BLRMatrix.cpp:1610-1665)
+void BLREngine::backward_rows(int s, double* dB, int ldB, cudaStream_t st) {
+  const int nb = nb_, n = n_;
+  const GemvTask* gt = reinterpret_cast<const GemvTask*>(gtasks_.p);
+  const size_t gsm = sizeof(double) * (size_t)(maxtile_ / 2 + 8);
+  for (int i = nsteps_ - 1; i >= 0; i--) {
     const int m = off_[i + 1] - off_[i], cnt = bwd_ptr_[i + 1] - bwd_ptr_[i];
     if (cnt) {
       blr_lr_gemv_kernel<<<dim3(cnt, s), kThreads, gsm, st>>>(gt + bwd_base_ + bwd_ptr_[i], doff_.p, nb, lr_.p,
@@ -831,6 +848,31 @@ void BLREngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
         A_.p + off_[i] + (size_t)off_[i] * n, n, m, dB + off_[i], ldB, s);
     launches_++;
   }
+}
+
+void BLREngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
+  if (!factored_) throw std::logic_error("BLR solve called on an unfactored matrix");
+  if (partial()) throw std::logic_error("BLR solve: the factorization is partial (use the partial forward / backward solves around the Schur system)");
+  if (s <= 0) return;
+  build_solve_tasks(s, dB, ldB, st);
+  forward_rows(s, dB, ldB, st);
+  backward_rows(s, dB, ldB, st);
+  SB200_CUDA(cudaGetLastError());
+}
+
+void BLREngine::partial_forward(int s, double* dB, int ldB, cudaStream_t st) {
+  if (!factored_) throw std::logic_error("BLR solve called on an unfactored matrix");
+  if (s <= 0) return;
+  build_solve_tasks(s, dB, ldB, st);
+  forward_rows(s, dB, ldB, st);
+  SB200_CUDA(cudaGetLastError());
+}
+
+void BLREngine::partial_backward(int s, double* dB, int ldB, cudaStream_t st) {
+  if (!factored_) throw std::logic_error("BLR solve called on an unfactored matrix");
+  if (s <= 0) return;
+  build_solve_tasks(s, dB, ldB, st);
+  backward_rows(s, dB, ldB, st);
   SB200_CUDA(cudaGetLastError());
 }
 

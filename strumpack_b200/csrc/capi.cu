@@ -213,6 +213,70 @@ int SB200_d_blr_compress_and_factor_device(CSPStructMat* S, int n, const double*
   });
 }
 
+static void blr_partial_impl(CSPStructMat* S, int n1, int n2, const double* A11, int ld11,
+                             const double* A12, int ld12, const double* A21, int ld21, double* A22,
+                             int ld22, const CSPOptions* opts, double pivot_threshold, bool device) {
+  require_gpu();
+  auto m = std::make_unique<Mat>();
+  m->type = SP_TYPE_BLR;
+  BLROpts bo;
+  bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
+  bo.leaf_size = opts->leaf_size; bo.max_rank = opts->max_rank;
+  bo.pivot_threshold = pivot_threshold;
+  m->blr = std::make_unique<BLREngine>(n1, n2, A11, ld11, A12, ld12, A21, ld21, A22, ld22, bo, device);
+  if (n2 > 0)   // A22 <- A22 - A21 A11^{-1} A12, in place like the reference
+    SB200_CUDA(cudaMemcpy2D(A22, sizeof(double) * ld22, m->blr->schur(), sizeof(double) * (n1 + n2),
+                            sizeof(double) * n2, n2,
+                            device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+  *S = m.release();
+}
+
+int SB200_d_blr_partial_factor(CSPStructMat* S, int n1, int n2, const double* A11, int ld11,
+                               const double* A12, int ld12, const double* A21, int ld21,
+                               double* A22, int ld22, const CSPOptions* opts,
+                               double pivot_threshold) {
+  return guarded([&] {
+    blr_partial_impl(S, n1, n2, A11, ld11, A12, ld12, A21, ld21, A22, ld22, opts, pivot_threshold, false);
+  });
+}
+
+int SB200_d_blr_partial_factor_device(CSPStructMat* S, int n1, int n2, const double* dA11, int ld11,
+                                      const double* dA12, int ld12, const double* dA21, int ld21,
+                                      double* dA22, int ld22, const CSPOptions* opts,
+                                      double pivot_threshold) {
+  return guarded([&] {
+    blr_partial_impl(S, n1, n2, dA11, ld11, dA12, ld12, dA21, ld21, dA22, ld22, opts, pivot_threshold, true);
+  });
+}
+
+int SB200_d_blr_sep_rows(const CSPStructMat S) {
+  return (S && M(S)->blr) ? M(S)->blr->sep_rows() : 0;
+}
+
+int SB200_d_blr_partial_forward_solve(const CSPStructMat S, int nrhs, double* B, int ldB) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    if (!mm->blr) throw std::logic_error("operation not supported for this type");
+    const int n = mm->blr->rows();
+    h2d(mm->dB, B, n, nrhs, ldB, 0);
+    mm->blr->partial_forward(nrhs, mm->dB.p, n, 0);
+    d2h(B, mm->dB, n, nrhs, ldB, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
+int SB200_d_blr_partial_backward_solve(const CSPStructMat S, int nrhs, double* Y, int ldY) {
+  return guarded([&] {
+    Mat* mm = M(S);
+    if (!mm->blr) throw std::logic_error("operation not supported for this type");
+    const int n = mm->blr->rows();
+    h2d(mm->dB, Y, n, nrhs, ldY, 0);
+    mm->blr->partial_backward(nrhs, mm->dB.p, n, 0);
+    d2h(Y, mm->dB, n, nrhs, ldY, 0);
+    SB200_CUDA(cudaStreamSynchronize(0));
+  });
+}
+
 int SB200_d_blr_tiles(const CSPStructMat S) {
   return (S && M(S)->blr) ? M(S)->blr->tiles() : 0;
 }

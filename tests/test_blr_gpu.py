@@ -132,3 +132,67 @@ def test_blr_dense_tiles_match_reference(built):
     assert rel(xs, X) <= 1e2 * tol and rel(xr, X) <= 1e2 * tol
     assert B.dense_tiles >= 2
     assert abs(B.rank - R.info()["rank"]) <= 3     # BLRMatrix::rank(): dense tiles count 0
+
+
+# ---- partially factored fronts (BLRMatrix::construct_and_partial_factor) -------
+def _front(n1, n2, shift=2.0):
+    A = toeplitz(n1 + n2) + shift * np.eye(n1 + n2)
+    return A, A[:n1, :n1], A[:n1, n1:], A[n1:, :n1], A[n1:, n1:]
+
+
+@pytest.mark.parametrize("n1,n2,leaf,tol", [(1024, 512, 256, 1e-4), (700, 500, 128, 1e-6),
+                                            (300, 900, 128, 1e-6), (512, 0, 128, 1e-6)])
+def test_blr_partial_factor_schur_and_solves(built, n1, n2, leaf, tol):
+    """The front [A11 A12; A21 A22] eliminated over A11 only (reference
+    BLRMatrix.cpp:739-1037): the trailing block becomes the Schur complement and
+    the two half solves (trsmLNU_gemm / gemm_trsmUNN, FrontBLR.cpp:525-568)
+    around a dense Schur solve give the solution of the whole system, to the
+    reference's own bound 1e2*tol (test_BLR_seq.cpp:192)."""
+    sb = built
+    A, A11, A12, A21, A22 = _front(n1, n2)
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    F, S = sb.BLRMatrix.construct_and_partial_factor(A11, A12, A21, A22, o)
+    assert (F.rows, F.sep_rows) == (n1 + n2, n1)
+    if n2:
+        S_exact = A22 - A21 @ np.linalg.solve(A11, A12)
+        assert rel(S, S_exact) <= 1e2 * tol
+        assert 0 < F.rank < leaf
+    X = np.random.default_rng(4).standard_normal((n1 + n2, 3))
+    B = A @ X
+    f = F.partial_forward_solve(B)
+    y2 = np.linalg.solve(S, f[n1:]) if n2 else f[n1:]
+    y = F.partial_backward_solve(np.vstack([f[:n1], y2]))
+    assert rel(y, X) <= 1e2 * tol
+    if n2:
+        with pytest.raises(RuntimeError):
+            F.solve(B)          # a partial factorization is not a solver for the whole front
+    else:                       # no update block: the two halves ARE the solve
+        o2 = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+        G = sb.BLRMatrix.compress_and_factor(A, o2)
+        assert rel(y, G.solve(B)) <= 1e-12
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_blr_partial_factor_matches_reference(built):
+    from oracle import ref
+    sb = built
+    n1, n2, leaf, tol = 1024, 768, 256, 1e-4
+    A, A11, A12, A21, A22 = _front(n1, n2)
+    R = ref.RefBLRFront(A11, A12, A21, A22, f"--blr_leaf_size {leaf} --blr_rel_tol {tol}")
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    F, S = sb.BLRMatrix.construct_and_partial_factor(A11, A12, A21, A22, o)
+    S_exact = A22 - A21 @ np.linalg.solve(A11, A12)
+    es, er = rel(S, S_exact), rel(R.S, S_exact)
+    assert es <= 1e2 * tol and er <= 1e2 * tol
+    assert rel(S, R.S) <= 10 * 1e2 * tol             # two approximations at the same tolerance
+    assert es <= 10 * max(er, 1e-12)                 # and no less accurate than the reference's
+    assert abs(F.rank - max(R.ranks())) <= 3
+    b = np.random.default_rng(6).standard_normal((n1 + n2, 2))
+    fs, fr = F.partial_forward_solve(b), R.partial_forward_solve(b)
+    # b_upd - A21 A11^{-1} b_sep does not depend on how the LU pivots
+    assert rel(fs[n1:], fr[n1:]) <= 10 * 1e2 * tol
+    y2 = np.linalg.solve(S_exact, fs[n1:])
+    ys = F.partial_backward_solve(np.vstack([fs[:n1], y2]))
+    yr = R.partial_backward_solve(np.vstack([fr[:n1], np.linalg.solve(S_exact, fr[n1:])]))
+    assert rel(ys, yr) <= 10 * 1e2 * tol
+    assert rel(A @ ys, b) <= 1e2 * tol
