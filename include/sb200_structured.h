@@ -85,6 +85,28 @@ int SP_d_struct_solve(const CSPStructMat S, int nrhs, double* B, int ldB);
 /* StructuredMatrix.h:395  S <- S + s*I (invalidates the factorization) */
 int SP_d_struct_shift(CSPStructMat S, double s);
 
+/* ---- reference interface, single precision (StructuredMatrix.h:103,130,158-259,
+ * 295,354,387,464,510,569): float operands at the boundary, fp64 arithmetic
+ * inside (operands are widened on the way in, results rounded on the way out;
+ * memory/nonzeros report the fp64 object).  The complex variants SP_c_* / SP_z_*
+ * are not provided. */
+void SP_s_struct_default_options(CSPOptions* opts);
+void SP_s_struct_destroy(CSPStructMat* S);
+int SP_s_struct_rows(const CSPStructMat S);
+int SP_s_struct_cols(const CSPStructMat S);
+long long int SP_s_struct_memory(const CSPStructMat S);
+long long int SP_s_struct_nonzeros(const CSPStructMat S);
+int SP_s_struct_rank(const CSPStructMat S);
+int SP_s_struct_from_dense(CSPStructMat* S, int rows, int cols, const float* A, int ldA,
+                           const CSPOptions* opts);
+int SP_s_struct_from_elements(CSPStructMat* S, int rows, int cols, float A(int i, int j),
+                              const CSPOptions* opts);
+int SP_s_struct_mult(const CSPStructMat S, char trans, int m, const float* B, int ldB,
+                     float* C, int ldC);
+int SP_s_struct_factor(CSPStructMat S);
+int SP_s_struct_solve(const CSPStructMat S, int nrhs, float* B, int ldB);
+int SP_s_struct_shift(CSPStructMat S, float s);
+
 /* ---- engine extensions --------------------------------------------------- */
 
 /* Kernel-matrix types for SB200_d_hss_from_kernel

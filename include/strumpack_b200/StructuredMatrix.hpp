@@ -1,20 +1,31 @@
 // strumpack_b200 -- C++ host-side mirror of the reference's structured-matrix
 // interface, header-only on top of the C ABI (include/sb200_structured.h).
 //
-// Same class/function names, argument meaning and error behaviour as
+// Same class / function names, argument meaning and error behaviour as
 //   strumpack::structured::StructuredMatrix<T>   reference src/structured/StructuredMatrix.hpp:209-418
 //   strumpack::structured::construct_from_dense  reference src/structured/StructuredMatrix.cpp:53-127
 //   strumpack::structured::StructuredOptions<T>  reference src/structured/StructuredOptions.hpp:106-162
-//   strumpack::HSS::HSSMatrix<T>                 reference src/HSS/HSSMatrix.hpp:95-511 (hot-path subset)
+//   strumpack::HSS::HSSOptions<T>                reference src/HSS/HSSOptions.hpp:151-491
+//   strumpack::HSS::HSSMatrix<T>                 reference src/HSS/HSSMatrix.hpp:95-511, free apply_HSS :705-713
+//   strumpack::BLR::BLROptions<T>                reference src/BLR/BLROptions.hpp:81-142
+//   strumpack::BLR::BLRMatrix<T>                 reference src/BLR/BLRMatrix.hpp:68-291
 //   strumpack::DenseMatrix<T> / DenseMatrixWrapper<T>  reference src/dense/DenseMatrix.hpp:139-146
-// so that code written against the reference (e.g. examples/dense/testStructured.cpp,
-// test/test_HSS_seq.cpp:235-250) compiles against this header with only the
-// include changed.  Only T = double is implemented in round 1.
+// so that code written against the reference (examples/dense/testStructured.cpp,
+// test/test_HSS_seq.cpp, test/test_BLR_seq.cpp, the calls FrontHSS / FrontBLR make)
+// compiles against this header with only the include changed.  Everything
+// numeric happens in libstrumpack_b200.so on the GPU; there is no CPU path
+// here (a call without a CUDA device throws).  Only T = double is implemented.
 #pragma once
+#include <cmath>
 #include <cstddef>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
 #include <memory>
+#include <random>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../sb200_structured.h"
@@ -30,16 +41,75 @@ template <typename scalar_t> class DenseMatrix {
   DenseMatrix(std::size_t m, std::size_t n) : rows_(m), cols_(n), ld_(m ? m : 1), own_(m * n) {
     data_ = own_.data();
   }
+  // copy of a column-major block (reference DenseMatrix(m, n, D, ld))
+  DenseMatrix(std::size_t m, std::size_t n, const scalar_t* D, std::size_t ld) : DenseMatrix(m, n) {
+    for (std::size_t j = 0; j < n; j++)
+      for (std::size_t i = 0; i < m; i++) data_[i + j * ld_] = D[i + j * ld];
+  }
+  DenseMatrix(const DenseMatrix& o) : DenseMatrix(o.rows_, o.cols_, o.data_, o.ld_) {}
+  DenseMatrix(DenseMatrix&& o) noexcept { swap_in(std::move(o)); }
+  DenseMatrix& operator=(const DenseMatrix& o) {
+    if (this != &o) { DenseMatrix t(o); swap_in(std::move(t)); }
+    return *this;
+  }
+  DenseMatrix& operator=(DenseMatrix&& o) noexcept {
+    if (this != &o) swap_in(std::move(o));
+    return *this;
+  }
   virtual ~DenseMatrix() = default;
   std::size_t rows() const { return rows_; }
   std::size_t cols() const { return cols_; }
   std::size_t ld() const { return ld_; }
   scalar_t* data() { return data_; }
   const scalar_t* data() const { return data_; }
+  scalar_t* ptr(std::size_t i, std::size_t j) { return data_ + i + j * ld_; }
+  const scalar_t* ptr(std::size_t i, std::size_t j) const { return data_ + i + j * ld_; }
   scalar_t& operator()(std::size_t i, std::size_t j) { return data_[i + j * ld_]; }
   const scalar_t& operator()(std::size_t i, std::size_t j) const { return data_[i + j * ld_]; }
+  void fill(scalar_t v) {
+    for (std::size_t j = 0; j < cols_; j++)
+      for (std::size_t i = 0; i < rows_; i++) data_[i + j * ld_] = v;
+  }
+  void zero() { fill(scalar_t(0)); }
+  void eye() {
+    zero();
+    for (std::size_t i = 0; i < std::min(rows_, cols_); i++) data_[i + i * ld_] = scalar_t(1);
+  }
+  void random() {   // reference DenseMatrix::random(): standard normal entries
+    std::mt19937 g(0);
+    std::normal_distribution<double> d;
+    for (std::size_t j = 0; j < cols_; j++)
+      for (std::size_t i = 0; i < rows_; i++) data_[i + j * ld_] = scalar_t(d(g));
+  }
+  double normF() const {
+    double s = 0;
+    for (std::size_t j = 0; j < cols_; j++)
+      for (std::size_t i = 0; i < rows_; i++) s += double(data_[i + j * ld_]) * double(data_[i + j * ld_]);
+    return std::sqrt(s);
+  }
+  double norm() const { return normF(); }
+  // this <- this - B     (reference DenseMatrix::sub)
+  DenseMatrix& sub(const DenseMatrix& B) {
+    for (std::size_t j = 0; j < cols_; j++)
+      for (std::size_t i = 0; i < rows_; i++) data_[i + j * ld_] -= B(i, j);
+    return *this;
+  }
+  DenseMatrix& add(const DenseMatrix& B) {
+    for (std::size_t j = 0; j < cols_; j++)
+      for (std::size_t i = 0; i < rows_; i++) data_[i + j * ld_] += B(i, j);
+    return *this;
+  }
+  std::size_t nonzeros() const { return rows_ * cols_; }
+  void clear() { own_.clear(); own_.shrink_to_fit(); data_ = nullptr; rows_ = cols_ = 0; ld_ = 1; }
 
  protected:
+  void swap_in(DenseMatrix&& o) {
+    const bool owned = !o.own_.empty() || o.data_ == nullptr;
+    own_ = std::move(o.own_);
+    rows_ = o.rows_; cols_ = o.cols_; ld_ = o.ld_;
+    data_ = owned ? own_.data() : o.data_;
+    o.data_ = nullptr; o.rows_ = o.cols_ = 0; o.ld_ = 1;
+  }
   scalar_t* data_ = nullptr;
   std::size_t rows_ = 0, cols_ = 0, ld_ = 1;
   std::vector<scalar_t> own_;
@@ -49,18 +119,60 @@ template <typename scalar_t> class DenseMatrix {
 template <typename scalar_t> class DenseMatrixWrapper : public DenseMatrix<scalar_t> {
  public:
   DenseMatrixWrapper(std::size_t m, std::size_t n, scalar_t* D, std::size_t ld) {
-    this->data_ = D; this->rows_ = m; this->cols_ = n; this->ld_ = ld;
+    this->data_ = D; this->rows_ = m; this->cols_ = n; this->ld_ = ld ? ld : 1;
   }
+  // sub-block view (reference DenseMatrixWrapper(m, n, D, i, j))
+  DenseMatrixWrapper(std::size_t m, std::size_t n, DenseMatrix<scalar_t>& D, std::size_t i, std::size_t j)
+      : DenseMatrixWrapper(m, n, D.ptr(i, j), D.ld()) {}
 };
+
+namespace detail {
+inline void check(int rc, const char* what) {
+  if (rc) throw std::logic_error(std::string("strumpack_b200: ") + what + " failed");
+}
+// "--prefix_name value" command-line scanning shared by the option classes
+// (the reference uses getopt_long, e.g. StructuredOptions.cpp:62-140; unknown
+// options are ignored there as well)
+inline const char* arg_value(int argc, const char* const* argv, const std::string& name) {
+  for (int i = 1; i + 1 < argc; i++)
+    if (argv[i] && name == argv[i]) return argv[i + 1];
+  return nullptr;
+}
+inline bool arg_flag(int argc, const char* const* argv, const std::string& name) {
+  for (int i = 1; i < argc; i++)
+    if (argv[i] && name == argv[i]) return true;
+  return false;
+}
+}  // namespace detail
 
 namespace structured {
 
-enum class Type : int { HSS = SP_TYPE_HSS, BLR = SP_TYPE_BLR };
+// reference StructuredOptions.hpp:49-74
+enum class Type : int {
+  HSS = SP_TYPE_HSS, BLR = SP_TYPE_BLR, HODLR = SP_TYPE_HODLR, HODBF = SP_TYPE_HODBF,
+  BUTTERFLY = SP_TYPE_BUTTERFLY, LR = SP_TYPE_LR, LOSSY = SP_TYPE_LOSSY, LOSSLESS = SP_TYPE_LOSSLESS
+};
+inline std::string get_name(Type a) {
+  switch (a) {
+    case Type::HSS: return "HSS";
+    case Type::BLR: return "BLR";
+    case Type::HODLR: return "HODLR";
+    case Type::HODBF: return "HODBF";
+    case Type::BUTTERFLY: return "BUTTERFLY";
+    case Type::LR: return "LR";
+    case Type::LOSSY: return "LOSSY";
+    case Type::LOSSLESS: return "LOSSLESS";
+  }
+  return "UNKNOWN";
+}
 
-// reference StructuredOptions.hpp:106-162 (same defaults)
+// reference StructuredOptions.hpp:106-162 (same defaults: BLR, 1e-4, 1e-10, 128, 5000)
 template <typename scalar_t> class StructuredOptions {
  public:
+  using real_t = double;
   StructuredOptions() { SP_d_struct_default_options(&o_); }
+  explicit StructuredOptions(Type t) : StructuredOptions() { set_type(t); }
+  virtual ~StructuredOptions() = default;
   void set_type(Type t) { o_.type = static_cast<SP_STRUCTURED_TYPE>(t); }
   void set_rel_tol(double t) { o_.rel_tol = t; }
   void set_abs_tol(double t) { o_.abs_tol = t; }
@@ -74,59 +186,80 @@ template <typename scalar_t> class StructuredOptions {
   int max_rank() const { return o_.max_rank; }
   bool verbose() const { return o_.verbose; }
   const CSPOptions* c() const { return &o_; }
+  // --structured_{rel_tol,abs_tol,leaf_size,max_rank,type,verbose,quiet}
+  // (reference StructuredOptions.cpp:62-140)
+  virtual void set_from_command_line(int argc, const char* const* argv) { scan(argc, argv, "--structured_"); }
+  virtual void describe_options() const {
+    std::cout << "# Structured Options:\n#   --structured_rel_tol real (default " << rel_tol()
+              << ")\n#   --structured_abs_tol real (default " << abs_tol()
+              << ")\n#   --structured_leaf_size int (default " << leaf_size()
+              << ")\n#   --structured_max_rank int (default " << max_rank()
+              << ")\n#   --structured_type [HSS|BLR] (default " << get_name(type())
+              << ")\n#   --structured_verbose or -v / --structured_quiet or -q\n";
+  }
 
- private:
+ protected:
+  void scan(int argc, const char* const* argv, const std::string& pre) {
+    if (auto v = detail::arg_value(argc, argv, pre + "rel_tol")) set_rel_tol(std::atof(v));
+    if (auto v = detail::arg_value(argc, argv, pre + "abs_tol")) set_abs_tol(std::atof(v));
+    if (auto v = detail::arg_value(argc, argv, pre + "leaf_size")) set_leaf_size(std::atoi(v));
+    if (auto v = detail::arg_value(argc, argv, pre + "max_rank")) set_max_rank(std::atoi(v));
+    if (auto v = detail::arg_value(argc, argv, pre + "type")) {
+      const std::string s(v);
+      if (s == "HSS") set_type(Type::HSS);
+      else if (s == "BLR") set_type(Type::BLR);
+      else std::cerr << "# WARNING: structured type " << s << " not supported by strumpack_b200" << std::endl;
+    }
+    if (detail::arg_flag(argc, argv, pre + "verbose")) set_verbose(true);
+    if (detail::arg_flag(argc, argv, pre + "quiet")) set_verbose(false);
+  }
   CSPOptions o_;
 };
 
 // reference StructuredMatrix.hpp:209-418: unsupported operations throw
 template <typename scalar_t> class StructuredMatrix {
-  static_assert(sizeof(scalar_t) == sizeof(double), "round 1 implements double only");
+  static_assert(sizeof(scalar_t) == sizeof(double), "strumpack_b200 implements double only");
 
  public:
+  StructuredMatrix() = default;
   explicit StructuredMatrix(CSPStructMat h) : h_(h) {}
   StructuredMatrix(const StructuredMatrix&) = delete;
   StructuredMatrix& operator=(const StructuredMatrix&) = delete;
+  StructuredMatrix(StructuredMatrix&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  StructuredMatrix& operator=(StructuredMatrix&& o) noexcept {
+    if (this != &o) { SP_d_struct_destroy(&h_); h_ = o.h_; o.h_ = nullptr; }
+    return *this;
+  }
   virtual ~StructuredMatrix() { SP_d_struct_destroy(&h_); }
 
-  std::size_t rows() const { return SP_d_struct_rows(h_); }
-  std::size_t cols() const { return SP_d_struct_cols(h_); }
-  std::size_t memory() const { return SP_d_struct_memory(h_); }
-  std::size_t nonzeros() const { return SP_d_struct_nonzeros(h_); }
-  std::size_t rank() const { return SP_d_struct_rank(h_); }
+  virtual std::size_t rows() const { return SP_d_struct_rows(h_); }
+  virtual std::size_t cols() const { return SP_d_struct_cols(h_); }
+  virtual std::size_t memory() const { return SP_d_struct_memory(h_); }
+  virtual std::size_t nonzeros() const { return SP_d_struct_nonzeros(h_); }
+  virtual std::size_t rank() const { return SP_d_struct_rank(h_); }
 
   // y = op(A) x                                  (StructuredMatrix.hpp:280-300)
-  void mult(Trans op, const DenseMatrix<scalar_t>& x, DenseMatrix<scalar_t>& y) const {
+  virtual void mult(Trans op, const DenseMatrix<scalar_t>& x, DenseMatrix<scalar_t>& y) const {
     mult(op, int(x.cols()), x.data(), int(x.ld()), y.data(), int(y.ld()));
   }
-  void mult(Trans op, int m, const scalar_t* x, int ldx, scalar_t* y, int ldy) const {
-    check(SP_d_struct_mult(h_, char(op), m, x, ldx, y, ldy), "mult");
+  virtual void mult(Trans op, int m, const scalar_t* x, int ldx, scalar_t* y, int ldy) const {
+    detail::check(SP_d_struct_mult(h_, char(op), m, x, ldx, y, ldy), "mult");
   }
-  void factor() { check(SP_d_struct_factor(h_), "factor"); }
+  virtual void factor() { detail::check(SP_d_struct_factor(h_), "factor"); }
   // b <- A^{-1} b                                (StructuredMatrix.hpp:340-360)
-  void solve(DenseMatrix<scalar_t>& b) const { solve(int(b.cols()), b.data(), int(b.ld())); }
-  void solve(int nrhs, scalar_t* b, int ldb) const {
-    check(SP_d_struct_solve(h_, nrhs, b, ldb), "solve");
+  virtual void solve(DenseMatrix<scalar_t>& b) const { solve(int(b.cols()), b.data(), int(b.ld())); }
+  virtual void solve(int nrhs, scalar_t* b, int ldb) const {
+    detail::check(SP_d_struct_solve(h_, nrhs, b, ldb), "solve");
   }
-  void shift(scalar_t s) { check(SP_d_struct_shift(h_, s), "shift"); }
+  virtual void shift(scalar_t s) { detail::check(SP_d_struct_shift(h_, s), "shift"); }
   CSPStructMat handle() const { return h_; }
 
  protected:
-  static void check(int rc, const char* what) {
-    if (rc) throw std::logic_error(std::string("strumpack_b200: ") + what + " failed");
-  }
+  static void check(int rc, const char* what) { detail::check(rc, what); }
   CSPStructMat h_ = nullptr;
 };
 
 // reference StructuredMatrix.cpp:53-127
-template <typename scalar_t>
-std::unique_ptr<StructuredMatrix<scalar_t>> construct_from_dense(
-    const DenseMatrix<scalar_t>& A, const StructuredOptions<scalar_t>& opts) {
-  CSPStructMat h = nullptr;
-  if (SP_d_struct_from_dense(&h, int(A.rows()), int(A.cols()), A.data(), int(A.ld()), opts.c()))
-    throw std::invalid_argument("construct_from_dense failed");
-  return std::unique_ptr<StructuredMatrix<scalar_t>>(new StructuredMatrix<scalar_t>(h));
-}
 template <typename scalar_t>
 std::unique_ptr<StructuredMatrix<scalar_t>> construct_from_dense(
     int rows, int cols, const scalar_t* A, int ldA, const StructuredOptions<scalar_t>& opts) {
@@ -135,44 +268,389 @@ std::unique_ptr<StructuredMatrix<scalar_t>> construct_from_dense(
     throw std::invalid_argument("construct_from_dense failed");
   return std::unique_ptr<StructuredMatrix<scalar_t>>(new StructuredMatrix<scalar_t>(h));
 }
+template <typename scalar_t>
+std::unique_ptr<StructuredMatrix<scalar_t>> construct_from_dense(
+    const DenseMatrix<scalar_t>& A, const StructuredOptions<scalar_t>& opts) {
+  return construct_from_dense(int(A.rows()), int(A.cols()), A.data(), int(A.ld()), opts);
+}
+// reference StructuredMatrix.cpp:193-312: the callback is a plain function
+// pointer at the C boundary (StructuredMatrix.h:244)
+template <typename scalar_t>
+std::unique_ptr<StructuredMatrix<scalar_t>> construct_from_elements(
+    int rows, int cols, scalar_t (*A)(int, int), const StructuredOptions<scalar_t>& opts) {
+  CSPStructMat h = nullptr;
+  if (SP_d_struct_from_elements(&h, rows, cols, A, opts.c()))
+    throw std::invalid_argument("construct_from_elements failed");
+  return std::unique_ptr<StructuredMatrix<scalar_t>>(new StructuredMatrix<scalar_t>(h));
+}
 
 }  // namespace structured
 
 namespace HSS {
 
-// hot-path subset of reference HSSMatrix<T> (src/HSS/HSSMatrix.hpp:95-511)
+// reference HSSOptions.hpp:59-148
+enum class CompressionAlgorithm { ORIGINAL, STABLE, HARD_RESTART };
+enum class CompressionSketch { GAUSSIAN, SJLT };
+enum class ClusteringAlgorithm { NATURAL, TWO_MEANS, KD_TREE, PCA, COBBLE };
+
+// reference HSSOptions.hpp:151-491, defaults :465-490 (rel 1e-2, abs 1e-8, leaf
+// 512, max_rank 50000, d0 128, dd 64, p 10).  The engine's GPU compressor is a
+// sampled interpolative decomposition: it honours rel_tol,
+// abs_tol, leaf_size and max_rank; the sampling parameters d0/dd/p and the
+// algorithm enums are kept so that option-setting code compiles unchanged.
+template <typename scalar_t> class HSSOptions : public structured::StructuredOptions<scalar_t> {
+ public:
+  HSSOptions() : structured::StructuredOptions<scalar_t>(structured::Type::HSS) {
+    this->set_rel_tol(1e-2); this->set_abs_tol(1e-8);
+    this->set_leaf_size(512); this->set_max_rank(50000);
+  }
+  HSSOptions(const structured::StructuredOptions<scalar_t>& s) : structured::StructuredOptions<scalar_t>(s) {
+    this->set_type(structured::Type::HSS);
+  }
+  void set_d0(int v) { d0_ = v; }
+  void set_dd(int v) { dd_ = v; }
+  void set_p(int v) { p_ = v; }
+  void set_compression_algorithm(CompressionAlgorithm a) { alg_ = a; }
+  void set_compression_sketch(CompressionSketch a) { sketch_ = a; }
+  void set_clustering_algorithm(ClusteringAlgorithm a) { clus_ = a; }
+  void set_approximate_neighbors(int v) { ann_ = v; }
+  void set_ann_iterations(int v) { ann_it_ = v; }
+  void set_user_defined_random(bool v) { user_rand_ = v; }
+  void set_synchronized_compression(bool v) { sync_ = v; }
+  void set_log_ranks(bool v) { log_ranks_ = v; }
+  int d0() const { return d0_; }
+  int dd() const { return dd_; }
+  int p() const { return p_; }
+  CompressionAlgorithm compression_algorithm() const { return alg_; }
+  CompressionSketch compression_sketch() const { return sketch_; }
+  ClusteringAlgorithm clustering_algorithm() const { return clus_; }
+  int approximate_neighbors() const { return ann_; }
+  int ann_iterations() const { return ann_it_; }
+  bool user_defined_random() const { return user_rand_; }
+  bool synchronized_compression() const { return sync_; }
+  bool log_ranks() const { return log_ranks_; }
+  // --hss_{rel_tol,abs_tol,leaf_size,max_rank,d0,dd,p,verbose,quiet}  (HSSOptions.cpp:67-240)
+  void set_from_command_line(int argc, const char* const* argv) override {
+    this->scan(argc, argv, "--hss_");
+    if (auto v = detail::arg_value(argc, argv, "--hss_d0")) set_d0(std::atoi(v));
+    if (auto v = detail::arg_value(argc, argv, "--hss_dd")) set_dd(std::atoi(v));
+    if (auto v = detail::arg_value(argc, argv, "--hss_p")) set_p(std::atoi(v));
+  }
+
+ private:
+  int d0_ = 128, dd_ = 64, p_ = 10, ann_ = 64, ann_it_ = 5;
+  CompressionAlgorithm alg_ = CompressionAlgorithm::STABLE;
+  CompressionSketch sketch_ = CompressionSketch::GAUSSIAN;
+  ClusteringAlgorithm clus_ = ClusteringAlgorithm::TWO_MEANS;
+  bool user_rand_ = false, sync_ = true, log_ranks_ = false;
+};
+
+// state handed from forward_solve to backward_solve (reference WorkSolve,
+// HSSExtra.hpp:216-226); here the intermediate vectors stay on the device
+// inside the matrix object, the struct only remembers the shape
+template <typename scalar_t> struct WorkSolve { int nrhs = 0; bool partial = false; };
+
+// reference HSSMatrix<T> (src/HSS/HSSMatrix.hpp:95-511)
 template <typename scalar_t> class HSSMatrix : public structured::StructuredMatrix<scalar_t> {
   using base = structured::StructuredMatrix<scalar_t>;
+  using DenseM_t = DenseMatrix<scalar_t>;
 
  public:
+  using opts_t = HSSOptions<scalar_t>;
+  HSSMatrix() = default;
   explicit HSSMatrix(CSPStructMat h) : base(h) {}
-  // HSSMatrix::read(fname)                        (HSSMatrix.cpp:488-510)
+  // HSSMatrix(const DenseM_t& A, const opts_t& opts)          (HSSMatrix.cpp:49-54)
+  HSSMatrix(const DenseM_t& A, const opts_t& opts) { compress(A, opts); }
+  HSSMatrix(HSSMatrix&& o) noexcept = default;
+  HSSMatrix& operator=(HSSMatrix&& o) noexcept = default;
+  // HSSMatrix(kernel::Kernel&, opts) (HSSMatrix.cpp:88-106): the d x n points
+  // are reordered in place into the cluster ordering; perm (0-based, may be
+  // null) receives the permutation.
+  static HSSMatrix from_kernel(int n, int d, scalar_t* pts, SB200_KERNEL_TYPE kernel, double h,
+                               double lambda, const opts_t& opts, int* perm = nullptr) {
+    CSPStructMat s = nullptr;
+    if (SB200_d_hss_from_kernel(&s, n, d, pts, kernel, h, lambda, opts.c(), perm))
+      throw std::invalid_argument("HSSMatrix(kernel) failed");
+    return HSSMatrix(s);
+  }
+  // HSSMatrix::compress(A, opts)                               (HSSMatrix.cpp:158-171)
+  void compress(const DenseM_t& A, const opts_t& opts) {
+    opts_t o(opts);
+    CSPStructMat s = nullptr;
+    if (SP_d_struct_from_dense(&s, int(A.rows()), int(A.cols()), A.data(), int(A.ld()), o.c()))
+      throw std::invalid_argument("HSSMatrix::compress failed");
+    SP_d_struct_destroy(&this->h_);
+    this->h_ = s;
+  }
+  // HSSMatrix::read(fname) / write(fname)                      (HSSMatrix.cpp:438-510)
   static HSSMatrix read(const std::string& fname) {
     CSPStructMat h = nullptr;
     if (SB200_d_hss_read(&h, fname.c_str())) throw std::runtime_error("HSSMatrix::read failed");
     return HSSMatrix(h);
   }
-  HSSMatrix(HSSMatrix&& o) noexcept : base(o.h_) { o.h_ = nullptr; }
   void write(const std::string& fname) const { base::check(SB200_d_hss_write(this->h_, fname.c_str()), "write"); }
-  DenseMatrix<scalar_t> apply(const DenseMatrix<scalar_t>& b) const {   // apply.hpp:39-45
-    DenseMatrix<scalar_t> c(this->rows(), b.cols());
+
+  // apply / applyC / mult                                      (HSSMatrix.apply.hpp:34-53)
+  DenseM_t apply(const DenseM_t& b) const {
+    DenseM_t c(this->rows(), b.cols());
     this->mult(Trans::N, b, c);
     return c;
   }
-  DenseMatrix<scalar_t> applyC(const DenseMatrix<scalar_t>& b) const {  // apply.hpp:47-53
-    DenseMatrix<scalar_t> c(this->cols(), b.cols());
+  DenseM_t applyC(const DenseM_t& b) const {
+    DenseM_t c(this->cols(), b.cols());
     this->mult(Trans::C, b, c);
     return c;
   }
+  // ULV: factor (base), partial_factor, solve (base), forward / backward solve
+  //                                    (HSSMatrix.factor.hpp:35-50, solve.hpp:35-66)
+  void partial_factor() { base::check(SB200_d_hss_partial_factor(this->h_), "partial_factor"); }
+  void forward_solve(WorkSolve<scalar_t>& w, const DenseM_t& b, bool partial = false) const {
+    if (partial) throw std::logic_error("forward_solve(partial = true) is a member of child(0): use child0_forward_solve");
+    base::check(SB200_d_hss_forward_solve(this->h_, int(b.cols()), b.data(), int(b.ld())), "forward_solve");
+    w.nrhs = int(b.cols()); w.partial = false;
+  }
+  void backward_solve(WorkSolve<scalar_t>& w, DenseM_t& x) const {
+    base::check(SB200_d_hss_backward_solve(this->h_, w.nrhs, x.data(), int(x.ld())), "backward_solve");
+  }
+  // child(0)->forward_solve(w, b0, true) / child(0)->backward_solve(w, x0) as
+  // FrontHSS calls them (FrontHSS.cpp:452-462, 487-495); returns reduced_rhs
+  DenseM_t child0_forward_solve(WorkSolve<scalar_t>& w, const DenseM_t& b0) const {
+    int z[7];
+    base::check(SB200_d_hss_schur_sizes(this->h_, z), "schur_sizes");
+    DenseM_t red(z[2], b0.cols());
+    base::check(SB200_d_hss_partial_forward_solve(this->h_, int(b0.cols()), b0.data(), int(b0.ld()),
+                                                  red.data(), int(red.ld())), "partial forward_solve");
+    w.nrhs = int(b0.cols()); w.partial = true;
+    return red;
+  }
+  DenseM_t child0_x(const WorkSolve<scalar_t>& w) const {          // w.x of the reference
+    int z[7];
+    base::check(SB200_d_hss_schur_sizes(this->h_, z), "schur_sizes");
+    DenseM_t x(z[3], w.nrhs);
+    base::check(SB200_d_hss_partial_x(this->h_, w.nrhs, x.data(), int(x.ld()), 0), "partial_x");
+    return x;
+  }
+  void set_child0_x(const WorkSolve<scalar_t>& w, DenseM_t& x) const {
+    base::check(SB200_d_hss_partial_x(this->h_, w.nrhs, x.data(), int(x.ld()), 1), "partial_x");
+  }
+  void child0_backward_solve(WorkSolve<scalar_t>& w, DenseM_t& x0) const {
+    base::check(SB200_d_hss_partial_backward_solve(this->h_, w.nrhs, x0.data(), int(x0.ld())),
+                "partial backward_solve");
+  }
+  // Schur complement of the (0,0) block                       (HSSMatrix.Schur.hpp:40-215)
+  void Schur_update(DenseM_t& Theta, DenseM_t& DUB01, DenseM_t& Phi) const {
+    int z[7];
+    base::check(SB200_d_hss_schur_sizes(this->h_, z), "schur_sizes");
+    Theta = DenseM_t(z[0], z[2]); DUB01 = DenseM_t(z[3], z[4]); Phi = DenseM_t(z[1], z[3]);
+    base::check(SB200_d_hss_schur_update(this->h_, Theta.data(), int(Theta.ld()), DUB01.data(),
+                                         int(DUB01.ld()), Phi.data(), int(Phi.ld())), "Schur_update");
+  }
+  DenseM_t Vhat() const {                                        // child(0)->ULV().Vhat()
+    int z[7];
+    base::check(SB200_d_hss_schur_sizes(this->h_, z), "schur_sizes");
+    DenseM_t V(z[3], z[2]);
+    base::check(SB200_d_hss_vhat(this->h_, V.data(), int(V.ld())), "Vhat");
+    return V;
+  }
+  // the reference's 4th argument (Theta Vhat^H or Vhat^H Phi^H) is a cached
+  // product of the others; the engine recomputes nothing from it
+  void Schur_product_direct(const DenseM_t& Theta, const DenseM_t& DUB01, const DenseM_t& Phi,
+                            const DenseM_t& /*ThetaVhatC_or_VhatCPhiC*/, const DenseM_t& R,
+                            DenseM_t& Sr, DenseM_t& Sc) const {
+    if (Sr.rows() != R.rows() || Sr.cols() != R.cols()) Sr = DenseM_t(R.rows(), R.cols());
+    if (Sc.rows() != R.rows() || Sc.cols() != R.cols()) Sc = DenseM_t(R.rows(), R.cols());
+    base::check(SB200_d_hss_schur_product_direct(
+                    this->h_, Theta.data(), int(Theta.ld()), DUB01.data(), int(DUB01.ld()), Phi.data(),
+                    int(Phi.ld()), int(R.cols()), R.data(), int(R.ld()), Sr.data(), int(Sr.ld()),
+                    Sc.data(), int(Sc.ld())), "Schur_product_direct");
+  }
+  void Schur_product_indirect(const DenseM_t& DUB01, const DenseM_t& R0, const DenseM_t& R1,
+                              const DenseM_t& Sr1, const DenseM_t& Sc1, DenseM_t& Sr, DenseM_t& Sc) const {
+    Sr = DenseM_t(R1.rows(), R1.cols()); Sc = DenseM_t(R1.rows(), R1.cols());
+    base::check(SB200_d_hss_schur_product_indirect(
+                    this->h_, DUB01.data(), int(DUB01.ld()), int(R1.cols()), R0.data(), int(R0.ld()),
+                    R1.data(), int(R1.ld()), Sr1.data(), int(Sr1.ld()), Sc1.data(), int(Sc1.ld()),
+                    Sr.data(), int(Sr.ld()), Sc.data(), int(Sc.ld())), "Schur_product_indirect");
+  }
+  // element extraction                                        (HSSMatrix.extract.hpp:8-188)
+  scalar_t get(std::size_t i, std::size_t j) const {
+    const int I = int(i), J = int(j);
+    scalar_t v = 0;
+    base::check(SB200_d_hss_extract(this->h_, 1, &I, 1, &J, &v, 1, 0), "get");
+    return v;
+  }
+  DenseM_t extract(const std::vector<std::size_t>& I, const std::vector<std::size_t>& J) const {
+    DenseM_t B(I.size(), J.size());
+    extract_impl(I, J, B, 0);
+    return B;
+  }
+  void extract_add(const std::vector<std::size_t>& I, const std::vector<std::size_t>& J, DenseM_t& B) const {
+    extract_impl(I, J, B, 1);
+  }
+  // statistics                                                (HSSMatrix.cpp:290-356)
   std::size_t levels() const { return SB200_d_struct_levels(this->h_); }
   std::size_t factor_nonzeros() const { return SB200_d_struct_factor_nonzeros(this->h_); }
   void print_info() const { SB200_d_struct_print_info(this->h_); }
-  DenseMatrix<scalar_t> dense() const {
-    DenseMatrix<scalar_t> A(this->rows(), this->cols());
+  DenseM_t dense() const {
+    DenseM_t A(this->rows(), this->cols());
     base::check(SB200_d_struct_dense(this->h_, A.data(), int(A.ld())), "dense");
     return A;
   }
+
+ private:
+  void extract_impl(const std::vector<std::size_t>& I, const std::vector<std::size_t>& J, DenseM_t& B,
+                    int add) const {
+    if (I.empty() || J.empty()) return;
+    std::vector<int> i(I.begin(), I.end()), j(J.begin(), J.end());
+    base::check(SB200_d_hss_extract(this->h_, int(i.size()), i.data(), int(j.size()), j.data(), B.data(),
+                                    int(B.ld()), add), "extract");
+  }
 };
 
+// free function apply_HSS(op, A, B, beta, C): C = op(A) B + beta C   (HSSMatrix.hpp:705-713)
+template <typename scalar_t>
+void apply_HSS(Trans op, const HSSMatrix<scalar_t>& A, const DenseMatrix<scalar_t>& B, scalar_t beta,
+               DenseMatrix<scalar_t>& C) {
+  detail::check(SB200_d_hss_apply(A.handle(), char(op), int(B.cols()), B.data(), int(B.ld()), beta, C.data(),
+                                  int(C.ld())), "apply_HSS");
+}
+
 }  // namespace HSS
+
+namespace BLR {
+
+// reference BLROptions.hpp:59-69
+enum class LowRankAlgorithm { RRQR, ACA, BACA };
+enum class Admissibility { STRONG, WEAK };
+enum class BLRFactorAlgorithm { COLWISE, RL, LL, COMB, STAR };
+enum class CompressionKernel { HALF, FULL };
+inline std::string get_name(LowRankAlgorithm a) {
+  return a == LowRankAlgorithm::RRQR ? "RRQR" : a == LowRankAlgorithm::ACA ? "ACA" : "BACA";
+}
+inline std::string get_name(Admissibility a) { return a == Admissibility::STRONG ? "strong" : "weak"; }
+inline std::string get_name(BLRFactorAlgorithm a) {
+  switch (a) {
+    case BLRFactorAlgorithm::COLWISE: return "Colwise";
+    case BLRFactorAlgorithm::RL: return "RL";
+    case BLRFactorAlgorithm::LL: return "LL";
+    case BLRFactorAlgorithm::COMB: return "Comb";
+    case BLRFactorAlgorithm::STAR: return "Star";
+  }
+  return "UNKNOWN";
+}
+
+// reference BLROptions.hpp:81-142 (defaults :128-140: rel 1e-4, abs 1e-12, leaf
+// 256, max_rank 5000, RRQR, WEAK, RL, HALF).  The engine implements RRQR
+// compression, weak admissibility and the right-looking factorization; the
+// other enum values are accepted and mapped onto those (LL/COMB/STAR order the
+// same tile operations differently and give the same factors up to the
+// compression tolerance).
+template <typename scalar_t> class BLROptions : public structured::StructuredOptions<scalar_t> {
+ public:
+  BLROptions() : structured::StructuredOptions<scalar_t>(structured::Type::BLR) {
+    this->set_rel_tol(1e-4); this->set_abs_tol(1e-12);
+    this->set_leaf_size(256); this->set_max_rank(5000);
+  }
+  BLROptions(const structured::StructuredOptions<scalar_t>& s) : structured::StructuredOptions<scalar_t>(s) {
+    this->set_type(structured::Type::BLR);
+  }
+  void set_low_rank_algorithm(LowRankAlgorithm a) { lr_ = a; }
+  void set_admissibility(Admissibility a) { adm_ = a; }
+  void set_BACA_blocksize(int b) { baca_ = b; }
+  void set_BLR_factor_algorithm(BLRFactorAlgorithm a) { alg_ = a; }
+  void set_compression_kernel(CompressionKernel a) { ck_ = a; }
+  void set_pivot_threshold(double t) { pivot_ = t; }
+  LowRankAlgorithm low_rank_algorithm() const { return lr_; }
+  Admissibility admissibility() const { return adm_; }
+  int BACA_blocksize() const { return baca_; }
+  BLRFactorAlgorithm BLR_factor_algorithm() const { return alg_; }
+  CompressionKernel compression_kernel() const { return ck_; }
+  double pivot_threshold() const { return pivot_; }
+  // --blr_{rel_tol,abs_tol,leaf_size,max_rank,verbose,quiet}   (BLROptions.cpp:58-200)
+  void set_from_command_line(int argc, const char* const* argv) override {
+    this->scan(argc, argv, "--blr_");
+    if (auto v = detail::arg_value(argc, argv, "--blr_pivot_threshold")) set_pivot_threshold(std::atof(v));
+    if (auto v = detail::arg_value(argc, argv, "--blr_factor_algorithm")) {
+      const std::string s(v);
+      if (s == "RL") alg_ = BLRFactorAlgorithm::RL;
+      else if (s == "LL") alg_ = BLRFactorAlgorithm::LL;
+      else if (s == "Comb") alg_ = BLRFactorAlgorithm::COMB;
+      else if (s == "Star") alg_ = BLRFactorAlgorithm::STAR;
+      else if (s == "Colwise") alg_ = BLRFactorAlgorithm::COLWISE;
+    }
+  }
+
+ private:
+  LowRankAlgorithm lr_ = LowRankAlgorithm::RRQR;
+  Admissibility adm_ = Admissibility::WEAK;
+  BLRFactorAlgorithm alg_ = BLRFactorAlgorithm::RL;
+  CompressionKernel ck_ = CompressionKernel::HALF;
+  int baca_ = 4;
+  double pivot_ = -1.;
+};
+
+// reference BLRMatrix<T> (src/BLR/BLRMatrix.hpp:68-291).  Tiles come from
+// ClusterTree(n).refine(opts.leaf_size()) as in test/test_BLR_seq.cpp:136-145;
+// admissibility is weak (every off-diagonal tile is a compression candidate).
+template <typename scalar_t> class BLRMatrix : public structured::StructuredMatrix<scalar_t> {
+  using base = structured::StructuredMatrix<scalar_t>;
+  using DenseM_t = DenseMatrix<scalar_t>;
+
+ public:
+  using Opts_t = BLROptions<scalar_t>;
+  using adm_t = DenseMatrix<bool>;
+  BLRMatrix() = default;
+  explicit BLRMatrix(CSPStructMat h) : base(h) {}
+  BLRMatrix(BLRMatrix&& o) noexcept = default;
+  BLRMatrix& operator=(BLRMatrix&& o) noexcept = default;
+  // BLRMatrix::compress(A, admissible, opts)                   (BLRMatrix.cpp:91-111)
+  void compress(const DenseM_t& A, const Opts_t& opts) {
+    CSPStructMat s = nullptr;
+    if (SP_d_struct_from_dense(&s, int(A.rows()), int(A.cols()), A.data(), int(A.ld()), opts.c()))
+      throw std::invalid_argument("BLRMatrix::compress failed");
+    reset(s);
+  }
+  // BLRMatrix::compress_and_factor(A, admissible, opts)        (BLRMatrix.cpp:113-241)
+  void compress_and_factor(const DenseM_t& A, const Opts_t& opts) {
+    if (A.rows() != A.cols()) throw std::invalid_argument("BLR: only square matrices are supported");
+    CSPStructMat s = nullptr;
+    if (SB200_d_blr_compress_and_factor(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), opts.pivot_threshold()))
+      throw std::invalid_argument("BLRMatrix::compress_and_factor failed");
+    reset(s);
+  }
+  void compress_and_factor(const DenseM_t& A, const adm_t& /*weak admissibility*/, const Opts_t& opts) {
+    compress_and_factor(A, opts);
+  }
+  // BLRMatrix::construct_and_partial_factor(A11, A12, A21, A22, B11, B12, B21,
+  // tiles1, tiles2, admissible, opts) (BLRMatrix.cpp:739-1037): one object
+  // holds F11, F12 and F21; A22 is overwritten with the Schur complement and
+  // A11, A12, A21 are cleared, as in the reference.
+  static BLRMatrix construct_and_partial_factor(DenseM_t& A11, DenseM_t& A12, DenseM_t& A21, DenseM_t& A22,
+                                                const Opts_t& opts) {
+    CSPStructMat s = nullptr;
+    if (SB200_d_blr_partial_factor(&s, int(A11.rows()), int(A22.rows()), A11.data(), int(A11.ld()), A12.data(),
+                                   int(A12.ld()), A21.data(), int(A21.ld()), A22.data(), int(A22.ld()),
+                                   opts.c(), opts.pivot_threshold()))
+      throw std::invalid_argument("BLRMatrix::construct_and_partial_factor failed");
+    A11.clear(); A12.clear(); A21.clear();
+    return BLRMatrix(s);
+  }
+  // the two halves of the front solve on b = [b_sep; b_upd]
+  // (laswp + trsmLNU_gemm, gemm_trsmUNN; BLRMatrix.cpp:1552-1665)
+  void trsmLNU_gemm(DenseM_t& b) const {
+    base::check(SB200_d_blr_partial_forward_solve(this->h_, int(b.cols()), b.data(), int(b.ld())), "trsmLNU_gemm");
+  }
+  void gemm_trsmUNN(DenseM_t& y) const {
+    base::check(SB200_d_blr_partial_backward_solve(this->h_, int(y.cols()), y.data(), int(y.ld())), "gemm_trsmUNN");
+  }
+  std::size_t sep_rows() const { return SB200_d_blr_sep_rows(this->h_); }
+  std::size_t rowblocks() const { return SB200_d_blr_tiles(this->h_); }
+  std::size_t colblocks() const { return SB200_d_blr_tiles(this->h_); }
+  std::size_t dense_tiles() const { return SB200_d_blr_dense_tiles(this->h_); }
+
+ private:
+  void reset(CSPStructMat s) { SP_d_struct_destroy(&this->h_); this->h_ = s; }
+};
+
+}  // namespace BLR
 }  // namespace strumpack

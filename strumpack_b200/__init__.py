@@ -52,6 +52,19 @@ SYMBOLS = {
     "SP_d_struct_factor": (_i, [_vp]),
     "SP_d_struct_solve": (_i, [_vp, _i, _vp, _i]),
     "SP_d_struct_shift": (_i, [_vp, _d]),
+    "SP_s_struct_default_options": (None, [_po]),
+    "SP_s_struct_destroy": (None, [_pvp]),
+    "SP_s_struct_rows": (_i, [_vp]),
+    "SP_s_struct_cols": (_i, [_vp]),
+    "SP_s_struct_memory": (_ll, [_vp]),
+    "SP_s_struct_nonzeros": (_ll, [_vp]),
+    "SP_s_struct_rank": (_i, [_vp]),
+    "SP_s_struct_from_dense": (_i, [_pvp, _i, _i, _vp, _i, _po]),
+    "SP_s_struct_from_elements": (_i, [_pvp, _i, _i, _vp, _po]),
+    "SP_s_struct_mult": (_i, [_vp, C.c_char, _i, _vp, _i, _vp, _i]),
+    "SP_s_struct_factor": (_i, [_vp]),
+    "SP_s_struct_solve": (_i, [_vp, _i, _vp, _i]),
+    "SP_s_struct_shift": (_i, [_vp, C.c_float]),
     "SB200_d_hss_from_kernel": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp]),
     "SB200_d_blr_compress_and_factor": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),
@@ -305,12 +318,20 @@ class StructuredMatrix:
         return A
 
     # -- the hot path, host operands (the reference-facing call) --------------
-    def mult(self, x, trans="N"):
-        """y = op(S) x  (StructuredMatrix::mult, StructuredMatrix.hpp:280-300)"""
+    def mult(self, x, trans="N", out=None):
+        """y = op(S) x  (StructuredMatrix::mult, StructuredMatrix.hpp:280-300).
+        ``out``: caller-allocated result (column-major ny x s, e.g. a view of
+        pinned memory), as in the C interface where C is the caller's buffer."""
         x = _fortran(x)
         t = trans.upper() != "N"
         ny = self.cols if t else self.rows
-        y = np.zeros((ny, x.shape[1]), order="F")
+        if out is None:
+            y = np.zeros((ny, x.shape[1]), order="F")
+        else:
+            y = out
+            if (y.dtype != np.float64 or y.shape != (ny, x.shape[1])
+                    or not y.flags.f_contiguous):
+                raise ValueError("mult: out must be a column-major float64 array of the result shape")
         _check(lib().SP_d_struct_mult(self._h, trans.encode()[:1], x.shape[1],
                                       x.ctypes.data, x.shape[0],
                                       y.ctypes.data, ny), "mult")
@@ -319,10 +340,16 @@ class StructuredMatrix:
     def factor(self):
         _check(lib().SP_d_struct_factor(self._h), "factor")
 
-    def solve(self, b):
+    def solve(self, b, overwrite=False):
         """x = S^{-1} b (StructuredMatrix::solve, StructuredMatrix.hpp:340-360;
-        the C call overwrites its argument, this wrapper returns a copy)."""
-        x = _fortran(b).copy(order="F")
+        the C call overwrites its argument, this wrapper returns a copy unless
+        ``overwrite`` is set)."""
+        if overwrite:      # the C semantics: b <- S^{-1} b in the caller's buffer
+            x = b
+            if x.dtype != np.float64 or x.ndim != 2 or not x.flags.f_contiguous:
+                raise ValueError("solve(overwrite=True): b must be a column-major float64 matrix")
+        else:
+            x = _fortran(b).copy(order="F")
         _check(lib().SP_d_struct_solve(self._h, x.shape[1], x.ctypes.data,
                                        x.shape[0]), "solve")
         return x

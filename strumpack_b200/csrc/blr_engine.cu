@@ -459,28 +459,44 @@ blr_lr_gemv_kernel(const GemvTask* __restrict__ tasks, const int* __restrict__ o
                    const double* __restrict__ lr, const long long* __restrict__ lroff,
                    const int* __restrict__ rcap, const int* __restrict__ rank_tab,
                    const double* __restrict__ x, long long ldx, double* __restrict__ y,
-                   long long ldy, double alpha, const double* __restrict__ A, long long ld) {
+                   long long ldy, double alpha, const double* __restrict__ A, long long ld,
+                   int trans = 0) {
   extern __shared__ double sm[];
   const GemvTask tk = tasks[blockIdx.x];
   const int col = blockIdx.y;
   const int r = rank_tab[tk.k + tk.j * nb];
   if (r == 0) return;
-  const int m = off[tk.k + 1] - off[tk.k], n = off[tk.j + 1] - off[tk.j];
+  const int tm = off[tk.k + 1] - off[tk.k], tn = off[tk.j + 1] - off[tk.j];
+  // trans: y_j += alpha * T_kj^T x_k  (T^T = Vt U^T: the two factors swap roles)
+  const int m = trans ? tn : tm, n = trans ? tm : tn;
+  const int xb = trans ? tk.k : tk.j, yb = trans ? tk.j : tk.k;
   if (r < 0) {   // dense tile, lives in A (DenseTile::gemv_a)
     const double* D = A + off[tk.k] + (size_t)off[tk.j] * ld;
-    const double* xj = x + off[tk.j] + col * ldx;
-    double* yk = y + off[tk.k] + col * ldy;
-    for (int i = threadIdx.x; i < m; i += kThreads) {
-      double acc = 0.;
-      for (int c = 0; c < n; c++) acc += D[i + (size_t)c * ld] * xj[c];
-      atomicAdd(yk + i, alpha * acc);
+    const double* xj = x + off[xb] + col * ldx;
+    double* yk = y + off[yb] + col * ldy;
+    if (!trans) {
+      for (int i = threadIdx.x; i < m; i += kThreads) {
+        double acc = 0.;
+        for (int c = 0; c < n; c++) acc += D[i + (size_t)c * ld] * xj[c];
+        atomicAdd(yk + i, alpha * acc);
+      }
+    } else {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int c = warp; c < m; c += kWarps) {      // column c of D = row c of D^T
+        double acc = 0.;
+        for (int i = lane; i < n; i += 32) acc += D[i + (size_t)c * ld] * xj[i];
+        acc = warp_sum(acc);
+        if (lane == 0) atomicAdd(yk + c, alpha * acc);
+      }
     }
     return;
   }
-  const double* U = lr + lroff[tk.k + tk.j * nb];
-  const double* Vt = U + (size_t)m * rcap[tk.k + tk.j * nb];
-  const double* xj = x + off[tk.j] + col * ldx;
-  double* yk = y + off[tk.k] + col * ldy;
+  const double* U0 = lr + lroff[tk.k + tk.j * nb];
+  const double* Vt0 = U0 + (size_t)tm * rcap[tk.k + tk.j * nb];
+  const double* U = trans ? Vt0 : U0;      // m x r
+  const double* Vt = trans ? U0 : Vt0;     // n x r
+  const double* xj = x + off[xb] + col * ldx;
+  double* yk = y + off[yb] + col * ldy;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* tv = sm;   // r
   for (int a = warp; a < r; a += kWarps) {
@@ -882,7 +898,6 @@ void BLREngine::mult(char trans, int s, const double* dB, int ldB, double* dC, i
                      cudaStream_t st) {
   if (factored_) throw std::logic_error("BLR mult: the tiles hold LU factors (use solve)");
   const bool T = !(trans == 'N' || trans == 'n');
-  if (T) throw std::logic_error("BLR transposed mult is not implemented yet");
   const int nb = nb_;
   if (!mtasks_.p) {
     std::vector<GemvTask> tl;
@@ -893,12 +908,12 @@ void BLREngine::mult(char trans, int s, const double* dB, int ldB, double* dC, i
     SB200_CUDA(cudaMemcpy(mtasks_.p, tl.data(), tl.size() * sizeof(GemvTask), cudaMemcpyHostToDevice));
   }
   blr_zero_kernel<<<256, 256, 0, st>>>(dC, ldC, n_, s);
-  blr_diag_gemv_kernel<<<dim3(nb, s), kThreads, 0, st>>>(A_.p, n_, doff_.p, dB, ldB, dC, ldC, 0);
+  blr_diag_gemv_kernel<<<dim3(nb, s), kThreads, 0, st>>>(A_.p, n_, doff_.p, dB, ldB, dC, ldC, T ? 1 : 0);
   if (nmt_) {
     const size_t gsm = sizeof(double) * (size_t)(maxtile_ / 2 + 8);
     blr_lr_gemv_kernel<<<dim3(nmt_, s), kThreads, gsm, st>>>(reinterpret_cast<const GemvTask*>(mtasks_.p),
                                                             doff_.p, nb, lr_.p, dlroff_.p, drcap_.p, drank_.p,
-                                                            dB, ldB, dC, ldC, 1., A_.p, n_);
+                                                            dB, ldB, dC, ldC, 1., A_.p, n_, T ? 1 : 0);
   }
   launches_ += 3;
   SB200_CUDA(cudaGetLastError());

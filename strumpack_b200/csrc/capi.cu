@@ -79,6 +79,18 @@ void d2h(double* h, const DevBuf<double>& d, int rows, int cols, int ld,
                                cudaMemcpyDeviceToHost, st));
 }
 
+// float <-> double at the SP_s_* boundary
+std::vector<double> widen(const float* A, int rows, int cols, int ld) {
+  std::vector<double> D((size_t)rows * cols);
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < rows; i++) D[i + (size_t)j * rows] = A[i + (size_t)j * ld];
+  return D;
+}
+void narrow(const std::vector<double>& D, float* A, int rows, int cols, int ld) {
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < rows; i++) A[i + (size_t)j * ld] = (float)D[i + (size_t)j * rows];
+}
+
 }  // namespace
 
 extern "C" {
@@ -153,10 +165,26 @@ int SP_d_struct_from_elements(CSPStructMat* S, int rows, int cols,
                               double A(int i, int j), const CSPOptions* opts) {
   return guarded([&] {
     require_gpu();
-    if (opts->type != SP_TYPE_HSS)
-      throw std::invalid_argument("structured type not supported (HSS only)");
     auto m = std::make_unique<Mat>();
     m->type = opts->type;
+    if (opts->type == SP_TYPE_BLR) {
+      // construct_from_elements, Type::BLR (StructuredMatrix.cpp:230-252): every
+      // tile is filled through the callback, then compressed; the callback is a
+      // host function, so the n^2 evaluations happen here and the tiles are
+      // compressed on the device
+      if (rows != cols) throw std::invalid_argument("BLR: only square matrices are supported");
+      std::vector<double> Ad((size_t)rows * cols);
+      for (int j = 0; j < cols; j++)
+        for (int i = 0; i < rows; i++) Ad[i + (size_t)j * rows] = A(i, j);
+      BLROpts bo;
+      bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
+      bo.leaf_size = opts->leaf_size; bo.max_rank = opts->max_rank;
+      m->blr = std::make_unique<BLREngine>(rows, Ad.data(), rows, bo, false);
+      *S = m.release();
+      return;
+    }
+    if (opts->type != SP_TYPE_HSS)
+      throw std::invalid_argument("structured type not supported (HSS and BLR only)");
     CompressOptions co;
     co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
     co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
@@ -722,5 +750,62 @@ int SB200_d_struct_dense(const CSPStructMat S, double* A, int ldA) {
     }
   });
 }
+
+/* ---- single precision interface (reference StructuredMatrix.h SP_s_*) -------
+ * float at the boundary, fp64 inside: operands are widened on the way in and
+ * rounded on the way out, every kernel is the double precision one.  (B200's
+ * fp64 tensor pipe is what the engine is built on; the results are at least
+ * as accurate as a float implementation's.) */
+void SP_s_struct_default_options(CSPOptions* o) { SP_d_struct_default_options(o); }
+void SP_s_struct_destroy(CSPStructMat* S) { SP_d_struct_destroy(S); }
+int SP_s_struct_rows(const CSPStructMat S) { return SP_d_struct_rows(S); }
+int SP_s_struct_cols(const CSPStructMat S) { return SP_d_struct_cols(S); }
+/* bytes / nonzeros of the object as it is stored (fp64) */
+long long int SP_s_struct_memory(const CSPStructMat S) { return SP_d_struct_memory(S); }
+long long int SP_s_struct_nonzeros(const CSPStructMat S) { return SP_d_struct_nonzeros(S); }
+int SP_s_struct_rank(const CSPStructMat S) { return SP_d_struct_rank(S); }
+
+int SP_s_struct_from_dense(CSPStructMat* S, int rows, int cols, const float* A, int ldA,
+                           const CSPOptions* opts) {
+  if (rows < 0 || cols < 0 || !A) return guarded([] { throw std::invalid_argument("from_dense: bad arguments"); });
+  std::vector<double> D = widen(A, rows, cols, ldA);
+  return SP_d_struct_from_dense(S, rows, cols, D.data(), std::max(rows, 1), opts);
+}
+
+int SP_s_struct_from_elements(CSPStructMat* S, int rows, int cols, float A(int i, int j),
+                              const CSPOptions* opts) {
+  if (rows < 0 || cols < 0 || !A) return guarded([] { throw std::invalid_argument("from_elements: bad arguments"); });
+  if ((long long)rows * cols > (1LL << 28))
+    return guarded([] { throw std::invalid_argument("from_elements: host callbacks are limited to n <= 16384"); });
+  std::vector<double> D((size_t)rows * cols);
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < rows; i++) D[i + (size_t)j * rows] = A(i, j);
+  return SP_d_struct_from_dense(S, rows, cols, D.data(), std::max(rows, 1), opts);
+}
+
+int SP_s_struct_mult(const CSPStructMat S, char trans, int m, const float* B, int ldB, float* C,
+                     int ldC) {
+  if (!S || m <= 0) return S ? 0 : guarded([] { throw std::invalid_argument("null CSPStructMat"); });
+  const bool T = !(trans == 'N' || trans == 'n');
+  const int r = SP_d_struct_rows(S), c = SP_d_struct_cols(S);
+  const int nb = T ? r : c, nc = T ? c : r;
+  std::vector<double> Bd = widen(B, nb, m, ldB), Cd((size_t)nc * m);
+  const int rc = SP_d_struct_mult(S, trans, m, Bd.data(), std::max(nb, 1), Cd.data(), std::max(nc, 1));
+  if (!rc) narrow(Cd, C, nc, m, ldC);
+  return rc;
+}
+
+int SP_s_struct_factor(CSPStructMat S) { return SP_d_struct_factor(S); }
+
+int SP_s_struct_solve(const CSPStructMat S, int nrhs, float* B, int ldB) {
+  if (!S || nrhs <= 0) return S ? 0 : guarded([] { throw std::invalid_argument("null CSPStructMat"); });
+  const int n = SP_d_struct_rows(S);
+  std::vector<double> Bd = widen(B, n, nrhs, ldB);
+  const int rc = SP_d_struct_solve(S, nrhs, Bd.data(), std::max(n, 1));
+  if (!rc) narrow(Bd, B, n, nrhs, ldB);
+  return rc;
+}
+
+int SP_s_struct_shift(CSPStructMat S, float s) { return SP_d_struct_shift(S, (double)s); }
 
 }  // extern "C"

@@ -196,3 +196,29 @@ def test_blr_partial_factor_matches_reference(built):
     yr = R.partial_backward_solve(np.vstack([fr[:n1], np.linalg.solve(S_exact, fr[n1:])]))
     assert rel(ys, yr) <= 10 * 1e2 * tol
     assert rel(A @ ys, b) <= 1e2 * tol
+
+
+def test_blr_transposed_mult_and_from_elements(built):
+    """StructuredMatrix::mult(Trans::T/C) on a compressed BLR matrix (gemv with
+    the transposed tiles, reference BLRMatrix.cpp:1742-1763) -- on a
+    non-symmetric matrix with low-rank, dense and zero tiles -- and
+    construct_from_elements for Type::BLR (StructuredMatrix.cpp:230-252)."""
+    sb = built
+    n, leaf, tol = 1024, 128, 1e-8
+    i = np.arange(n)
+    A = 1.0 / (1.0 + np.abs(i[:, None] - 1.7 * i[None, :]) / 3.0) + np.triu(toeplitz(n), 300)
+    A[0:128, 256:384] += 0.1 * np.random.default_rng(9).standard_normal((128, 128))   # a dense tile
+    A[640:768, 0:128] = 0.0                                                            # a zero tile
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-14, leaf_size=leaf)
+    B = sb.StructuredMatrix.from_dense(A, o)
+    x = np.random.default_rng(2).standard_normal((n, 3))
+    assert rel(B.mult(x), A @ x) <= 1e2 * tol
+    assert rel(B.mult(x, "T"), A.T @ x) <= 1e2 * tol
+    assert rel(B.mult(x[:, :1], "C"), A.T @ x[:, :1]) <= 1e2 * tol
+
+    m = 300
+    M = toeplitz(m) + np.eye(m)
+    E = sb.StructuredMatrix.from_elements(m, m, lambda r, c: float(M[r, c]),
+                                          sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=1e-8, leaf_size=64))
+    xm = x[:m]
+    assert rel(E.mult(xm), M @ xm) <= 1e2 * 1e-8

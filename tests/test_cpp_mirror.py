@@ -1,6 +1,8 @@
 """The C++ host-side mirror (include/strumpack_b200/StructuredMatrix.hpp) of the
-reference interface compiles against the C ABI; on a GPU the C++ program that
-restates test/test_HSS_seq.cpp's Toeplitz ULV check passes."""
+reference interface compiles against the C ABI; on a GPU the C++ programs that
+restate test/test_HSS_seq.cpp's Toeplitz ULV check and walk the HSSMatrix /
+BLRMatrix / options class surface (including the front operations FrontHSS and
+FrontBLR use) pass."""
 import os
 import subprocess
 
@@ -8,19 +10,22 @@ import pytest
 
 from conftest import ROOT
 
+PROGRAMS = ["test_structured", "test_classes"]
 
-def _build(tmp_path, built):
-    exe = str(tmp_path / "test_structured")
+
+def _build(tmp_path, name):
+    exe = str(tmp_path / name)
     so_dir = os.path.join(ROOT, "strumpack_b200")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "test_structured.cpp"), "-o", exe,
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe,
                            "-L" + so_dir, "-lstrumpack_b200", "-Wl,-rpath," + so_dir])
     return exe
 
 
-def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(built, tmp_path):
+@pytest.mark.parametrize("name", PROGRAMS)
+def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(built, tmp_path, name):
     import torch
-    exe = _build(tmp_path, built)
+    exe = _build(tmp_path, name)
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     r = subprocess.run([exe, "64"], capture_output=True, text=True)
@@ -30,7 +35,15 @@ def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(built, tmp_path):
 
 @pytest.mark.gpu
 def test_cpp_mirror_toeplitz_ulv(built, tmp_path):
-    exe = _build(tmp_path, built)
+    exe = _build(tmp_path, "test_structured")
     r = subprocess.run([exe, "1000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "exiting" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_class_surface(built, tmp_path):
+    exe = _build(tmp_path, "test_classes")
+    r = subprocess.run([exe, "600"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "exiting" in r.stdout

@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol(built):
     sb = built
     hdr = open(os.path.join(ROOT, "include", "sb200_structured.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b((?:SP_d|SB200)_[A-Za-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b((?:SP_d|SP_s|SB200)_[A-Za-z0-9_]+)\s*\(", hdr))
     assert len(declared) >= 25
     L = sb.lib()
     for name in declared:
