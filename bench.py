@@ -29,9 +29,12 @@ sys.path.insert(0, ROOT)
 sys.setrecursionlimit(100000)
 
 FP64_DMMA_PEAK_TFLOPS = 37.1   # profiles/microbench/fp64_peak (this pool's B200)
-# dram__bytes_read.sum + dram__bytes_write.sum of the leaf-class ulv_qr_kernel launch from the
-# ncu --set full capture at N = 2^20 (profiles/r1_ncu_qr_summary.md): 9.947 GB for 4096 leaves
-QR_DRAM_BYTES_PER_LEAF = 9.946588e9 / 4096
+# dram__bytes_read.sum + dram__bytes_write.sum of the leaf-class ulv_qr_kernel launch (the default
+# variant: 16-column panels, 128-thread CTAs, 4 per SM) from the ncu --set full capture of
+# profiles/r1c_ncu_summary.md: 2.954 + 2.965 GB for 1024 leaves of 256 (N = 2^18).  The algorithmic
+# bytes are 2 x 8 x 256 x 281 B = 1.15 MB per leaf: the right-looking trailing matrix of the ~590
+# leaves in flight (340 MB) does not stay in the 126 MB L2.
+QR_DRAM_BYTES_PER_LEAF = (2.954075e9 + 2.965289e9) / 1024
 LEAF, TOL, H_GAUSS, LAMBDA = 256, 1e-4, 0.1, 1.0
 
 
@@ -336,7 +339,7 @@ def run_ours(args):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS,
                 "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
                 "traffic": QR_DRAM_BYTES_PER_LEAF * (n // LEAF) * share if n % LEAF == 0 else None,
-                "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r1_ncu_qr_summary.md, scaled by leaves)",
+                "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r1c_ncu_summary.md, scaled by leaves)",
                 "kernel": "ulv_qr_kernel (leaf class)", "kernel_ms": qr_avg_ms,
                 "executed_tflops": qr_exec / (qr_avg_ms * 1e-3) / 1e12,
                 "peak_source": "fp64 mma.sync (DMMA) peak measured on this pool's B200 by "
