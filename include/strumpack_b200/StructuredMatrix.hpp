@@ -541,10 +541,9 @@ inline std::string get_name(BLRFactorAlgorithm a) {
 
 // reference BLROptions.hpp:81-142 (defaults :128-140: rel 1e-4, abs 1e-12, leaf
 // 256, max_rank 5000, RRQR, WEAK, RL, HALF).  The engine implements RRQR
-// compression, weak admissibility and the right-looking factorization; the
-// other enum values are accepted and mapped onto those (LL/COMB/STAR order the
-// same tile operations differently and give the same factors up to the
-// compression tolerance).
+// compression, weak admissibility and the RL and LL schedules of the
+// factorization; the other enum values are accepted and mapped onto those
+// (COLWISE / COMB / STAR run as RL).
 template <typename scalar_t> class BLROptions : public structured::StructuredOptions<scalar_t> {
  public:
   BLROptions() : structured::StructuredOptions<scalar_t>(structured::Type::BLR) {
@@ -614,7 +613,8 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
   void compress_and_factor(const DenseM_t& A, const Opts_t& opts) {
     if (A.rows() != A.cols()) throw std::invalid_argument("BLR: only square matrices are supported");
     CSPStructMat s = nullptr;
-    if (SB200_d_blr_compress_and_factor(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), opts.pivot_threshold()))
+    if (SB200_d_blr_compress_and_factor_alg(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), opts.pivot_threshold(),
+                                            int(opts.BLR_factor_algorithm())))
       throw std::invalid_argument("BLRMatrix::compress_and_factor failed");
     reset(s);
   }
@@ -628,9 +628,9 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
   static BLRMatrix construct_and_partial_factor(DenseM_t& A11, DenseM_t& A12, DenseM_t& A21, DenseM_t& A22,
                                                 const Opts_t& opts) {
     CSPStructMat s = nullptr;
-    if (SB200_d_blr_partial_factor(&s, int(A11.rows()), int(A22.rows()), A11.data(), int(A11.ld()), A12.data(),
-                                   int(A12.ld()), A21.data(), int(A21.ld()), A22.data(), int(A22.ld()),
-                                   opts.c(), opts.pivot_threshold()))
+    if (SB200_d_blr_partial_factor_alg(&s, int(A11.rows()), int(A22.rows()), A11.data(), int(A11.ld()), A12.data(),
+                                       int(A12.ld()), A21.data(), int(A21.ld()), A22.data(), int(A22.ld()),
+                                       opts.c(), opts.pivot_threshold(), int(opts.BLR_factor_algorithm())))
       throw std::invalid_argument("BLRMatrix::construct_and_partial_factor failed");
     A11.clear(); A12.clear(); A21.clear();
     return BLRMatrix(s);

@@ -22,6 +22,8 @@ _SO = os.environ.get("SB200_LIB") or os.path.join(_HERE, "libstrumpack_b200.so")
 _lib = None
 
 SP_TYPE_HSS, SP_TYPE_BLR = 0, 1
+# reference BLRFactorAlgorithm (src/BLR/BLROptions.hpp:65)
+BLR_COLWISE, BLR_RL, BLR_LL, BLR_COMB, BLR_STAR = 0, 1, 2, 3, 4
 KERNEL_GAUSS, KERNEL_LAPLACE, KERNEL_TOEPLITZ_INVDIST = 0, 1, 2
 NODE_FIELDS = 16
 
@@ -70,6 +72,8 @@ SYMBOLS = {
     "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_partial_factor": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_partial_factor_device": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d]),
+    "SB200_d_blr_compress_and_factor_alg": (_i, [_pvp, _i, _vp, _i, _po, _d, _i]),
+    "SB200_d_blr_partial_factor_alg": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d, _i]),
     "SB200_d_blr_sep_rows": (_i, [_vp]),
     "SB200_d_blr_partial_forward_solve": (_i, [_vp, _i, _vp, _i]),
     "SB200_d_blr_partial_backward_solve": (_i, [_vp, _i, _vp, _i]),
@@ -399,16 +403,16 @@ class BLRMatrix(StructuredMatrix):
     """Mirror of ``BLR::BLRMatrix<double>`` (reference src/BLR/BLRMatrix.hpp:68-291)."""
 
     @classmethod
-    def compress_and_factor(cls, A, opts=None, pivot_threshold=-1.0):
+    def compress_and_factor(cls, A, opts=None, pivot_threshold=-1.0, factor_algorithm=BLR_RL):
         """BLRMatrix::compress_and_factor with weak admissibility and tiles from
         ClusterTree(n).refine(leaf) (reference BLRMatrix.cpp:113-241,
-        test/test_BLR_seq.cpp:136-156)."""
+        test/test_BLR_seq.cpp:136-156); factor_algorithm: BLR_RL / BLR_LL / ..."""
         A = _fortran(A)
         opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
         h = C.c_void_p()
-        _check(lib().SB200_d_blr_compress_and_factor(
+        _check(lib().SB200_d_blr_compress_and_factor_alg(
             C.byref(h), A.shape[0], A.ctypes.data, A.shape[0], C.byref(opts),
-            float(pivot_threshold)), "compress_and_factor")
+            float(pivot_threshold), int(factor_algorithm)), "compress_and_factor")
         return cls(h.value)
 
     @classmethod
@@ -424,7 +428,8 @@ class BLRMatrix(StructuredMatrix):
         return cls(h.value)
 
     @classmethod
-    def construct_and_partial_factor(cls, A11, A12, A21, A22, opts=None, pivot_threshold=-1.0):
+    def construct_and_partial_factor(cls, A11, A12, A21, A22, opts=None, pivot_threshold=-1.0,
+                                     factor_algorithm=BLR_RL):
         """BLRMatrix::construct_and_partial_factor (reference BLRMatrix.cpp:739-1037,
         RL, weak admissibility, tiles from ClusterTree(n1/n2).refine(leaf)).
         Returns (F, S): F holds F11 = LU(A11), F12, F21 in BLR form, S is the dense
@@ -434,10 +439,10 @@ class BLRMatrix(StructuredMatrix):
         n1, n2 = A11.shape[0], S.shape[0]
         opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
         h = C.c_void_p()
-        _check(lib().SB200_d_blr_partial_factor(
+        _check(lib().SB200_d_blr_partial_factor_alg(
             C.byref(h), n1, n2, A11.ctypes.data, n1, A12.ctypes.data, max(n1, 1),
             A21.ctypes.data, max(n2, 1), S.ctypes.data, max(n2, 1), C.byref(opts),
-            float(pivot_threshold)), "construct_and_partial_factor")
+            float(pivot_threshold), int(factor_algorithm)), "construct_and_partial_factor")
         return cls(h.value), S
 
     @property

@@ -357,19 +357,43 @@ blr_trsm_right_upper_dense_kernel(double* __restrict__ A, long long ld, const do
 // matrix, one CTA per pair (RL update, BLRMatrix.cpp:170-185; the 3-stage
 // batched GEMM of BLRBatch.hpp:85-118 fused: the rank x rank core never leaves
 // shared memory).  Ranks above KC are processed in chunks of KC columns.
+// mode 0 (right-looking): the CTAs are the (k, j) pairs behind step `pstep`,
+//   each subtracts the contribution of that one step;
+// mode 1 (left-looking, BLRFactorAlgorithm::LL, BLRMatrix.cpp:186-212): the
+//   CTAs are the tiles of block row and block column `pstep` (diagonal tile
+//   included), each subtracts the contributions of ALL earlier steps, in the
+//   same order and with the same arithmetic as mode 0 -- the factors are
+//   bitwise those of the right-looking schedule;
+// mode 2: the trailing block behind a partial factorization of `pstep` steps
+//   (the LL update of A22, BLRMatrix.cpp:998-1013).
 template <int KC>
 __global__ void __launch_bounds__(kThreads)
-blr_schur_kernel(double* A, long long ld, const int* __restrict__ off, int nb, int istep,
+blr_schur_kernel(double* A, long long ld, const int* __restrict__ off, int nb, int pstep,
                  const double* __restrict__ lr, const long long* __restrict__ lroff,
                  const int* __restrict__ rcap, const int* __restrict__ rank_tab, int ldp,
-                 const double* __restrict__ ident, int ldi) {
+                 const double* __restrict__ ident, int ldi, int mode) {
   extern __shared__ double sm[];
-  const int nrem = nb - istep - 1;
-  const int k = istep + 1 + blockIdx.x % nrem, j = istep + 1 + blockIdx.x / nrem;
-  int ra = rank_tab[k + istep * nb], rb = rank_tab[istep + j * nb];
-  if (ra == 0 || rb == 0) return;    // zero tile: nothing to subtract
-  const int mk = off[k + 1] - off[k], mi = off[istep + 1] - off[istep], nj = off[j + 1] - off[j];
+  int k, j, sbeg, send;
+  if (mode == 0) {
+    const int nrem = nb - pstep - 1;
+    k = pstep + 1 + blockIdx.x % nrem; j = pstep + 1 + blockIdx.x / nrem;
+    sbeg = pstep; send = pstep + 1;
+  } else if (mode == 1) {
+    const int nrow = nb - pstep;          // tiles (pstep, pstep .. nb-1), then (pstep+1 .. nb-1, pstep)
+    if ((int)blockIdx.x < nrow) { k = pstep; j = pstep + blockIdx.x; }
+    else { k = pstep + 1 + (blockIdx.x - nrow); j = pstep; }
+    sbeg = 0; send = pstep;
+  } else {
+    const int nrem = nb - pstep;
+    k = pstep + blockIdx.x % nrem; j = pstep + blockIdx.x / nrem;
+    sbeg = 0; send = pstep;
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int istep = sbeg; istep < send; istep++) {
+  int ra = rank_tab[k + istep * nb], rb = rank_tab[istep + j * nb];
+  if (ra == 0 || rb == 0) continue;    // zero tile: nothing to subtract
+  __syncthreads();                     // the shared buffers of the previous step are free
+  const int mk = off[k + 1] - off[k], mi = off[istep + 1] - off[istep], nj = off[j + 1] - off[j];
   constexpr int LDM = KC + 4;
   double* S1 = sm;                       // ldp x KC
   double* S2 = S1 + (size_t)ldp * KC;    // ldp x KC
@@ -447,6 +471,7 @@ blr_schur_kernel(double* A, long long ld, const int* __restrict__ off, int nb, i
           }
     }
   }
+  }   // istep
 }
 
 // ------------------------------------------------------------- vector kernels
@@ -702,10 +727,22 @@ void BLREngine::run(bool do_factor) {
   set_smem(id_cpqr_kernel, cpqr_smem);
   const int ldp = smem_ld(maxtile_);
   const int KC = maxtile_ <= 256 ? 32 : 16;
+  const bool ll = do_factor && opts_.factor_algorithm == 1;
+  auto schur_launch = [&](int pstep, int mode, int nblocks) {
+    const size_t smem = sizeof(double) * ((size_t)3 * ldp * KC + (size_t)(KC + 4) * KC);
+    if (KC == 32) { set_smem(blr_schur_kernel<32>, smem);
+      blr_schur_kernel<32><<<nblocks, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, pstep, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp, ident.p, maxtile_, mode);
+    } else { set_smem(blr_schur_kernel<16>, smem);
+      blr_schur_kernel<16><<<nblocks, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, pstep, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp, ident.p, maxtile_, mode);
+    }
+    launches_++;
+  };
   for (int i = 0; i < nsteps; i++) {
     const int m = off_[i + 1] - off_[i];
     const int cnt = step_ptr[i + 1] - step_ptr[i];
     double* Aii = A_.p + off_[i] + (size_t)off_[i] * n;
+    // left-looking schedule: block row / column i receive the updates of all earlier steps now
+    if (ll && i > 0) schur_launch(i, 1, 2 * (nb - i) - 1);
     if (do_factor) {
       {
         const int lp = smem_ld(maxtile_);
@@ -754,18 +791,19 @@ void BLREngine::run(bool do_factor) {
       blr_trsm_right_upper_dense_kernel<<<cnt, kThreads, 0, st>>>(A_.p, n, Aii, m, tds, drank_.p, nb);
       launches_ += 7;
     }
-    // K13: trailing update
+    // K13: trailing update (right-looking schedule)
     const int nrem = nb - i - 1;
-    if (nrem > 0) {
+    if (nrem > 0 && !ll) {
       const size_t smem = sizeof(double) * ((size_t)3 * ldp * KC + (size_t)(KC + 4) * KC);
       if (KC == 32) { set_smem(blr_schur_kernel<32>, smem);
-        blr_schur_kernel<32><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp, ident.p, maxtile_);
+        blr_schur_kernel<32><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp, ident.p, maxtile_, 0);
       } else { set_smem(blr_schur_kernel<16>, smem);
-        blr_schur_kernel<16><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp, ident.p, maxtile_);
+        blr_schur_kernel<16><<<nrem * nrem, kThreads, smem, st>>>(A_.p, n, doff_.p, nb, i, lr_.p, dlroff_.p, drcap_.p, drank_.p, ldp, ident.p, maxtile_, 0);
       }
       launches_++;
     }
   }
+  if (do_factor && ll && nsteps < nb) schur_launch(nsteps, 2, (nb - nsteps) * (nb - nsteps));   // A22 of a front
   SB200_CUDA(cudaGetLastError());
   SB200_CUDA(cudaStreamSynchronize(st));
   hrank_.resize((size_t)nb * nb);

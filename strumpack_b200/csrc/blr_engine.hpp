@@ -12,6 +12,9 @@ struct BLROpts {            // reference BLROptions defaults, src/BLR/BLROptions
   int leaf_size = 256;
   int max_rank = 5000;
   double pivot_threshold = -1.;
+  // BLRFactorAlgorithm (BLROptions.hpp:65): 0 = RL (default), 1 = LL.  COMB / STAR
+  // (LUAR accumulation with recompression) and COLWISE are mapped to RL.
+  int factor_algorithm = 0;
 };
 
 struct SolveTask { double* B; long long ldb; int ncols; };   // one column block of a batched trsm

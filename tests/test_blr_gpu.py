@@ -222,3 +222,38 @@ def test_blr_transposed_mult_and_from_elements(built):
                                           sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=1e-8, leaf_size=64))
     xm = x[:m]
     assert rel(E.mult(xm), M @ xm) <= 1e2 * 1e-8
+
+
+def test_blr_left_looking_equals_right_looking(built):
+    """BLRFactorAlgorithm::LL (reference BLRMatrix.cpp:186-212, 846-1013): block row /
+    column i receives the updates of all earlier steps right before step i.  The
+    engine applies the same tile updates in the same order as in the RL schedule,
+    so the factors -- hence ranks and Schur complements -- are identical; the solves
+    agree to roundoff (the block substitution accumulates with atomics)."""
+    sb = built
+    n, leaf, tol = 1536, 128, 1e-6
+    A = _with_noise_tiles(n, leaf, [(0, 3), (5, 2)])        # low-rank, dense and updated tiles
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    X = np.random.default_rng(0).standard_normal((n, 3))
+    Y = A @ X
+    R = sb.BLRMatrix.compress_and_factor(A, o, factor_algorithm=sb.BLR_RL)
+    L = sb.BLRMatrix.compress_and_factor(A, o, factor_algorithm=sb.BLR_LL)
+    xr, xl = R.solve(Y), L.solve(Y)
+    assert rel(xl, X) <= 1e2 * tol
+    assert rel(xl, xr) <= 1e-12
+    assert (R.rank, R.nonzeros, R.dense_tiles) == (L.rank, L.nonzeros, L.dense_tiles)
+    for alg in (sb.BLR_COLWISE, sb.BLR_COMB, sb.BLR_STAR):   # accepted, run as RL
+        assert rel(sb.BLRMatrix.compress_and_factor(A, o, factor_algorithm=alg).solve(Y), xr) <= 1e-12
+    with pytest.raises(RuntimeError):
+        sb.BLRMatrix.compress_and_factor(A, o, factor_algorithm=7)
+    # the front: A22 receives its update at the end in the LL schedule
+    n1 = 896
+    Fr, Sr = sb.BLRMatrix.construct_and_partial_factor(A[:n1, :n1], A[:n1, n1:], A[n1:, :n1], A[n1:, n1:], o,
+                                                       factor_algorithm=sb.BLR_RL)
+    Fl, Sl = sb.BLRMatrix.construct_and_partial_factor(A[:n1, :n1], A[:n1, n1:], A[n1:, :n1], A[n1:, n1:], o,
+                                                       factor_algorithm=sb.BLR_LL)
+    assert rel(Sl, Sr) <= 1e-13
+    print("LL Schur complement bitwise equal to RL:", np.array_equal(Sr, Sl))
+    S_exact = A[n1:, n1:] - A[n1:, :n1] @ np.linalg.solve(A[:n1, :n1], A[:n1, n1:])
+    assert rel(Sl, S_exact) <= 1e2 * tol
+    assert rel(Fl.partial_forward_solve(Y), Fr.partial_forward_solve(Y)) <= 1e-12
