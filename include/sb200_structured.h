@@ -159,19 +159,31 @@ int SB200_d_blr_partial_factor_device(CSPStructMat* S, int n1, int n2, const dou
                                       const double* dA12, int ld12, const double* dA21, int ld21,
                                       double* dA22, int ld22, const CSPOptions* opts,
                                       double pivot_threshold);
-/* The same two factorizations with the reference's BLRFactorAlgorithm
- * (src/BLR/BLROptions.hpp:65; BLRMatrix.cpp:170-235, 846-1013) chosen by its
- * enum value: 0 COLWISE, 1 RL, 2 LL, 3 COMB, 4 STAR.  RL and LL are implemented
- * as schedules of the same tile kernels (LL: block row / column i receives the
- * updates of all earlier steps right before it is factored; identical factors);
- * COLWISE, COMB and STAR run as RL. */
-int SB200_d_blr_compress_and_factor_alg(CSPStructMat* S, int n, const double* A, int ldA,
-                                        const CSPOptions* opts, double pivot_threshold,
-                                        int factor_algorithm);
-int SB200_d_blr_partial_factor_alg(CSPStructMat* S, int n1, int n2, const double* A11, int ld11,
-                                   const double* A12, int ld12, const double* A21, int ld21,
-                                   double* A22, int ld22, const CSPOptions* opts,
-                                   double pivot_threshold, int factor_algorithm);
+/* The same two factorizations with the BLROptions members that CSPOptions does
+ * not carry (reference src/BLR/BLROptions.hpp:81-142):
+ *   factor_algorithm  BLRFactorAlgorithm by its enum value (BLROptions.hpp:65;
+ *                     BLRMatrix.cpp:170-235, 846-1013): 0 COLWISE, 1 RL, 2 LL,
+ *                     3 COMB, 4 STAR.  RL and LL are schedules of the same tile
+ *                     kernels (LL: block row / column i receives the updates of
+ *                     all earlier steps right before it is factored; identical
+ *                     factors); COLWISE, COMB and STAR run as RL.
+ *   admissible        the reference's adm_t (BLRMatrix.hpp:78, strong
+ *                     admissibility: FrontBLR.cpp:262-281): nb x nb column-major
+ *                     over the tiles of the eliminated block, nonzero = the tile
+ *                     may be compressed, 0 = it stays a DenseTile
+ *                     (BLRMatrix.cpp:146-147).  NULL = weak admissibility. */
+typedef struct SB200BLRParams {
+  double pivot_threshold;
+  int factor_algorithm;
+  const int* admissible;
+  int n_admissible;
+} SB200BLRParams;
+int SB200_d_blr_compress_and_factor_ex(CSPStructMat* S, int n, const double* A, int ldA,
+                                       const CSPOptions* opts, const SB200BLRParams* params);
+int SB200_d_blr_partial_factor_ex(CSPStructMat* S, int n1, int n2, const double* A11, int ld11,
+                                  const double* A12, int ld12, const double* A21, int ld21,
+                                  double* A22, int ld22, const CSPOptions* opts,
+                                  const SB200BLRParams* params);
 /* n1 of a partially factored front (rows of S otherwise). */
 int SB200_d_blr_sep_rows(const CSPStructMat S);
 /* The two halves of the front solve (FrontBLR::fwd_solve_node / bwd_solve_node,

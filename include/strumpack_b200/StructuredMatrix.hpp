@@ -613,13 +613,22 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
   void compress_and_factor(const DenseM_t& A, const Opts_t& opts) {
     if (A.rows() != A.cols()) throw std::invalid_argument("BLR: only square matrices are supported");
     CSPStructMat s = nullptr;
-    if (SB200_d_blr_compress_and_factor_alg(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), opts.pivot_threshold(),
-                                            int(opts.BLR_factor_algorithm())))
+    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), nullptr, 0};
+    if (SB200_d_blr_compress_and_factor_ex(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), &p))
       throw std::invalid_argument("BLRMatrix::compress_and_factor failed");
     reset(s);
   }
-  void compress_and_factor(const DenseM_t& A, const adm_t& /*weak admissibility*/, const Opts_t& opts) {
-    compress_and_factor(A, opts);
+  // admissible: (number of tiles)^2, true = the tile may be compressed
+  void compress_and_factor(const DenseM_t& A, const adm_t& admissible, const Opts_t& opts) {
+    if (A.rows() != A.cols()) throw std::invalid_argument("BLR: only square matrices are supported");
+    std::vector<int> adm(admissible.rows() * admissible.cols());
+    for (std::size_t j = 0; j < admissible.cols(); j++)
+      for (std::size_t i = 0; i < admissible.rows(); i++) adm[i + j * admissible.rows()] = admissible(i, j) ? 1 : 0;
+    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), adm.data(), int(admissible.rows())};
+    CSPStructMat s = nullptr;
+    if (SB200_d_blr_compress_and_factor_ex(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), &p))
+      throw std::invalid_argument("BLRMatrix::compress_and_factor failed");
+    reset(s);
   }
   // BLRMatrix::construct_and_partial_factor(A11, A12, A21, A22, B11, B12, B21,
   // tiles1, tiles2, admissible, opts) (BLRMatrix.cpp:739-1037): one object
@@ -628,9 +637,10 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
   static BLRMatrix construct_and_partial_factor(DenseM_t& A11, DenseM_t& A12, DenseM_t& A21, DenseM_t& A22,
                                                 const Opts_t& opts) {
     CSPStructMat s = nullptr;
-    if (SB200_d_blr_partial_factor_alg(&s, int(A11.rows()), int(A22.rows()), A11.data(), int(A11.ld()), A12.data(),
-                                       int(A12.ld()), A21.data(), int(A21.ld()), A22.data(), int(A22.ld()),
-                                       opts.c(), opts.pivot_threshold(), int(opts.BLR_factor_algorithm())))
+    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), nullptr, 0};
+    if (SB200_d_blr_partial_factor_ex(&s, int(A11.rows()), int(A22.rows()), A11.data(), int(A11.ld()), A12.data(),
+                                      int(A12.ld()), A21.data(), int(A21.ld()), A22.data(), int(A22.ld()),
+                                      opts.c(), &p))
       throw std::invalid_argument("BLRMatrix::construct_and_partial_factor failed");
     A11.clear(); A12.clear(); A21.clear();
     return BLRMatrix(s);

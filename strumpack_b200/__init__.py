@@ -35,6 +35,21 @@ class CSPOptions(C.Structure):
                 ("max_rank", C.c_int), ("verbose", C.c_int)]
 
 
+class SB200BLRParams(C.Structure):
+    """include/sb200_structured.h: BLROptions members CSPOptions does not carry"""
+    _fields_ = [("pivot_threshold", C.c_double), ("factor_algorithm", C.c_int),
+                ("admissible", C.c_void_p), ("n_admissible", C.c_int)]
+
+
+def _blr_params(pivot_threshold, factor_algorithm, admissible):
+    p = SB200BLRParams(float(pivot_threshold), int(factor_algorithm), None, 0)
+    keep = None
+    if admissible is not None:
+        keep = np.asfortranarray(np.asarray(admissible) != 0, dtype=np.int32)
+        p.admissible, p.n_admissible = keep.ctypes.data, keep.shape[0]
+    return p, keep
+
+
 # every symbol include/sb200_structured.h declares: name -> (restype, argtypes)
 _vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
 _pvp = C.POINTER(C.c_void_p)
@@ -72,8 +87,8 @@ SYMBOLS = {
     "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_partial_factor": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_partial_factor_device": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d]),
-    "SB200_d_blr_compress_and_factor_alg": (_i, [_pvp, _i, _vp, _i, _po, _d, _i]),
-    "SB200_d_blr_partial_factor_alg": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d, _i]),
+    "SB200_d_blr_compress_and_factor_ex": (_i, [_pvp, _i, _vp, _i, _po, _vp]),
+    "SB200_d_blr_partial_factor_ex": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _vp]),
     "SB200_d_blr_sep_rows": (_i, [_vp]),
     "SB200_d_blr_partial_forward_solve": (_i, [_vp, _i, _vp, _i]),
     "SB200_d_blr_partial_backward_solve": (_i, [_vp, _i, _vp, _i]),
@@ -403,16 +418,19 @@ class BLRMatrix(StructuredMatrix):
     """Mirror of ``BLR::BLRMatrix<double>`` (reference src/BLR/BLRMatrix.hpp:68-291)."""
 
     @classmethod
-    def compress_and_factor(cls, A, opts=None, pivot_threshold=-1.0, factor_algorithm=BLR_RL):
-        """BLRMatrix::compress_and_factor with weak admissibility and tiles from
+    def compress_and_factor(cls, A, opts=None, pivot_threshold=-1.0, factor_algorithm=BLR_RL,
+                            admissible=None):
+        """BLRMatrix::compress_and_factor(A, admissible, opts) with tiles from
         ClusterTree(n).refine(leaf) (reference BLRMatrix.cpp:113-241,
-        test/test_BLR_seq.cpp:136-156); factor_algorithm: BLR_RL / BLR_LL / ..."""
+        test/test_BLR_seq.cpp:136-156); factor_algorithm: BLR_RL / BLR_LL / ...;
+        admissible: nb x nb matrix (None: weak admissibility)."""
         A = _fortran(A)
         opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
+        p, keep = _blr_params(pivot_threshold, factor_algorithm, admissible)
         h = C.c_void_p()
-        _check(lib().SB200_d_blr_compress_and_factor_alg(
+        _check(lib().SB200_d_blr_compress_and_factor_ex(
             C.byref(h), A.shape[0], A.ctypes.data, A.shape[0], C.byref(opts),
-            float(pivot_threshold), int(factor_algorithm)), "compress_and_factor")
+            C.addressof(p)), "compress_and_factor")
         return cls(h.value)
 
     @classmethod
@@ -429,7 +447,7 @@ class BLRMatrix(StructuredMatrix):
 
     @classmethod
     def construct_and_partial_factor(cls, A11, A12, A21, A22, opts=None, pivot_threshold=-1.0,
-                                     factor_algorithm=BLR_RL):
+                                     factor_algorithm=BLR_RL, admissible=None):
         """BLRMatrix::construct_and_partial_factor (reference BLRMatrix.cpp:739-1037,
         RL, weak admissibility, tiles from ClusterTree(n1/n2).refine(leaf)).
         Returns (F, S): F holds F11 = LU(A11), F12, F21 in BLR form, S is the dense
@@ -439,10 +457,11 @@ class BLRMatrix(StructuredMatrix):
         n1, n2 = A11.shape[0], S.shape[0]
         opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
         h = C.c_void_p()
-        _check(lib().SB200_d_blr_partial_factor_alg(
+        p, keep = _blr_params(pivot_threshold, factor_algorithm, admissible)
+        _check(lib().SB200_d_blr_partial_factor_ex(
             C.byref(h), n1, n2, A11.ctypes.data, n1, A12.ctypes.data, max(n1, 1),
             A21.ctypes.data, max(n2, 1), S.ctypes.data, max(n2, 1), C.byref(opts),
-            float(pivot_threshold), int(factor_algorithm)), "construct_and_partial_factor")
+            C.addressof(p)), "construct_and_partial_factor")
         return cls(h.value), S
 
     @property

@@ -33,6 +33,7 @@ struct TileDesc {     // one off-diagonal tile of the current step
   int ro, co, m, n;   // row/col offset and size in the matrix
   long long lr;       // offset of [U (m x rc) | Vt (n x rc)] in the LR arena
   int rc;             // rank capacity
+  int adm;            // 0: inadmissible tile, stays dense whatever its numerical rank
 };
 
 // ---------------------------------------------------------------- diagonal LU
@@ -226,7 +227,7 @@ blr_extract_lr_kernel(const TileDesc* __restrict__ tiles, const double* __restri
                       const int* __restrict__ order, int ostride, const int* __restrict__ ranks_step,
                       double* __restrict__ lr, int* __restrict__ rank_tab, int nb) {
   const TileDesc t = tiles[blockIdx.x];
-  const int rank = ranks_step[blockIdx.x];
+  const int rank = t.adm ? ranks_step[blockIdx.x] : -1;   // inadmissible: a DenseTile (BLRMatrix.cpp:146-147)
   if (threadIdx.x == 0) rank_tab[t.i + t.j * nb] = rank;
   if (rank <= 0) return;
   const double* Q = scratch + blockIdx.x * stride;
@@ -633,6 +634,10 @@ void BLREngine::setup(const std::vector<int>& tiles, bool do_factor) {
   off_.assign(nb_ + 1, 0);
   for (int t = 0; t < nb_; t++) off_[t + 1] = off_[t] + tiles[t];
   maxtile_ = *std::max_element(tiles.begin(), tiles.end());
+  if (!opts_.admissible.empty() &&
+      (opts_.nadm != nsteps_ || opts_.admissible.size() != (size_t)opts_.nadm * opts_.nadm))
+    throw std::invalid_argument("BLR admissibility matrix must be (tiles of the eliminated block)^2 = " +
+                                std::to_string(nsteps_) + "^2");
   if (maxtile_ > 1024) throw std::invalid_argument("BLR tiles larger than 1024 are not supported");
   // LR arena: tile (i,j) gets [U m x rc | Vt n x rc], rc = min(m,n)/2 (a tile
   // is kept low-rank only if rank*(m+n) <= m*n, BLRMatrix.cpp:563-570).  In a
@@ -682,6 +687,9 @@ void BLREngine::run(bool do_factor) {
     t.i = i; t.j = j; t.ro = off_[i]; t.co = off_[j];
     t.m = off_[i + 1] - off_[i]; t.n = off_[j + 1] - off_[j];
     t.lr = lroff_[i + (size_t)j * nb]; t.rc = rcap_[i + (size_t)j * nb];
+    t.adm = 1;
+    if (!opts_.admissible.empty() && i < opts_.nadm && j < opts_.nadm)
+      t.adm = opts_.admissible[i + (size_t)j * opts_.nadm] != 0;
     td.push_back(t);
     IDTask q;
     q.M = scratch.p + slot * tstride; q.R = Rbuf.p + slot * tstride;

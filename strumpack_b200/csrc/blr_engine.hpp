@@ -15,6 +15,12 @@ struct BLROpts {            // reference BLROptions defaults, src/BLR/BLROptions
   // BLRFactorAlgorithm (BLROptions.hpp:65): 0 = RL (default), 1 = LL.  COMB / STAR
   // (LUAR accumulation with recompression) and COLWISE are mapped to RL.
   int factor_algorithm = 0;
+  // admissibility of the tiles of the eliminated block (BLRMatrix adm_t,
+  // BLRMatrix.hpp:78; strong admissibility marks neighbouring tiles
+  // inadmissible = kept dense): nadm x nadm, column-major, nonzero = the tile
+  // may be compressed.  Empty = weak admissibility (every off-diagonal tile).
+  std::vector<int> admissible;
+  int nadm = 0;
 };
 
 struct SolveTask { double* B; long long ldb; int ncols; };   // one column block of a batched trsm

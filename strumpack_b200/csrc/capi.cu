@@ -214,31 +214,39 @@ int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
 // BLRFactorAlgorithm of the reference (BLROptions.hpp:65): COLWISE 0, RL 1, LL 2,
 // COMB 3, STAR 4.  The engine has the right-looking and the left-looking
 // schedule; COMB / STAR / COLWISE run as RL.
-static int engine_alg(int factor_algorithm) {
-  if (factor_algorithm < 0 || factor_algorithm > 4) throw std::invalid_argument("unknown BLR factor algorithm");
-  return factor_algorithm == 2 ? 1 : 0;
+static BLROpts blr_opts(const CSPOptions* opts, const SB200BLRParams* p) {
+  BLROpts bo;
+  bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
+  bo.leaf_size = opts->leaf_size; bo.max_rank = opts->max_rank;
+  if (p) {
+    if (p->factor_algorithm < 0 || p->factor_algorithm > 4)
+      throw std::invalid_argument("unknown BLR factor algorithm");
+    bo.pivot_threshold = p->pivot_threshold;
+    bo.factor_algorithm = p->factor_algorithm == 2 ? 1 : 0;
+    if (p->admissible) {
+      if (p->n_admissible <= 0) throw std::invalid_argument("BLR admissibility matrix without a size");
+      bo.nadm = p->n_admissible;
+      bo.admissible.assign(p->admissible, p->admissible + (size_t)bo.nadm * bo.nadm);
+    }
+  }
+  return bo;
 }
 
-int SB200_d_blr_compress_and_factor_alg(CSPStructMat* S, int n, const double* A, int ldA,
-                                        const CSPOptions* opts, double pivot_threshold,
-                                        int factor_algorithm) {
+int SB200_d_blr_compress_and_factor_ex(CSPStructMat* S, int n, const double* A, int ldA,
+                                       const CSPOptions* opts, const SB200BLRParams* params) {
   return guarded([&] {
     require_gpu();
     auto m = std::make_unique<Mat>();
     m->type = SP_TYPE_BLR;
-    BLROpts bo;
-    bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
-    bo.leaf_size = opts->leaf_size; bo.max_rank = opts->max_rank;
-    bo.pivot_threshold = pivot_threshold;
-    bo.factor_algorithm = engine_alg(factor_algorithm);
-    m->blr = std::make_unique<BLREngine>(n, A, ldA, bo, true);
+    m->blr = std::make_unique<BLREngine>(n, A, ldA, blr_opts(opts, params), true);
     *S = m.release();
   });
 }
 
 int SB200_d_blr_compress_and_factor(CSPStructMat* S, int n, const double* A, int ldA,
                                     const CSPOptions* opts, double pivot_threshold) {
-  return SB200_d_blr_compress_and_factor_alg(S, n, A, ldA, opts, pivot_threshold, 1);
+  SB200BLRParams p{pivot_threshold, 1, nullptr, 0};
+  return SB200_d_blr_compress_and_factor_ex(S, n, A, ldA, opts, &p);
 }
 
 int SB200_d_blr_compress_and_factor_device(CSPStructMat* S, int n, const double* dA, int ldA,
@@ -258,16 +266,11 @@ int SB200_d_blr_compress_and_factor_device(CSPStructMat* S, int n, const double*
 
 static void blr_partial_impl(CSPStructMat* S, int n1, int n2, const double* A11, int ld11,
                              const double* A12, int ld12, const double* A21, int ld21, double* A22,
-                             int ld22, const CSPOptions* opts, double pivot_threshold, bool device,
-                             int factor_algorithm = 1) {
+                             int ld22, const CSPOptions* opts, const SB200BLRParams* params, bool device) {
   require_gpu();
   auto m = std::make_unique<Mat>();
   m->type = SP_TYPE_BLR;
-  BLROpts bo;
-  bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
-  bo.leaf_size = opts->leaf_size; bo.max_rank = opts->max_rank;
-  bo.pivot_threshold = pivot_threshold;
-  bo.factor_algorithm = engine_alg(factor_algorithm);
+  BLROpts bo = blr_opts(opts, params);
   m->blr = std::make_unique<BLREngine>(n1, n2, A11, ld11, A12, ld12, A21, ld21, A22, ld22, bo, device);
   if (n2 > 0)   // A22 <- A22 - A21 A11^{-1} A12, in place like the reference
     SB200_CUDA(cudaMemcpy2D(A22, sizeof(double) * ld22, m->blr->schur(), sizeof(double) * (n1 + n2),
@@ -281,7 +284,8 @@ int SB200_d_blr_partial_factor(CSPStructMat* S, int n1, int n2, const double* A1
                                double* A22, int ld22, const CSPOptions* opts,
                                double pivot_threshold) {
   return guarded([&] {
-    blr_partial_impl(S, n1, n2, A11, ld11, A12, ld12, A21, ld21, A22, ld22, opts, pivot_threshold, false);
+    SB200BLRParams p{pivot_threshold, 1, nullptr, 0};
+    blr_partial_impl(S, n1, n2, A11, ld11, A12, ld12, A21, ld21, A22, ld22, opts, &p, false);
   });
 }
 
@@ -290,17 +294,17 @@ int SB200_d_blr_partial_factor_device(CSPStructMat* S, int n1, int n2, const dou
                                       double* dA22, int ld22, const CSPOptions* opts,
                                       double pivot_threshold) {
   return guarded([&] {
-    blr_partial_impl(S, n1, n2, dA11, ld11, dA12, ld12, dA21, ld21, dA22, ld22, opts, pivot_threshold, true);
+    SB200BLRParams p{pivot_threshold, 1, nullptr, 0};
+    blr_partial_impl(S, n1, n2, dA11, ld11, dA12, ld12, dA21, ld21, dA22, ld22, opts, &p, true);
   });
 }
 
-int SB200_d_blr_partial_factor_alg(CSPStructMat* S, int n1, int n2, const double* A11, int ld11,
-                                   const double* A12, int ld12, const double* A21, int ld21,
-                                   double* A22, int ld22, const CSPOptions* opts,
-                                   double pivot_threshold, int factor_algorithm) {
+int SB200_d_blr_partial_factor_ex(CSPStructMat* S, int n1, int n2, const double* A11, int ld11,
+                                  const double* A12, int ld12, const double* A21, int ld21,
+                                  double* A22, int ld22, const CSPOptions* opts,
+                                  const SB200BLRParams* params) {
   return guarded([&] {
-    blr_partial_impl(S, n1, n2, A11, ld11, A12, ld12, A21, ld21, A22, ld22, opts, pivot_threshold, false,
-                     factor_algorithm);
+    blr_partial_impl(S, n1, n2, A11, ld11, A12, ld12, A21, ld21, A22, ld22, opts, params, false);
   });
 }
 

@@ -257,3 +257,29 @@ def test_blr_left_looking_equals_right_looking(built):
     S_exact = A[n1:, n1:] - A[n1:, :n1] @ np.linalg.solve(A[:n1, :n1], A[:n1, n1:])
     assert rel(Sl, S_exact) <= 1e2 * tol
     assert rel(Fl.partial_forward_solve(Y), Fr.partial_forward_solve(Y)) <= 1e-12
+
+
+def test_blr_strong_admissibility(built):
+    """compress_and_factor(A, admissible, opts) with a strong-admissibility mask
+    (reference adm_t, BLRMatrix.hpp:78; FrontBLR.cpp:262-281): inadmissible tiles
+    are DenseTiles (BLRMatrix.cpp:146-147) even though they would compress."""
+    sb = built
+    n, leaf, tol = 1024, 128, 1e-6
+    A = toeplitz(n) + 2.0 * np.eye(n)
+    nb = n // leaf
+    t = np.arange(nb)
+    adm = np.abs(t[:, None] - t[None, :]) > 1              # neighbours of the diagonal stay dense
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    W = sb.BLRMatrix.compress_and_factor(A, o)
+    S = sb.BLRMatrix.compress_and_factor(A, o, admissible=adm)
+    assert W.dense_tiles == 0
+    assert S.dense_tiles == 2 * (nb - 1)
+    assert S.nonzeros > W.nonzeros
+    X = np.random.default_rng(0).standard_normal((n, 2))
+    Y = A @ X
+    es, ew = rel(S.solve(Y), X), rel(W.solve(Y), X)
+    assert es <= 1e2 * tol and es <= 2 * ew + 1e-14        # fewer approximations, no less accurate
+    L = sb.BLRMatrix.compress_and_factor(A, o, admissible=adm, factor_algorithm=sb.BLR_LL)
+    assert rel(L.solve(Y), S.solve(Y)) <= 1e-12
+    with pytest.raises(RuntimeError):
+        sb.BLRMatrix.compress_and_factor(A, o, admissible=np.ones((3, 3)))     # wrong size
