@@ -590,7 +590,10 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
   double* Df = scratch + scratch_off[blockIdx.x];
   const double* B01 = vals + nd.B01;
   const double* B10 = vals + nd.B10;
-  for (int idx = tid; idx < m * m; idx += kThreads) {
+  // gridDim.y CTAs share one node (the upper classes have few nodes and are
+  // latency bound): each takes a strided slice of the entries
+  const int step = kThreads * gridDim.y, first = tid + blockIdx.y * kThreads;
+  for (int idx = first; idx < m * m; idx += step) {
     int i = idx % m, j = idx / m;
     double v;
     if (i < ru0 && j < ru0) v = child_Dt(fact, c0, i, j);
@@ -611,13 +614,13 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
   // pinv[j] of [I; E_v]; only the inverse permutation sits in smem.
   const double* E = vals + nd.Ev;
   double* Vh = fact + nd.F + (size_t)nd.k * m;
-  for (int idx = tid; idx < m * rv; idx += kThreads) {
+  for (int idx = first; idx < m * rv; idx += step) {
     int i = idx % m, c = idx / m;
     double v = 0.;
-    const bool first = i < ru0;
-    const double* vv = first ? v0 : v1;
-    const int ldv_ = first ? ld0 : ld1;
-    const int a = first ? i : i - ru0, qoff = first ? 0 : rv0, nq = first ? rv0 : rv1;
+    const bool top = i < ru0;
+    const double* vv = top ? v0 : v1;
+    const int ldv_ = top ? ld0 : ld1;
+    const int a = top ? i : i - ru0, qoff = top ? 0 : rv0, nq = top ? rv0 : rv1;
     for (int q = 0; q < nq; q++) {
       const int pi = pinv[qoff + q];
       const double vd = pi < rv ? (pi == c ? 1. : 0.) : E[(pi - rv) + (size_t)c * kv];
@@ -2256,6 +2259,262 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Streaming variants of the two solve sweeps (single right-hand side per CTA).
+// ulv_fwd_kernel / ulv_bwd_kernel walk the factor block in column blocks and
+// every block starts with a dependent global load: ~15 exposed HBM round trips
+// per leaf, 3-4x the time the bytes need.  None of those loads depends on the
+// vector being solved, so here the factor block is streamed through shared
+// memory by cp.async (LDGSTS) one column chunk AHEAD of its use, double
+// buffered: the chain of barriers stays, the memory latency leaves it, and
+// three CTAs per SM keep ~100 KB of loads in flight (HBM-bound by design:
+// the sweep reads the block once).  Same arithmetic as the kernels above.
+// ---------------------------------------------------------------------------
+
+// Backward sweep: x = Q^H [y; x_c], reflector blocks of `nbq` columns (the
+// panel width of the class, <= nbw) applied last to first.
+__global__ void __launch_bounds__(kThreads)
+ulv_bwd_pipe_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                    const double* __restrict__ fact, const double* __restrict__ tfac,
+                    double* __restrict__ b, int ldb, const double* __restrict__ ysol,
+                    double* __restrict__ xsol, int s, int ldbuf, int nbw) {
+  extern __shared__ __align__(16) double sm[];
+  const int id = list[blockIdx.x];
+  const DNode nd = nodes[id];
+  if (nd.parent < 0) return;
+  const DNode par = nodes[nd.parent];
+  const int col = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = nd.m, k = nd.k;
+  double* v = sm;                              // ldbuf
+  double* w = v + ldbuf;                       // 32
+  double* w2 = w + 32;                         // 32
+  double* Tb = w2 + 32;                        // 2 x (nbw x nbw)
+  double* Vb = Tb + 2 * nbw * nbw;             // 2 x (ldbuf x nbw)
+  const int xoff = (par.ch0 == id) ? 0 : nodes[par.ch0].u_rank;
+  const double* xp = xsol + (size_t)par.x_off * s + (size_t)col * par.m + xoff;
+  const double* yi = ysol + (size_t)nd.y_off * s + (size_t)col * k;
+  const double* A = fact + nd.F;
+  const double* Tg = tfac + nd.T;
+  const int nbq = nd.nbq;
+  const int nblk = (k + nbq - 1) / nbq;
+  // rows j0..m-1 of the block's columns (the reflector tails; the entries on and
+  // above the diagonal are R and are masked out below) + its T block
+  auto issue = [&](int bi, int buf) {
+    const int j0 = bi * nbq, jb = min(nbq, k - j0), rows = m - j0;
+    double* dst = Vb + (size_t)buf * ldbuf * nbw;
+    for (int a = warp; a < jb; a += kWarps) {
+      const double* src = A + j0 + (size_t)(j0 + a) * m;
+      for (int i = lane; i < rows; i += 32) cp_async8(dst + i + a * ldbuf, src + i, true);
+    }
+    double* td = Tb + buf * nbw * nbw;
+    for (int idx = tid; idx < jb * nbw; idx += kThreads) {
+      const int r = idx % nbw, c = idx / nbw;
+      if (r < jb) cp_async8(td + r + c * nbw, Tg + r + (size_t)(j0 + c) * nbq, true);
+    }
+    cp_async_commit();
+  };
+  if (nblk > 0) issue(nblk - 1, 0);            // in flight while v is gathered
+  for (int i = tid; i < m; i += kThreads) v[i] = i < k ? yi[i] : xp[i - k];
+  int buf = 0;
+  for (int bi = nblk - 1; bi >= 0; bi--, buf ^= 1) {
+    if (bi > 0) { issue(bi - 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int j0 = bi * nbq, jb = min(nbq, k - j0), rows = m - j0;
+    const double* Vc = Vb + (size_t)buf * ldbuf * nbw;
+    const double* Tc = Tb + buf * nbw * nbw;
+    for (int a = warp; a < jb; a += kWarps) {
+      const double* Va = Vc + a * ldbuf;
+      double acc = 0.;
+      for (int i = a + 1 + lane; i < rows; i += 32) acc += Va[i] * v[j0 + i];
+      acc = warp_sum(acc);
+      if (lane == 0) w[a] = acc + v[j0 + a];
+    }
+    __syncthreads();
+    if (tid < jb) {
+      double acc = 0.;
+      for (int c = tid; c < jb; c++) acc += Tc[tid + c * nbw] * w[c];
+      w2[tid] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < rows; i += kThreads) {
+      double acc = 0.;
+      const int amax = min(jb, i);       // columns a with j0 + a < j0 + i
+      for (int a = 0; a < amax; a++) acc += Vc[i + a * ldbuf] * w2[a];
+      if (i < jb) acc += w2[i];
+      v[j0 + i] -= acc;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (nd.leaf) {
+    double* bb = b + nd.row_off + (size_t)col * ldb;
+    for (int i = tid; i < m; i += kThreads) bb[i] = v[i];
+  } else {
+    double* xo = xsol + (size_t)nd.x_off * s + (size_t)col * m;
+    for (int i = tid; i < m; i += kThreads) xo[i] = v[i];
+  }
+}
+
+// Forward sweep: the first k rows of the factor block are streamed in chunks
+// of kFC columns: chunks inside [0, k) are steps of the triangular solve
+// y = R^{-T} rhs, the chunks of the last r_v + r_u columns are the products
+// z = Vt0^H y and ft1 -= (W1 Q0^H) y.
+constexpr int kFC = 16;
+__global__ void __launch_bounds__(kThreads)
+ulv_fwd_pipe_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
+                    const double* __restrict__ vals, const int* __restrict__ perms,
+                    const double* __restrict__ fact, const double* __restrict__ b, int ldb,
+                    double* __restrict__ ysol, double* __restrict__ zsol,
+                    double* __restrict__ fsol, int s, int ldm, int ldbuf) {
+  extern __shared__ __align__(16) double sm[];
+  const DNode nd = nodes[list[blockIdx.x]];
+  if (nd.parent < 0) return;
+  const int col = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = nd.m, r = nd.u_rank, k = nd.k, rv = nd.v_rank;
+  double* f = sm;              // ldm
+  double* fp = f + ldm;        // ldm  (P^T f) ; fp[0:r] = ft1, then y in fp[r:]
+  double* zc = fp + ldm;       // ldm  children z concat (inner nodes)
+  double* Cb = zc + ldm;       // 2 x (ldbuf x kFC)
+  const double* A = fact + nd.F;
+  const int nextra = rv + r;
+  const int nsolve = (k + kFC - 1) / kFC;                // chunks of the triangular solve
+  const int nchunk = k > 0 ? nsolve + (nextra + kFC - 1) / kFC : 0;
+  // chunk c: columns [c0, c0 + cw) of the factor block, rows [0, nr)
+  auto issue = [&](int c, int buf) {
+    int c0, cw, nr;
+    if (c < nsolve) { c0 = c * kFC; cw = min(kFC, k - c0); nr = c0 + cw; }
+    else { c0 = k + (c - nsolve) * kFC; cw = min(kFC, k + nextra - c0); nr = k; }
+    double* dst = Cb + (size_t)buf * ldbuf * kFC;
+    for (int a = warp; a < cw; a += kWarps) {
+      const double* src = A + (size_t)(c0 + a) * m;
+      for (int i = lane; i < nr; i += 32) cp_async8(dst + i + a * ldbuf, src + i, true);
+    }
+    cp_async_commit();
+  };
+  if (nchunk > 0) issue(0, 0);       // in flight while the right-hand side is assembled
+  // ---- gather f
+  if (nd.leaf) {
+    const double* bb = b + nd.row_off + (size_t)col * ldb;
+    for (int i = tid; i < m; i += kThreads) f[i] = bb[i];
+  } else {
+    const DNode c0 = nodes[nd.ch0], c1 = nodes[nd.ch1];
+    const int ru0 = c0.u_rank, ru1 = c1.u_rank, rv0 = c0.v_rank, rv1 = c1.v_rank;
+    const double* f0 = fsol + (size_t)c0.f_off * s + (size_t)col * ru0;
+    const double* f1 = fsol + (size_t)c1.f_off * s + (size_t)col * ru1;
+    const double* z0 = zsol + (size_t)c0.z_off * s + (size_t)col * rv0;
+    const double* z1 = zsol + (size_t)c1.z_off * s + (size_t)col * rv1;
+    const double* B01 = vals + nd.B01;
+    const double* B10 = vals + nd.B10;
+    for (int i = tid; i < m; i += kThreads) {
+      double v;
+      if (i < ru0) { v = f0[i]; for (int j = 0; j < rv1; j++) v -= B01[i + (size_t)j * ru0] * z1[j]; }
+      else { int ii = i - ru0; v = f1[ii]; for (int j = 0; j < rv0; j++) v -= B10[ii + (size_t)j * ru1] * z0[j]; }
+      f[i] = v;
+    }
+    for (int i = tid; i < rv0 + rv1; i += kThreads) zc[i] = i < rv0 ? z0[i] : z1[i - rv0];
+  }
+  __syncthreads();
+  const int* P = perms + nd.Pu;
+  for (int i = tid; i < m; i += kThreads) fp[i] = f[P[i]];
+  __syncthreads();
+  double* y = fp + r;
+  if (k > 0) {
+    // rhs = fp[r:] - E ft1
+    const double* E = vals + nd.Eu;
+    for (int i = tid; i < k; i += kThreads) {
+      double v = fp[r + i];
+      for (int l = 0; l < r; l++) v -= E[i + (size_t)l * k] * fp[l];
+      f[i] = v;  // reuse f as rhs
+    }
+    __syncthreads();
+    for (int i = tid; i < k; i += kThreads) y[i] = f[i];
+    __syncthreads();
+  }
+  double* zo = zsol + (size_t)nd.z_off * s + (size_t)col * rv;
+  double* fo = fsol + (size_t)nd.f_off * s + (size_t)col * r;
+  const int* Pv = perms + nd.Pv;
+  const double* Ev = vals + nd.Ev;
+  const int kv = nd.v_rows - rv;
+  int buf = 0;
+  for (int c = 0; c < nchunk; c++, buf ^= 1) {
+    if (c + 1 < nchunk) { issue(c + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const double* Cc = Cb + (size_t)buf * ldbuf * kFC;
+    if (c < nsolve) {
+      // subtract the contribution of the solved prefix, then a cw-step
+      // substitution with the diagonal block (L = R^T, solve.hpp:160-161)
+      const int c0 = c * kFC, cw = min(kFC, k - c0);
+      for (int a = warp; a < cw; a += kWarps) {
+        const double* Ra = Cc + a * ldbuf;
+        double acc = 0.;
+        for (int j = lane; j < c0; j += 32) acc += Ra[j] * y[j];
+        acc = warp_sum(acc);
+        if (lane == 0) y[c0 + a] -= acc;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // the substitution is a chain of cw dependent steps: keep it to
+        // multiply + shuffle + fma by taking the reciprocal pivots and this
+        // lane's column of the diagonal block into registers beforehand
+        const bool lin = lane < cw;
+        double val = lin ? y[c0 + lane] : 0.;
+        const double* Rl = Cc + c0 + (lin ? lane : 0) * ldbuf;     // column c0 + lane, rows c0..
+        const double dinv = lin ? 1. / Rl[lane] : 0.;
+        double rc[kFC];
+#pragma unroll
+        for (int a = 0; a < kFC; a++) rc[a] = (lin && a < lane) ? Rl[a] : 0.;
+#pragma unroll
+        for (int a = 0; a < kFC; a++) {
+          if (lane == a) val *= dinv;
+          const double ya = __shfl_sync(0xffffffffu, val, a);
+          val -= rc[a] * ya;          // rc[a] = 0 unless a < lane < cw
+        }
+        if (lin) y[c0 + lane] = val;
+      }
+      __syncthreads();
+    } else {
+      // columns k + e of the factor block: z = Vt0^H y (+ V^H [z0; z1]) ; ft1 -= (W1 Q0^H) y
+      const int e0 = (c - nsolve) * kFC, cw = min(kFC, nextra - e0);
+      for (int a = warp; a < cw; a += kWarps) {
+        const int e = e0 + a;
+        const double* Xa = Cc + a * ldbuf;
+        double acc = 0.;
+        for (int i = lane; i < k; i += 32) acc += Xa[i] * y[i];
+        if (e < rv && !nd.leaf) {
+          for (int i = lane; i < kv; i += 32) acc += Ev[i + (size_t)e * kv] * zc[Pv[rv + i]];
+          if (lane == 0) acc += zc[Pv[e]];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          if (e < rv) zo[e] = acc;
+          else fo[e - rv] = fp[e - rv] - acc;
+        }
+      }
+      __syncthreads();     // the buffer is refilled two chunks later
+    }
+  }
+  if (k > 0) {
+    double* yo = ysol + (size_t)nd.y_off * s + (size_t)col * k;
+    for (int i = tid; i < k; i += kThreads) yo[i] = y[i];
+  } else {
+    // nothing to eliminate: z = V^H [z0; z1] (or 0 at a leaf), ft1 = P^T f
+    for (int e = warp; e < nextra; e += kWarps) {
+      double acc = 0.;
+      if (e < rv && !nd.leaf) {
+        for (int i = lane; i < kv; i += 32) acc += Ev[i + (size_t)e * kv] * zc[Pv[rv + i]];
+        if (lane == 0) acc += zc[Pv[e]];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (e < rv) zo[e] = acc;
+        else fo[e - rv] = fp[e - rv] - acc;
+      }
+    }
+  }
+}
+
 // ===========================================================================
 //            SCHUR COMPLEMENT OF THE (0,0) BLOCK / PARTIAL FACTORIZATION
 // ===========================================================================
@@ -2403,6 +2662,8 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   if (const char* e = std::getenv("SB200_QR_VARIANT")) qr_variant_ = std::atoi(e);
   if (const char* e = std::getenv("SB200_APPLY_MM_MIN")) mm_min_ = std::max(1, std::atoi(e));   // rhs count from which the GEMM-shaped apply kernels run
   if (const char* e = std::getenv("SB200_QR_NOWIDE")) qr_nowide_ = std::atoi(e);   // 1: 64-bit one-slab trailing update
+  // cp.async-streamed solve sweeps: bit 0 backward, bit 1 forward (default: both)
+  if (const char* e = std::getenv("SB200_SOLVE_PIPE")) solve_pipe_ = std::atoi(e);
   if (qr_split_) qr_variant_ = 0;   // the per-panel launch experiment assumes nb_-wide panels
   build_tables();
 }
@@ -2852,7 +3113,9 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       const int stage = need <= 160 * 1024;
       size_t smem = stage ? need : sizeof(int) * (size_t)(mm + 8);
       set_smem(ulv_build_inner_kernel, smem);
-      ulv_build_inner_kernel<<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so, stage);
+      // few nodes: several CTAs per node (the kernel slices its entry loops over gridDim.y)
+      const int ny = cnt >= 2 * nsm_ ? 1 : std::min(8, std::max(1, 2 * nsm_ / cnt));
+      ulv_build_inner_kernel<<<dim3(cnt, ny), kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so, stage);
       launches_++;
     }
     if (cnt == 1 && L.host[L.hptr[h]] == lu_node) {   // the root (of the factored subtree): LU
@@ -3200,8 +3463,20 @@ void HSSEngine::solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaSt
     const int cnt = L.hptr[h + 1] - L.hptr[h];
     if (!cnt) continue;
     const int mm = std::max(L.max_m[h], 1);
-    size_t smem = sizeof(double) * (size_t)(3 * mm + 32 * 33 + 8);
     dim3 grid(cnt, s);
+    if (solve_pipe_ & 2) {      // stream the factor block through shared memory (cp.async, double buffered)
+      const int ldm = (mm + 1) & ~1;
+      const int ldbuf = mm | 1;   // odd: the column-strided reads of the diagonal block are conflict free
+      const size_t psm = sizeof(double) * ((size_t)3 * ldm + (size_t)2 * ldbuf * kFC);
+      if (psm <= kMaxSmem) {
+        set_smem(ulv_fwd_pipe_kernel, psm);
+        ulv_fwd_pipe_kernel<<<grid, kThreads, psm, st>>>(dn_.p, L.list.p + L.hptr[h], vals_.p, perms_.p, fact_.p, dB, ldB,
+                                                         ysol_.p, zsol_.p, fsol_.p, s, ldm, ldbuf);
+        launches_++;
+        continue;
+      }
+    }
+    size_t smem = sizeof(double) * (size_t)(3 * mm + 32 * 33 + 8);
     set_smem(ulv_fwd_kernel<32>, smem);
     ulv_fwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p + L.hptr[h], vals_.p, perms_.p, fact_.p, dB, ldB, ysol_.p, zsol_.p, fsol_.p, s);
     launches_++;
@@ -3226,9 +3501,21 @@ void HSSEngine::solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaSt
     const int cnt = L.hptr[h + 1] - L.hptr[h];
     if (!cnt) continue;
     const int mm = std::max(L.max_m[h], 1);
-    size_t smem = sizeof(double) * (size_t)(mm + 2 * 32 + 8);
     dim3 grid(cnt, s);
     const int* lst = L.list.p + L.hptr[h];
+    if (solve_pipe_ & 1) {
+      const int ldbuf = (mm + 1) & ~1;
+      const int nbw = std::max(hn_[L.host[L.hptr[h]]].nbq, 1);     // panel width of the class
+      const size_t psm = sizeof(double) * ((size_t)ldbuf + 64 + (size_t)2 * nbw * nbw + (size_t)2 * ldbuf * nbw);
+      if (psm <= kMaxSmem) {
+        set_smem(ulv_bwd_pipe_kernel, psm);
+        ulv_bwd_pipe_kernel<<<grid, kThreads, psm, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s,
+                                                         ldbuf, nbw);
+        launches_++;
+        continue;
+      }
+    }
+    size_t smem = sizeof(double) * (size_t)(mm + 2 * 32 + 8);
     set_smem(ulv_bwd_kernel<32>, smem);   // the panel width (<= 32) is a per-node field
     ulv_bwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
     launches_++;

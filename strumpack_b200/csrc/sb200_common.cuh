@@ -75,6 +75,13 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, 
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
+// software pipelines: close a group of copies / wait until at most N groups are pending
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 // Leading dimension for fp64 tiles in shared memory: ld % 16 == 4 makes both
 // "k along rows" and "k along columns" DMMA fragment loads conflict-free per
