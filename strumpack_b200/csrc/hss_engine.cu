@@ -639,8 +639,10 @@ ulv_build_inner_kernel(const DNode* __restrict__ nodes, const int* __restrict__ 
 // warp owns 8-column slabs of the output, A fragments are gathered rows of the
 // tile, B fragments (E^T) stay in registers across the tile's row blocks.
 // HBM-bound: reads D once, writes the m x (k + r) block once.
-template <int TJ>
-__global__ void __launch_bounds__(kThreads, 3)
+// PIPE: the column tiles are prefetched one ahead with cp.async into a second
+// buffer (the loads of tile t+1 overlap the products and stores of tile t).
+template <int TJ, int MINB = 3, bool PIPE = false>
+__global__ void __launch_bounds__(kThreads, MINB)
 ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                      const double* __restrict__ vals, const int* __restrict__ perms,
                      double* __restrict__ fact, const double* __restrict__ scratch,
@@ -658,18 +660,36 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
   constexpr int LD = TJ + 1;
   constexpr int RT = TJ / 8;       // row tiles of the output per column tile
   constexpr int KS = 8;            // k-steps held in registers (r <= 32 per pass)
-  double* Dn = sm;                 // m x LD : Dn[i*LD + jj] = Dsrc[i, j0+jj]
-  int* Ps = reinterpret_cast<int*>(Dn + (size_t)m * LD);   // m
+  double* Dn0 = sm;                // m x LD : Dn[i*LD + jj] = Dsrc[i, j0+jj]  (x 2 buffers if PIPE)
+  int* Ps = reinterpret_cast<int*>(Dn0 + (size_t)m * LD * (PIPE ? 2 : 1));   // m
   for (int i = tid; i < m; i += kThreads) Ps[i] = P[i];
-  for (int j0 = 0; j0 < m; j0 += TJ) {
+  auto issue = [&](int j0, int buf) {
+    const int tj = min(TJ, m - j0);
+    double* D = Dn0 + (size_t)buf * m * LD;
+    for (int jj = warp; jj < TJ; jj += kWarps) {
+      const bool jin = jj < tj;
+      const double* src = Dsrc + (size_t)(jin ? j0 + jj : 0) * m;
+      for (int i = lane; i < m; i += 32) cp_async8(D + i * LD + jj, src + i, jin);
+    }
+    cp_async_commit();
+  };
+  if (PIPE) issue(0, 0);
+  int buf = 0;
+  for (int j0 = 0; j0 < m; j0 += TJ, buf ^= (PIPE ? 1 : 0)) {
     const int tj = min(TJ, m - j0);
     __syncthreads();
-    for (int jj = warp; jj < TJ; jj += kWarps) {
-      const double* src = Dsrc + (size_t)(j0 + jj) * m;
-      const bool jin = jj < tj;
-      for (int i = lane; i < m; i += 32) Dn[i * LD + jj] = jin ? src[i] : 0.;
+    if (PIPE) {
+      if (j0 + TJ < m) { issue(j0 + TJ, buf ^ 1); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+    } else {
+      for (int jj = warp; jj < TJ; jj += kWarps) {
+        const double* src = Dsrc + (size_t)(j0 + jj) * m;
+        const bool jin = jj < tj;
+        for (int i = lane; i < m; i += 32) Dn0[i * LD + jj] = jin ? src[i] : 0.;
+      }
     }
     __syncthreads();
+    const double* Dn = Dn0 + (size_t)buf * m * LD;
     // W1^T[j, l] = Dp[l, j]
     for (int l = warp; l < r; l += kWarps) {
       const double* src = Dn + Ps[l] * LD;
@@ -2662,6 +2682,7 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   if (const char* e = std::getenv("SB200_QR_VARIANT")) qr_variant_ = std::atoi(e);
   if (const char* e = std::getenv("SB200_APPLY_MM_MIN")) mm_min_ = std::max(1, std::atoi(e));   // rhs count from which the GEMM-shaped apply kernels run
   if (const char* e = std::getenv("SB200_QR_NOWIDE")) qr_nowide_ = std::atoi(e);   // 1: 64-bit one-slab trailing update
+  if (const char* e = std::getenv("SB200_ELIM_VARIANT")) elim_variant_ = std::atoi(e);   // see factor_classes
   // cp.async-streamed solve sweeps: bit 0 backward, bit 1 forward (default: both)
   if (const char* e = std::getenv("SB200_SOLVE_PIPE")) solve_pipe_ = std::atoi(e);
   if (qr_split_) qr_variant_ = 0;   // the per-panel launch experiment assumes nb_-wide panels
@@ -3134,7 +3155,15 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       continue;
     }
     // elimination
-    if (mm <= 640) {
+    if (mm <= 640 && elim_variant_ == 1) {          // 16-column tiles, 4 CTAs per SM
+      size_t smem = sizeof(double) * (size_t)mm * 17 + sizeof(int) * (size_t)(mm + 8);
+      set_smem(ulv_eliminate_kernel<16, 4, false>, smem);
+      ulv_eliminate_kernel<16, 4, false><<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
+    } else if (mm <= 640 && elim_variant_ == 2) {   // 16-column tiles, prefetched one ahead (cp.async)
+      size_t smem = sizeof(double) * (size_t)mm * 17 * 2 + sizeof(int) * (size_t)(mm + 8);
+      set_smem(ulv_eliminate_kernel<16, 3, true>, smem);
+      ulv_eliminate_kernel<16, 3, true><<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);
+    } else if (mm <= 640) {
       size_t smem = sizeof(double) * (size_t)mm * 33 + sizeof(int) * (size_t)(mm + 8);
       set_smem(ulv_eliminate_kernel<32>, smem);
       ulv_eliminate_kernel<32><<<cnt, kThreads, smem, st>>>(dn_.p, lst, vals_.p, perms_.p, fact_.p, scratch_.p, so);

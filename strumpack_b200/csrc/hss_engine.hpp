@@ -186,6 +186,7 @@ class HSSEngine {
   DevBuf<int> pf_piv_;
   int nb_ = 32;
   int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0, qr_ll_ = 0, qr_variant_ = 1, qr_nowide_ = 0;   // switches; env SB200_QR_*
+  int elim_variant_ = 0;   // ulv_eliminate_kernel: 0 = 32-column tiles, 1 = 16-column tiles x 4 CTAs/SM, 2 = 16-column tiles prefetched (SB200_ELIM_VARIANT)
   int solve_pipe_ = 3;  // bit 0: ulv_bwd_pipe_kernel, bit 1: ulv_fwd_pipe_kernel (SB200_SOLVE_PIPE; 0 = the non-streamed kernels)
   int mm_min_ = 4;      // >= this many right-hand sides: GEMM-shaped (tensor pipe) apply kernels
   bool profile_ = false;
