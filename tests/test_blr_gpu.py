@@ -283,3 +283,33 @@ def test_blr_strong_admissibility(built):
     assert rel(L.solve(Y), S.solve(Y)) <= 1e-12
     with pytest.raises(RuntimeError):
         sb.BLRMatrix.compress_and_factor(A, o, admissible=np.ones((3, 3)))     # wrong size
+
+
+def test_blr_matches_reference_golden(built):
+    """Against the committed outputs of the reference's BLRMatrix<double> on the
+    same matrix (tests/golden/blr_toeplitz_1024.npz): full factorization + solve
+    and the partially factored front.  Both are approximations at rel_tol: they
+    agree to the compression tolerance (north star: 10 * eps_compress), and the
+    engine's error against the exact answer is no worse than the reference's."""
+    import os
+    from conftest import GOLDEN
+    sb = built
+    g = np.load(os.path.join(GOLDEN, "blr_toeplitz_1024.npz"))
+    rank, nnz, ntiles, n1, leaf = (int(v) for v in g["info"])
+    tol = float(g["tol"][0])
+    n = g["Y"].shape[0]
+    A = toeplitz(n) + 2.0 * np.eye(n)
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    B = sb.BLRMatrix.compress_and_factor(A, o)
+    assert B.tiles == ntiles and abs(B.rank - rank) <= 3
+    assert abs(B.nonzeros - nnz) <= 0.1 * nnz
+    xs = B.solve(g["Y"])
+    x_exact = np.linalg.solve(A, g["Y"])
+    assert rel(xs, g["X"]) <= 10 * tol
+    assert rel(xs, x_exact) <= max(10 * rel(g["X"], x_exact), 1e-12)
+    F, S = sb.BLRMatrix.construct_and_partial_factor(A[:n1, :n1], A[:n1, n1:], A[n1:, :n1], A[n1:, n1:], o)
+    assert rel(S @ g["R"], g["SR"]) <= 10 * tol and rel(S.T @ g["R"], g["STR"]) <= 10 * tol
+    f = F.partial_forward_solve(g["b"])
+    assert rel(f[n1:], g["fwd"][n1:]) <= 10 * tol           # b_upd - A21 A11^{-1} b_sep: pivot independent
+    mid = np.vstack([f[:n1], np.linalg.solve(S, f[n1:])])
+    assert rel(F.partial_backward_solve(mid), g["bwd"]) <= 10 * tol

@@ -112,3 +112,49 @@ def test_schur_restatement_matches_reference_golden(case):
     assert rel(g["Sr"], S @ g["R"]) < 1e-12 and rel(g["Sc"], S.T @ g["R"]) < 1e-12
     assert rel(g["Theta"] @ g["red"], A[n0:, :n0] @ g["x0"]) < 1e-12
     assert rel(g["x0"], np.linalg.solve(A[:n0, :n0], g["b0"])) < 1e-12
+
+
+def _blr_matrix(n):
+    i = np.arange(n)
+    return 1.0 / (1.0 + np.abs(i[:, None] - i[None, :])) + 2.0 * np.eye(n)
+
+
+def test_blr_restatement_matches_reference_golden():
+    """oracle/blr_oracle.py (RRQR tiles, right-looking tile LU, block substitution,
+    partial factorization of a front) against outputs of the reference's
+    BLRMatrix<double> (tests/golden/make_golden_blr.py).  Same algorithm, same
+    LAPACK primitives: agreement to roundoff although both are 1e-6 approximations."""
+    from oracle import blr_oracle as bo
+    g = np.load(os.path.join(GOLDEN, "blr_toeplitz_1024.npz"))
+    rank, nnz, ntiles, n1, leaf = (int(v) for v in g["info"])
+    tol = float(g["tol"][0])
+    A = _blr_matrix(g["Y"].shape[0])
+    F = bo.compress_and_factor(A, leaf, tol)
+    assert F.nb == ntiles and F.rank() == rank
+    assert rel(F.solve(g["Y"]), g["X"]) < 1e-12
+    assert rel(A @ g["X"], g["Y"]) <= 1e2 * tol              # the reference's own bound (test_BLR_seq.cpp:192)
+    P = bo.construct_and_partial_factor(A[:n1, :n1], A[:n1, n1:], A[n1:, :n1], A[n1:, n1:], leaf, tol)
+    S = P.schur()
+    assert rel(S @ g["R"], g["SR"]) < 1e-12 and rel(S.T @ g["R"], g["STR"]) < 1e-12
+    assert P.rank() == int(max(g["ranks"]))
+    f = P.forward(g["b"])
+    assert rel(f, g["fwd"]) < 1e-12
+    mid = np.vstack([f[:n1], np.linalg.solve(S, f[n1:])])
+    assert rel(P.backward(mid), g["bwd"]) < 1e-12
+    S_exact = A[n1:, n1:] - A[n1:, :n1] @ np.linalg.solve(A[:n1, :n1], A[:n1, n1:])
+    assert rel(g["SR"], S_exact @ g["R"]) <= 1e2 * tol
+
+
+@pytest.mark.skipif(not have_ref(), reason="reference library not built")
+def test_blr_restatement_matches_live_reference():
+    from oracle import blr_oracle as bo, ref
+    n, leaf, tol = 600, 64, 1e-4
+    A = _blr_matrix(n)
+    A[64:128, 320:384] += 0.05 * np.random.default_rng(3).standard_normal((64, 64))   # a tile that stays dense
+    R = ref.RefBLR(A, f"--blr_leaf_size {leaf} --blr_rel_tol {tol}")
+    F = bo.compress_and_factor(A, leaf, tol)
+    assert list(R.tiles) == list(np.diff(F.off))
+    assert F.rank() == R.info()["rank"]
+    assert sum(t.nonzeros() for t in F.t.values()) + sum(l[0].size for l in F.lu.values()) == R.info()["nonzeros"]
+    Y = np.random.default_rng(4).standard_normal((n, 2))
+    assert rel(F.solve(Y), R.solve(Y)) < 1e-11
