@@ -33,6 +33,14 @@ def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(built, tmp_path, name)
     assert "no CUDA device" in r.stderr
 
 
+def test_cpp_mirror_options_and_dense_helpers(built, tmp_path):
+    """CPU-only: option defaults / command-line parsing / DenseMatrix helpers of the mirror."""
+    exe = _build(tmp_path, "test_options")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "options ok" in r.stdout
+
+
 @pytest.mark.gpu
 def test_cpp_mirror_toeplitz_ulv(built, tmp_path):
     exe = _build(tmp_path, "test_structured")
