@@ -206,3 +206,16 @@ def test_extract_sub_blocks(sb, case):
     assert abs(H.get(5, 5) - A[5, 5]) <= 1e-13
     with pytest.raises(RuntimeError):
         H.extract([n], [0])
+
+
+def test_ulv_factor_export(sb):
+    """HSSMatrix::ULV() accessor (reference HSSMatrix.hpp:497/511): the factor arena
+    comes back to the host with the advertised size; before factor() it is an error."""
+    H = sb.HSSMatrix.read(os.path.join(GOLDEN, CASES[0] + ".hss"))
+    with pytest.raises(RuntimeError):
+        H.ulv_data()
+    H.factor()
+    f, t = H.ulv_data()
+    assert f.size == H.factor_nonzeros and t.size > 0
+    assert np.all(np.isfinite(f)) and np.all(np.isfinite(t))
+    assert np.count_nonzero(f) > 0.5 * f.size * 0.5 and np.count_nonzero(t) > 0
