@@ -333,9 +333,10 @@ int SB200_d_hss_dist_solve_end(const CSPStructMat S, int nrhs, double* dB,
 int SB200_d_struct_levels(const CSPStructMat S);
 long long int SB200_d_struct_factor_nonzeros(const CSPStructMat S);
 /* Download the ULV factors (reference accessor HSSMatrix::ULV(),
- * HSSMatrix.hpp:497; layout DESIGN.md 3): the factor arena (factor_nonzeros
- * doubles) and the block-reflector T arena; sizes[0..1] receive the two
- * lengths, either pointer may be NULL to query sizes only. */
+ * HSSMatrix.hpp:497; layout DESIGN.md 3): the arena of factor blocks and the
+ * block-reflector T arena; sizes[0..1] receive the two lengths (their sum is
+ * SB200_d_struct_factor_nonzeros), either pointer may be NULL to query sizes
+ * only. */
 int SB200_d_struct_ulv_data(const CSPStructMat S, double* factors, double* tfactors,
                             long long int* sizes);
 /* Algorithmic flop counts in the reference's own accounting:

@@ -2759,6 +2759,7 @@ void HSSEngine::build_tables() {
   }
   ws_total_ = woff;
   tot_k_ = yoff; tot_rv_ = zoff; tot_ru_ = fo; tot_m_ = xo;
+  fact_len_ = foff;
   fact_nnz_ = foff + toff;
   dn_.upload(hn_.data(), hn_.size());
   vals_.upload(H_.vals.data(), H_.vals.size());
@@ -3043,7 +3044,7 @@ void HSSEngine::sync_host_values() {
 
 void HSSEngine::export_ulv(double* factors, double* tfactors, long long* sizes) {
   if (!factored_) throw std::logic_error("ULV factors requested before factor()");
-  const long long nf = fact_nnz_, nt = (long long)nb_ * tot_k_;
+  const long long nf = fact_len_, nt = (long long)nb_ * tot_k_;
   if (sizes) { sizes[0] = nf; sizes[1] = nt; }
   SB200_CUDA(cudaDeviceSynchronize());
   if (factors) SB200_CUDA(cudaMemcpy(factors, fact_.p, nf * sizeof(double), cudaMemcpyDeviceToHost));
@@ -3111,8 +3112,10 @@ void HSSEngine::factor_prepare(bool whole) {
       if (n.leaf() && n.rows != n.cols)
         throw std::invalid_argument("ULV factorization needs square diagonal blocks");
   }
-  fact_.ensure((size_t)std::max<long long>(fact_nnz_, 1));
-  tfac_.ensure((size_t)std::max<long long>((long long)nb_ * tot_k_, 1));
+  // zero-filled on allocation: the alignment padding between blocks is never written
+  const size_t nf = (size_t)std::max<long long>(fact_len_, 1), nt = (size_t)std::max<long long>((long long)nb_ * tot_k_, 1);
+  if (fact_.n < nf) { fact_.alloc(nf); SB200_CUDA(cudaMemset(fact_.p, 0, nf * sizeof(double))); }
+  if (tfac_.n < nt) { tfac_.alloc(nt); SB200_CUDA(cudaMemset(tfac_.p, 0, nt * sizeof(double))); }
   rootpiv_.ensure(std::max(hn_[0].m, 1));
   scratch_.ensure((size_t)std::max<long long>(std::max(std::max(own_.smax, top_.smax), sub0_.smax), 1));
 }

@@ -174,7 +174,7 @@ class HSSEngine {
   DevBuf<double> ysol_, zsol_, fsol_, xsol_;
   int solve_s_ = 0, fwd_s_ = 0;
   long long tot_k_ = 0, tot_rv_ = 0, tot_ru_ = 0, tot_m_ = 0;
-  long long fact_nnz_ = 0;
+  long long fact_nnz_ = 0, fact_len_ = 0;   // factor blocks + T factors; factor blocks alone
   long long scratch_per_node_max_ = 0;
   bool factored_ = false;
   long long launches_ = 0;

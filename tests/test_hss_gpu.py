@@ -216,6 +216,6 @@ def test_ulv_factor_export(sb):
         H.ulv_data()
     H.factor()
     f, t = H.ulv_data()
-    assert f.size == H.factor_nonzeros and t.size > 0
+    assert f.size + t.size == H.factor_nonzeros and t.size > 0
     assert np.all(np.isfinite(f)) and np.all(np.isfinite(t))
-    assert np.count_nonzero(f) > 0.5 * f.size * 0.5 and np.count_nonzero(t) > 0
+    assert np.count_nonzero(f) > 0.25 * f.size and np.count_nonzero(t) > 0
