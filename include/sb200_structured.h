@@ -296,6 +296,15 @@ int SB200_d_hss_schur_product_indirect(const CSPStructMat S, const double* DUB01
                                        const double* R0, int ldR0, const double* R1, int ldR1,
                                        const double* Sr1, int ldSr1, const double* Sc1, int ldSc1,
                                        double* Sr, int ldSr, double* Sc, int ldSc);
+/* device-resident forms (device pointers, queued on `stream`, not synchronised;
+ * leading dimensions >= 1 also for empty matrices) */
+int SB200_d_hss_partial_factor_device(CSPStructMat S, void* stream);
+int SB200_d_hss_schur_update_device(const CSPStructMat S, double* dTheta, int ldT, double* dDUB01,
+                                    int ldD, double* dPhi, int ldP, void* stream);
+int SB200_d_hss_schur_product_direct_device(const CSPStructMat S, const double* dTheta, int ldT,
+                                            const double* dDUB01, int ldD, const double* dPhi,
+                                            int ldP, int c, const double* dR, int ldR, double* dSr,
+                                            int ldSr, double* dSc, int ldSc, void* stream);
 int SB200_d_hss_partial_forward_solve(const CSPStructMat S, int nrhs, const double* B0, int ldB,
                                       double* reduced_rhs, int ldR);
 int SB200_d_hss_partial_x(const CSPStructMat S, int nrhs, double* X, int ldX, int set);

@@ -116,6 +116,10 @@ SYMBOLS = {
                                              _vp, _i, _vp, _i]),
     "SB200_d_hss_schur_product_indirect": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i,
                                                _vp, _i, _vp, _i, _vp, _i]),
+    "SB200_d_hss_partial_factor_device": (_i, [_vp, _vp]),
+    "SB200_d_hss_schur_update_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "SB200_d_hss_schur_product_direct_device": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i,
+                                                    _vp, _i, _vp, _i, _vp]),
     "SB200_d_hss_partial_forward_solve": (_i, [_vp, _i, _vp, _i, _vp, _i]),
     "SB200_d_hss_partial_x": (_i, [_vp, _i, _vp, _i, _i]),
     "SB200_d_hss_partial_backward_solve": (_i, [_vp, _i, _vp, _i]),
@@ -571,6 +575,28 @@ class HSSMatrix(StructuredMatrix):
             self._h, Theta.ctypes.data, max(z["rows1"], 1), DUB01.ctypes.data, max(z["m0"], 1),
             Phi.ctypes.data, max(z["cols1"], 1)), "Schur_update")
         return Theta, DUB01, Phi
+
+    def schur_device(self, RT):
+        """Device-resident path: partial_factor + Schur_update + Schur_product_direct with
+        torch CUDA tensors on the current stream.  RT: (c, rows1) contiguous float64
+        tensor (= column-major rows1 x c).  Returns (SrT, ScT) of the same shape."""
+        import torch
+        z = self.schur_sizes()
+        dev = RT.device
+        c = RT.shape[0]
+        mk = lambda r, q: torch.empty((max(q, 1), max(r, 1)), dtype=torch.float64, device=dev)
+        Th, Du, Ph = mk(z["rows1"], z["rv0"]), mk(z["m0"], z["rv1"]), mk(z["cols1"], z["m0"])
+        SrT, ScT = torch.empty_like(RT), torch.empty_like(RT)
+        st = self._stream()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _check(lib().SB200_d_hss_partial_factor_device(self._h, st), "partial_factor_device")
+        _check(lib().SB200_d_hss_schur_update_device(
+            self._h, p(Th), max(z["rows1"], 1), p(Du), max(z["m0"], 1), p(Ph), max(z["cols1"], 1), st),
+            "schur_update_device")
+        _check(lib().SB200_d_hss_schur_product_direct_device(
+            self._h, p(Th), max(z["rows1"], 1), p(Du), max(z["m0"], 1), p(Ph), max(z["cols1"], 1), c,
+            p(RT), z["rows1"], p(SrT), z["rows1"], p(ScT), z["cols1"], st), "schur_product_direct_device")
+        return SrT, ScT
 
     def vhat(self):
         """child(0)->ULV().Vhat() (reference HSSExtra.hpp:197-212)."""

@@ -531,6 +531,29 @@ int SB200_d_hss_partial_factor(CSPStructMat S) {
   });
 }
 
+/* device-resident variants: every matrix argument is a DEVICE pointer, the work
+ * is queued on `stream` and not synchronised */
+int SB200_d_hss_partial_factor_device(CSPStructMat S, void* stream) {
+  return guarded([&] { hss(S).partial_factor(static_cast<cudaStream_t>(stream)); });
+}
+
+int SB200_d_hss_schur_update_device(const CSPStructMat S, double* dTheta, int ldT, double* dDUB01,
+                                    int ldD, double* dPhi, int ldP, void* stream) {
+  return guarded([&] {
+    hss(S).schur_update(dTheta, ldT, dDUB01, ldD, dPhi, ldP, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int SB200_d_hss_schur_product_direct_device(const CSPStructMat S, const double* dTheta, int ldT,
+                                            const double* dDUB01, int ldD, const double* dPhi,
+                                            int ldP, int c, const double* dR, int ldR, double* dSr,
+                                            int ldSr, double* dSc, int ldSc, void* stream) {
+  return guarded([&] {
+    hss(S).schur_product_direct(dTheta, ldT, dDUB01, ldD, dPhi, ldP, c, dR, ldR, dSr, ldSr, dSc, ldSc,
+                                static_cast<cudaStream_t>(stream));
+  });
+}
+
 int SB200_d_hss_schur_sizes(const CSPStructMat S, int* out) {
   return guarded([&] { hss(S).schur_sizes(out); });
 }

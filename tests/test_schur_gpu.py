@@ -177,3 +177,16 @@ def test_schur_live_reference_two_level(sb):
     red = H.partial_forward_solve(b0)
     assert rel(red, Href.partial_forward_solve(b0, Vhat.shape[1])) < 1e-11
     assert rel(H.partial_backward_solve(), Href.partial_backward_solve()) < 1e-11
+
+
+def test_schur_device_resident(sb):
+    """The device-pointer forms (SB200_d_hss_*_device) on torch's current stream."""
+    import torch
+    case = CASES[2]
+    g = np.load(os.path.join(GOLDEN, case + "_schur.npz"))
+    H = sb.HSSMatrix.read(os.path.join(GOLDEN, case + ".hss"))
+    RT = torch.tensor(np.ascontiguousarray(g["R"].T), device="cuda")
+    SrT, ScT = H.schur_device(RT)
+    torch.cuda.synchronize()
+    assert rel(SrT.cpu().numpy().T, g["Sr"]) < 1e-11
+    assert rel(ScT.cpu().numpy().T, g["Sc"]) < 1e-11
