@@ -2043,13 +2043,15 @@ __global__ void copy_block_kernel(const double* __restrict__ src, double* __rest
 //                                ULV SOLVE
 // ===========================================================================
 // Forward sweep over one height class (root excluded)   solve.hpp:69-197
+// pf: prefetch the next column block (and E, and at the end the extra columns)
+// into L2 while the current one is processed (experiment, SB200_SOLVE_PIPE bit 3)
 template <int NB>
 __global__ void __launch_bounds__(kThreads)
 ulv_fwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                const double* __restrict__ vals, const int* __restrict__ perms,
                const double* __restrict__ fact, const double* __restrict__ b, int ldb,
                double* __restrict__ ysol, double* __restrict__ zsol,
-               double* __restrict__ fsol, int s) {
+               double* __restrict__ fsol, int s, int pf = 0) {
   extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0) return;
@@ -2059,6 +2061,19 @@ ulv_fwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   double* fp = f + m;        // m   (P^T f) ; fp[0:r] = ft1, then y in fp[r:]
   double* zc = fp + m;       // v_rows (children z concat) for inner nodes
   double* Rd = zc + max(nd.v_rows, 1);  // 32 x 33 diagonal block
+  // lines [0, rows) of columns [c0, c0 + nc) of the factor block -> L2
+  auto pf_cols = [&](int c0, int nc, int rows) {
+    const double* Ab = fact + nd.F;
+    for (int a = warp; a < nc; a += kWarps) {
+      const double* src = Ab + (size_t)(c0 + a) * m;
+      for (int i = lane * 16; i < rows; i += 32 * 16) prefetch_l2(src + i);
+    }
+  };
+  if (pf && k > 0) {
+    const double* E = vals + nd.Eu;
+    for (long long i = (long long)tid * 16; i < (long long)k * r; i += kThreads * 16) prefetch_l2(E + i);
+    pf_cols(0, min(32, k), min(32, k));
+  }
   // ---- gather f
   if (nd.leaf) {
     const double* bb = b + nd.row_off + (size_t)col * ldb;
@@ -2100,6 +2115,10 @@ ulv_fwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
     // y = R^{-T} rhs, blocked by 32 columns (L = R^T, solve.hpp:160-161)
     for (int i0 = 0; i0 < k; i0 += 32) {
       const int ib = min(32, k - i0);
+      if (pf) {
+        if (i0 + 32 < k) pf_cols(i0 + 32, min(32, k - i0 - 32), min(k, i0 + 64));
+        if (i0 + 64 >= k) pf_cols(k + (i0 + 32 >= k ? (rv + r) / 2 : 0), (rv + r + 1) / 2, k);   // the extra columns, in two halves
+      }
       for (int c = warp; c < ib; c += kWarps) {
         const double* Rc = A + (size_t)(i0 + c) * m;
         double acc = 0.;
@@ -2225,7 +2244,7 @@ __global__ void __launch_bounds__(kThreads)
 ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
                const double* __restrict__ fact, const double* __restrict__ tfac,
                double* __restrict__ b, int ldb, const double* __restrict__ ysol,
-               double* __restrict__ xsol, int s) {
+               double* __restrict__ xsol, int s, int pf = 0) {
   extern __shared__ __align__(16) double sm[];
   const int id = list[blockIdx.x];
   const DNode nd = nodes[id];
@@ -2245,8 +2264,19 @@ ulv_bwd_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   const double* Tg = tfac + nd.T;
   const int nbq = nd.nbq;          // panel width the node was factored with (<= NB)
   const int nblk = (k + nbq - 1) / nbq;
+  // pf: pull the reflector block that comes next (and its T) into L2 while this one is applied
+  auto pf_block = [&](int pb) {
+    const int pj0 = pb * nbq, pjb = min(nbq, k - pj0);
+    for (int a = warp; a < pjb; a += kWarps) {
+      const double* src = A + pj0 + (size_t)(pj0 + a) * m;
+      for (int i = lane * 16; i < m - pj0; i += 32 * 16) prefetch_l2(src + i);
+    }
+    if (tid < pjb) prefetch_l2(Tg + (size_t)(pj0 + tid) * nbq);
+  };
+  if (pf && nblk > 1) pf_block(nblk - 2);
   for (int bi = nblk - 1; bi >= 0; bi--) {
     const int j0 = bi * nbq, jb = min(nbq, k - j0);
+    if (pf && bi > 1) pf_block(bi - 2);
     for (int a = warp; a < jb; a += kWarps) {
       const double* Va = A + (size_t)(j0 + a) * m;
       double acc = 0.;
@@ -2683,7 +2713,8 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   if (const char* e = std::getenv("SB200_APPLY_MM_MIN")) mm_min_ = std::max(1, std::atoi(e));   // rhs count from which the GEMM-shaped apply kernels run
   if (const char* e = std::getenv("SB200_QR_NOWIDE")) qr_nowide_ = std::atoi(e);   // 1: 64-bit one-slab trailing update
   if (const char* e = std::getenv("SB200_ELIM_VARIANT")) elim_variant_ = std::atoi(e);   // see factor_classes
-  // cp.async-streamed solve sweeps: bit 0 backward, bit 1 forward (default: both)
+  // cp.async-streamed solve sweeps: bit 0 backward, bit 1 forward (default: both);
+  // bits 2 / 3 (with bit 0 / 1 clear): the non-streamed kernels with L2 prefetch of the next block
   if (const char* e = std::getenv("SB200_SOLVE_PIPE")) solve_pipe_ = std::atoi(e);
   if (qr_split_) qr_variant_ = 0;   // the per-panel launch experiment assumes nb_-wide panels
   build_tables();
@@ -3510,7 +3541,7 @@ void HSSEngine::solve_fwd(const NodeLists& L, int s, double* dB, int ldB, cudaSt
     }
     size_t smem = sizeof(double) * (size_t)(3 * mm + 32 * 33 + 8);
     set_smem(ulv_fwd_kernel<32>, smem);
-    ulv_fwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p + L.hptr[h], vals_.p, perms_.p, fact_.p, dB, ldB, ysol_.p, zsol_.p, fsol_.p, s);
+    ulv_fwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, L.list.p + L.hptr[h], vals_.p, perms_.p, fact_.p, dB, ldB, ysol_.p, zsol_.p, fsol_.p, s, (solve_pipe_ & 8) ? 1 : 0);
     launches_++;
   }
 }
@@ -3549,7 +3580,7 @@ void HSSEngine::solve_bwd(const NodeLists& L, int s, double* dB, int ldB, cudaSt
     }
     size_t smem = sizeof(double) * (size_t)(mm + 2 * 32 + 8);
     set_smem(ulv_bwd_kernel<32>, smem);   // the panel width (<= 32) is a per-node field
-    ulv_bwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s);
+    ulv_bwd_kernel<32><<<grid, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, dB, ldB, ysol_.p, xsol_.p, s, (solve_pipe_ & 4) ? 1 : 0);
     launches_++;
   }
 }

@@ -83,6 +83,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// pull one 128-byte line into L2 ahead of a dependent load
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
 // Leading dimension for fp64 tiles in shared memory: ld % 16 == 4 makes both
 // "k along rows" and "k along columns" DMMA fragment loads conflict-free per
 // half-warp (an LDS.64 is two 128-byte wavefronts at best).
