@@ -314,6 +314,7 @@ class _SolveState:
         # as the GPU engine does, because Q, W1, y of a remote child are not
         # available to the parent)
         self.folded = set()
+        self.root = 0    # the node that is LU-solved (child 0 of the root in a partial solve)
 
     def fwd_node(self, i):
         """solve_fwd at one node (HSSMatrix.solve.hpp:69-197)."""
@@ -333,7 +334,7 @@ class _SolveState:
                     Q0 = f.Q[c][:cn.U_rows - cn.U_rank, :]
                     fc -= f.W1[c] @ (Q0.conj().T @ y[c])
             fv = np.vstack([f0, f1])
-        if i == 0:
+        if i == self.root:
             self.xs[i] = sla.lu_solve(f.lu, fv)              # :133-135
             return
         g = ipiv_to_gather(nd.Pu)
@@ -362,7 +363,7 @@ class _SolveState:
         sharded run only touches Q/y of nodes it owns."""
         nodes, f = self.nodes, self.f
         nd = nodes[i]
-        if i != 0:
+        if i != self.root:
             if nd.U_rows > nd.U_rank:
                 self.xs[i] = f.Q[i].conj().T @ np.vstack([self.y[i], self.xc[i]])
             else:
@@ -387,6 +388,35 @@ def solve(nodes, f, b):
     for i in range(len(nodes)):
         st.bwd_node(i)
     return st.x
+
+
+def partial_forward_solve(nodes, f, b0):
+    """child(0)->forward_solve(w, b0, partial=true) after partial_factor
+    (HSSMatrix.solve.hpp:52-60, :133-152; FrontHSS.cpp:452-462): returns the
+    solve state (w) and reduced_rhs = Vhat^H x + V^H [z0; z1]."""
+    b0 = np.asarray(b0, dtype=np.float64)
+    if b0.ndim == 1:
+        b0 = b0[:, None]
+    c0 = nodes[0].ch[0]
+    n0 = nodes[c0]
+    b = np.zeros((nodes[0].rows, b0.shape[1]))
+    b[:n0.rows, :] = b0
+    st = _SolveState(nodes, f, b)
+    st.root = c0
+    for i in reversed(_subtree(nodes, c0)):
+        st.fwd_node(i)
+    red = f.Vhat.conj().T @ st.xs[c0]
+    if not n0.leaf:
+        red = red + basis_applyC(n0.Pv, n0.Ev, np.vstack([st.z[n0.ch[0]], st.z[n0.ch[1]]]))
+    return st, red
+
+
+def partial_backward_solve(nodes, st):
+    """child(0)->backward_solve(w, x0) (HSSMatrix.solve.hpp:62-66, :199-238);
+    st.xs[st.root] may have been updated in between (FrontHSS.cpp:487-495)."""
+    for i in _subtree(nodes, st.root):
+        st.bwd_node(i)
+    return st.x[:nodes[st.root].rows, :]
 
 
 def to_dense(nodes):

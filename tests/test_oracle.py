@@ -110,6 +110,13 @@ def test_schur_restatement_matches_reference_golden(case):
     S = A[n0:, n0:] - A[n0:, :n0] @ np.linalg.solve(A[:n0, :n0], A[:n0, n0:])
     assert rel(A[n0:, n0:] - Theta @ f.Vhat.T @ Phi.T, S) < 1e-12
     assert rel(g["Sr"], S @ g["R"]) < 1e-12 and rel(g["Sc"], S.T @ g["R"]) < 1e-12
+    # partial forward / backward solves of child(0), with the update in between
+    st, red = ho.partial_forward_solve(nodes, f, g["b0"])
+    assert rel(red, g["red"]) < 1e-12
+    assert rel(ho.partial_backward_solve(nodes, st), g["x0"]) < 1e-12
+    st, _ = ho.partial_forward_solve(nodes, f, g["b0"])
+    st.xs[st.root] = st.xs[st.root] - Phi.T @ g["yupd"]
+    assert rel(ho.partial_backward_solve(nodes, st), g["x0u"]) < 1e-12
     assert rel(g["Theta"] @ g["red"], A[n0:, :n0] @ g["x0"]) < 1e-12
     assert rel(g["x0"], np.linalg.solve(A[:n0, :n0], g["b0"])) < 1e-12
 
