@@ -127,6 +127,21 @@ int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
                             int kernel_type, double h, double lambda,
                             const CSPOptions* opts, int* perm);
 
+/* HSSMatrix::compress(Amult, Aelem, opts) (reference src/HSS/HSSMatrix.cpp:173-186;
+ * what FrontHSS calls, src/sparse/fronts/FrontHSS.cpp:385): construction from a
+ * callback that fills whole sub-blocks, the reference's elem_t
+ * (std::function<void(I, J, B)>, HSSMatrix.hpp:68-70): elem must write
+ * B[a + b*ldB] = A(I[a], J[b]) for the 0-based index lists I (nI) and J (nJ).
+ * The engine's compressor is a sampled interpolative decomposition: it asks
+ * only for the O(n * samples) entries it needs (no Amult, no n^2 buffer; for
+ * n <= 8192 the whole complement of every node is used and the ID is exact to
+ * the tolerance).  The callback runs on the host, the factorizations of the
+ * sampled blocks on the device. */
+typedef void (*SB200ElemBlockFn)(int nI, const int* I, int nJ, const int* J, double* B, int ldB,
+                                 void* user);
+int SB200_d_hss_from_element_blocks(CSPStructMat* S, int n, SB200ElemBlockFn elem, void* user,
+                                    const CSPOptions* opts);
+
 /* BLRMatrix<double>::compress_and_factor(A, weak admissibility, opts)
  * (reference src/BLR/BLRMatrix.cpp:113-241, RL variant; tiles from
  * ClusterTree(n).refine(leaf_size) as in test/test_BLR_seq.cpp:136-145;

@@ -20,6 +20,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iostream>
 #include <memory>
 #include <random>
@@ -361,6 +362,11 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
   explicit HSSMatrix(CSPStructMat h) : base(h) {}
   // HSSMatrix(const DenseM_t& A, const opts_t& opts)          (HSSMatrix.cpp:49-54)
   HSSMatrix(const DenseM_t& A, const opts_t& opts) { compress(A, opts); }
+  // HSSMatrix(m, n, opts): an uncompressed m x n matrix, to be filled by compress(...)
+  //                                                             (HSSMatrix.cpp:56-58)
+  HSSMatrix(std::size_t m, std::size_t n, const opts_t& /*opts*/) : m0_(m), n0_(n) {}
+  std::size_t rows() const override { return this->h_ ? base::rows() : m0_; }
+  std::size_t cols() const override { return this->h_ ? base::cols() : n0_; }
   HSSMatrix(HSSMatrix&& o) noexcept = default;
   HSSMatrix& operator=(HSSMatrix&& o) noexcept = default;
   // HSSMatrix(kernel::Kernel&, opts) (HSSMatrix.cpp:88-106): the d x n points
@@ -379,6 +385,23 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
     CSPStructMat s = nullptr;
     if (SP_d_struct_from_dense(&s, int(A.rows()), int(A.cols()), A.data(), int(A.ld()), o.c()))
       throw std::invalid_argument("HSSMatrix::compress failed");
+    SP_d_struct_destroy(&this->h_);
+    this->h_ = s;
+  }
+  // HSSMatrix::compress(Amult, Aelem, opts) (HSSMatrix.cpp:173-186).  The
+  // engine's sampled interpolative decomposition needs element access only:
+  // Amult is accepted for source compatibility and not called.
+  using elem_t = std::function<void(const std::vector<std::size_t>& I, const std::vector<std::size_t>& J, DenseM_t& B)>;
+  using mult_t = std::function<void(DenseM_t& Rr, DenseM_t& Rc, DenseM_t& Sr, DenseM_t& Sc)>;
+  void compress(const mult_t& Amult, const elem_t& Aelem, const opts_t& opts) {
+    if (rows() != cols() || rows() == 0) throw std::invalid_argument("HSSMatrix::compress: square matrices only");
+    compress(Amult, Aelem, rows(), opts);
+  }
+  void compress(const mult_t& /*Amult*/, const elem_t& Aelem, std::size_t n, const opts_t& opts) {
+    opts_t o(opts);
+    CSPStructMat s = nullptr;
+    if (SB200_d_hss_from_element_blocks(&s, int(n), &elem_trampoline, const_cast<elem_t*>(&Aelem), o.c()))
+      throw std::invalid_argument("HSSMatrix::compress(Amult, Aelem) failed");
     SP_d_struct_destroy(&this->h_);
     this->h_ = s;
   }
@@ -498,6 +521,12 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
   }
 
  private:
+  std::size_t m0_ = 0, n0_ = 0;     // dimensions before compression
+  static void elem_trampoline(int nI, const int* I, int nJ, const int* J, double* B, int ldB, void* user) {
+    std::vector<std::size_t> Iv(I, I + nI), Jv(J, J + nJ);
+    DenseMatrixWrapper<scalar_t> Bw(nI, nJ, B, ldB);
+    (*static_cast<const elem_t*>(user))(Iv, Jv, Bw);
+  }
   void extract_impl(const std::vector<std::size_t>& I, const std::vector<std::size_t>& J, DenseM_t& B,
                     int add) const {
     if (I.empty() || J.empty()) return;

@@ -82,6 +82,7 @@ SYMBOLS = {
     "SP_s_struct_factor": (_i, [_vp]),
     "SP_s_struct_solve": (_i, [_vp, _i, _vp, _i]),
     "SP_s_struct_shift": (_i, [_vp, C.c_float]),
+    "SB200_d_hss_from_element_blocks": (_i, [_pvp, _i, _vp, _vp, _po]),
     "SB200_d_hss_from_kernel": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp]),
     "SB200_d_blr_compress_and_factor": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),
@@ -684,6 +685,25 @@ class HSSMatrix(StructuredMatrix):
         _check(lib().SB200_d_hss_from_generators(
             C.byref(h), len(nodes), tab.ctypes.data, vals.ctypes.data,
             vals.size, perms.ctypes.data, perms.size), "from_generators")
+        return cls(h.value)
+
+    @classmethod
+    def from_element_blocks(cls, n, fn, opts=None):
+        """HSSMatrix::compress(Amult, Aelem, opts) with the reference's block
+        extraction callback (HSSMatrix.hpp:68-70): ``fn(I, J)`` returns the dense
+        sub-block A[I, J] for integer index arrays."""
+        opts = opts or default_options()
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+        def tramp(nI, I, nJ, J, B, ldB, user):
+            Ia = np.ctypeslib.as_array(I, shape=(nI,))
+            Ja = np.ctypeslib.as_array(J, shape=(nJ,))
+            out = np.ctypeslib.as_array(B, shape=(nJ, ldB))      # column-major nI x nJ with ld ldB
+            out[:, :nI] = np.asarray(fn(Ia, Ja), dtype=np.float64).T
+        cb = C.CFUNCTYPE(None, C.c_int, ip, C.c_int, ip, dp, C.c_int, C.c_void_p)(tramp)
+        h = C.c_void_p()
+        _check(lib().SB200_d_hss_from_element_blocks(C.byref(h), int(n), C.cast(cb, C.c_void_p), None,
+                                                     C.byref(opts)), "from_element_blocks")
         return cls(h.value)
 
     @classmethod

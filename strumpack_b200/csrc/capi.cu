@@ -194,6 +194,21 @@ int SP_d_struct_from_elements(CSPStructMat* S, int rows, int cols,
   });
 }
 
+int SB200_d_hss_from_element_blocks(CSPStructMat* S, int n, SB200ElemBlockFn elem, void* user,
+                                    const CSPOptions* opts) {
+  return guarded([&] {
+    require_gpu();
+    auto m = std::make_unique<Mat>();
+    m->type = SP_TYPE_HSS;
+    CompressOptions co;
+    co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
+    co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
+    co.verbose = opts->verbose;
+    m->hss = std::make_unique<HSSEngine>(compress_element_blocks(n, elem, user, co));
+    *S = m.release();
+  });
+}
+
 int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
                             int kernel_type, double h, double lambda,
                             const CSPOptions* opts, int* perm) {

@@ -160,6 +160,9 @@ struct Problem {
   std::vector<double> pts;     // d x n in permuted ordering (may be 1-D indices)
   double h = 1, lambda = 0;
   const double* hostA = nullptr; long long lda = 0;   // dense input (host)
+  // type 4: entries come from a host callback that fills whole sub-blocks
+  // A(I, J) (the reference's elem_t of compress(Amult, Aelem, opts))
+  BlockElemFn elem_fn = nullptr; void* elem_user = nullptr;
   bool symmetric = false;
   bool full_complement = false;
 };
@@ -191,7 +194,7 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
   // (thousands of far columns with the same small residual add up; without the
   // weights slowly decaying kernels such as 1/(1+|i-j|) lose 2-3 digits at large N)
   std::vector<std::vector<double>> mass(N);
-  bool weighted = o.weighted_samples < 0 ? (P.type == 2 || P.type == 3) : o.weighted_samples != 0;
+  bool weighted = o.weighted_samples < 0 ? (P.type == 2 || P.type == 3 || P.type == 4) : o.weighted_samples != 0;
   if (const char* e = std::getenv("SB200_COMPRESS_WEIGHTED")) weighted = std::atoi(e) != 0;
   weighted = weighted && !P.full_complement;
   std::mt19937 rng(12345);
@@ -343,7 +346,9 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
   DevBuf<double> dpts, dA;
   ElemSrc src{};
   src.type = P.type; src.d = d; src.h = P.h; src.lambda = P.lambda;
-  if (P.type == 3) {
+  if (P.type == 4) {
+    if (!P.elem_fn) throw std::invalid_argument("compress: no element callback");
+  } else if (P.type == 3) {
     dA.alloc((size_t)n * n);
     SB200_CUDA(cudaMemcpy2D(dA.p, sizeof(double) * n, P.hostA, sizeof(double) * P.lda,
                             sizeof(double) * n, n, cudaMemcpyHostToDevice));
@@ -393,7 +398,7 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
       std::vector<IDTask> it(cnt);
       size_t oI = 0, oJ = 0, oM = 0, oR = 0, oE = 0;
       int max_nc = 1;
-      std::vector<size_t> offI(cnt), offE(cnt);
+      std::vector<size_t> offI(cnt), offE(cnt), offJ(cnt), offM(cnt);
       for (int q = 0; q < cnt; q++) {
         const int t = nodes[q];
         const int nc = (int)I[q].size(), ns = (int)J[t].size();
@@ -406,7 +411,7 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
         if (which == 0) bt[q] = {dI.p + oI, dJ.p + oJ, nc, ns, dM.p + oM, ns, 1, nullptr, wq};
         else            bt[q] = {dJ.p + oJ, dI.p + oI, ns, nc, dM.p + oM, ns, 0, wq, nullptr};
         it[q] = {dM.p + oM, dR.p + oR, ns, nc, rcap[q], dOrder.p + oI, dRank.p + q, dE.p + oE, 0};
-        offI[q] = oI; offE[q] = oE;
+        offI[q] = oI; offE[q] = oE; offJ[q] = oJ; offM[q] = oM;
         oI += nc; oJ += ns; oM += (size_t)ns * nc; oR += (size_t)rcap[q] * nc;
         oE += (size_t)nc * rcap[q];
         max_nc = std::max(max_nc, nc);
@@ -416,7 +421,33 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
       if (weighted) dW.upload(hW.data(), totJ);
       DevBuf<BlockTask> dbt; dbt.upload(bt.data(), cnt);
       DevBuf<IDTask> dit; dit.upload(it.data(), cnt);
-      eval_blocks_kernel<<<dim3(cnt, 16), kThreads>>>(src, dbt.p);
+      if (P.type == 4) {
+        // host callback: the sampled blocks are filled on the host (same layout
+        // and weights as eval_blocks_kernel writes) and uploaded in one copy
+        std::vector<double> stage(totM), blk;
+        for (int q = 0; q < cnt; q++) {
+          const int t = nodes[q];
+          const int nc = (int)I[q].size(), ns = (int)J[t].size();
+          if (!nc || !ns) continue;
+          const int* Iq = hI.data() + offI[q];
+          const int* Jq = hJ.data() + offJ[q];
+          const double* wq = weighted ? hW.data() + offJ[q] : nullptr;
+          double* out = stage.data() + offM[q];            // ns x nc, ld = ns
+          blk.assign((size_t)nc * ns, 0.);
+          if (which == 0) {   // out[s + i*ns] = A(I[i], J[s]) w[s]
+            P.elem_fn(nc, Iq, ns, Jq, blk.data(), nc, P.elem_user);
+            for (int i = 0; i < nc; i++)
+              for (int a = 0; a < ns; a++) out[a + (size_t)i * ns] = blk[i + (size_t)a * nc] * (wq ? wq[a] : 1.);
+          } else {            // out[s + i*ns] = A(J[s], I[i]) w[s]
+            P.elem_fn(ns, Jq, nc, Iq, blk.data(), ns, P.elem_user);
+            for (int i = 0; i < nc; i++)
+              for (int a = 0; a < ns; a++) out[a + (size_t)i * ns] = blk[a + (size_t)i * ns] * (wq ? wq[a] : 1.);
+          }
+        }
+        if (totM) SB200_CUDA(cudaMemcpy(dM.p, stage.data(), sizeof(double) * totM, cudaMemcpyHostToDevice));
+      } else {
+        eval_blocks_kernel<<<dim3(cnt, 16), kThreads>>>(src, dbt.p);
+      }
       size_t smem = (sizeof(double) + sizeof(int)) * (size_t)max_nc + 16;
       if (smem > 48 * 1024)
         SB200_CUDA(cudaFuncSetAttribute(id_cpqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -500,12 +531,14 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
     DevBuf<double> dout(total ? total : 1);
     bt.resize(pend.size());
     size_t oi = 0, oo = 0;
+    std::vector<size_t> offO(pend.size());
     const int64_t base = (int64_t)Hh.vals.size();
     for (size_t q = 0; q < pend.size(); q++) {
       const int nr = (int)rowsL[q].size(), nc = (int)colsL[q].size();
       std::copy(rowsL[q].begin(), rowsL[q].end(), hidx.begin() + oi);
       std::copy(colsL[q].begin(), colsL[q].end(), hidx.begin() + oi + nr);
       bt[q] = {didx.p + oi, didx.p + oi + nr, nr, nc, dout.p + oo, std::max(nr, 1), 0};
+      offO[q] = oo;
       auto& hn = Hh.nodes[pend[q].node];
       int64_t off = (size_t)nr * nc ? base + (int64_t)oo : -1;
       if (pend[q].which == 0) hn.off_D = off;
@@ -513,13 +546,22 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
       else hn.off_B10 = off;
       oi += nr + nc; oo += (size_t)nr * nc;
     }
-    didx.upload(hidx.data(), nidx);
-    DevBuf<BlockTask> dbt; dbt.upload(bt.data(), bt.size());
-    if (!bt.empty()) eval_blocks_kernel<<<dim3((unsigned)bt.size(), 8), kThreads>>>(src, dbt.p);
-    SB200_CUDA(cudaGetLastError());
-    Hh.vals.resize(base + total);
-    SB200_CUDA(cudaMemcpy(Hh.vals.data() + base, dout.p, sizeof(double) * total,
-                          cudaMemcpyDeviceToHost));
+    if (P.type == 4) {       // D / B01 / B10 straight from the callback into the generator arena
+      Hh.vals.resize(base + total);
+      for (size_t q = 0; q < pend.size(); q++) {
+        const int nr = (int)rowsL[q].size(), nc = (int)colsL[q].size();
+        if (nr && nc)
+          P.elem_fn(nr, rowsL[q].data(), nc, colsL[q].data(), Hh.vals.data() + base + offO[q], nr, P.elem_user);
+      }
+    } else {
+      didx.upload(hidx.data(), nidx);
+      DevBuf<BlockTask> dbt; dbt.upload(bt.data(), bt.size());
+      if (!bt.empty()) eval_blocks_kernel<<<dim3((unsigned)bt.size(), 8), kThreads>>>(src, dbt.p);
+      SB200_CUDA(cudaGetLastError());
+      Hh.vals.resize(base + total);
+      SB200_CUDA(cudaMemcpy(Hh.vals.data() + base, dout.p, sizeof(double) * total,
+                            cudaMemcpyDeviceToHost));
+    }
   }
   Hh.finalize();
   return Hh;
@@ -552,6 +594,18 @@ HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
   for (int j = 0; j < cols; j++)
     for (int i = 0; i < rows; i++) D[i + (size_t)j * rows] = A(i, j);
   return compress_dense(rows, cols, D.data(), rows, o);
+}
+
+HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const CompressOptions& o) {
+  if (n <= 0 || !elem) throw std::invalid_argument("compress_element_blocks: bad arguments");
+  Problem P;
+  P.n = n; P.d = 1; P.type = 4; P.elem_fn = elem; P.elem_user = user;
+  P.pts.resize(n);
+  for (int i = 0; i < n; i++) P.pts[i] = i;
+  P.full_complement = n <= 8192;
+  std::vector<TNode> T;
+  build_tree_index(T, 0, n, -1, std::max(1, o.leaf_size));
+  return compress_impl(P, T, o);
 }
 
 HSSHost compress_kernel(int n, int d, double* pts, int kernel_type, double h,

@@ -30,12 +30,20 @@ struct CompressOptions {
   int weighted_samples = -1;
 };
 
+// host callback that fills the sub-block B (nI x nJ, column-major, ld ldB) =
+// A(I, J) for 0-based index lists: the reference's elem_t
+// (HSSMatrix.hpp:68-70, compress(Amult, Aelem, opts) HSSMatrix.cpp:173-186)
+using BlockElemFn = void (*)(int nI, const int* I, int nJ, const int* J, double* B, int ldB, void* user);
+
 // A: host column-major rows x cols
 HSSHost compress_dense(int rows, int cols, const double* A, int ldA,
                        const CompressOptions& o);
 // element callback evaluated on the host
 HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
                           const CompressOptions& o);
+// entries from a block callback: only the sampled blocks are evaluated
+// (O(n * samples) entries), so n is not limited by a dense n^2 buffer
+HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const CompressOptions& o);
 // kernel matrix on n points (d x n, column-major); pts is reordered in place,
 // perm[new] = old (may be null). kernel_type: SB200_KERNEL_TYPE.
 HSSHost compress_kernel(int n, int d, double* pts, int kernel_type, double h,

@@ -68,6 +68,22 @@ int main(int argc, char* argv[]) {
   H.backward_solve(w, S2);
   CHECK(rel(S2, S) < 1e-13, "forward/backward solve");
 
+  // ---- compress(Amult, Aelem, opts) through the block-extraction callback (FrontHSS.cpp:385)
+  {
+    HSS::HSSMatrix<double> He(m, m, hopts);
+    int calls = 0;
+    HSS::HSSMatrix<double>::elem_t Aelem = [&](const std::vector<std::size_t>& I, const std::vector<std::size_t>& J,
+                                               DenseM& Bk) {
+      calls++;
+      for (std::size_t b = 0; b < J.size(); b++)
+        for (std::size_t a = 0; a < I.size(); a++) Bk(a, b) = A(I[a], J[b]);
+    };
+    HSS::HSSMatrix<double>::mult_t Amult;      // not needed by the sampled ID
+    He.compress(Amult, Aelem, hopts);
+    CHECK(calls > 0 && He.rows() == std::size_t(m), "element callback");
+    CHECK(rel(He.dense(), A) < 1e2 * 1e-8, "compress(Amult, Aelem) error too big");
+  }
+
   // ---- the HSS front: partial_factor + Schur_update + Schur_product_direct
   H.partial_factor();
   DenseM Theta, DUB01, Phi;
