@@ -199,6 +199,18 @@ int SB200_d_blr_partial_factor_ex(CSPStructMat* S, int n1, int n2, const double*
                                   const double* A12, int ld12, const double* A21, int ld21,
                                   double* A22, int ld22, const CSPOptions* opts,
                                   const SB200BLRParams* params);
+/* The extract_t forms (reference BLRMatrix::compress / compress_and_factor(const
+ * extract_t& Aelem, admissible, opts), BLRMatrix.hpp:104-112, and
+ * construct_and_partial_factor(n1, n2, A11, A12, A21, A22 extractors, ...),
+ * BLRMatrix.hpp:223-232): the matrix (resp. the whole front, indices
+ * 0 .. n1+n2-1) is defined by the block callback, which is called once per
+ * tile pair.  factor = 0: compress only (supports mult), 1: compress_and_factor.
+ * The partial form writes the Schur complement to A22 (n2 x n2, may be NULL). */
+int SB200_d_blr_from_element_blocks(CSPStructMat* S, int n, SB200ElemBlockFn elem, void* user,
+                                    const CSPOptions* opts, const SB200BLRParams* params, int factor);
+int SB200_d_blr_partial_factor_element_blocks(CSPStructMat* S, int n1, int n2, SB200ElemBlockFn elem,
+                                              void* user, double* A22, int ld22,
+                                              const CSPOptions* opts, const SB200BLRParams* params);
 /* n1 of a partially factored front (rows of S otherwise). */
 int SB200_d_blr_sep_rows(const CSPStructMat S);
 /* The two halves of the front solve (FrontBLR::fwd_solve_node / bwd_solve_node,
@@ -381,7 +393,8 @@ double SB200_d_struct_kernel_ms(const CSPStructMat S, int which);
 long long int SB200_d_struct_launches(const CSPStructMat S);
 /* H.print_info() equivalent to stdout (HSSMatrix.cpp:333-356). */
 int SB200_d_struct_print_info(const CSPStructMat S);
-/* Dense reconstruction into a host buffer (HSSMatrix::dense). */
+/* Dense reconstruction into a host buffer (HSSMatrix::dense, BLRMatrix::dense of
+ * a compressed, unfactored BLR matrix). */
 int SB200_d_struct_dense(const CSPStructMat S, double* A, int ldA);
 
 /* Host-only helpers (no GPU needed): parse a reference HSS dump and report

@@ -90,6 +90,8 @@ SYMBOLS = {
     "SB200_d_blr_partial_factor_device": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_compress_and_factor_ex": (_i, [_pvp, _i, _vp, _i, _po, _vp]),
     "SB200_d_blr_partial_factor_ex": (_i, [_pvp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _po, _vp]),
+    "SB200_d_blr_from_element_blocks": (_i, [_pvp, _i, _vp, _vp, _po, _vp, _i]),
+    "SB200_d_blr_partial_factor_element_blocks": (_i, [_pvp, _i, _i, _vp, _vp, _vp, _i, _po, _vp]),
     "SB200_d_blr_sep_rows": (_i, [_vp]),
     "SB200_d_blr_partial_forward_solve": (_i, [_vp, _i, _vp, _i]),
     "SB200_d_blr_partial_backward_solve": (_i, [_vp, _i, _vp, _i]),
@@ -248,6 +250,18 @@ def hss_file_info(path):
 def hss_file_copy(src, dst):
     _check(lib().SB200_d_hss_file_copy(str(src).encode(), str(dst).encode()),
            "hss_file_copy")
+
+
+def _block_callback(fn):
+    """ctypes trampoline for SB200ElemBlockFn around ``fn(I, J) -> A[I, J]``."""
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+    def tramp(nI, I, nJ, J, B, ldB, user):
+        Ia = np.ctypeslib.as_array(I, shape=(nI,))
+        Ja = np.ctypeslib.as_array(J, shape=(nJ,))
+        out = np.ctypeslib.as_array(B, shape=(nJ, ldB))      # column-major nI x nJ with ld ldB
+        out[:, :nI] = np.asarray(fn(Ia, Ja), dtype=np.float64).T
+    return C.CFUNCTYPE(None, C.c_int, ip, C.c_int, ip, dp, C.c_int, C.c_void_p)(tramp)
 
 
 class StructuredMatrix:
@@ -467,6 +481,35 @@ class BLRMatrix(StructuredMatrix):
             C.byref(h), n1, n2, A11.ctypes.data, n1, A12.ctypes.data, max(n1, 1),
             A21.ctypes.data, max(n2, 1), S.ctypes.data, max(n2, 1), C.byref(opts),
             C.addressof(p)), "construct_and_partial_factor")
+        return cls(h.value), S
+
+    @classmethod
+    def from_element_blocks(cls, n, fn, opts=None, factor=True, pivot_threshold=-1.0,
+                            factor_algorithm=BLR_RL, admissible=None):
+        """BLRMatrix::compress / compress_and_factor(const extract_t& Aelem, admissible, opts)
+        (reference BLRMatrix.hpp:104-112): ``fn(I, J)`` returns A[I, J]."""
+        opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
+        p, keep = _blr_params(pivot_threshold, factor_algorithm, admissible)
+        cb = _block_callback(fn)
+        h = C.c_void_p()
+        _check(lib().SB200_d_blr_from_element_blocks(C.byref(h), int(n), C.cast(cb, C.c_void_p), None,
+                                                     C.byref(opts), C.addressof(p), int(bool(factor))),
+               "from_element_blocks")
+        return cls(h.value)
+
+    @classmethod
+    def construct_and_partial_factor_elements(cls, n1, n2, fn, opts=None, pivot_threshold=-1.0,
+                                              factor_algorithm=BLR_RL):
+        """construct_and_partial_factor(n1, n2, extractors, ...) (reference BLRMatrix.hpp:223-232):
+        ``fn(I, J)`` defines the whole front.  Returns (F, Schur complement)."""
+        opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
+        p, keep = _blr_params(pivot_threshold, factor_algorithm, None)
+        cb = _block_callback(fn)
+        S = np.zeros((n2, n2), order="F")
+        h = C.c_void_p()
+        _check(lib().SB200_d_blr_partial_factor_element_blocks(
+            C.byref(h), int(n1), int(n2), C.cast(cb, C.c_void_p), None, S.ctypes.data, max(n2, 1),
+            C.byref(opts), C.addressof(p)), "construct_and_partial_factor_elements")
         return cls(h.value), S
 
     @property
@@ -693,14 +736,7 @@ class HSSMatrix(StructuredMatrix):
         extraction callback (HSSMatrix.hpp:68-70): ``fn(I, J)`` returns the dense
         sub-block A[I, J] for integer index arrays."""
         opts = opts or default_options()
-        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
-
-        def tramp(nI, I, nJ, J, B, ldB, user):
-            Ia = np.ctypeslib.as_array(I, shape=(nI,))
-            Ja = np.ctypeslib.as_array(J, shape=(nJ,))
-            out = np.ctypeslib.as_array(B, shape=(nJ, ldB))      # column-major nI x nJ with ld ldB
-            out[:, :nI] = np.asarray(fn(Ia, Ja), dtype=np.float64).T
-        cb = C.CFUNCTYPE(None, C.c_int, ip, C.c_int, ip, dp, C.c_int, C.c_void_p)(tramp)
+        cb = _block_callback(fn)
         h = C.c_void_p()
         _check(lib().SB200_d_hss_from_element_blocks(C.byref(h), int(n), C.cast(cb, C.c_void_p), None,
                                                      C.byref(opts)), "from_element_blocks")

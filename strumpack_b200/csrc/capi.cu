@@ -323,6 +323,64 @@ int SB200_d_blr_partial_factor_ex(CSPStructMat* S, int n1, int n2, const double*
   });
 }
 
+// ClusterTree(n).refine(leaf) (reference src/structured/ClusterTree.hpp:104-114)
+static void refine_tiles(std::vector<int>& t, int size, int leaf) {
+  if (size >= 2 * leaf) { refine_tiles(t, size / 2, leaf); refine_tiles(t, size - size / 2, leaf); }
+  else t.push_back(size);
+}
+
+// fill the dense n x n host matrix tile by tile through the block callback (the
+// granularity at which the reference calls its extract_t, BLRMatrix.cpp:91-111)
+static std::vector<double> fill_by_tiles(int n, const std::vector<int>& tiles, SB200ElemBlockFn elem, void* user) {
+  if (!elem) throw std::invalid_argument("no element callback");
+  std::vector<double> A((size_t)n * n);
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; i++) idx[i] = i;
+  std::vector<int> off(tiles.size() + 1, 0);
+  for (size_t t = 0; t < tiles.size(); t++) off[t + 1] = off[t] + tiles[t];
+  for (size_t j = 0; j < tiles.size(); j++)
+    for (size_t i = 0; i < tiles.size(); i++)
+      elem(tiles[i], idx.data() + off[i], tiles[j], idx.data() + off[j], A.data() + off[i] + (size_t)off[j] * n, n, user);
+  return A;
+}
+
+int SB200_d_blr_from_element_blocks(CSPStructMat* S, int n, SB200ElemBlockFn elem, void* user,
+                                    const CSPOptions* opts, const SB200BLRParams* params, int factor) {
+  return guarded([&] {
+    require_gpu();
+    if (n <= 0) throw std::invalid_argument("empty matrix");
+    std::vector<int> tiles;
+    refine_tiles(tiles, n, std::max(1, opts->leaf_size));
+    std::vector<double> A = fill_by_tiles(n, tiles, elem, user);
+    auto m = std::make_unique<Mat>();
+    m->type = SP_TYPE_BLR;
+    m->blr = std::make_unique<BLREngine>(n, A.data(), n, blr_opts(opts, params), factor != 0);
+    *S = m.release();
+  });
+}
+
+int SB200_d_blr_partial_factor_element_blocks(CSPStructMat* S, int n1, int n2, SB200ElemBlockFn elem,
+                                              void* user, double* A22, int ld22,
+                                              const CSPOptions* opts, const SB200BLRParams* params) {
+  return guarded([&] {
+    if (n1 <= 0 || n2 < 0) throw std::invalid_argument("partial factorization needs n1 > 0, n2 >= 0");
+    const int n = n1 + n2;
+    std::vector<int> tiles;
+    refine_tiles(tiles, n1, std::max(1, opts->leaf_size));
+    if (n2 > 0) refine_tiles(tiles, n2, std::max(1, opts->leaf_size));
+    std::vector<double> A = fill_by_tiles(n, tiles, elem, user);
+    const double* a = A.data();
+    // the callback defines the whole front; the Schur complement goes to the caller's A22
+    std::vector<double> S22((size_t)std::max(n2, 1) * std::max(n2, 1));
+    for (int j = 0; j < n2; j++)
+      for (int i = 0; i < n2; i++) S22[i + (size_t)j * n2] = a[(n1 + i) + (size_t)(n1 + j) * n];
+    blr_partial_impl(S, n1, n2, a, n, a + (size_t)n1 * n, n, a + n1, n, S22.data(), std::max(n2, 1), opts, params, false);
+    if (A22)
+      for (int j = 0; j < n2; j++)
+        for (int i = 0; i < n2; i++) A22[i + (size_t)j * ld22] = S22[i + (size_t)j * n2];
+  });
+}
+
 int SB200_d_blr_sep_rows(const CSPStructMat S) {
   return (S && M(S)->blr) ? M(S)->blr->sep_rows() : 0;
 }
@@ -798,6 +856,22 @@ int SB200_d_struct_print_info(const CSPStructMat S) {
 }
 int SB200_d_struct_dense(const CSPStructMat S, double* A, int ldA) {
   return guarded([&] {
+    if (M(S)->blr) {     // BLRMatrix::dense() (BLRMatrix.cpp:296-305): B * I in slabs, compressed matrices only
+      auto& B = *M(S)->blr;
+      const int n = B.rows(), sb = 128;
+      DevBuf<double> I((size_t)n * sb), Y((size_t)n * sb);
+      std::vector<double> hI((size_t)n * sb);
+      for (int c0 = 0; c0 < n; c0 += sb) {
+        const int nc = std::min(sb, n - c0);
+        std::fill(hI.begin(), hI.end(), 0.);
+        for (int c = 0; c < nc; c++) hI[(size_t)c * n + c0 + c] = 1.;
+        SB200_CUDA(cudaMemcpy(I.p, hI.data(), sizeof(double) * (size_t)n * nc, cudaMemcpyHostToDevice));
+        B.mult('N', nc, I.p, n, Y.p, n, 0);
+        SB200_CUDA(cudaMemcpy2D(A + (size_t)c0 * ldA, sizeof(double) * ldA, Y.p, sizeof(double) * n,
+                                sizeof(double) * n, nc, cudaMemcpyDeviceToHost));
+      }
+      return;
+    }
     auto& H = hss(S);
     const int n = H.cols(), m = H.rows();
     // H * I, in slabs of 256 columns

@@ -313,3 +313,35 @@ def test_blr_matches_reference_golden(built):
     assert rel(f[n1:], g["fwd"][n1:]) <= 10 * tol           # b_upd - A21 A11^{-1} b_sep: pivot independent
     mid = np.vstack([f[:n1], np.linalg.solve(S, f[n1:])])
     assert rel(F.partial_backward_solve(mid), g["bwd"]) <= 10 * tol
+
+
+def test_blr_from_element_blocks_and_dense(built):
+    """The extract_t forms (reference BLRMatrix.hpp:104-112, 223-232): compress,
+    compress_and_factor and construct_and_partial_factor from a block callback,
+    and BLRMatrix::dense() of a compressed matrix."""
+    sb = built
+    n, leaf, tol = 900, 128, 1e-6
+    A = toeplitz(n) + 2.0 * np.eye(n)
+    A[np.triu_indices(n, 200)] *= 0.5                      # non-symmetric
+    ncalls = []
+
+    def block(I, J):
+        ncalls.append((len(I), len(J)))
+        return A[np.ix_(I, J)]
+
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    C_ = sb.BLRMatrix.from_element_blocks(n, block, o, factor=False)
+    assert len(ncalls) == C_.tiles ** 2                     # one call per tile pair
+    assert rel(C_.dense(), A) <= 1e2 * tol
+    x = np.random.default_rng(0).standard_normal((n, 2))
+    assert rel(C_.mult(x, "T"), A.T @ x) <= 1e2 * tol
+    F = sb.BLRMatrix.from_element_blocks(n, block, o, factor=True)
+    D = sb.BLRMatrix.compress_and_factor(A, o)
+    y = A @ x
+    assert rel(F.solve(y), x) <= 1e2 * tol
+    assert rel(F.solve(y), D.solve(y)) <= 1e-12            # same matrix, same algorithm
+    n1 = 500
+    P, S = sb.BLRMatrix.construct_and_partial_factor_elements(n1, n - n1, block, o)
+    P2, S2 = sb.BLRMatrix.construct_and_partial_factor(A[:n1, :n1], A[:n1, n1:], A[n1:, :n1], A[n1:, n1:], o)
+    assert rel(S, S2) <= 1e-13
+    assert rel(S, A[n1:, n1:] - A[n1:, :n1] @ np.linalg.solve(A[:n1, :n1], A[n1:, :n1].T * 0 + A[:n1, n1:])) <= 1e2 * tol
