@@ -165,3 +165,23 @@ def test_blr_restatement_matches_live_reference():
     assert sum(t.nonzeros() for t in F.t.values()) + sum(l[0].size for l in F.lu.values()) == R.info()["nonzeros"]
     Y = np.random.default_rng(4).standard_normal((n, 2))
     assert rel(F.solve(Y), R.solve(Y)) < 1e-11
+
+
+@pytest.mark.skipif(not have_ref(), reason="reference library not built")
+def test_reference_factor_algorithms_agree():
+    """What the engine's treatment of BLRFactorAlgorithm rests on:
+    in the reference itself LL produces exactly the RL factors (the same tile
+    updates in another order), and COMB / STAR (LUAR accumulation) differ from RL
+    far below the compression tolerance, with the same ranks."""
+    from oracle import ref
+    n, leaf, tol = 1024, 128, 1e-6
+    A = _blr_matrix(n)
+    Y = np.random.default_rng(0).standard_normal((n, 2))
+    res = {}
+    for alg in ("RL", "LL", "Comb", "Star"):
+        B = ref.RefBLR(A, f"--blr_leaf_size {leaf} --blr_rel_tol {tol} --blr_factor_algorithm {alg}")
+        res[alg] = (B.solve(Y), B.info())
+    assert np.array_equal(res["LL"][0], res["RL"][0])
+    for alg in ("Comb", "Star"):
+        assert rel(res[alg][0], res["RL"][0]) < 1e-2 * tol
+        assert res[alg][1]["rank"] == res["RL"][1]["rank"]
