@@ -1,0 +1,152 @@
+"""Drop-in check of the C boundary: ONE call sequence written
+against the reference's C interface src/structured/StructuredMatrix.h
+(SP_d_struct_default_options / from_dense / rows / cols / rank / nonzeros /
+memory / mult / factor / solve / shift / destroy) is run
+
+  * against the reference's OWN implementation of that interface
+    (oracle/_ref/libsb200_ref_capi.so = the unmodified
+    src/structured/StructuredMatrixC.cpp + HSS/BLR sources, CPU), and
+  * against libstrumpack_b200.so (GPU),
+
+with identical arguments; both must satisfy the reference's acceptance bounds
+(compression error <= 1e2*tol, ULV residual <= 1e-12: test/test_HSS_seq.cpp:148-152,
+247-250) and agree with each other to the compression tolerance."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+REF_CAPI = os.path.join(ROOT, "oracle", "_ref", "libsb200_ref_capi.so")
+OBLAS_DIR = "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs"
+
+
+class CSPOptions(C.Structure):   # reference StructuredMatrix.h:68-75
+    _fields_ = [("type", C.c_int), ("rel_tol", C.c_double), ("abs_tol", C.c_double),
+                ("leaf_size", C.c_int), ("max_rank", C.c_int), ("verbose", C.c_int)]
+
+
+def _bind(L):
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    L.SP_d_struct_default_options.argtypes = [C.POINTER(CSPOptions)]
+    L.SP_d_struct_default_options.restype = None
+    L.SP_d_struct_destroy.argtypes = [C.POINTER(vp)]
+    L.SP_d_struct_destroy.restype = None
+    # StructuredMatrix.h:158-277 declares rows / cols / memory / nonzeros / rank, but the reference's
+    # StructuredMatrixC.cpp (this version) does not define them: a client that calls them links only
+    # against the engine.  The program below uses them when the library has them.
+    L.has_queries = hasattr(L, "SP_d_struct_rows")
+    if L.has_queries:
+        for f in ("rows", "cols", "rank"):
+            getattr(L, "SP_d_struct_" + f).argtypes = [vp]
+            getattr(L, "SP_d_struct_" + f).restype = i
+        for f in ("memory", "nonzeros"):
+            getattr(L, "SP_d_struct_" + f).argtypes = [vp]
+            getattr(L, "SP_d_struct_" + f).restype = C.c_longlong
+    L.SP_d_struct_from_dense.argtypes = [C.POINTER(vp), i, i, vp, i, C.POINTER(CSPOptions)]
+    L.SP_d_struct_mult.argtypes = [vp, C.c_char, i, vp, i, vp, i]
+    L.SP_d_struct_factor.argtypes = [vp]
+    L.SP_d_struct_solve.argtypes = [vp, i, vp, i]
+    L.SP_d_struct_shift.argtypes = [vp, d]
+    for f in ("from_dense", "mult", "factor", "solve", "shift"):
+        getattr(L, "SP_d_struct_" + f).restype = i
+    return L
+
+
+def reference_lib():
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    for pat in ("libquadmath*.so*", "libgfortran*.so*", "libopenblasp*.so"):
+        for f in sorted(glob.glob(os.path.join(OBLAS_DIR, pat))):
+            try:
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+    return _bind(C.CDLL(REF_CAPI))           # RTLD_LOCAL: its SP_* symbols stay private to this handle
+
+
+def engine_lib(built):
+    return _bind(C.CDLL(os.path.join(ROOT, "strumpack_b200", "libstrumpack_b200.so")))
+
+
+def matrix(n):
+    i = np.arange(n)
+    return np.asfortranarray(1.0 / (1.0 + np.abs(i[:, None] - i[None, :])) + 2.0 * np.eye(n))
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def program(L, stype, n=600, tol=1e-6, leaf=64, blr_transposed=True):
+    """The client program.  Returns what it observed.  (blr_transposed = False for the
+    reference: its transposed BLR product aborts on an assertion in this version,
+    DenseMatrix.hpp:1058 reached from BLRMatrix gemm.)"""
+    A = matrix(n)
+    o = CSPOptions()
+    L.SP_d_struct_default_options(C.byref(o))
+    defaults = (o.type, o.rel_tol, o.abs_tol, o.leaf_size, o.max_rank)
+    o.type, o.rel_tol, o.leaf_size, o.verbose = stype, tol, leaf, 0
+    S = C.c_void_p()
+    assert L.SP_d_struct_from_dense(C.byref(S), n, n, A.ctypes.data, n, C.byref(o)) == 0
+    out = {"defaults": defaults}
+    if L.has_queries:
+        out.update(dims=(L.SP_d_struct_rows(S), L.SP_d_struct_cols(S)), rank=L.SP_d_struct_rank(S),
+                   nnz=L.SP_d_struct_nonzeros(S), mem=L.SP_d_struct_memory(S))
+    X = np.asfortranarray(np.random.default_rng(5).standard_normal((n, 3)))
+    Y = np.zeros((n, 3), order="F")
+    assert L.SP_d_struct_mult(S, b"N", 3, X.ctypes.data, n, Y.ctypes.data, n) == 0
+    out["Y"] = Y.copy()
+    if stype == 0 or blr_transposed:
+        Yt = np.zeros((n, 3), order="F")
+        assert L.SP_d_struct_mult(S, b"T", 3, X.ctypes.data, n, Yt.ctypes.data, n) == 0
+        out["Yt"] = Yt.copy()
+    if stype == 0:      # HSS: factor + solve + shift
+        assert L.SP_d_struct_factor(S) == 0
+        B = Y.copy(order="F")
+        assert L.SP_d_struct_solve(S, 3, B.ctypes.data, n) == 0
+        out["X"] = B.copy()
+        assert L.SP_d_struct_shift(S, 0.75) == 0
+        Ys = np.zeros((n, 3), order="F")
+        assert L.SP_d_struct_mult(S, b"N", 3, X.ctypes.data, n, Ys.ctypes.data, n) == 0
+        out["Yshift"] = Ys.copy()
+    L.SP_d_struct_destroy(C.byref(S))
+    out["destroyed"] = S.value is None
+    out["A"], out["Xin"], out["tol"] = A, X, tol
+    return out
+
+
+def check(out, stype):
+    A, X, tol = out["A"], out["Xin"], out["tol"]
+    n = A.shape[0]
+    assert out["defaults"] == (1, 1e-4, 1e-10, 128, 5000)        # StructuredOptions.hpp:106-162
+    assert out["destroyed"]
+    if "dims" in out:
+        assert out["dims"] == (n, n)
+        assert 0 < out["rank"] < 64 and 0 < out["nnz"] < n * n and out["mem"] > 0
+    assert rel(out["Y"], A @ X) <= 1e2 * tol
+    if "Yt" in out:
+        assert rel(out["Yt"], A.T @ X) <= 1e2 * tol
+    if stype == 0:
+        assert rel(out["X"], X) <= 1e-10                          # H \ (H X) = X: ULV is a direct solver for H
+        assert rel(out["Yshift"], out["Y"] + 0.75 * X) <= 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CAPI), reason="reference C interface not built")
+@pytest.mark.parametrize("stype", [0, 1])
+def test_program_against_reference_c_interface(stype):
+    check(program(reference_lib(), stype, blr_transposed=False), stype)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stype", [0, 1])
+def test_program_against_engine(built, stype):
+    ours = program(engine_lib(built), stype)
+    check(ours, stype)
+    if os.path.exists(REF_CAPI):         # and the two implementations agree to the compression tolerance
+        ref = program(reference_lib(), stype, blr_transposed=False)
+        assert rel(ours["Y"], ref["Y"]) <= 1e2 * ours["tol"]
+        if stype == 0:
+            assert rel(ours["X"], ref["X"]) <= 1e-9
