@@ -163,7 +163,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "HSS apply+ULV GFLOP/s", "value": gf, "unit": "GFLOP/s",
         "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"HSS apply+ULV factor+solve, 2-D Gaussian kernel (h={H_GAUSS}, "
                                f"lambda={LAMBDA}), leaf {LEAF}, tol {TOL}, 1 rhs; bounded sample "
@@ -353,7 +353,7 @@ def run_ours(args):
         line = {
             "metric": "HSS apply+ULV GFLOP/s", "value": value, "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",   # one N = 2^20 matrix whatever the number of GPUs
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"HSS apply (1 rhs) + ULV factor + ULV solve (1 rhs), 2-D Gaussian "
