@@ -150,3 +150,47 @@ def test_program_against_engine(built, stype):
         assert rel(ours["Y"], ref["Y"]) <= 1e2 * ours["tol"]
         if stype == 0:
             assert rel(ours["X"], ref["X"]) <= 1e-9
+
+
+# ---- the reference's own C example, compiled UNMODIFIED against both boundaries ------------------
+# oracle/Makefile builds /root/reference/examples/dense/dstructured.c twice (where the reference
+# sources exist; the binaries travel with the repository snapshot):
+#   oracle/_ref/dstructured_ref    reference header + reference C interface (CPU)
+#   oracle/_ref/dstructured_sb200  include/compat/structured/StructuredMatrix.h + libstrumpack_b200.so
+EX_REF = os.path.join(ROOT, "oracle", "_ref", "dstructured_ref")
+EX_OURS = os.path.join(ROOT, "oracle", "_ref", "dstructured_sb200")
+
+
+def _run_example(exe, n):
+    import re
+    import subprocess
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="4")
+    r = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=600, env=env)
+    vals = [float(v) for v in re.findall(r"=\s*([0-9.eE+-]+)\s*$", r.stdout, flags=re.M)]
+    return r, vals
+
+
+@pytest.mark.skipif(not os.path.exists(EX_REF), reason="reference example not built")
+def test_reference_example_against_reference():
+    r, vals = _run_example(EX_REF, 500)
+    assert r.returncode == 0 and len(vals) == 2, r.stdout + r.stderr
+    assert vals[0] <= 1e2 * 1e-8 and vals[1] <= 1e-12       # its opts.rel_tol = 1e-8; ULV residual
+
+
+@pytest.mark.skipif(not os.path.exists(EX_OURS), reason="example not built against the engine")
+def test_reference_example_links_against_engine_and_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r, _ = _run_example(EX_OURS, 64)
+    assert "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(EX_OURS), reason="example not built against the engine")
+def test_reference_example_against_engine():
+    """examples/dense/dstructured.c (SP_d_struct_from_elements, mult with the identity,
+    factor, solve with 10 right-hand sides) on the GPU through the engine."""
+    r, vals = _run_example(EX_OURS, 500)
+    assert r.returncode == 0 and len(vals) == 2, r.stdout + r.stderr
+    assert vals[0] <= 1e2 * 1e-8 and vals[1] <= 1e-10
