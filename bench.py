@@ -87,117 +87,202 @@ def clocks_stop(p, path):
 
 
 # ------------------------------------------------------------------ reference
-def reference_problem(n, threads):
-    from oracle import ref
-    ref.set_num_threads(threads)
-    t0 = time.perf_counter()
-    H = ref.RefHSS.gauss(points(n), H_GAUSS, LAMBDA,
-                         f"--hss_leaf_size {LEAF} --hss_rel_tol {TOL}")
-    tc = time.perf_counter() - t0
-    return H, tc
+WORKLOAD = ("HSS apply (1 rhs) + ULV factor + ULV solve (1 rhs), 2-D Gaussian kernel "
+            "(h={h}, lambda={lam}), N={n}, leaf {leaf}, tol {tol}")
 
 
-def reference_flops(H, n):
-    """apply flops from the generators, factor/solve from the reference's own
-    counters (one factor + one 1-rhs solve)."""
-    from oracle import ref
+def workload(n):
+    return WORKLOAD.format(h=H_GAUSS, lam=LAMBDA, n=n, leaf=LEAF, tol=TOL)
+
+
+def rhs_vector(n):
+    """The step's input vector: the same in both arms (parity is checked on it)."""
+    return np.random.default_rng(1234).standard_normal((n, 1))
+
+
+def reexec_with_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; libgomp latches that at
+    load time and the reference's task tree then runs ~10x slower whatever
+    omp_set_num_threads() says later (round 1's N>=2 reference lines).  The
+    reference arm therefore restarts itself once with the variable set to the
+    host's core count BEFORE any OpenMP runtime is loaded."""
+    cores = str(os.cpu_count() or 1)
+    if os.environ.get("SB200_REF_REEXEC") == "1":
+        return
+    env = dict(os.environ)
+    env["SB200_REF_REEXEC"] = "1"
+    env["OMP_NUM_THREADS"] = cores
+    env.pop("OMP_THREAD_LIMIT", None)
+    env.pop("OMP_PROC_BIND", None)
+    env.pop("GOMP_CPU_AFFINITY", None)
+    sys.stdout.flush()
+    os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env)
+
+
+def engine_generators(n, path):
+    """Compress the workload's matrix with the engine (GPU, untimed) and dump the
+    generators in the reference's own HSSMatrix::write format, so that the
+    reference times EXACTLY the matrix (tree, ranks, generators) the engine times."""
     import strumpack_b200 as sb
-    with tempfile.TemporaryDirectory() as td:
-        p = os.path.join(td, "h.hss")
-        H.write(p)
-        inf = sb.hss_file_info(p)     # host-only parser, no GPU involved
+    sb.lib()
+    opts = sb.default_options(type=sb.SP_TYPE_HSS, rel_tol=TOL, abs_tol=1e-10, leaf_size=LEAF)
+    t0 = time.perf_counter()
+    H, _, _ = sb.HSSMatrix.from_kernel(points(n, seed=42), sb.KERNEL_GAUSS, H_GAUSS, LAMBDA, opts)
+    tc = time.perf_counter() - t0
+    H.write(path)
+    H.close()
+    return tc
+
+
+def reference_flops(path):
+    """apply flops from the generators (2 nnz), factor/solve = the reference's
+    own counters' formulas (params::ULV_factor_flops, hss_solve_flops) -- the
+    host-only file parser, no GPU involved."""
+    import strumpack_b200 as sb
+    inf = sb.hss_file_info(path)
     return inf["apply_flops"], inf["factor_flops"], inf["solve_flops"]
 
 
 def reference_step(H, x):
     y = H.mult(x)
     H.factor()
-    return H.solve(y)
+    return y, H.solve(y)
 
 
-def reference_best_threads(H, x):
+def reference_best_threads(H, x, cands):
     """The reference's OpenMP task tree does not scale to every core count
-    (on the 128-core B200 host 128 threads are slower than 16): time one pass
-    per candidate and keep the fastest, so the baseline is the reference at its
+    (on a 128-core host 128 threads are slower than 16): time one pass per
+    candidate and keep the fastest, so the baseline is the reference at its
     best, with all the host threads it can use profitably."""
     from oracle import ref
-    cores = os.cpu_count() or 1
-    best, best_t = cores, float("inf")
-    for t in sorted({cores, 64, 32, 16, 8}, reverse=True):
-        if t > cores:
-            continue
+    best, best_t = cands[0], float("inf")
+    for t in cands:
         ref.set_num_threads(t)
-        reference_step(H, x)
         t0 = time.perf_counter()
         reference_step(H, x)
         dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = t, dt
     ref.set_num_threads(best)
-    return best
+    return best, best_t
 
 
 def run_reference(args):
     """Reference arm: the reference's own OpenMP CPU implementation (oracle/_ref,
-    compiled from /root/reference) on a bounded sample of the workload."""
+    compiled from /root/reference, unmodified) of apply + ULV factor + ULV solve on
+    the SAME generators the engine arm times (N = 2^20 by default)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    reexec_with_all_cores()
     from oracle import ref
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
         return
     cores = os.cpu_count() or 1
-    n = args.ref_n
-    H, tc = reference_problem(n, cores)
-    fa, ff, fs = reference_flops(H, n)
-    x = np.random.default_rng(0).standard_normal((n, 1))
-    threads = reference_best_threads(H, x)
-    for _ in range(args.warmup):
+    n = args.n
+    tmp = None
+    path = args.hss_file
+    same = True
+    tc = 0.0
+    gen = "file given by the caller"
+    if path is None:
+        tmp = tempfile.TemporaryDirectory()
+        path = os.path.join(tmp.name, "workload.hss")
+        try:
+            tc = engine_generators(n, path)
+            gen = f"engine compressor on the GPU, {tc:.1f}s untimed, dumped with SB200_d_hss_write"
+        except Exception as e:   # no GPU here: the reference compresses a smaller sample itself
+            same = False
+            n = args.ref_n
+            ref.set_num_threads(cores)
+            t0 = time.perf_counter()
+            Hc = ref.RefHSS.gauss(points(n), H_GAUSS, LAMBDA, f"--hss_leaf_size {LEAF} --hss_rel_tol {TOL}")
+            tc = time.perf_counter() - t0
+            Hc.write(path)
+            del Hc
+            gen = (f"reference's own compressor (2-means tree) at N={n}, {tc:.1f}s untimed "
+                   f"[engine generators unavailable: {str(e)[:80]}]")
+    fa, ff, fs = reference_flops(path)
+    H = ref.RefHSS.read(path)
+    n = H.info()["rows"]
+    x = rhs_vector(n)
+    ref.set_num_threads(cores)
+    got = ref.lib().ref_get_max_threads()
+    if got != cores:
+        raise SystemExit(f"bench.py --impl reference: asked for {cores} OpenMP threads, runtime reports {got}")
+    cands = [t for t in sorted({cores, 64, 32, 16, 8}, reverse=True) if t <= cores]
+    reference_step(H, x)                      # first touch / warm-up
+    threads, _ = reference_best_threads(H, x, cands)
+    for _ in range(max(args.warmup - 1 - len(cands), 0)):
         reference_step(H, x)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        reference_step(H, x)
-    dt = (time.perf_counter() - t0) / args.steps
+    ts = []
+    t_end = time.perf_counter() + args.ref_budget
+    for k in range(args.steps):
+        t0 = time.perf_counter()
+        y, xs = reference_step(H, x)
+        ts.append(time.perf_counter() - t0)
+        if time.perf_counter() > t_end:
+            break
+    dt = float(np.mean(ts))
+    resid = float(np.linalg.norm(xs - x) / np.linalg.norm(x))
+    if args.dump_results:
+        np.save(args.dump_results + ".y.npy", y)
+        np.save(args.dump_results + ".x.npy", xs)
     gf = (fa + ff + fs) / dt / 1e9
     print(json.dumps({
         "impl": "reference", "metric": "HSS apply+ULV GFLOP/s", "value": gf, "unit": "GFLOP/s",
-        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "n_gpus": 0, "steps": len(ts), "steps_requested": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"HSS apply+ULV factor+solve, 2-D Gaussian kernel (h={H_GAUSS}, "
-                               f"lambda={LAMBDA}), leaf {LEAF}, tol {TOL}, 1 rhs; bounded sample "
-                               f"N={n} of the N=2^20 workload", "N": n},
+        "config": {"workload": workload(n), "N": n, "leaf": LEAF, "rel_tol": TOL,
+                   "same_generators_as_engine_arm": same, "generators": gen,
+                   "flops_per_step": {"apply": fa, "factor": ff, "solve": fs},
+                   "solve_residual": resid},
         "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": "reference",
-                         "sample": f"N={n} (compress {tc:.1f}s untimed), {args.steps} steps, "
-                                   f"{threads} OpenMP threads = fastest of a sweep on the {cores}-core host"},
+                         "sample": f"N={n}, {len(ts)} apply+factor+solve passes of {dt*1e3:.0f} ms, "
+                                   f"{threads} OpenMP threads = fastest of a sweep over {cands} on the "
+                                   f"{cores}-core host (runtime max threads {got})"},
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+    if tmp is not None:
+        tmp.cleanup()
 
 
-def cpu_baseline(n, budget_s=25.0):
+def cpu_baseline(H, n, xs_dev, y_dev, steps=3, budget_s=30.0):
+    """The reference on the host cores, on the engine's own generators (dumped to
+    a scratch file), in a clean subprocess (its OpenMP runtime must not inherit
+    this process's environment).  Also returns the parity of the engine's y / x
+    against the reference's on the same x."""
     from oracle import ref
     if not ref.available():
-        return None
-    cores = os.cpu_count() or 1
-    H, tc = reference_problem(n, cores)
-    fa, ff, fs = reference_flops(H, n)
-    x = np.random.default_rng(0).standard_normal((n, 1))
-    threads = reference_best_threads(H, x)
-    reference_step(H, x)  # warm-up
-    ts = []
-    t_end = time.perf_counter() + budget_s
-    while len(ts) < 5 and time.perf_counter() < t_end:
-        t0 = time.perf_counter()
-        reference_step(H, x)
-        ts.append(time.perf_counter() - t0)
-    dt = float(np.median(ts))
-    return {"value": (fa + ff + fs) / dt / 1e9, "unit": "GFLOP/s", "cores": threads,
-            "kind": "reference",
-            "sample": f"N={n} Gaussian 2-D, leaf {LEAF}, tol {TOL}: median of {len(ts)} "
-                      f"apply+factor+solve passes ({dt*1e3:.1f} ms each), compress {tc:.1f}s untimed; "
-                      f"{threads} OpenMP threads = fastest of a sweep on the {cores}-core host"}
+        return None, None
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "workload.hss")
+        H.write(path)
+        env = dict(os.environ)
+        for k in ("OMP_NUM_THREADS", "SB200_REF_REEXEC", "RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--hss-file", path,
+               "--steps", str(steps), "--warmup", "1", "--ref-budget", str(budget_s),
+               "--dump-results", os.path.join(td, "ref")]
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        line = None
+        for ln in out.stdout.splitlines():
+            if ln.startswith("{"):
+                line = json.loads(ln)
+        if line is None or "cpu_baseline" not in line:
+            return {"error": (out.stderr or out.stdout)[-300:]}, None
+        base = line["cpu_baseline"]
+        base["ms_per_step"] = line["ms_per_step"]
+        y_ref = np.load(os.path.join(td, "ref.y.npy")).ravel()
+        x_ref = np.load(os.path.join(td, "ref.x.npy")).ravel()
+    parity = {"apply_rel_err_vs_reference": float(np.linalg.norm(y_dev - y_ref) / np.linalg.norm(y_ref)),
+              "solve_rel_err_vs_reference": float(np.linalg.norm(xs_dev - x_ref) / np.linalg.norm(x_ref)),
+              "what": "engine y = Hx and x = H^-1 y against the reference's on the same generators and the same x"}
+    return base, parity
 
 
 # ----------------------------------------------------------------------- ours
@@ -230,8 +315,7 @@ def run_ours(args):
     flops_step = fa + ff + fs
 
     dev = torch.device("cuda", local)
-    g = torch.Generator(device="cpu").manual_seed(1234)
-    x_host = torch.randn(1, n, dtype=torch.float64, generator=g).pin_memory()
+    x_host = torch.from_numpy(rhs_vector(n).reshape(1, n).copy()).pin_memory()
     y_host = torch.empty_like(x_host).pin_memory()
     xT = x_host.to(dev)
     yT = torch.zeros_like(xT)
@@ -264,8 +348,11 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    # parity inside the bench: x must come back (ULV is a direct solver for H)
+    # parity inside the bench: x must come back (ULV is a direct solver for H); the
+    # comparison with the reference's y and x on the same generators is made below
     resid = float((bT[:, lo:hi] - xT[:, lo:hi]).norm() / xT[:, lo:hi].norm())
+    yT_result = yT.cpu().numpy().ravel().copy()
+    bT_result = bT.cpu().numpy().ravel().copy()
 
     launches0 = H.launches
     cp, cpath = clocks_start()
@@ -347,17 +434,16 @@ def run_ours(args):
                                "no fp64 figure (tcgen05 has no f64 kind)"}
 
     if rank == 0:
-        base = None
+        base, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
-            base = cpu_baseline(args.ref_n)
+            base, parity = cpu_baseline(H, n, bT_result, yT_result)
         line = {
             "metric": "HSS apply+ULV GFLOP/s", "value": value, "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",   # one N = 2^20 matrix whatever the number of GPUs
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"HSS apply (1 rhs) + ULV factor + ULV solve (1 rhs), 2-D Gaussian "
-                            f"kernel (h={H_GAUSS}, lambda={LAMBDA}), N={n}, leaf {LEAF}, tol {TOL}",
+                "workload": workload(n),
                 "N": n, "leaf": LEAF, "rel_tol": TOL, "rank": H.rank, "levels": H.levels,
                 "parallelism": (f"one matrix sharded by subtree over {world} GPUs, replicated top "
                                 f"{world - 1} nodes, one NCCL all-gather per sweep") if world > 1 else "1 GPU",
@@ -373,6 +459,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": base,
+            "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
@@ -387,7 +474,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1 << 20, help="matrix size (default 2^20)")
     ap.add_argument("--ref-n", type=int, default=1 << 16,
-                    help="size of the bounded CPU sample of the workload")
+                    help="reference arm only, when no GPU is there to produce the engine's generators: "
+                         "size of the matrix the reference compresses itself")
+    ap.add_argument("--hss-file", default=None, help="reference arm: generators to time (HSSMatrix::write format)")
+    ap.add_argument("--ref-budget", type=float, default=900.0, help="reference arm: stop timing after this many seconds")
+    ap.add_argument("--dump-results", default=None, help="reference arm: save y and x (npy) under this prefix")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -91,6 +91,69 @@ void narrow(const std::vector<double>& D, float* A, int rows, int cols, int ld) 
     for (int i = 0; i < rows; i++) A[i + (size_t)j * ld] = (float)D[i + (size_t)j * rows];
 }
 
+// y[i, 0..3] = sum_j A[i, j] r[j, 0..3]; A packed column-major n x n on the device
+__global__ void dense_matvec4_kernel(const double* __restrict__ A, int n,
+                                     const double* __restrict__ R, double* __restrict__ Y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double y0 = 0., y1 = 0., y2 = 0., y3 = 0.;
+  for (int j = 0; j < n; j++) {
+    const double a = A[i + (size_t)j * n];
+    y0 += a * R[j]; y1 += a * R[j + n]; y2 += a * R[j + 2 * (size_t)n]; y3 += a * R[j + 3 * (size_t)n];
+  }
+  Y[i] = y0; Y[i + n] = y1; Y[i + 2 * (size_t)n] = y2; Y[i + 3 * (size_t)n] = y3;
+}
+
+// || A R - H R ||_F / || A R ||_F for 4 random vectors, all on the device
+double dense_check(HSSEngine& E, int n, const double* dA) {
+  std::vector<double> R((size_t)n * 4), YA((size_t)n * 4), YH((size_t)n * 4);
+  unsigned long long x = 0x9E3779B97F4A7C15ull;
+  for (auto& v : R) {   // xorshift64*, uniform in [-1, 1)
+    x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+    v = (double)((x * 0x2545F4914F6CDD1Dull) >> 11) / 4503599627370496.0 - 1.0;
+  }
+  DevBuf<double> dR, dYA((size_t)n * 4), dYH((size_t)n * 4);
+  dR.upload(R.data(), R.size());
+  dense_matvec4_kernel<<<(n + 127) / 128, 128>>>(dA, n, dR.p, dYA.p);
+  SB200_CUDA(cudaGetLastError());
+  E.mult('N', 4, dR.p, n, dYH.p, n, 0);
+  SB200_CUDA(cudaMemcpy(YA.data(), dYA.p, sizeof(double) * YA.size(), cudaMemcpyDeviceToHost));
+  SB200_CUDA(cudaMemcpy(YH.data(), dYH.p, sizeof(double) * YH.size(), cudaMemcpyDeviceToHost));
+  double num = 0., den = 0.;
+  for (size_t q = 0; q < YA.size(); q++) { num += (YA[q] - YH[q]) * (YA[q] - YH[q]); den += YA[q] * YA[q]; }
+  return den > 0. ? std::sqrt(num / den) : std::sqrt(num);
+}
+
+// HSS from a dense matrix.  Up to n = 8192 every node is compressed against its
+// whole complement (exact).  Above that the construction samples complement
+// columns by index distance, which misses columns of a matrix that does not
+// decay with |i-j| (round-1 advisor finding): the result is therefore checked a
+// posteriori with random products against A (the role the reference's adaptive
+// randomized sampling plays, HSSMatrix.compress_stable.hpp) and the sample is
+// enlarged, then replaced by the whole complement, until the tolerance is met.
+std::unique_ptr<HSSEngine> hss_from_dense_checked(int rows, int cols, const double* A, int ldA,
+                                                  CompressOptions co) {
+  for (int attempt = 0;; attempt++) {
+    DevBuf<double> dA;
+    auto E = std::make_unique<HSSEngine>(compress_dense(rows, cols, A, ldA, co, &dA));
+    const bool sampled = co.full_complement == 0 || (co.full_complement < 0 && rows > 8192);
+    if (!sampled || !dA.p) return E;
+    const double err = dense_check(*E, rows, dA.p);
+    const double bound = 20. * co.rel_tol;
+    if (co.verbose)
+      std::printf("# sb200 compress: sampled construction, a-posteriori ||AR - HR||/||AR|| = %.3e (bound %.1e)\n", err, bound);
+    if (err <= bound) return E;
+    if (attempt == 0) { co.sample_near *= 4; co.sample_far *= 4; }
+    else if (attempt == 1 && rows <= 32768) co.full_complement = 1;
+    else {
+      std::cerr << "sb200 warning: HSS construction from sampled columns of a dense matrix reached relative error "
+                << err << " > " << bound << " (rel_tol " << co.rel_tol
+                << "); the matrix does not decay with |i-j|: reorder it or pass coordinates" << std::endl;
+      return E;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -104,7 +167,7 @@ void SP_d_struct_default_options(CSPOptions* o) {
   o->abs_tol = 1e-10;
   o->leaf_size = 128;
   o->max_rank = 5000;
-  o->verbose = 0;
+  o->verbose = 1;   // StructuredOptions::verbose_ = true (StructuredOptions.hpp:160)
 }
 
 void SP_d_struct_destroy(CSPStructMat* S) {
@@ -113,25 +176,32 @@ void SP_d_struct_destroy(CSPStructMat* S) {
   *S = nullptr;
 }
 
+// queries never throw across the C boundary: a handle that holds neither kind
+// of matrix (or a null one) answers 0
 int SP_d_struct_rows(const CSPStructMat S) {
   if (!S) return 0;
-  return M(S)->blr ? M(S)->blr->rows() : hss(S).rows();
+  const Mat* m = static_cast<const Mat*>(S);
+  return m->blr ? m->blr->rows() : m->hss ? m->hss->rows() : 0;
 }
 int SP_d_struct_cols(const CSPStructMat S) {
   if (!S) return 0;
-  return M(S)->blr ? M(S)->blr->cols() : hss(S).cols();
+  const Mat* m = static_cast<const Mat*>(S);
+  return m->blr ? m->blr->cols() : m->hss ? m->hss->cols() : 0;
 }
 long long int SP_d_struct_memory(const CSPStructMat S) {
   if (!S) return 0;
-  return M(S)->blr ? M(S)->blr->memory_bytes() : hss(S).host().memory_bytes();
+  const Mat* m = static_cast<const Mat*>(S);
+  return m->blr ? m->blr->memory_bytes() : m->hss ? m->hss->host().memory_bytes() : 0;
 }
 long long int SP_d_struct_nonzeros(const CSPStructMat S) {
   if (!S) return 0;
-  return M(S)->blr ? M(S)->blr->nonzeros() : hss(S).host().nonzeros();
+  const Mat* m = static_cast<const Mat*>(S);
+  return m->blr ? m->blr->nonzeros() : m->hss ? m->hss->host().nonzeros() : 0;
 }
 int SP_d_struct_rank(const CSPStructMat S) {
   if (!S) return 0;
-  return M(S)->blr ? M(S)->blr->max_rank() : hss(S).host().max_rank();
+  const Mat* m = static_cast<const Mat*>(S);
+  return m->blr ? m->blr->max_rank() : m->hss ? m->hss->host().max_rank() : 0;
 }
 
 int SP_d_struct_from_dense(CSPStructMat* S, int rows, int cols, const double* A,
@@ -156,7 +226,7 @@ int SP_d_struct_from_dense(CSPStructMat* S, int rows, int cols, const double* A,
     co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
     co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
     co.verbose = opts->verbose;
-    m->hss = std::make_unique<HSSEngine>(compress_dense(rows, cols, A, ldA, co));
+    m->hss = hss_from_dense_checked(rows, cols, A, ldA, co);
     *S = m.release();
   });
 }
@@ -189,7 +259,14 @@ int SP_d_struct_from_elements(CSPStructMat* S, int rows, int cols,
     co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
     co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
     co.verbose = opts->verbose;
-    m->hss = std::make_unique<HSSEngine>(compress_elements(rows, cols, A, co));
+    if (rows != cols) throw std::invalid_argument("HSS: only square matrices are supported");
+    if (rows > 16384)
+      throw std::invalid_argument("from_elements: scalar host callbacks are limited to n <= 16384; use "
+                                  "SB200_d_hss_from_element_blocks or SB200_d_hss_from_kernel for larger matrices");
+    std::vector<double> Ad((size_t)rows * cols);
+    for (int j = 0; j < cols; j++)
+      for (int i = 0; i < rows; i++) Ad[i + (size_t)j * rows] = A(i, j);
+    m->hss = hss_from_dense_checked(rows, cols, Ad.data(), rows, co);
     *S = m.release();
   });
 }
@@ -813,11 +890,14 @@ int SB200_d_hss_file_copy(const char* in_path, const char* out_path) {
   return guarded([&] { HSSHost::read_file(in_path).write_file(out_path); });
 }
 
+// HSS-only statistics: 0 for a BLR handle (queries never throw across the C boundary)
 int SB200_d_struct_levels(const CSPStructMat S) {
-  return S ? hss(S).host().levels() : 0;
+  const Mat* m = static_cast<const Mat*>(S);
+  return m && m->hss ? m->hss->host().levels() : 0;
 }
 long long int SB200_d_struct_factor_nonzeros(const CSPStructMat S) {
-  return S ? hss(S).factor_nonzeros() : 0;
+  const Mat* m = static_cast<const Mat*>(S);
+  return m && m->hss ? m->hss->factor_nonzeros() : 0;
 }
 int SB200_d_struct_ulv_data(const CSPStructMat S, double* factors, double* tfactors,
                             long long int* sizes) {
@@ -827,8 +907,9 @@ int SB200_d_struct_ulv_data(const CSPStructMat S, double* factors, double* tfact
   });
 }
 long long int SB200_d_struct_flops(const CSPStructMat S, int which) {
-  if (!S) return 0;
-  const auto& h = hss(S).host();
+  const Mat* m = static_cast<const Mat*>(S);
+  if (!m || !m->hss) return 0;
+  const auto& h = m->hss->host();
   switch (which) {
     case 0: return h.apply_flops();
     case 1: return h.factor_flops_ref();
@@ -848,8 +929,9 @@ double SB200_d_struct_kernel_ms(const CSPStructMat S, int which) {
   return ms;
 }
 long long int SB200_d_struct_launches(const CSPStructMat S) {
-  if (!S) return 0;
-  return M(S)->blr ? M(S)->blr->launches() : hss(S).launches();
+  const Mat* m = static_cast<const Mat*>(S);
+  if (!m) return 0;
+  return m->blr ? m->blr->launches() : m->hss ? m->hss->launches() : 0;
 }
 int SB200_d_struct_print_info(const CSPStructMat S) {
   return guarded([&] { hss(S).host().print_info(); });
@@ -899,7 +981,13 @@ int SB200_d_struct_dense(const CSPStructMat S, double* A, int ldA) {
  * rounded on the way out, every kernel is the double precision one.  (B200's
  * fp64 tensor pipe is what the engine is built on; the results are at least
  * as accurate as a float implementation's.) */
-void SP_s_struct_default_options(CSPOptions* o) { SP_d_struct_default_options(o); }
+void SP_s_struct_default_options(CSPOptions* o) {
+  SP_d_struct_default_options(o);
+  // StructuredOptions<float>: default_structured_rel_tol / abs_tol specialisations
+  // (reference StructuredOptions.hpp:49-54)
+  o->rel_tol = 1e-2;
+  o->abs_tol = 1e-5;
+}
 void SP_s_struct_destroy(CSPStructMat* S) { SP_d_struct_destroy(S); }
 int SP_s_struct_rows(const CSPStructMat S) { return SP_d_struct_rows(S); }
 int SP_s_struct_cols(const CSPStructMat S) { return SP_d_struct_cols(S); }

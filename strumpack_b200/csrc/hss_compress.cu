@@ -167,7 +167,8 @@ struct Problem {
   bool full_complement = false;
 };
 
-HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& o) {
+HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& o,
+                      DevBuf<double>* keep_dA = nullptr) {
   const int N = (int)T.size(), n = P.n;
   // heights and classes
   int maxh = 0;
@@ -564,23 +565,24 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
     }
   }
   Hh.finalize();
+  if (keep_dA && P.type == 3) *keep_dA = std::move(dA);
   return Hh;
 }
 
 }  // namespace
 
 HSSHost compress_dense(int rows, int cols, const double* A, int ldA,
-                       const CompressOptions& o) {
+                       const CompressOptions& o, DevBuf<double>* keep_dA) {
   if (rows != cols)
     throw std::invalid_argument("compress_dense: only square matrices are supported");
   Problem P;
   P.n = rows; P.d = 1; P.type = 3; P.hostA = A; P.lda = ldA;
   P.pts.resize(rows);
   for (int i = 0; i < rows; i++) P.pts[i] = i;
-  P.full_complement = rows <= 8192;
+  P.full_complement = o.full_complement < 0 ? rows <= 8192 : o.full_complement != 0;
   std::vector<TNode> T;
   build_tree_index(T, 0, rows, -1, std::max(1, o.leaf_size));
-  return compress_impl(P, T, o);
+  return compress_impl(P, T, o, keep_dA);
 }
 
 HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
@@ -602,7 +604,7 @@ HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const Compr
   P.n = n; P.d = 1; P.type = 4; P.elem_fn = elem; P.elem_user = user;
   P.pts.resize(n);
   for (int i = 0; i < n; i++) P.pts[i] = i;
-  P.full_complement = n <= 8192;
+  P.full_complement = o.full_complement < 0 ? n <= 8192 : o.full_complement != 0;
   std::vector<TNode> T;
   build_tree_index(T, 0, n, -1, std::max(1, o.leaf_size));
   return compress_impl(P, T, o);

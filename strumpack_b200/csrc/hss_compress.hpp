@@ -9,6 +9,7 @@
 // height class on the device).
 #pragma once
 #include "hss_tree.hpp"
+#include "sb200_common.cuh"
 
 namespace sb200 {
 
@@ -28,6 +29,10 @@ struct CompressOptions {
   // threshold).  Measured: profiles/r1b_compress_accuracy.txt.
   // env SB200_COMPRESS_WEIGHTED=0/1 overrides.
   int weighted_samples = -1;
+  // dense / block-callback input: use the whole complement of every node instead
+  // of a sample (exact interpolative decomposition, O(n^2) entries per level).
+  // -1 = automatic (n <= 8192)
+  int full_complement = -1;
 };
 
 // host callback that fills the sub-block B (nI x nJ, column-major, ld ldB) =
@@ -36,8 +41,11 @@ struct CompressOptions {
 using BlockElemFn = void (*)(int nI, const int* I, int nJ, const int* J, double* B, int ldB, void* user);
 
 // A: host column-major rows x cols
+// keep_dA: if given, receives the packed device copy of A (ld = rows) that the
+// construction made, so that the caller can verify the result without a second
+// host-to-device copy
 HSSHost compress_dense(int rows, int cols, const double* A, int ldA,
-                       const CompressOptions& o);
+                       const CompressOptions& o, DevBuf<double>* keep_dA = nullptr);
 // element callback evaluated on the host
 HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
                           const CompressOptions& o);

@@ -2759,6 +2759,7 @@ void HSSEngine::build_tables() {
                             : H_.nodes[n.ch0].u_rank + H_.nodes[n.ch1].u_rank;
     int& g = class_gmm_[n.height];
     g = std::max(g, std::max(mi, std::max(n.u_rows, n.v_rows)));
+    if (!n.leaf()) g = std::max(g, H_.nodes[n.ch0].v_rank + H_.nodes[n.ch1].v_rank);
   }
   if (maxm > 1600)
     throw std::invalid_argument("HSS block larger than 1600 not supported");
@@ -2863,6 +2864,14 @@ void HSSEngine::make_lists(NodeLists& L, const std::vector<int>& nodes) {
       const DNode& d = hn_[L.host[q]];
       L.max_m[h] = std::max(L.max_m[h], std::max(d.m, std::max(d.rows * d.leaf, d.cols * d.leaf)));
       L.max_m[h] = std::max(L.max_m[h], std::max(d.u_rows, d.v_rows));
+      if (!d.leaf) {
+        // the apply kernels stage the children's t1 / t2 pieces (v_rank and
+        // u_rank rows each) of an inner node in one buffer sized by max_m: the
+        // V side can be larger than the U side for a nonsymmetric matrix
+        const DNode& a = hn_[d.ch0];
+        const DNode& b = hn_[d.ch1];
+        L.max_m[h] = std::max(L.max_m[h], std::max(a.u_rank + b.u_rank, a.v_rank + b.v_rank));
+      }
       L.max_k[h] = std::max(L.max_k[h], d.k);
       L.soff[q] = o;
       if (!d.leaf) o += (long long)d.m * d.m;

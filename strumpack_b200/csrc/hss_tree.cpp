@@ -298,8 +298,20 @@ long long HSSHost::factor_flops_exec() const {
 namespace {
 struct Reader {
   std::ifstream f;
+  std::uint64_t size = 0;   // file size: no record may claim more bytes than are left
   explicit Reader(const std::string& p) : f(p, std::ios::binary) {
     if (!f) throw std::runtime_error("cannot open " + p);
+    f.seekg(0, std::ios::end);
+    size = std::uint64_t(f.tellg());
+    f.seekg(0, std::ios::beg);
+  }
+  std::uint64_t left() { return size - std::uint64_t(f.tellg()); }
+  // every size field of the file is checked against what is left of the file
+  // before anything is allocated or read (a truncated / corrupt dump must not
+  // turn into a huge allocation or garbage generators)
+  void need(std::uint64_t bytes, const char* what) {
+    if (!f || bytes > left())
+      throw std::runtime_error(std::string("corrupt or truncated HSS file (") + what + ")");
   }
   template <typename T> T get() {
     T v;
@@ -307,16 +319,21 @@ struct Reader {
     if (!f) throw std::runtime_error("truncated HSS file");
     return v;
   }
-  void skip(std::size_t n) { f.seekg(std::streamoff(n), std::ios::cur); }
+  void skip(std::size_t n) { need(n, "header"); f.seekg(std::streamoff(n), std::ios::cur); }
   // DenseMatrix record: int v[3], 40-byte object image, data
   // (reference src/dense/DenseMatrix.cpp:881-889)
   void dense(std::vector<double>& arena, int64_t& off, int& rows, int& cols) {
     skip(3 * sizeof(int));
     uint64_t img[5];
+    need(sizeof(img), "DenseMatrix record");
     f.read(reinterpret_cast<char*>(img), sizeof(img));
+    if (!f) throw std::runtime_error("truncated HSS file");
+    if (img[2] > 0x7fffffffull || img[3] > 0x7fffffffull)
+      throw std::runtime_error("corrupt HSS file (DenseMatrix dimensions)");
     rows = int(img[2]);
     cols = int(img[3]);
     std::size_t n = std::size_t(rows) * cols;
+    need(std::uint64_t(n) * sizeof(double), "DenseMatrix data");
     off = n ? int64_t(arena.size()) : -1;
     if (n) {
       arena.resize(arena.size() + n);
@@ -355,8 +372,13 @@ HSSHost HSSHost::read_file(const std::string& path) {
   std::function<int(int)> rec = [&](int parent) -> int {
     HSSNode n;
     n.parent = parent;
-    n.rows = int(r.get<uint64_t>());
-    n.cols = int(r.get<uint64_t>());
+    const uint64_t rows64 = r.get<uint64_t>(), cols64 = r.get<uint64_t>();
+    if (rows64 > 0x7fffffffull || cols64 > 0x7fffffffull)
+      throw std::runtime_error("corrupt HSS file (node dimensions)");
+    n.rows = int(rows64);
+    n.cols = int(cols64);
+    if (parent >= 0 && (n.rows > H.nodes[parent].rows || n.cols > H.nodes[parent].cols))
+      throw std::runtime_error("corrupt HSS file (child larger than its parent)");
     r.get<char>(); r.get<char>();   // U_state_, V_state_
     r.get<int>();                   // openmp_task_depth_
     r.get<char>();                  // active_
@@ -367,8 +389,18 @@ HSSHost HSSHost::read_file(const std::string& path) {
     r.dense(scratch, off, a, b);    // Asub_
     for (int w = 0; w < 2; w++) {   // U_, V_   (HSSBasisID.hpp:93-101)
       uint64_t ps = r.get<uint64_t>();
+      // a basis has at most rows (leaf) / sum of the children's ranks <= rows entries
+      if (ps > uint64_t(std::max(n.rows, n.cols)))
+        throw std::runtime_error("corrupt HSS file (basis permutation longer than the node)");
+      r.need(ps * 4, "basis permutation");
       std::vector<int32_t> ipiv(ps);
-      if (ps) r.f.read(reinterpret_cast<char*>(ipiv.data()), ps * 4);
+      if (ps) {
+        r.f.read(reinterpret_cast<char*>(ipiv.data()), ps * 4);
+        if (!r.f) throw std::runtime_error("truncated HSS file");
+        for (uint64_t q = 0; q < ps; q++)
+          if (ipiv[q] < 1 || uint64_t(ipiv[q]) > ps)
+            throw std::runtime_error("corrupt HSS file (pivot index out of range)");
+      }
       int64_t offE; int er, ec;
       r.dense(H.vals, offE, er, ec);
       int64_t offP = -1;
@@ -384,6 +416,7 @@ HSSHost HSSHost::read_file(const std::string& path) {
     r.dense(H.vals, n.off_B01, a, b);
     r.dense(H.vals, n.off_B10, a, b);
     int nc = r.get<int>();
+    if (H.nodes.size() > 0x3fffffffu) throw std::runtime_error("corrupt HSS file (too many nodes)");
     int me = int(H.nodes.size());
     H.nodes.push_back(n);
     if (nc == 2) {

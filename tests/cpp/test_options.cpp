@@ -12,7 +12,7 @@ using namespace strumpack;
 int main() {
   structured::StructuredOptions<double> so;
   CHECK(so.type() == structured::Type::BLR && so.rel_tol() == 1e-4 && so.abs_tol() == 1e-10);
-  CHECK(so.leaf_size() == 128 && so.max_rank() == 5000 && !so.verbose());
+  CHECK(so.leaf_size() == 128 && so.max_rank() == 5000 && so.verbose());
   const char* a1[] = {"prog", "--structured_type", "HSS", "--structured_rel_tol", "1e-7", "--structured_leaf_size", "200",
                       "--structured_max_rank", "77", "--structured_abs_tol", "1e-13", "--structured_verbose", nullptr};
   so.set_from_command_line(12, a1);

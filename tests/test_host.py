@@ -81,3 +81,37 @@ def test_no_cpu_fallback(built, capfd):
     with pytest.raises(RuntimeError):
         built.HSSMatrix.read(os.path.join(GOLDEN, CASES[0] + ".hss"))
     assert "no CUDA device" in capfd.readouterr().err
+
+
+def test_truncated_and_corrupt_hss_files_are_rejected(built, tmp_path, capfd):
+    """HSSHost::read_file checks every size field against what is left of the
+    file before allocating (round-1 advisor finding): a truncated dump, a dump
+    with a huge Psize and one with an out-of-range pivot fail with an error
+    instead of a giant allocation / garbage generators."""
+    import struct
+    sb = built
+    src = os.path.join(GOLDEN, "toeplitz_512_leaf64.hss")
+    raw = open(src, "rb").read()
+    assert sb.hss_file_info(src)["rows"] == 512
+    for cut in (7, 40, len(raw) // 3, len(raw) - 5):
+        p = tmp_path / f"cut{cut}.hss"
+        p.write_bytes(raw[:cut])
+        with pytest.raises(RuntimeError):
+            sb.hss_file_info(str(p))
+    # root record: 12 (version) + 16 (rows, cols) + 2 + 4 + 1 + 16 (ranks) = 51, then the
+    # Asub DenseMatrix record (12 + 40 bytes, empty), then U's Psize (u64)
+    off_psize = 51 + 52
+    assert struct.unpack_from("<Q", raw, off_psize)[0] == 0        # root has no basis
+    bad = bytearray(raw)
+    struct.pack_into("<Q", bad, off_psize, 1 << 40)                # absurd permutation length
+    p = tmp_path / "psize.hss"
+    p.write_bytes(bytes(bad))
+    with pytest.raises(RuntimeError):
+        sb.hss_file_info(str(p))
+    bad = bytearray(raw)
+    struct.pack_into("<Q", bad, 12, 1 << 40)                       # absurd row count
+    p = tmp_path / "rows.hss"
+    p.write_bytes(bytes(bad))
+    with pytest.raises(RuntimeError):
+        sb.hss_file_info(str(p))
+    assert "Operation failed" in capfd.readouterr().err

@@ -219,3 +219,52 @@ def test_ulv_factor_export(sb):
     assert f.size + t.size == H.factor_nonzeros and t.size > 0
     assert np.all(np.isfinite(f)) and np.all(np.isfinite(t))
     assert np.count_nonzero(f) > 0.25 * f.size and np.count_nonzero(t) > 0
+
+
+def _random_hss(rng, leaf_rows, ru_leaf, rv_leaf, ru_in, rv_in):
+    """A random 2-level HSS (root, two inner nodes, four leaves) given by its
+    generators, with independent U and V ranks (nonsymmetric)."""
+    N = hss_file.Node
+
+    def ipiv(n):
+        return np.array([rng.integers(i, n) + 1 for i in range(n)], dtype=np.int32)
+
+    def E(rows, rank):
+        return np.asfortranarray(rng.standard_normal((rows - rank, rank)) / np.sqrt(rows))
+
+    z = np.zeros((0, 0), order="F")
+    zi = np.zeros(0, dtype=np.int32)
+    nodes = [None] * 7
+    m = leaf_rows
+    nodes[0] = N(0, -1, 4 * m, 4 * m, 0, 0, 0, 0, zi, z, zi, z, z,
+                 rng.standard_normal((ru_in, rv_in)), rng.standard_normal((ru_in, rv_in)), [1, 4])
+    for a, base in ((1, 0), (4, 2)):
+        nodes[a] = N(a, 0, 2 * m, 2 * m, ru_in, 2 * ru_leaf, rv_in, 2 * rv_leaf,
+                     ipiv(2 * ru_leaf), E(2 * ru_leaf, ru_in), ipiv(2 * rv_leaf), E(2 * rv_leaf, rv_in), z,
+                     rng.standard_normal((ru_leaf, rv_leaf)), rng.standard_normal((ru_leaf, rv_leaf)),
+                     [a + 1, a + 2], base * m, base * m)
+        for q in (1, 2):
+            nodes[a + q] = N(a + q, a, m, m, ru_leaf, m, rv_leaf, m, ipiv(m), E(m, ru_leaf), ipiv(m),
+                             E(m, rv_leaf), np.asfortranarray(rng.standard_normal((m, m)) + m * np.eye(m)), z, z,
+                             [], (base + q - 1) * m, (base + q - 1) * m)
+    return nodes
+
+
+@pytest.mark.parametrize("ru_in,rv_in", [(5, 29), (29, 5), (12, 12)])
+def test_nonsymmetric_ranks_transposed_multi_rhs(sb, ru_in, rv_in):
+    """V ranks much larger than U ranks (and the reverse) at the root's children
+    and below: shared-memory staging of the apply kernels is sized by the larger
+    side (round-1 advisor finding), N and T products, 1 and many right-hand sides."""
+    rng = np.random.default_rng(5)
+    nodes = _random_hss(rng, 48, ru_leaf=7 if ru_in < rv_in else 20, rv_leaf=20 if ru_in < rv_in else 7,
+                        ru_in=ru_in, rv_in=rv_in)
+    H = sb.HSSMatrix.from_generators(nodes)
+    A = ho.to_dense(nodes)
+    for s in (1, 3, 4, 9, 37):
+        x = rng.standard_normal((H.rows, s))
+        assert rel(H.mult(x), A @ x) < 1e-13
+        assert rel(H.mult(x, "T"), A.T @ x) < 1e-13
+    assert rel(H.dense(), A) < 1e-13
+    H.factor()
+    b = rng.standard_normal((H.rows, 5))
+    assert rel(A @ H.solve(b), b) < 1e-10
