@@ -25,7 +25,9 @@ def test_float_interface(built, stype):
     A = (1.0 / (1.0 + np.abs(i[:, None] - i[None, :])) + 2.0 * np.eye(n)).astype(np.float32, order="F")
     o = sb.CSPOptions()
     L.SP_s_struct_default_options(C.byref(o))
-    assert o.type == sb.SP_TYPE_BLR and o.rel_tol == 1e-4 and o.leaf_size == 128
+    # StructuredOptions<float>: rel_tol 1e-2, abs_tol 1e-5 (reference StructuredOptions.hpp:49-54)
+    assert o.type == sb.SP_TYPE_BLR and o.rel_tol == 1e-2 and o.abs_tol == 1e-5 and o.leaf_size == 128
+    o.abs_tol = 1e-10
     o.type = sb.SP_TYPE_HSS if stype == "HSS" else sb.SP_TYPE_BLR
     o.rel_tol, o.leaf_size = tol, 64
     h = C.c_void_p()
