@@ -406,6 +406,16 @@ int SB200_d_hss_file_info(const char* path, long long int* out);
 int SB200_d_hss_file_copy(const char* in_path, const char* out_path);
 
 /* Library identification: returns "strumpack_b200 <ver> sm_100a". */
+/* Test / microbenchmark hook for the ULV leaf QR kernels, outside any tree:
+ * `count` copies of the column-major m x naug block A (m <= 256) get the
+ * blocked Householder QR of their first k columns, reflectors applied to all
+ * naug columns.  variant 0: right-looking ulv_qr_kernel, 1: left-looking
+ * warp-specialised ulv_qr3_kernel.  out (m x naug) / T (16 x k, one 16 x 16
+ * block-reflector factor per 16-column panel) receive the last copy's result,
+ * ms the best kernel time of `reps` launches (CUDA events). */
+int SB200_debug_qr_batch(int m, int k, int naug, int count, const double* A, double* out, double* T,
+                         int variant, int reps, float* ms);
+
 const char* SB200_version(void);
 
 #ifdef __cplusplus

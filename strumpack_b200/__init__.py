@@ -56,6 +56,7 @@ _pvp = C.POINTER(C.c_void_p)
 _po = C.POINTER(CSPOptions)
 SYMBOLS = {
     "SB200_version": (C.c_char_p, []),
+    "SB200_debug_qr_batch": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "SP_d_struct_default_options": (None, [_po]),
     "SP_d_struct_destroy": (None, [_pvp]),
     "SP_d_struct_rows": (_i, [_vp]),
@@ -235,6 +236,18 @@ def pack_generators(nodes):
     v = np.concatenate(vals) if vals else np.zeros(0)
     p = np.concatenate(perms) if perms else np.zeros(0, dtype=np.int32)
     return tab, v, p
+
+
+def debug_qr_batch(A, k, count=1, variant=1, reps=1):
+    """Leaf-QR kernel hook (tests / microbenchmark): returns (out, T, ms)."""
+    A = np.asfortranarray(np.asarray(A, dtype=np.float64))
+    m, naug = A.shape
+    out = np.zeros_like(A, order="F")
+    T = np.zeros((16, max(k, 1)), order="F")
+    ms = C.c_float(0.0)
+    _check(lib().SB200_debug_qr_batch(m, k, naug, count, A.ctypes.data, out.ctypes.data, T.ctypes.data,
+                                      variant, reps, C.addressof(ms)), "debug_qr_batch")
+    return out, T, float(ms.value)
 
 
 def hss_file_info(path):

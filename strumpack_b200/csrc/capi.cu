@@ -886,6 +886,14 @@ int SB200_d_hss_file_info(const char* path, long long int* out) {
   });
 }
 
+int SB200_debug_qr_batch(int m, int k, int naug, int count, const double* A, double* out, double* T,
+                         int variant, int reps, float* ms) {
+  return guarded([&] {
+    require_gpu();
+    debug_qr_batch(m, k, naug, count, A, out, T, variant, reps, ms);
+  });
+}
+
 int SB200_d_hss_file_copy(const char* in_path, const char* out_path) {
   return guarded([&] { HSSHost::read_file(in_path).write_file(out_path); });
 }

@@ -1,6 +1,9 @@
 // strumpack_b200 -- HSS apply / ULV factor / ULV solve on sm_100a.
 // See hss_engine.hpp for the reference routines each kernel family replaces.
 #include "hss_engine.hpp"
+#include "ulv_qr3.cuh"
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <algorithm>
 #include <cmath>
@@ -2716,6 +2719,8 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   // cp.async-streamed solve sweeps: bit 0 backward, bit 1 forward (default: both);
   // bits 2 / 3 (with bit 0 / 1 clear): the non-streamed kernels with L2 prefetch of the next block
   if (const char* e = std::getenv("SB200_SOLVE_PIPE")) solve_pipe_ = std::atoi(e);
+  // 1: left-looking warp-specialised TMA-fed QR (ulv_qr3.cuh) for classes with m <= 256; default: the right-looking kernel
+  if (const char* e = std::getenv("SB200_QR3")) qr3_ = std::atoi(e);
   if (qr_split_) qr_variant_ = 0;   // the per-panel launch experiment assumes nb_-wide panels
   build_tables();
 }
@@ -2821,6 +2826,42 @@ template <typename K> static void set_smem(K kernel, size_t bytes) {
     SB200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
+// One TMA descriptor per node for ulv_qr3_kernel's reflector ring: the node's
+// factor block as a 2-D fp64 tensor {m rows (contiguous), naug columns}, tiles of
+// 16 x 16 written to shared memory with the 128-byte swizzle.  128 bytes per node
+// in `out` (zeros for nodes the kernel does not feed through TMA).
+static void build_qr3_tmaps(const std::vector<DNode>& nodes, double* fact_base, DevBuf<unsigned char>& out) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    SB200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled not available");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+  std::vector<CUtensorMap> host(nodes.size());
+  std::memset(host.data(), 0, host.size() * sizeof(CUtensorMap));
+  for (size_t i = 0; i < nodes.size(); i++) {
+    const DNode& d = nodes[i];
+    if (d.parent < 0 || d.k == 0 || d.m > qr3::MAXM || (d.m & 1) || (d.F & 1)) continue;
+    const cuuint64_t dims[2] = {(cuuint64_t)d.m, (cuuint64_t)d.naug};
+    const cuuint64_t strides[1] = {(cuuint64_t)d.m * sizeof(double)};
+    const cuuint32_t box[2] = {16, 16}, estr[2] = {1, 1};
+    const CUresult r = encode(&host[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, fact_base + d.F, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for an " +
+                               std::to_string(d.m) + " x " + std::to_string(d.naug) + " factor block");
+  }
+  out.upload(reinterpret_cast<const unsigned char*>(host.data()), host.size() * sizeof(CUtensorMap));
+  SB200_CUDA(cudaStreamSynchronize(0));
+}
+
 __global__ void copy2d_kernel(double* __restrict__ dst, long long ldd,
                               const double* __restrict__ src, long long lds,
                               int rows, int cols) {
@@ -2889,6 +2930,7 @@ void HSSEngine::make_lists(NodeLists& L, const std::vector<int>& nodes) {
 
 int HSSEngine::class_nb(int h, int max_m) const {
   if (nb_ != 32 || max_m > 256) return nb_;
+  if (qr3_) return 16;
   if (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0)) return 32;   // the left-looking kernel writes 32-wide T
   return (qr_regpanel_ && qr_variant_ >= 1) ? 16 : 32;
 }
@@ -3154,7 +3196,11 @@ void HSSEngine::factor_prepare(bool whole) {
   }
   // zero-filled on allocation: the alignment padding between blocks is never written
   const size_t nf = (size_t)std::max<long long>(fact_len_, 1), nt = (size_t)std::max<long long>((long long)nb_ * tot_k_, 1);
-  if (fact_.n < nf) { fact_.alloc(nf); SB200_CUDA(cudaMemset(fact_.p, 0, nf * sizeof(double))); }
+  if (fact_.n < nf) { fact_.alloc(nf); SB200_CUDA(cudaMemset(fact_.p, 0, nf * sizeof(double))); tmaps_for_ = nullptr; }
+  if (qr3_ && tmaps_for_ != fact_.p) {   // TMA descriptors of the factor blocks (they carry the arena's address)
+    build_qr3_tmaps(hn_, fact_.p, tmaps_);
+    tmaps_for_ = fact_.p;
+  }
   if (tfac_.n < nt) { tfac_.alloc(nt); SB200_CUDA(cudaMemset(tfac_.p, 0, nt * sizeof(double))); }
   rootpiv_.ensure(std::max(hn_[0].m, 1));
   scratch_.ensure((size_t)std::max<long long>(std::max(std::max(own_.smax, top_.smax), sub0_.smax), 1));
@@ -3228,7 +3274,10 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       for (int pp = 0; pp < npan; pp++)
         for (int phase0 = split ? 1 : 0; phase0 <= (split ? 2 : 0); phase0++) {
           const int phase = phase0 + (qr_nowide_ ? 8 : 0) + (h == 0 ? (qr_skew_ << 4) : 0);
-          if (nb_ == 32 && gmm <= 256 && !split && (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0))) {
+          if (nb_ == 32 && gmm <= 256 && qr3_ && !split) {
+            set_smem(qr3::ulv_qr3_kernel, qr3::SMEM_BYTES);
+            qr3::ulv_qr3_kernel<<<cnt, qr3::NTHREADS, qr3::SMEM_BYTES, st>>>(dn_.p, lst, fact_.p, tfac_.p, tmaps_.p);
+          } else if (nb_ == 32 && gmm <= 256 && !split && (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0))) {
             const size_t smem = qr_ll_smem(ldv);
             set_smem(ulv_qr_ll_kernel, smem);
             if (std::getenv("SB200_DEBUG_OCC")) {
@@ -3652,6 +3701,65 @@ void HSSEngine::dist_solve_end(int s, double* dB, int ldB, const double* recv, c
   solve_bwd(top_, s, dB, ldB, st);
   solve_bwd(own_, s, dB, ldB, st);
   SB200_CUDA(cudaGetLastError());
+}
+
+
+// ---------------------------------------------------------------------------
+// Test / microbenchmark hook: `count` copies of one m x naug block (QR of the
+// first k columns) through the leaf QR kernels, outside any HSS tree.
+// variant 0: ulv_qr_kernel<16, true, 128> (right-looking), 1: qr3::ulv_qr3_kernel
+// ---------------------------------------------------------------------------
+void debug_qr_batch(int m, int k, int naug, int count, const double* hA, double* hOut, double* hT, int variant,
+                    int reps, float* ms) {
+  if (m < 1 || m > 256 || k < 0 || k > m || naug < k || count < 1)
+    throw std::invalid_argument("debug_qr_batch: need 1 <= m <= 256, 0 <= k <= m <= ..., naug >= k");
+  const long long fsz = (((long long)m * naug) + 1) & ~1LL, tsz = 32LL * std::max(k, 1);
+  std::vector<DNode> nodes(count);
+  std::vector<int> list(count);
+  for (int i = 0; i < count; i++) {
+    DNode d{};
+    d.parent = 0; d.leaf = 1; d.m = m; d.k = k; d.naug = naug; d.nbq = 16;
+    d.F = fsz * i; d.T = tsz * i;
+    nodes[i] = d; list[i] = i;
+  }
+  DevBuf<DNode> dn; dn.upload(nodes.data(), nodes.size());
+  DevBuf<int> dl; dl.upload(list.data(), list.size());
+  DevBuf<double> src((size_t)fsz * count), fact((size_t)fsz * count), tf((size_t)tsz * count);
+  SB200_CUDA(cudaMemset(src.p, 0, sizeof(double) * fsz * count));
+  for (int i = 0; i < count; i++)
+    SB200_CUDA(cudaMemcpy(src.p + fsz * i, hA, sizeof(double) * (size_t)m * naug, cudaMemcpyHostToDevice));
+  DevBuf<unsigned char> tmaps;
+  if (variant == 1) build_qr3_tmaps(nodes, fact.p, tmaps);
+  cudaEvent_t e0, e1;
+  SB200_CUDA(cudaEventCreate(&e0));
+  SB200_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  const int ldv = smem_ld(m);
+  for (int r = 0; r < std::max(reps, 1); r++) {
+    SB200_CUDA(cudaMemcpy(fact.p, src.p, sizeof(double) * fsz * count, cudaMemcpyDeviceToDevice));
+    SB200_CUDA(cudaMemset(tf.p, 0, sizeof(double) * tsz * count));
+    SB200_CUDA(cudaEventRecord(e0, 0));
+    if (variant == 1) {
+      set_smem(qr3::ulv_qr3_kernel, qr3::SMEM_BYTES);
+      qr3::ulv_qr3_kernel<<<count, qr3::NTHREADS, qr3::SMEM_BYTES>>>(dn.p, dl.p, fact.p, tf.p, tmaps.p);
+    } else {
+      size_t smem = qr_smem<16>(ldv);
+      set_smem(ulv_qr_kernel<16, true, 128>, smem);
+      ulv_qr_kernel<16, true, 128><<<count, 128, smem>>>(dn.p, dl.p, fact.p, tf.p, ldv, 0, 0);
+    }
+    SB200_CUDA(cudaEventRecord(e1, 0));
+    SB200_CUDA(cudaEventSynchronize(e1));
+    SB200_CUDA(cudaGetLastError());
+    float t = 0.f;
+    SB200_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    best = std::min(best, t);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms) *ms = best;
+  // the last copy (its neighbours ran concurrently: races between CTAs would show)
+  if (hOut) SB200_CUDA(cudaMemcpy(hOut, fact.p + fsz * (count - 1), sizeof(double) * (size_t)m * naug, cudaMemcpyDeviceToHost));
+  if (hT) SB200_CUDA(cudaMemcpy(hT, tf.p + tsz * (count - 1), sizeof(double) * 16 * (size_t)std::max(k, 1), cudaMemcpyDeviceToHost));
 }
 
 }  // namespace sb200

@@ -185,6 +185,10 @@ class HSSEngine {
   DevBuf<double> pf_lu_, vhat_, zeros_, stmp_[4];
   DevBuf<int> pf_piv_;
   int nb_ = 32;
+  DevBuf<unsigned char> tmaps_;          // one CUtensorMap (128 B) per node: ulv_qr3_kernel's TMA feed
+  const double* tmaps_for_ = nullptr;    // the factor arena those descriptors point into
+  int qr3_ = 0;        // SB200_QR3=1: ulv_qr3.cuh (left-looking, TMA-fed, warp-specialised) for classes with m <= 256;
+                       // measured slower than the right-looking kernel, kept as an option
   int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0, qr_ll_ = 0, qr_variant_ = 1, qr_nowide_ = 0;   // switches; env SB200_QR_*
   int elim_variant_ = 0;   // ulv_eliminate_kernel: 0 = 32-column tiles, 1 = 16-column tiles x 4 CTAs/SM, 2 = 16-column tiles prefetched (SB200_ELIM_VARIANT)
   int solve_pipe_ = 3;  // bit 0: ulv_bwd_pipe_kernel, bit 1: ulv_fwd_pipe_kernel (SB200_SOLVE_PIPE; 0 = the non-streamed kernels)
@@ -192,5 +196,9 @@ class HSSEngine {
   bool profile_ = false;
   cudaEvent_t ev_[2] = {nullptr, nullptr};
 };
+
+// test / microbenchmark hook for the leaf QR kernels (see hss_engine.cu)
+void debug_qr_batch(int m, int k, int naug, int count, const double* hA, double* hOut, double* hT, int variant,
+                    int reps, float* ms);
 
 }  // namespace sb200
