@@ -28,13 +28,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.setrecursionlimit(100000)
 
-FP64_DMMA_PEAK_TFLOPS = 37.1   # profiles/microbench/fp64_peak (this pool's B200)
-# dram__bytes_read.sum + dram__bytes_write.sum of the leaf-class ulv_qr_kernel launch (the default
-# variant: 16-column panels, 128-thread CTAs, 4 per SM) from the ncu --set full capture of
-# profiles/r1c_ncu_summary.md: 2.954 + 2.965 GB for 1024 leaves of 256 (N = 2^18).  The algorithmic
-# bytes are 2 x 8 x 256 x 281 B = 1.15 MB per leaf: the right-looking trailing matrix of the ~590
-# leaves in flight (340 MB) does not stay in the 126 MB L2.
-QR_DRAM_BYTES_PER_LEAF = (2.954075e9 + 2.965289e9) / 1024
+FP64_DMMA_PEAK_FALLBACK_TFLOPS = 37.1   # profiles/r1_fp64_peak.txt; the bench measures it live (SB200_fp64_dmma_peak_tflops)
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch come from an ncu --set full capture
+# (they cannot be measured outside a profiler): profiles/qr_dram_traffic.json holds the per-leaf figure of the
+# latest capture and names the .md summary it was read from.
+def qr_dram_bytes_per_leaf():
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "qr_dram_traffic.json")))
+        return float(d["bytes_per_leaf"]), d["source"]
+    except Exception:
+        return None, None
+
+
 LEAF, TOL, H_GAUSS, LAMBDA = 256, 1e-4, 0.1, 1.0
 
 
@@ -422,16 +427,19 @@ def run_ours(args):
     qr_alg = H.flops("qr_leaf") * share
     qr_exec = H.flops("qr_leaf_exec") * share
     qr_avg_ms = float(np.mean(qr_ms))
-    achieved = qr_alg / (qr_avg_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS,
-                "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
-                "traffic": QR_DRAM_BYTES_PER_LEAF * (n // LEAF) * share if n % LEAF == 0 else None,
-                "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r1c_ncu_summary.md, scaled by leaves)",
+    peak = sb.fp64_dmma_peak_tflops() or FP64_DMMA_PEAK_FALLBACK_TFLOPS     # measured now, on this GPU
+    executed = qr_exec / (qr_avg_ms * 1e-3) / 1e12
+    ref_accounted = qr_alg / (qr_avg_ms * 1e-3) / 1e12
+    per_leaf, traffic_src = qr_dram_bytes_per_leaf()
+    roofline = {"bound": "tensor", "achieved": executed, "peak": peak,
+                "unit": "TFLOP/s", "frac": executed / peak,
+                "what": "flops the kernel EXECUTES (Q is never formed) / measured fp64 tensor-pipe peak",
+                "reference_accounted_tflops": ref_accounted, "frac_reference_accounted": ref_accounted / peak,
+                "traffic": per_leaf * (n // LEAF) * share if (per_leaf and n % LEAF == 0) else None,
+                "traffic_unit": f"bytes/launch: ncu dram read+write per leaf ({traffic_src}) x leaves of this launch",
                 "kernel": "ulv_qr_kernel (leaf class)", "kernel_ms": qr_avg_ms,
-                "executed_tflops": qr_exec / (qr_avg_ms * 1e-3) / 1e12,
-                "peak_source": "fp64 mma.sync (DMMA) peak measured on this pool's B200 by "
-                               "profiles/microbench/fp64_peak.cu; MEASURED_PEAKS.json holds "
-                               "no fp64 figure (tcgen05 has no f64 kind)"}
+                "peak_source": "mma.sync.m8n8k4.f64 stream measured in this run by SB200_fp64_dmma_peak_tflops "
+                               "(MEASURED_PEAKS.json holds no fp64 figure; tcgen05 has no f64 kind)"}
 
     if rank == 0:
         base, parity = None, None
@@ -466,6 +474,101 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------ BLR
+def run_blr(args):
+    """configs[3]: BLRMatrix LU (compress_and_factor, RL, weak admissibility) of the root frontal matrix of the
+    7-point Laplacian on a 181^3 grid (N = 32761), tile 256, tol 1e-4, one B200.  One step = one factorization.
+    value: matrix resident in HBM; e2e: through SB200_d_blr_compress_and_factor with a HOST matrix (H2D inside)."""
+    import torch
+    import strumpack_b200 as sb
+    from strumpack_b200.fronts import laplacian_root_front
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                     # single-GPU by spec (SURVEY 8e): replicas only
+    torch.cuda.set_device(0)
+    sb.lib()
+    k, leaf, tol = args.blr_k, 256, 1e-4
+    F, _ = laplacian_root_front(k, leaf, device="cuda")
+    n = F.shape[0]
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=leaf)
+    X = torch.randn(n, 4, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    Y = (F @ X).cpu().numpy()
+    for _ in range(max(args.warmup, 1)):
+        B = sb.BLRMatrix.compress_and_factor_device(F, o)
+    torch.cuda.synchronize()
+    cp, cpath = clocks_start()
+    l0 = B.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        B = sb.BLRMatrix.compress_and_factor_device(F, o)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = clocks_stop(cp, cpath)
+    launches = B.launches
+    xs = B.solve(Y)
+    err = float(np.linalg.norm(xs - X.cpu().numpy()) / np.linalg.norm(X.cpu().numpy()))
+    nb = B.tiles
+    # RL schedule with a dense trailing matrix: every step reads and writes every trailing tile once
+    alg_bytes = sum((nb - i - 1) ** 2 for i in range(nb)) * 2 * 8 * (n / nb) ** 2 + 2 * 8 * n * n
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    # e2e: host matrix through the C ABI
+    Fh = F.cpu().numpy()             # symmetric: row-major == column-major
+    Fh = np.asfortranarray(Fh)
+    sb.BLRMatrix.compress_and_factor(Fh, o)
+    t0 = time.perf_counter()
+    Bh = sb.BLRMatrix.compress_and_factor(Fh, o)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    base = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import ref
+            if ref.available():
+                kk = args.blr_ref_k
+                Fr, _ = laplacian_root_front(kk, leaf, device="cuda")
+                Fr = np.asfortranarray(Fr.cpu().numpy())
+                cores = os.cpu_count() or 1
+                ref.set_num_threads(cores)
+                t0 = time.perf_counter()
+                R = ref.RefBLR(Fr, f"--blr_leaf_size {leaf} --blr_rel_tol {tol}")
+                tr = time.perf_counter() - t0
+                Bs = sb.BLRMatrix.compress_and_factor(Fr, o)          # same sample through the engine
+                t0 = time.perf_counter()
+                Bs = sb.BLRMatrix.compress_and_factor(Fr, o)
+                ts = time.perf_counter() - t0
+                base = {"value": tr * 1e3, "unit": "ms", "cores": cores, "kind": "reference",
+                        "sample": f"the same front on a {kk}^3 grid (N={kk*kk}), one compress_and_factor; the engine "
+                                  f"takes {ts*1e3:.1f} ms on that sample through the host-pointer C ABI",
+                        "rank_reference": R.info()["rank"], "rank_engine": Bs.rank}
+        except Exception as e:
+            base = {"error": str(e)[:200]}
+    print(json.dumps({
+        "metric": "BLR LU (compress_and_factor) time", "value": ms, "unit": "ms", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": False,
+        "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BLRMatrix LU, root front of the 7-point Laplacian on a {k}^3 grid (N={n}), tile {leaf}, "
+                               f"tol {tol}, RL, weak admissibility", "N": n, "tiles": nb, "rank": B.rank,
+                   "nonzeros_frac": B.nonzeros / (n * n), "solve_rel_err": err,
+                   "l2": "the dense trailing matrix (8.6 GB) is far larger than L2"},
+        "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 8 * n * n, "d2h_bytes_per_step": 0,
+                "what": "SB200_d_blr_compress_and_factor with the matrix in pageable host memory"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                     "traffic": None, "algorithmic_bytes": alg_bytes,
+                     "what": "right-looking schedule on a dense trailing matrix: sum over steps of the trailing "
+                             "tiles read+written once (+ the input read and written once) / time",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+        "cpu_baseline": base,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -480,8 +583,14 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=900.0, help="reference arm: stop timing after this many seconds")
     ap.add_argument("--dump-results", default=None, help="reference arm: save y and x (npy) under this prefix")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="hss", choices=["hss", "blr"],
+                    help="hss: the BASELINE metric (default); blr: configs[3], BLR LU of the Laplacian root front")
+    ap.add_argument("--blr-k", type=int, default=181, help="grid size of the BLR front (N = k^2)")
+    ap.add_argument("--blr-ref-k", type=int, default=91, help="grid size of the bounded CPU sample of the BLR workload")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "blr" and args.impl == "ours":
+        run_blr(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

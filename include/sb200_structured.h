@@ -406,6 +406,11 @@ int SB200_d_hss_file_info(const char* path, long long int* out);
 int SB200_d_hss_file_copy(const char* in_path, const char* out_path);
 
 /* Library identification: returns "strumpack_b200 <ver> sm_100a". */
+/* The roofline denominator of the factor kernels, measured on the current device
+ * when called (about 10 ms): TFLOP/s of a register-resident stream of
+ * mma.sync.m8n8k4.f64 (fp64 has no tcgen05 kind; this is the fp64 tensor pipe). */
+double SB200_fp64_dmma_peak_tflops(void);
+
 /* Test / microbenchmark hook for the ULV leaf QR kernels, outside any tree:
  * `count` copies of the column-major m x naug block A (m <= 256) get the
  * blocked Householder QR of their first k columns, reflectors applied to all

@@ -638,10 +638,19 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
       throw std::invalid_argument("BLRMatrix::compress failed");
     reset(s);
   }
+  // what the engine does not build is refused, never replaced by something else:
+  // ACA / BACA tile compression (LRTile.cpp:77-115); COLWISE / COMB / STAR are
+  // refused by the library itself (SB200_d_blr_*_ex)
+  static void check_supported(const Opts_t& opts) {
+    if (opts.low_rank_algorithm() != LowRankAlgorithm::RRQR)
+      throw std::invalid_argument("BLR: low-rank algorithm " + get_name(opts.low_rank_algorithm()) +
+                                  " is not implemented by this engine (RRQR, the reference's default, is)");
+  }
   // BLRMatrix::compress_and_factor(A, admissible, opts)        (BLRMatrix.cpp:113-241)
   void compress_and_factor(const DenseM_t& A, const Opts_t& opts) {
     if (A.rows() != A.cols()) throw std::invalid_argument("BLR: only square matrices are supported");
     CSPStructMat s = nullptr;
+    check_supported(opts);
     SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), nullptr, 0};
     if (SB200_d_blr_compress_and_factor_ex(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), &p))
       throw std::invalid_argument("BLRMatrix::compress_and_factor failed");
@@ -653,6 +662,7 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
     std::vector<int> adm(admissible.rows() * admissible.cols());
     for (std::size_t j = 0; j < admissible.cols(); j++)
       for (std::size_t i = 0; i < admissible.rows(); i++) adm[i + j * admissible.rows()] = admissible(i, j) ? 1 : 0;
+    check_supported(opts);
     SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), adm.data(), int(admissible.rows())};
     CSPStructMat s = nullptr;
     if (SB200_d_blr_compress_and_factor_ex(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), &p))
@@ -666,6 +676,7 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
   static BLRMatrix construct_and_partial_factor(DenseM_t& A11, DenseM_t& A12, DenseM_t& A21, DenseM_t& A22,
                                                 const Opts_t& opts) {
     CSPStructMat s = nullptr;
+    check_supported(opts);
     SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), nullptr, 0};
     if (SB200_d_blr_partial_factor_ex(&s, int(A11.rows()), int(A22.rows()), A11.data(), int(A11.ld()), A12.data(),
                                       int(A12.ld()), A21.data(), int(A21.ld()), A22.data(), int(A22.ld()),

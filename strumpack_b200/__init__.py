@@ -56,6 +56,7 @@ _pvp = C.POINTER(C.c_void_p)
 _po = C.POINTER(CSPOptions)
 SYMBOLS = {
     "SB200_version": (C.c_char_p, []),
+    "SB200_fp64_dmma_peak_tflops": (_d, []),
     "SB200_debug_qr_batch": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "SP_d_struct_default_options": (None, [_po]),
     "SP_d_struct_destroy": (None, [_pvp]),
@@ -236,6 +237,11 @@ def pack_generators(nodes):
     v = np.concatenate(vals) if vals else np.zeros(0)
     p = np.concatenate(perms) if perms else np.zeros(0, dtype=np.int32)
     return tab, v, p
+
+
+def fp64_dmma_peak_tflops():
+    """fp64 tensor-pipe peak of the current GPU, measured now (TFLOP/s)."""
+    return float(lib().SB200_fp64_dmma_peak_tflops())
 
 
 def debug_qr_batch(A, k, count=1, variant=1, reps=1):

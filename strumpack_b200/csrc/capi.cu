@@ -9,6 +9,7 @@
 #include <cstring>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <vector>
 
@@ -21,10 +22,23 @@ using namespace sb200;
 
 namespace {
 
+// One handle = one matrix + its own CUDA stream + its own staging buffers.  The
+// host-pointer entry points take the handle's lock, queue copies and kernels on
+// the handle's stream and wait for that stream only: calls on DIFFERENT handles
+// from different threads overlap on the device, calls on the SAME handle are
+// serialised (re-entrant per object, thread-safe across objects).
+// The stream is a blocking one, so the few legacy-default-stream operations of
+// the set-up paths (allocations, memsets, table uploads) still order against it.
 struct Mat {
   SP_STRUCTURED_TYPE type = SP_TYPE_HSS;
   std::unique_ptr<HSSEngine> hss;
   std::unique_ptr<BLREngine> blr;
+  cudaStream_t st = nullptr;
+  std::mutex mu;
+  Mat() { if (cudaStreamCreate(&st) != cudaSuccess) st = nullptr; }
+  ~Mat() { if (st) cudaStreamDestroy(st); }
+  Mat(const Mat&) = delete;
+  Mat& operator=(const Mat&) = delete;
   // staging buffers for the host-pointer entry points
   DevBuf<double> dB, dC;
   // device copies of Theta / DUB01 / Phi of the last Schur_update and staging
@@ -304,8 +318,10 @@ int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
 }
 
 // BLRFactorAlgorithm of the reference (BLROptions.hpp:65): COLWISE 0, RL 1, LL 2,
-// COMB 3, STAR 4.  The engine has the right-looking and the left-looking
-// schedule; COMB / STAR / COLWISE run as RL.
+// COMB 3, STAR 4.  The engine has the right-looking (the reference's default)
+// and the left-looking schedule.  COLWISE, COMB and STAR (LUAR accumulation with
+// recompression, BLRMatrix.cpp:216-235,1039-1187) are not built: asking for them
+// is an error, not a silent substitution.
 static BLROpts blr_opts(const CSPOptions* opts, const SB200BLRParams* p) {
   BLROpts bo;
   bo.rel_tol = opts->rel_tol; bo.abs_tol = opts->abs_tol;
@@ -313,6 +329,11 @@ static BLROpts blr_opts(const CSPOptions* opts, const SB200BLRParams* p) {
   if (p) {
     if (p->factor_algorithm < 0 || p->factor_algorithm > 4)
       throw std::invalid_argument("unknown BLR factor algorithm");
+    if (p->factor_algorithm != 1 && p->factor_algorithm != 2)
+      throw std::invalid_argument(
+          std::string("BLR factor algorithm ") +
+          (p->factor_algorithm == 0 ? "COLWISE" : p->factor_algorithm == 3 ? "COMB" : "STAR") +
+          " is not implemented by this engine (RL, the reference's default, and LL are)");
     bo.pivot_threshold = p->pivot_threshold;
     bo.factor_algorithm = p->factor_algorithm == 2 ? 1 : 0;
     if (p->admissible) {
@@ -465,24 +486,26 @@ int SB200_d_blr_sep_rows(const CSPStructMat S) {
 int SB200_d_blr_partial_forward_solve(const CSPStructMat S, int nrhs, double* B, int ldB) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     if (!mm->blr) throw std::logic_error("operation not supported for this type");
     const int n = mm->blr->rows();
-    h2d(mm->dB, B, n, nrhs, ldB, 0);
-    mm->blr->partial_forward(nrhs, mm->dB.p, n, 0);
-    d2h(B, mm->dB, n, nrhs, ldB, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    h2d(mm->dB, B, n, nrhs, ldB, mm->st);
+    mm->blr->partial_forward(nrhs, mm->dB.p, n, mm->st);
+    d2h(B, mm->dB, n, nrhs, ldB, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
 int SB200_d_blr_partial_backward_solve(const CSPStructMat S, int nrhs, double* Y, int ldY) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     if (!mm->blr) throw std::logic_error("operation not supported for this type");
     const int n = mm->blr->rows();
-    h2d(mm->dB, Y, n, nrhs, ldY, 0);
-    mm->blr->partial_backward(nrhs, mm->dB.p, n, 0);
-    d2h(Y, mm->dB, n, nrhs, ldY, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    h2d(mm->dB, Y, n, nrhs, ldY, mm->st);
+    mm->blr->partial_backward(nrhs, mm->dB.p, n, mm->st);
+    d2h(Y, mm->dB, n, nrhs, ldY, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -527,7 +550,8 @@ int SP_d_struct_mult(const CSPStructMat S, char trans, int m, const double* B,
                      int ldB, double* C, int ldC) {
   return guarded([&] {
     Mat* mm = M(S);
-    cudaStream_t st = 0;
+    std::lock_guard<std::mutex> lk(mm->mu);
+    cudaStream_t st = mm->st;
     if (mm->blr) {
       const int n = mm->blr->rows();
       h2d(mm->dB, B, n, m, ldB, st);
@@ -553,15 +577,18 @@ int SP_d_struct_factor(CSPStructMat S) {
     if (M(S)->blr)   // as in the reference: BLRMatrix has no factor() (StructuredMatrix.cpp:1539-1589)
       throw std::logic_error("factor() is not supported for a compressed BLR matrix; "
                              "use SB200_d_blr_compress_and_factor");
-    hss(S).factor(0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
+    hss(S).factor(mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
 int SP_d_struct_solve(const CSPStructMat S, int nrhs, double* B, int ldB) {
   return guarded([&] {
     Mat* mm = M(S);
-    cudaStream_t st = 0;
+    std::lock_guard<std::mutex> lk(mm->mu);
+    cudaStream_t st = mm->st;
     if (mm->blr) {
       const int n = mm->blr->rows();
       h2d(mm->dB, B, n, nrhs, ldB, st);
@@ -580,8 +607,10 @@ int SP_d_struct_solve(const CSPStructMat S, int nrhs, double* B, int ldB) {
 
 int SP_d_struct_shift(CSPStructMat S, double s) {
   return guarded([&] {
-    hss(S).shift(s, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
+    hss(S).shift(s, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -608,8 +637,9 @@ int SB200_d_hss_apply(const CSPStructMat S, char trans, int m, const double* B,
                       int ldB, double beta, double* C, int ldC) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
-    cudaStream_t st = 0;
+    cudaStream_t st = mm->st;
     const bool T = !(trans == 'N' || trans == 'n');
     const int nb = T ? H.rows() : H.cols(), nc = T ? H.cols() : H.rows();
     h2d(mm->dB, B, nb, m, ldB, st);
@@ -633,33 +663,36 @@ int SB200_d_hss_extract(const CSPStructMat S, int nI, const int* I, int nJ, cons
   return guarded([&] {
     if (nI <= 0 || nJ <= 0) return;
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
-    if (add) h2d(mm->dC, B, nI, nJ, ldB, 0);
+    if (add) h2d(mm->dC, B, nI, nJ, ldB, mm->st);
     else mm->dC.ensure((size_t)nI * nJ);
-    H.extract(nI, I, nJ, J, mm->dC.p, nI, add != 0, 0);
-    d2h(B, mm->dC, nI, nJ, ldB, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    H.extract(nI, I, nJ, J, mm->dC.p, nI, add != 0, mm->st);
+    d2h(B, mm->dC, nI, nJ, ldB, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
 int SB200_d_hss_forward_solve(const CSPStructMat S, int nrhs, const double* B, int ldB) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
-    h2d(mm->dB, B, H.rows(), nrhs, ldB, 0);
-    H.forward_solve(nrhs, mm->dB.p, H.rows(), 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    h2d(mm->dB, B, H.rows(), nrhs, ldB, mm->st);
+    H.forward_solve(nrhs, mm->dB.p, H.rows(), mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
 int SB200_d_hss_backward_solve(const CSPStructMat S, int nrhs, double* X, int ldX) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
     mm->dB.ensure((size_t)H.rows() * nrhs);
-    H.backward_solve(nrhs, mm->dB.p, H.rows(), 0);
-    d2h(X, mm->dB, H.rows(), nrhs, ldX, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    H.backward_solve(nrhs, mm->dB.p, H.rows(), mm->st);
+    d2h(X, mm->dB, H.rows(), nrhs, ldX, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -676,8 +709,10 @@ int SB200_d_hss_backward_solve_device(const CSPStructMat S, int nrhs, double* dX
 /* ---- Schur complement of the (0,0) block (HSS fronts) --------------------- */
 int SB200_d_hss_partial_factor(CSPStructMat S) {
   return guarded([&] {
-    hss(S).partial_factor(0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
+    hss(S).partial_factor(mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -712,6 +747,7 @@ int SB200_d_hss_schur_update(const CSPStructMat S, double* Theta, int ldT, doubl
                              int ldD, double* Phi, int ldP) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
     int z[7];
     H.schur_sizes(z);
@@ -720,11 +756,11 @@ int SB200_d_hss_schur_update(const CSPStructMat S, double* Theta, int ldT, doubl
     mm->dDUB01.ensure((size_t)std::max(m0, 1) * std::max(rv1, 1));
     mm->dPhi.ensure((size_t)std::max(cols1, 1) * std::max(m0, 1));
     H.schur_update(mm->dTheta.p, std::max(rows1, 1), mm->dDUB01.p, std::max(m0, 1), mm->dPhi.p,
-                   std::max(cols1, 1), 0);
-    if (Theta && rows1 && rv0) d2h(Theta, mm->dTheta, rows1, rv0, ldT, 0);
-    if (DUB01 && m0 && rv1) d2h(DUB01, mm->dDUB01, m0, rv1, ldD, 0);
-    if (Phi && cols1 && m0) d2h(Phi, mm->dPhi, cols1, m0, ldP, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+                   std::max(cols1, 1), mm->st);
+    if (Theta && rows1 && rv0) d2h(Theta, mm->dTheta, rows1, rv0, ldT, mm->st);
+    if (DUB01 && m0 && rv1) d2h(DUB01, mm->dDUB01, m0, rv1, ldD, mm->st);
+    if (Phi && cols1 && m0) d2h(Phi, mm->dPhi, cols1, m0, ldP, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -746,26 +782,27 @@ int SB200_d_hss_schur_product_direct(const CSPStructMat S, const double* Theta, 
                                      double* Sc, int ldSc) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
     int z[7];
     H.schur_sizes(z);
     const int rows1 = z[0], cols1 = z[1], rv0 = z[2], m0 = z[3], rv1 = z[4];
     if (c <= 0) return;
     // NULL: use the device copies kept by the last SB200_d_hss_schur_update
-    if (Theta && rows1 && rv0) h2d(mm->dTheta, Theta, rows1, rv0, ldT, 0);
-    if (DUB01 && m0 && rv1) h2d(mm->dDUB01, DUB01, m0, rv1, ldD, 0);
-    if (Phi && cols1 && m0) h2d(mm->dPhi, Phi, cols1, m0, ldP, 0);
+    if (Theta && rows1 && rv0) h2d(mm->dTheta, Theta, rows1, rv0, ldT, mm->st);
+    if (DUB01 && m0 && rv1) h2d(mm->dDUB01, DUB01, m0, rv1, ldD, mm->st);
+    if (Phi && cols1 && m0) h2d(mm->dPhi, Phi, cols1, m0, ldP, mm->st);
     if (!mm->dTheta.p || !mm->dDUB01.p || !mm->dPhi.p)
       throw std::logic_error("Schur_product_direct: no Theta / DUB01 / Phi (call Schur_update first)");
-    h2d(mm->dS[0], R, rows1, c, ldR, 0);
+    h2d(mm->dS[0], R, rows1, c, ldR, mm->st);
     mm->dS[1].ensure((size_t)rows1 * c);
     mm->dS[2].ensure((size_t)cols1 * c);
     H.schur_product_direct(mm->dTheta.p, std::max(rows1, 1), mm->dDUB01.p, std::max(m0, 1),
                            mm->dPhi.p, std::max(cols1, 1), c, mm->dS[0].p, rows1, mm->dS[1].p,
-                           rows1, mm->dS[2].p, cols1, 0);
-    d2h(Sr, mm->dS[1], rows1, c, ldSr, 0);
-    d2h(Sc, mm->dS[2], cols1, c, ldSc, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+                           rows1, mm->dS[2].p, cols1, mm->st);
+    d2h(Sr, mm->dS[1], rows1, c, ldSr, mm->st);
+    d2h(Sc, mm->dS[2], cols1, c, ldSc, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -775,23 +812,24 @@ int SB200_d_hss_schur_product_indirect(const CSPStructMat S, const double* DUB01
                                        double* Sr, int ldSr, double* Sc, int ldSc) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
     int z[7];
     H.schur_sizes(z);
     const int rows1 = z[0], cols1 = z[1], m0 = z[3], rv1 = z[4], rows0 = z[6];
     if (c <= 0) return;
-    if (DUB01 && m0 && rv1) h2d(mm->dDUB01, DUB01, m0, rv1, ldD, 0);
+    if (DUB01 && m0 && rv1) h2d(mm->dDUB01, DUB01, m0, rv1, ldD, mm->st);
     if (!mm->dDUB01.p) throw std::logic_error("Schur_product_indirect: no DUB01 (call Schur_update first)");
-    h2d(mm->dS[0], R0, rows0, c, ldR0, 0);
-    h2d(mm->dS[3], R1, rows1, c, ldR1, 0);
-    h2d(mm->dS[1], Sr1, rows1, c, ldSr1, 0);
-    h2d(mm->dS[2], Sc1, cols1, c, ldSc1, 0);
+    h2d(mm->dS[0], R0, rows0, c, ldR0, mm->st);
+    h2d(mm->dS[3], R1, rows1, c, ldR1, mm->st);
+    h2d(mm->dS[1], Sr1, rows1, c, ldSr1, mm->st);
+    h2d(mm->dS[2], Sc1, cols1, c, ldSc1, mm->st);
     H.schur_product_indirect(mm->dDUB01.p, std::max(m0, 1), c, mm->dS[0].p, rows0, mm->dS[3].p, rows1,
                              mm->dS[1].p, rows1, mm->dS[2].p, cols1, mm->dS[1].p, rows1,
-                             mm->dS[2].p, cols1, 0);
-    d2h(Sr, mm->dS[1], rows1, c, ldSr, 0);
-    d2h(Sc, mm->dS[2], cols1, c, ldSc, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+                             mm->dS[2].p, cols1, mm->st);
+    d2h(Sr, mm->dS[1], rows1, c, ldSr, mm->st);
+    d2h(Sc, mm->dS[2], cols1, c, ldSc, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -799,16 +837,17 @@ int SB200_d_hss_partial_forward_solve(const CSPStructMat S, int nrhs, const doub
                                       double* reduced_rhs, int ldR) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
     int z[7];
     H.schur_sizes(z);
     const int rv0 = z[2], rows0 = z[6];
     if (nrhs <= 0) return;
-    h2d(mm->dS[4], B0, rows0, nrhs, ldB, 0);
+    h2d(mm->dS[4], B0, rows0, nrhs, ldB, mm->st);
     mm->dS[5].ensure((size_t)std::max(rv0, 1) * nrhs);
-    H.partial_forward_solve(nrhs, mm->dS[4].p, rows0, mm->dS[5].p, std::max(rv0, 1), 0);
-    if (rv0 && reduced_rhs) d2h(reduced_rhs, mm->dS[5], rv0, nrhs, ldR, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    H.partial_forward_solve(nrhs, mm->dS[4].p, rows0, mm->dS[5].p, std::max(rv0, 1), mm->st);
+    if (rv0 && reduced_rhs) d2h(reduced_rhs, mm->dS[5], rv0, nrhs, ldR, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -832,15 +871,16 @@ int SB200_d_hss_partial_x(const CSPStructMat S, int nrhs, double* X, int ldX, in
 int SB200_d_hss_partial_backward_solve(const CSPStructMat S, int nrhs, double* X0, int ldX) {
   return guarded([&] {
     Mat* mm = M(S);
+    std::lock_guard<std::mutex> lk(mm->mu);
     auto& H = hss(S);
     int z[7];
     H.schur_sizes(z);
     const int rows0 = z[6];
     if (nrhs <= 0) return;
     mm->dS[4].ensure((size_t)rows0 * nrhs);
-    H.partial_backward_solve(nrhs, mm->dS[4].p, rows0, 0);
-    d2h(X0, mm->dS[4], rows0, nrhs, ldX, 0);
-    SB200_CUDA(cudaStreamSynchronize(0));
+    H.partial_backward_solve(nrhs, mm->dS[4].p, rows0, mm->st);
+    d2h(X0, mm->dS[4], rows0, nrhs, ldX, mm->st);
+    SB200_CUDA(cudaStreamSynchronize(mm->st));
   });
 }
 
@@ -884,6 +924,12 @@ int SB200_d_hss_file_info(const char* path, long long int* out) {
     out[6] = h.apply_flops(); out[7] = h.factor_flops_ref();
     out[8] = h.solve_flops_ref(); out[9] = h.factor_flops_exec();
   });
+}
+
+double SB200_fp64_dmma_peak_tflops(void) {
+  double v = 0.;
+  guarded([&] { require_gpu(); v = measure_fp64_dmma_peak_tflops(); });
+  return v;
 }
 
 int SB200_debug_qr_batch(int m, int k, int naug, int count, const double* A, double* out, double* T,

@@ -3705,6 +3705,51 @@ void HSSEngine::dist_solve_end(int s, double* dB, int ldB, const double* recv, c
 
 
 // ---------------------------------------------------------------------------
+// Roofline denominator, measured live: register-resident mma.sync.m8n8k4.f64
+// stream (8 independent accumulators per warp, 2 CTAs of 256 threads per SM),
+// the same microbenchmark as profiles/microbench/fp64_peak.cu.  Returns TFLOP/s.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = threadIdx.x * 1e-3 + i; c[i][1] = i; }
+  const double av = a + threadIdx.x * 1e-9, bv = b;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma(c[i][0], c[i][1], av, bv);
+  }
+  double s = 0.;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+double measure_fp64_dmma_peak_tflops() {
+  int dev = 0, nsm = 0;
+  SB200_CUDA(cudaGetDevice(&dev));
+  SB200_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = 2 * nsm, threads = 256, iters = 20000;
+  DevBuf<double> out((size_t)blocks * threads);
+  cudaEvent_t e0, e1;
+  SB200_CUDA(cudaEventCreate(&e0));
+  SB200_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int r = 0; r < 4; r++) {   // first pass warms up
+    SB200_CUDA(cudaEventRecord(e0, 0));
+    dmma_peak_kernel<<<blocks, threads>>>(out.p, iters, 1.0000001, 1e-9);
+    SB200_CUDA(cudaEventRecord(e1, 0));
+    SB200_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    SB200_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    if (r) best = std::min(best, t);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = 2. * 8 * 8 * 4 * 8. * iters * (double)(blocks * threads / 32);
+  return flops / (best * 1e-3) / 1e12;
+}
+
+// ---------------------------------------------------------------------------
 // Test / microbenchmark hook: `count` copies of one m x naug block (QR of the
 // first k columns) through the leaf QR kernels, outside any HSS tree.
 // variant 0: ulv_qr_kernel<16, true, 128> (right-looking), 1: qr3::ulv_qr3_kernel

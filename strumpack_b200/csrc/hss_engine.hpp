@@ -197,6 +197,9 @@ class HSSEngine {
   cudaEvent_t ev_[2] = {nullptr, nullptr};
 };
 
+// live-measured fp64 tensor-pipe (mma.sync m8n8k4) peak of the current device, TFLOP/s
+double measure_fp64_dmma_peak_tflops();
+
 // test / microbenchmark hook for the leaf QR kernels (see hss_engine.cu)
 void debug_qr_batch(int m, int k, int naug, int count, const double* hA, double* hOut, double* hT, int variant,
                     int reps, float* ms);

@@ -268,3 +268,33 @@ def test_nonsymmetric_ranks_transposed_multi_rhs(sb, ru_in, rv_in):
     H.factor()
     b = rng.standard_normal((H.rows, 5))
     assert rel(A @ H.solve(b), b) < 1e-10
+
+
+def test_two_handles_from_two_threads(sb):
+    """One handle = one stream + one lock (re-entrant per object,
+    thread-safe across objects): two host threads drive two matrices through
+    the host-pointer C ABI at the same time, and two threads share ONE matrix;
+    every result equals the single-threaded one."""
+    import threading
+    g = np.load(os.path.join(GOLDEN, CASES[0] + ".npz"))
+    H1 = sb.HSSMatrix.read(os.path.join(GOLDEN, CASES[0] + ".hss"))
+    H2 = sb.HSSMatrix.read(os.path.join(GOLDEN, CASES[2] + ".hss"))
+    g2 = np.load(os.path.join(GOLDEN, CASES[2] + ".npz"))
+    H1.factor()
+    H2.factor()
+    errs = []
+
+    def work(H, gg, reps):
+        try:
+            for _ in range(reps):
+                assert rel(H.mult(gg["x"]), gg["y"]) < 1e-13
+                assert rel(H.solve(gg["y"]), gg["xs"]) < 1e-10
+        except Exception as e:      # surfaced below (a thread's assertion is otherwise lost)
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=a) for a in ((H1, g, 40), (H2, g2, 40), (H1, g, 40))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs[0]
