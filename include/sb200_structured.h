@@ -141,6 +141,24 @@ typedef void (*SB200ElemBlockFn)(int nI, const int* I, int nJ, const int* J, dou
                                  void* user);
 int SB200_d_hss_from_element_blocks(CSPStructMat* S, int n, SB200ElemBlockFn elem, void* user,
                                     const CSPOptions* opts);
+/* The same with (a) a cluster tree given by the caller instead of recursive
+ * bisection down to leaf_size -- pre-order arrays of tree_nodes entries: rows
+ * and number of children (0 or 2) of every node; what HSSMatrix(const
+ * structured::ClusterTree&, opts) fixes in the reference (HSSMatrix.cpp:71-82);
+ * tree_nodes = 0: none -- and (b) coordinates (d x n, column-major) of the
+ * unknowns: sampled columns are then chosen by geometric distance
+ * (HSSMatrix::compress_with_coordinates, HSSMatrix.hpp:302); d = 0: none. */
+int SB200_d_hss_from_element_blocks_ex(CSPStructMat* S, int n, SB200ElemBlockFn elem, void* user,
+                                       const CSPOptions* opts, int tree_nodes, const int* tree_sizes,
+                                       const int* tree_nchild, int d, const double* coords);
+/* HSS from a dense matrix on a given cluster tree (see above). */
+int SB200_d_hss_from_dense_tree(CSPStructMat* S, int n, const double* A, int ldA, const CSPOptions* opts,
+                                int tree_nodes, const int* tree_sizes, const int* tree_nchild);
+/* The HSS tree: nodes x 10 int64 in pre-order (parent, child 0, child 1, rows,
+ * cols, row offset, column offset, U rank, V rank, height).  Returns the number
+ * of nodes (-1 on error); out may be NULL to query it. */
+int SB200_d_hss_node_table(const CSPStructMat S, long long int* out);
+
 
 /* BLRMatrix<double>::compress_and_factor(A, weak admissibility, opts)
  * (reference src/BLR/BLRMatrix.cpp:113-241, RL variant; tiles from

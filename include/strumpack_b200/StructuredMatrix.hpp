@@ -20,6 +20,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <functional>
 #include <iostream>
 #include <memory>
@@ -287,6 +288,71 @@ std::unique_ptr<StructuredMatrix<scalar_t>> construct_from_elements(
 
 }  // namespace structured
 
+// C = alpha op(A) op(B) + beta C on host matrices: the small dense products the
+// fronts do around the structured calls (reference DenseMatrix.hpp free gemm,
+// src/dense/DenseMatrix.cpp:936-...).  Plain loops: glue, not a kernel.
+template <typename scalar_t>
+void gemm(Trans ta, Trans tb, scalar_t alpha, const DenseMatrix<scalar_t>& A, const DenseMatrix<scalar_t>& B,
+          scalar_t beta, DenseMatrix<scalar_t>& C, int /*task_depth*/ = 0) {
+  const bool tA = ta != Trans::N, tB = tb != Trans::N;
+  const std::size_t M = C.rows(), N = C.cols(), K = tA ? A.rows() : A.cols();
+  if ((tA ? A.cols() : A.rows()) != M || (tB ? B.rows() : B.cols()) != N || (tB ? B.cols() : B.rows()) != K)
+    throw std::invalid_argument("gemm: dimension mismatch");
+  for (std::size_t j = 0; j < N; j++)
+    for (std::size_t i = 0; i < M; i++) {
+      scalar_t acc = 0;
+      for (std::size_t k = 0; k < K; k++) acc += (tA ? A(k, i) : A(i, k)) * (tB ? B(j, k) : B(k, j));
+      C(i, j) = alpha * acc + (beta == scalar_t(0) ? scalar_t(0) : beta * C(i, j));
+    }
+}
+
+namespace structured {
+// reference structured::ClusterTree (src/structured/ClusterTree.hpp:50-170): a
+// recursive partition of an index range
+class ClusterTree {
+ public:
+  int size = 0;
+  std::vector<ClusterTree> c;
+  ClusterTree() = default;
+  explicit ClusterTree(int n) : size(n) {}
+  // recursive bisection down to leaf_size                      (ClusterTree.hpp:104-114)
+  const ClusterTree& refine(int leaf_size) {
+    if (c.empty()) {
+      if (size >= 2 * leaf_size) {
+        c.resize(2);
+        c[0].size = size / 2;
+        c[1].size = size - size / 2;
+        c[0].refine(leaf_size);
+        c[1].refine(leaf_size);
+      }
+    } else
+      for (auto& ch : c) ch.refine(leaf_size);
+    return *this;
+  }
+  int levels() const {
+    int l = 0;
+    for (auto& ch : c) l = std::max(l, ch.levels());
+    return l + 1;
+  }
+  std::vector<int> leaf_sizes() const {
+    std::vector<int> out;
+    collect_leaves(out);
+    return out;
+  }
+  // pre-order (size, number of children) arrays: the form the C ABI takes
+  void serialize(std::vector<int>& sizes, std::vector<int>& nchild) const {
+    sizes.push_back(size);
+    nchild.push_back(int(c.size()));
+    for (auto& ch : c) ch.serialize(sizes, nchild);
+  }
+ private:
+  void collect_leaves(std::vector<int>& out) const {
+    if (c.empty()) out.push_back(size);
+    else for (auto& ch : c) ch.collect_leaves(out);
+  }
+};
+}  // namespace structured
+
 namespace HSS {
 
 // reference HSSOptions.hpp:59-148
@@ -349,7 +415,24 @@ template <typename scalar_t> class HSSOptions : public structured::StructuredOpt
 // state handed from forward_solve to backward_solve (reference WorkSolve,
 // HSSExtra.hpp:216-226); here the intermediate vectors stay on the device
 // inside the matrix object, the struct only remembers the shape
-template <typename scalar_t> struct WorkSolve { int nrhs = 0; bool partial = false; };
+template <typename scalar_t> struct WorkSolve {
+  // what FrontHSS reads and writes between the two partial solves
+  // (FrontHSS.cpp:452-462, 487-495): V-hat^H x of the eliminated block, and the
+  // reduced unknowns of child 0 (updated by the caller before backward_solve)
+  DenseMatrix<scalar_t> reduced_rhs, x;
+  int nrhs = 0;
+  bool partial = false;
+};
+
+// reference HSSFactors<T> (HSSExtra.hpp:161-213): the part of it callers use
+template <typename scalar_t> class HSSFactors {
+ public:
+  const DenseMatrix<scalar_t>& Vhat() const { return Vhat_; }
+  DenseMatrix<scalar_t>& Vhat() { return Vhat_; }
+ private:
+  DenseMatrix<scalar_t> Vhat_;
+  template <typename T> friend class HSSMatrix;
+};
 
 // reference HSSMatrix<T> (src/HSS/HSSMatrix.hpp:95-511)
 template <typename scalar_t> class HSSMatrix : public structured::StructuredMatrix<scalar_t> {
@@ -365,6 +448,11 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
   // HSSMatrix(m, n, opts): an uncompressed m x n matrix, to be filled by compress(...)
   //                                                             (HSSMatrix.cpp:56-58)
   HSSMatrix(std::size_t m, std::size_t n, const opts_t& /*opts*/) : m0_(m), n0_(n) {}
+  // HSSMatrix(const structured::ClusterTree& t, opts): uncompressed, the partition is t
+  //                                                             (HSSMatrix.cpp:71-82)
+  HSSMatrix(const structured::ClusterTree& t, const opts_t& /*opts*/) : m0_(t.size), n0_(t.size) {
+    t.serialize(tree_sizes_, tree_nchild_);
+  }
   std::size_t rows() const override { return this->h_ ? base::rows() : m0_; }
   std::size_t cols() const override { return this->h_ ? base::cols() : n0_; }
   HSSMatrix(HSSMatrix&& o) noexcept = default;
@@ -383,10 +471,12 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
   void compress(const DenseM_t& A, const opts_t& opts) {
     opts_t o(opts);
     CSPStructMat s = nullptr;
-    if (SP_d_struct_from_dense(&s, int(A.rows()), int(A.cols()), A.data(), int(A.ld()), o.c()))
-      throw std::invalid_argument("HSSMatrix::compress failed");
-    SP_d_struct_destroy(&this->h_);
-    this->h_ = s;
+    const int rc = tree_sizes_.empty()
+        ? SP_d_struct_from_dense(&s, int(A.rows()), int(A.cols()), A.data(), int(A.ld()), o.c())
+        : SB200_d_hss_from_dense_tree(&s, int(A.rows()), A.data(), int(A.ld()), o.c(), int(tree_sizes_.size()),
+                                      tree_sizes_.data(), tree_nchild_.data());
+    if (rc) throw std::invalid_argument("HSSMatrix::compress failed");
+    adopt(s);
   }
   // HSSMatrix::compress(Amult, Aelem, opts) (HSSMatrix.cpp:173-186).  The
   // engine's sampled interpolative decomposition needs element access only:
@@ -398,12 +488,98 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
     compress(Amult, Aelem, rows(), opts);
   }
   void compress(const mult_t& /*Amult*/, const elem_t& Aelem, std::size_t n, const opts_t& opts) {
-    opts_t o(opts);
-    CSPStructMat s = nullptr;
-    if (SB200_d_hss_from_element_blocks(&s, int(n), &elem_trampoline, const_cast<elem_t*>(&Aelem), o.c()))
-      throw std::invalid_argument("HSSMatrix::compress(Amult, Aelem) failed");
+    compress_elements(Aelem, n, opts, 0, nullptr);
+  }
+  // HSSMatrix::compress_with_coordinates(coords, Aelem, opts) (HSSMatrix.hpp:302):
+  // coords is d x n, one point per column; the sampled columns of every node are
+  // its geometric neighbours
+  void compress_with_coordinates(const DenseM_t& coords, const elem_t& Aelem, const opts_t& opts) {
+    if (coords.cols() != rows()) throw std::invalid_argument("compress_with_coordinates: one point per row of the matrix");
+    DenseM_t packed(coords.rows(), coords.cols());
+    for (std::size_t j = 0; j < coords.cols(); j++)
+      for (std::size_t i = 0; i < coords.rows(); i++) packed(i, j) = coords(i, j);
+    compress_elements(Aelem, rows(), opts, int(coords.rows()), packed.data());
+  }
+  // HSSMatrix::reset(): back to the uncompressed state, same dimensions and partition
+  //                                                             (HSSMatrix.cpp:138-146)
+  void reset() {
+    if (this->h_) { m0_ = base::rows(); n0_ = base::cols(); }
     SP_d_struct_destroy(&this->h_);
-    this->h_ = s;
+    ulv_ = HSSFactors<scalar_t>();
+    trailing_deleted_ = false;
+  }
+  bool is_compressed() const { return this->h_ != nullptr; }
+  bool is_untouched() const { return this->h_ == nullptr; }
+  bool active() const { return true; }
+  bool leaf() const { return levels() <= 1; }
+  void set_openmp_task_depth(int) {}
+  // HSSMatrix::delete_trailing_block() (HSSMatrix.cpp:358-368): after the Schur
+  // complement has been taken, only the eliminated (0,0) block is used again
+  // (child(0) solves).  The engine keeps its arenas (they are shared by both
+  // halves); what changes is that whole-matrix operations are refused from here on.
+  void delete_trailing_block() { trailing_deleted_ = true; }
+  // child(c): the view FrontHSS uses -- child(0)->forward_solve(w, b, true),
+  // child(0)->backward_solve(w, x), child(0)->ULV().Vhat(), rows / cols
+  class Child {
+   public:
+    std::size_t rows() const { return rows_; }
+    std::size_t cols() const { return cols_; }
+    const HSSFactors<scalar_t>& ULV() const {
+      if (c_ != 0) throw std::logic_error("child(1)->ULV(): only the eliminated (0,0) block has factors");
+      H_->ulv_.Vhat() = H_->Vhat();
+      return H_->ulv_;
+    }
+    void forward_solve(WorkSolve<scalar_t>& w, const DenseM_t& b, bool partial) const {
+      if (c_ != 0 || !partial) throw std::logic_error("child(c)->forward_solve: child 0 with partial = true (as FrontHSS calls it)");
+      w.reduced_rhs = H_->child0_forward_solve(w, b);
+      w.x = H_->child0_x(w);
+    }
+    void backward_solve(WorkSolve<scalar_t>& w, DenseM_t& x) const {
+      if (c_ != 0) throw std::logic_error("child(c)->backward_solve: child 0 only");
+      H_->set_child0_x(w, w.x);
+      H_->child0_backward_solve(w, x);
+    }
+   private:
+    const HSSMatrix* H_ = nullptr;
+    int c_ = 0;
+    std::size_t rows_ = 0, cols_ = 0;
+    friend class HSSMatrix;
+  };
+  const Child* child(int c) const {
+    if (c < 0 || c > 1 || !this->h_) throw std::out_of_range("HSSMatrix::child");
+    int z[7];
+    base::check(SB200_d_hss_schur_sizes(this->h_, z), "schur_sizes");
+    Child& ch = child_[c];
+    ch.H_ = this; ch.c_ = c;
+    ch.rows_ = c == 0 ? this->rows() - z[0] : z[0];
+    ch.cols_ = c == 0 ? this->cols() - z[1] : z[1];
+    return &ch;
+  }
+  const HSSFactors<scalar_t>& ULV() const { return ulv_; }
+  // HSSMatrix::draw(of, rlo, clo) (HSSMatrix.cpp:370-405): gnuplot rectangles,
+  // one per leaf diagonal block and per low-rank off-diagonal block, labelled
+  // with the ranks
+  void draw(std::ostream& of, std::size_t rlo = 0, std::size_t clo = 0) const {
+    const int N = SB200_d_hss_node_table(this->h_, nullptr);
+    if (N <= 0) return;
+    std::vector<long long> t(std::size_t(N) * 10);
+    SB200_d_hss_node_table(this->h_, t.data());
+    const long long n = t[3];
+    for (int i = 0; i < N; i++) {
+      const long long* r = &t[std::size_t(i) * 10];
+      const long long ro = rlo + r[5], co = clo + r[6];
+      if (r[1] < 0) {
+        of << "set obj rect from " << co << ", " << n - ro << " to " << co + r[4] << ", " << n - (ro + r[3])
+           << " fc rgb 'red'" << std::endl;
+      } else {
+        const long long* a = &t[std::size_t(r[1]) * 10];
+        const long long* b = &t[std::size_t(r[2]) * 10];
+        of << "set obj rect from " << co + a[4] << ", " << n - ro << " to " << co + r[4] << ", " << n - (ro + a[3])
+           << " fc rgb 'green' # B01 " << a[7] << " x " << b[8] << std::endl;
+        of << "set obj rect from " << co << ", " << n - (ro + a[3]) << " to " << co + a[4] << ", " << n - (ro + r[3])
+           << " fc rgb 'green' # B10 " << b[7] << " x " << a[8] << std::endl;
+      }
+    }
   }
   // HSSMatrix::read(fname) / write(fname)                      (HSSMatrix.cpp:438-510)
   static HSSMatrix read(const std::string& fname) {
@@ -415,6 +591,7 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
 
   // apply / applyC / mult                                      (HSSMatrix.apply.hpp:34-53)
   DenseM_t apply(const DenseM_t& b) const {
+    if (trailing_deleted_) throw std::logic_error("HSSMatrix::apply after delete_trailing_block()");
     DenseM_t c(this->rows(), b.cols());
     this->mult(Trans::N, b, c);
     return c;
@@ -522,6 +699,23 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
 
  private:
   std::size_t m0_ = 0, n0_ = 0;     // dimensions before compression
+  std::vector<int> tree_sizes_, tree_nchild_;   // partition given at construction (ClusterTree ctor), pre-order
+  bool trailing_deleted_ = false;
+  mutable HSSFactors<scalar_t> ulv_;
+  mutable Child child_[2];
+  void adopt(CSPStructMat s) {
+    SP_d_struct_destroy(&this->h_);
+    this->h_ = s;
+    trailing_deleted_ = false;
+  }
+  void compress_elements(const elem_t& Aelem, std::size_t n, const opts_t& opts, int d, const scalar_t* coords) {
+    opts_t o(opts);
+    CSPStructMat s = nullptr;
+    if (SB200_d_hss_from_element_blocks_ex(&s, int(n), &elem_trampoline, const_cast<elem_t*>(&Aelem), o.c(),
+                                           int(tree_sizes_.size()), tree_sizes_.data(), tree_nchild_.data(), d, coords))
+      throw std::invalid_argument("HSSMatrix::compress(Amult, Aelem) failed");
+    adopt(s);
+  }
   static void elem_trampoline(int nI, const int* I, int nJ, const int* J, double* B, int ldB, void* user) {
     std::vector<std::size_t> Iv(I, I + nI), Jv(J, J + nJ);
     DenseMatrixWrapper<scalar_t> Bw(nI, nJ, B, ldB);
@@ -537,6 +731,15 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
 };
 
 // free function apply_HSS(op, A, B, beta, C): C = op(A) B + beta C   (HSSMatrix.hpp:705-713)
+// free function draw(H, name): writes name.gnuplot                    (HSSMatrix.hpp:705-706)
+template <typename scalar_t> void draw(const HSSMatrix<scalar_t>& H, const std::string& name) {
+  std::ofstream of("plot" + name + ".gnuplot");
+  of << "set terminal pdf enhanced color size 5,4" << std::endl << "set output '" << name << ".pdf'" << std::endl;
+  H.draw(of);
+  of << "set xrange [0:" << H.cols() << "]" << std::endl << "set yrange [0:" << H.rows() << "]" << std::endl
+     << "plot x lt -1 notitle" << std::endl;
+}
+
 template <typename scalar_t>
 void apply_HSS(Trans op, const HSSMatrix<scalar_t>& A, const DenseMatrix<scalar_t>& B, scalar_t beta,
                DenseMatrix<scalar_t>& C) {

@@ -85,6 +85,9 @@ SYMBOLS = {
     "SP_s_struct_solve": (_i, [_vp, _i, _vp, _i]),
     "SP_s_struct_shift": (_i, [_vp, C.c_float]),
     "SB200_d_hss_from_element_blocks": (_i, [_pvp, _i, _vp, _vp, _po]),
+    "SB200_d_hss_from_element_blocks_ex": (_i, [_pvp, _i, _vp, _vp, _po, _i, _vp, _vp, _i, _vp]),
+    "SB200_d_hss_from_dense_tree": (_i, [_pvp, _i, _vp, _i, _po, _i, _vp, _vp]),
+    "SB200_d_hss_node_table": (_i, [_vp, _vp]),
     "SB200_d_hss_from_kernel": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp]),
     "SB200_d_blr_compress_and_factor": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),

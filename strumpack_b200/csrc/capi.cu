@@ -146,10 +146,10 @@ double dense_check(HSSEngine& E, int n, const double* dA) {
 // randomized sampling plays, HSSMatrix.compress_stable.hpp) and the sample is
 // enlarged, then replaced by the whole complement, until the tolerance is met.
 std::unique_ptr<HSSEngine> hss_from_dense_checked(int rows, int cols, const double* A, int ldA,
-                                                  CompressOptions co) {
+                                                  CompressOptions co, const GivenTree* tree = nullptr) {
   for (int attempt = 0;; attempt++) {
     DevBuf<double> dA;
-    auto E = std::make_unique<HSSEngine>(compress_dense(rows, cols, A, ldA, co, &dA));
+    auto E = std::make_unique<HSSEngine>(compress_dense(rows, cols, A, ldA, co, &dA, tree));
     const bool sampled = co.full_complement == 0 || (co.full_complement < 0 && rows > 8192);
     if (!sampled || !dA.p) return E;
     const double err = dense_check(*E, rows, dA.p);
@@ -298,6 +298,57 @@ int SB200_d_hss_from_element_blocks(CSPStructMat* S, int n, SB200ElemBlockFn ele
     m->hss = std::make_unique<HSSEngine>(compress_element_blocks(n, elem, user, co));
     *S = m.release();
   });
+}
+
+int SB200_d_hss_from_element_blocks_ex(CSPStructMat* S, int n, SB200ElemBlockFn elem, void* user,
+                                       const CSPOptions* opts, int tree_nodes, const int* tree_sizes,
+                                       const int* tree_nchild, int d, const double* coords) {
+  return guarded([&] {
+    require_gpu();
+    auto m = std::make_unique<Mat>();
+    m->type = SP_TYPE_HSS;
+    CompressOptions co;
+    co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
+    co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
+    co.verbose = opts->verbose;
+    GivenTree t{tree_nodes, tree_sizes, tree_nchild};
+    m->hss = std::make_unique<HSSEngine>(compress_element_blocks(n, elem, user, co, tree_nodes > 0 ? &t : nullptr, d, coords));
+    *S = m.release();
+  });
+}
+
+int SB200_d_hss_from_dense_tree(CSPStructMat* S, int n, const double* A, int ldA, const CSPOptions* opts,
+                                int tree_nodes, const int* tree_sizes, const int* tree_nchild) {
+  return guarded([&] {
+    require_gpu();
+    auto m = std::make_unique<Mat>();
+    m->type = SP_TYPE_HSS;
+    CompressOptions co;
+    co.rel_tol = opts->rel_tol; co.abs_tol = opts->abs_tol;
+    co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
+    co.verbose = opts->verbose;
+    GivenTree t{tree_nodes, tree_sizes, tree_nchild};
+    m->hss = hss_from_dense_checked(n, n, A, ldA, co, tree_nodes > 0 ? &t : nullptr);
+    *S = m.release();
+  });
+}
+
+/* nodes x 10 (pre-order): parent, child 0, child 1, rows, cols, row offset, column offset, U rank, V rank,
+ * height.  out == NULL: only the number of nodes is returned (-1 on error). */
+int SB200_d_hss_node_table(const CSPStructMat S, long long int* out) {
+  int count = -1;
+  guarded([&] {
+    const auto& nodes = hss(S).host().nodes;
+    count = (int)nodes.size();
+    if (!out) return;
+    for (size_t i = 0; i < nodes.size(); i++) {
+      const auto& n = nodes[i];
+      long long* r = out + 10 * i;
+      r[0] = n.parent; r[1] = n.ch0; r[2] = n.ch1; r[3] = n.rows; r[4] = n.cols;
+      r[5] = n.row_off; r[6] = n.col_off; r[7] = n.u_rank; r[8] = n.v_rank; r[9] = n.height;
+    }
+  });
+  return count;
 }
 
 int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,

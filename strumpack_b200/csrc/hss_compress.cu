@@ -154,6 +154,27 @@ void build_tree_kd(std::vector<TNode>& T, std::vector<int>& perm, const double* 
   }
 }
 
+// cluster tree given by the caller, pre-order: size and number of children (0 or 2) per node
+// (what structured::ClusterTree describes, reference src/structured/ClusterTree.hpp)
+void build_tree_given(std::vector<TNode>& T, int nnodes, const int* sizes, const int* nchild, int n) {
+  int next = 0;
+  std::function<int(int, int)> rec = [&](int lo, int parent) -> int {
+    if (next >= nnodes) throw std::invalid_argument("cluster tree: fewer nodes than the child counts announce");
+    const int q = next++, me = (int)T.size();
+    if (sizes[q] < 0) throw std::invalid_argument("cluster tree: negative size");
+    T.push_back({lo, lo + sizes[q], parent, -1, -1, 0});
+    if (nchild[q] == 2) {
+      const int c0 = rec(lo, me);
+      const int c1 = rec(T[c0].hi, me);
+      if (T[c1].hi != T[me].hi) throw std::invalid_argument("cluster tree: child sizes do not add up");
+      T[me].ch0 = c0; T[me].ch1 = c1;
+    } else if (nchild[q] != 0) throw std::invalid_argument("cluster tree: nodes have 0 or 2 children");
+    return me;
+  };
+  rec(0, -1);
+  if (next != nnodes || T[0].hi != n) throw std::invalid_argument("cluster tree does not cover the matrix");
+}
+
 struct Problem {
   int n = 0, d = 1;
   int type = 3;
@@ -572,7 +593,7 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
 }  // namespace
 
 HSSHost compress_dense(int rows, int cols, const double* A, int ldA,
-                       const CompressOptions& o, DevBuf<double>* keep_dA) {
+                       const CompressOptions& o, DevBuf<double>* keep_dA, const GivenTree* tree) {
   if (rows != cols)
     throw std::invalid_argument("compress_dense: only square matrices are supported");
   Problem P;
@@ -581,7 +602,8 @@ HSSHost compress_dense(int rows, int cols, const double* A, int ldA,
   for (int i = 0; i < rows; i++) P.pts[i] = i;
   P.full_complement = o.full_complement < 0 ? rows <= 8192 : o.full_complement != 0;
   std::vector<TNode> T;
-  build_tree_index(T, 0, rows, -1, std::max(1, o.leaf_size));
+  if (tree && tree->nnodes > 0) build_tree_given(T, tree->nnodes, tree->sizes, tree->nchild, rows);
+  else build_tree_index(T, 0, rows, -1, std::max(1, o.leaf_size));
   return compress_impl(P, T, o, keep_dA);
 }
 
@@ -598,15 +620,23 @@ HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
   return compress_dense(rows, cols, D.data(), rows, o);
 }
 
-HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const CompressOptions& o) {
+HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const CompressOptions& o,
+                                const GivenTree* tree, int d, const double* coords) {
   if (n <= 0 || !elem) throw std::invalid_argument("compress_element_blocks: bad arguments");
   Problem P;
-  P.n = n; P.d = 1; P.type = 4; P.elem_fn = elem; P.elem_user = user;
-  P.pts.resize(n);
-  for (int i = 0; i < n; i++) P.pts[i] = i;
+  P.n = n; P.type = 4; P.elem_fn = elem; P.elem_user = user;
+  if (coords && d > 0) {   // compress_with_coordinates: the samples are chosen by geometric distance
+    P.d = d;
+    P.pts.assign(coords, coords + (size_t)d * n);
+  } else {
+    P.d = 1;
+    P.pts.resize(n);
+    for (int i = 0; i < n; i++) P.pts[i] = i;
+  }
   P.full_complement = o.full_complement < 0 ? n <= 8192 : o.full_complement != 0;
   std::vector<TNode> T;
-  build_tree_index(T, 0, n, -1, std::max(1, o.leaf_size));
+  if (tree && tree->nnodes > 0) build_tree_given(T, tree->nnodes, tree->sizes, tree->nchild, n);
+  else build_tree_index(T, 0, n, -1, std::max(1, o.leaf_size));
   return compress_impl(P, T, o);
 }
 

@@ -40,18 +40,30 @@ struct CompressOptions {
 // (HSSMatrix.hpp:68-70, compress(Amult, Aelem, opts) HSSMatrix.cpp:173-186)
 using BlockElemFn = void (*)(int nI, const int* I, int nJ, const int* J, double* B, int ldB, void* user);
 
+// a cluster tree given by the caller (structured::ClusterTree), pre-order
+struct GivenTree {
+  int nnodes = 0;
+  const int* sizes = nullptr;    // rows of every node
+  const int* nchild = nullptr;   // 0 or 2
+};
+
 // A: host column-major rows x cols
 // keep_dA: if given, receives the packed device copy of A (ld = rows) that the
 // construction made, so that the caller can verify the result without a second
 // host-to-device copy
 HSSHost compress_dense(int rows, int cols, const double* A, int ldA,
-                       const CompressOptions& o, DevBuf<double>* keep_dA = nullptr);
+                       const CompressOptions& o, DevBuf<double>* keep_dA = nullptr,
+                       const GivenTree* tree = nullptr);
 // element callback evaluated on the host
 HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
                           const CompressOptions& o);
 // entries from a block callback: only the sampled blocks are evaluated
 // (O(n * samples) entries), so n is not limited by a dense n^2 buffer
-HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const CompressOptions& o);
+// tree: partition to use instead of recursive bisection down to leaf_size;
+// coords (d x n, column-major): sample selection by geometric distance
+// (HSSMatrix::compress_with_coordinates) instead of index distance
+HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const CompressOptions& o,
+                                const GivenTree* tree = nullptr, int d = 0, const double* coords = nullptr);
 // kernel matrix on n points (d x n, column-major); pts is reordered in place,
 // perm[new] = old (may be null). kernel_type: SB200_KERNEL_TYPE.
 HSSHost compress_kernel(int n, int d, double* pts, int kernel_type, double h,

@@ -103,6 +103,11 @@ hss_down_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   const int nout = o0 + o1;
   double* u = sm;            // nout
   double* tin = sm + nout;   // rout : this node's t2
+  // Latency-bound (the upper classes have a handful of nodes, their generators
+  // come from DRAM every step): one warp per output row, the lanes split the
+  // dot product, so that all loads of a stage are in flight at once -- three
+  // dependent memory round trips per node instead of one per few terms.
+  const int warp = tid >> 5, lane = tid & 31;
   const bool has_u = (nd.parent >= 0) && rout > 0;
   if (has_u) {
     const double* my = t2 + (size_t)nd.w_off * s + (size_t)c * rout;
@@ -111,14 +116,13 @@ hss_down_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
     const int* P = perms + (TRANS ? nd.Pv : nd.Pu);
     const double* E = vals + (TRANS ? nd.Ev : nd.Eu);
     const int k = nout - rout;
-    for (int i = tid; i < nout; i += kThreads) {
-      double v;
-      if (i < rout) v = tin[i];
-      else {
-        v = 0.;
-        for (int l = 0; l < rout; l++) v += E[(i - rout) + (size_t)l * k] * tin[l];
-      }
-      u[P[i]] = v;
+    for (int i = warp; i < nout; i += kWarps) {
+      double v = 0.;
+      if (i < rout) v = lane == 0 ? tin[i] : 0.;
+      else
+        for (int l = lane; l < rout; l += 32) v += E[(i - rout) + (size_t)l * k] * tin[l];
+      v = warp_sum(v);
+      if (lane == 0) u[P[i]] = v;
     }
   } else {
     for (int i = tid; i < nout; i += kThreads) u[i] = 0.;
@@ -130,16 +134,20 @@ hss_down_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   double* ob = t2 + (size_t)c1.w_off * s + (size_t)c * o1;
   const double* B01 = vals + nd.B01;  // u_rank(c0) x v_rank(c1)
   const double* B10 = vals + nd.B10;  // u_rank(c1) x v_rank(c0)
-  for (int i = tid; i < nout; i += kThreads) {
-    double v = u[i];
+  for (int i = warp; i < nout; i += kWarps) {
+    double v = 0.;
+    const bool first = i < o0;
+    const int ii = first ? i : i - o0;
     if (!TRANS) {
-      if (i < o0) { for (int j = 0; j < q1; j++) v += B01[i + (size_t)j * o0] * tb[j]; oa[i] = v; }
-      else { int ii = i - o0; for (int j = 0; j < q0; j++) v += B10[ii + (size_t)j * o1] * ta[j]; ob[ii] = v; }
+      if (first) { for (int j = lane; j < q1; j += 32) v += B01[ii + (size_t)j * o0] * tb[j]; }
+      else { for (int j = lane; j < q0; j += 32) v += B10[ii + (size_t)j * o1] * ta[j]; }
     } else {
       // t2(c0) += B10^H t1(c1) ; t2(c1) += B01^H t1(c0)   (apply.hpp:194-211)
-      if (i < o0) { for (int j = 0; j < q1; j++) v += B10[j + (size_t)i * q1] * tb[j]; oa[i] = v; }
-      else { int ii = i - o0; for (int j = 0; j < q0; j++) v += B01[j + (size_t)ii * q0] * ta[j]; ob[ii] = v; }
+      if (first) { for (int j = lane; j < q1; j += 32) v += B10[j + (size_t)ii * q1] * tb[j]; }
+      else { for (int j = lane; j < q0; j += 32) v += B01[j + (size_t)ii * q0] * ta[j]; }
     }
+    v = warp_sum(v);
+    if (lane == 0) (first ? oa : ob)[ii] = v + u[i];
   }
 }
 
@@ -1983,11 +1991,54 @@ ulv_root_lu_kernel(double* __restrict__ Ag, int n, int* __restrict__ piv, int us
   __shared__ int pivrow;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // the reduced system at the root is small (sum of two ranks): factor it in
-  // shared memory when it fits, every step is a latency chain of barriers
+  // shared memory when it fits.  Every column is a latency chain; two barriers
+  // per column: each warp finds the pivot itself (same data, same tie-break: no
+  // broadcast), rows are swapped across all columns, [barrier], the trailing
+  // block gets its rank-1 update with the multipliers formed on the fly,
+  // [barrier].  The column scalings 1/pivot are applied in one pass at the end
+  // (they commute with the later row interchanges).
   double* A = use_smem ? smA : Ag;
   if (use_smem) {
+    double* invp = smA + (size_t)n * n;   // n reciprocal pivots
     for (int idx = tid; idx < n * n; idx += kThreads) A[idx] = Ag[idx];
     __syncthreads();
+    for (int j = 0; j < n; j++) {
+      double best = -1.;
+      int bi = j;
+      for (int i = j + lane; i < n; i += 32) {
+        const double v = fabs(A[i + (size_t)j * n]);
+        if (v > best) { best = v; bi = i; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      const int p = bi;
+      const double d = A[p + (size_t)j * n];
+      const double inv = d != 0. ? 1. / d : 0.;
+      if (tid == 0) { piv[j] = p; invp[j] = inv; }
+      if (p != j) {        // uniform: every warp found the same pivot
+        __syncthreads();   // every warp has read column j
+        for (int c = tid; c < n; c += kThreads) {
+          const double t = A[j + (size_t)c * n];
+          A[j + (size_t)c * n] = A[p + (size_t)c * n];
+          A[p + (size_t)c * n] = t;
+        }
+        __syncthreads();
+      }
+      const int nt = n - j - 1;
+      for (int idx = tid; idx < nt * nt; idx += kThreads) {
+        const int i = j + 1 + idx % nt, c = j + 1 + idx / nt;
+        A[i + (size_t)c * n] -= (A[i + (size_t)j * n] * inv) * A[j + (size_t)c * n];
+      }
+      __syncthreads();
+    }
+    for (int idx = tid; idx < n * n; idx += kThreads) {
+      const int i = idx % n, c = idx / n;
+      Ag[idx] = i > c ? A[idx] * invp[c] : A[idx];
+    }
+    return;
   }
   for (int j = 0; j < n; j++) {
     // pivot search in column j
@@ -2219,17 +2270,38 @@ ulv_root_solve_kernel(const DNode* __restrict__ nodes, int node, const double* _
       if (p != j) { double t = x[j]; x[j] = x[p]; x[p] = t; }
     }
   __syncthreads();
-  for (int j = 0; j < n; j++) {   // unit lower
-    const double xj = x[j];
-    for (int i = j + 1 + tid; i < n; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+  if (n <= 128) {
+    // small system (the usual case: sum of two ranks): one warp runs both
+    // substitutions with warp-level synchronisation only -- a chain of n short
+    // steps instead of 3 n CTA barriers
+    if (tid < 32) {
+      for (int j = 0; j < n; j++) {   // unit lower
+        const double xj = x[j];
+        for (int i = j + 1 + tid; i < n; i += 32) x[i] -= A[i + (size_t)j * n] * xj;
+        __syncwarp();
+      }
+      for (int j = n - 1; j >= 0; j--) {  // upper
+        const double xj = x[j] / A[j + (size_t)j * n];
+        __syncwarp();
+        if (tid == 0) x[j] = xj;
+        for (int i = tid; i < j; i += 32) x[i] -= A[i + (size_t)j * n] * xj;
+        __syncwarp();
+      }
+    }
     __syncthreads();
-  }
-  for (int j = n - 1; j >= 0; j--) {  // upper
-    if (tid == 0) x[j] /= A[j + (size_t)j * n];
-    __syncthreads();
-    const double xj = x[j];
-    for (int i = tid; i < j; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
-    __syncthreads();
+  } else {
+    for (int j = 0; j < n; j++) {   // unit lower
+      const double xj = x[j];
+      for (int i = j + 1 + tid; i < n; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+      __syncthreads();
+    }
+    for (int j = n - 1; j >= 0; j--) {  // upper
+      if (tid == 0) x[j] /= A[j + (size_t)j * n];
+      __syncthreads();
+      const double xj = x[j];
+      for (int i = tid; i < j; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+      __syncthreads();
+    }
   }
   if (nd.leaf && node == 0) {
     double* bb = b + (size_t)col * ldb;
@@ -2632,17 +2704,38 @@ lu_solve_kernel(const double* __restrict__ A, int n, const int* __restrict__ piv
       if (p != j) { const double t = x[j]; x[j] = x[p]; x[p] = t; }
     }
   __syncthreads();
-  for (int j = 0; j < n; j++) {   // unit lower
-    const double xj = x[j];
-    for (int i = j + 1 + tid; i < n; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+  if (n <= 128) {
+    // small system (the usual case: sum of two ranks): one warp runs both
+    // substitutions with warp-level synchronisation only -- a chain of n short
+    // steps instead of 3 n CTA barriers
+    if (tid < 32) {
+      for (int j = 0; j < n; j++) {   // unit lower
+        const double xj = x[j];
+        for (int i = j + 1 + tid; i < n; i += 32) x[i] -= A[i + (size_t)j * n] * xj;
+        __syncwarp();
+      }
+      for (int j = n - 1; j >= 0; j--) {  // upper
+        const double xj = x[j] / A[j + (size_t)j * n];
+        __syncwarp();
+        if (tid == 0) x[j] = xj;
+        for (int i = tid; i < j; i += 32) x[i] -= A[i + (size_t)j * n] * xj;
+        __syncwarp();
+      }
+    }
     __syncthreads();
-  }
-  for (int j = n - 1; j >= 0; j--) {  // upper
-    if (tid == 0) x[j] /= A[j + (size_t)j * n];
-    __syncthreads();
-    const double xj = x[j];
-    for (int i = tid; i < j; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
-    __syncthreads();
+  } else {
+    for (int j = 0; j < n; j++) {   // unit lower
+      const double xj = x[j];
+      for (int i = j + 1 + tid; i < n; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+      __syncthreads();
+    }
+    for (int j = n - 1; j >= 0; j--) {  // upper
+      if (tid == 0) x[j] /= A[j + (size_t)j * n];
+      __syncthreads();
+      const double xj = x[j];
+      for (int i = tid; i < j; i += kThreads) x[i] -= A[i + (size_t)j * n] * xj;
+      __syncthreads();
+    }
   }
   for (int i = tid; i < n; i += kThreads) xg[i] = x[i];
 }
@@ -3235,7 +3328,7 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       double* dst = lu_dst ? lu_dst : fact_.p + root.F;
       if (n2 > 0) copy_block_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(src, dst, n2);
       {
-        const size_t bytes = sizeof(double) * (size_t)root.m * root.m;
+        const size_t bytes = sizeof(double) * ((size_t)root.m * root.m + root.m);   // + reciprocal pivots
         const int use_smem = bytes <= 200 * 1024;
         set_smem(ulv_root_lu_kernel, use_smem ? bytes : 0);
         ulv_root_lu_kernel<<<1, kThreads, use_smem ? bytes : 0, st>>>(dst, root.m, lu_piv ? lu_piv : rootpiv_.p, use_smem);

@@ -10,7 +10,7 @@ import pytest
 
 from conftest import ROOT
 
-PROGRAMS = ["test_structured", "test_classes"]
+PROGRAMS = ["test_structured", "test_classes", "test_front_sequence"]
 
 
 def _build(tmp_path, name):
@@ -53,5 +53,17 @@ def test_cpp_mirror_toeplitz_ulv(built, tmp_path):
 def test_cpp_mirror_class_surface(built, tmp_path):
     exe = _build(tmp_path, "test_classes")
     r = subprocess.run([exe, "600"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "exiting" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes", [("384", "256"), ("300", "217")])
+def test_cpp_mirror_front_hss_call_sequence(built, tmp_path, sizes):
+    """The statements of FrontHSS::multifrontal_factorization / fwd_solve_node / bwd_solve_node
+    (reference src/sparse/fronts/FrontHSS.cpp:371-412, 445-496) compile against the mirror and
+    solve the front's system."""
+    exe = _build(tmp_path, "test_front_sequence")
+    r = subprocess.run([exe, *sizes], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "exiting" in r.stdout
