@@ -126,6 +126,15 @@ typedef enum {
 int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
                             int kernel_type, double h, double lambda,
                             const CSPOptions* opts, int* perm);
+/* The same with the clustering algorithm of the reference's HSSOptions
+ * (HSS::ClusteringAlgorithm, HSSOptions.hpp): 0 NATURAL (the given order,
+ * recursive bisection), 1 TWO_MEANS (the reference's default: recursive 2-means,
+ * ragged leaves), 2 KD_TREE (median bisection; what SB200_d_hss_from_kernel
+ * uses).  3 PCA and 4 COBBLE are not implemented and refused. */
+int SB200_d_hss_from_kernel_ex(CSPStructMat* S, int n, int d, double* pts,
+                               int kernel_type, double h, double lambda,
+                               const CSPOptions* opts, int* perm, int clustering);
+
 
 /* HSSMatrix::compress(Amult, Aelem, opts) (reference src/HSS/HSSMatrix.cpp:173-186;
  * what FrontHSS calls, src/sparse/fronts/FrontHSS.cpp:385): construction from a

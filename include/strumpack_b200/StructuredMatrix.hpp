@@ -463,7 +463,9 @@ template <typename scalar_t> class HSSMatrix : public structured::StructuredMatr
   static HSSMatrix from_kernel(int n, int d, scalar_t* pts, SB200_KERNEL_TYPE kernel, double h,
                                double lambda, const opts_t& opts, int* perm = nullptr) {
     CSPStructMat s = nullptr;
-    if (SB200_d_hss_from_kernel(&s, n, d, pts, kernel, h, lambda, opts.c(), perm))
+    // opts.clustering_algorithm() is honoured (TWO_MEANS by default, as in the reference);
+    // PCA / COBBLE are refused by the library
+    if (SB200_d_hss_from_kernel_ex(&s, n, d, pts, kernel, h, lambda, opts.c(), perm, int(opts.clustering_algorithm())))
       throw std::invalid_argument("HSSMatrix(kernel) failed");
     return HSSMatrix(s);
   }

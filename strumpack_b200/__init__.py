@@ -51,6 +51,9 @@ def _blr_params(pivot_threshold, factor_algorithm, admissible):
 
 
 # every symbol include/sb200_structured.h declares: name -> (restype, argtypes)
+# HSS::ClusteringAlgorithm of the reference (HSSOptions.hpp)
+CLUSTER_NATURAL, CLUSTER_TWO_MEANS, CLUSTER_KD_TREE, CLUSTER_PCA, CLUSTER_COBBLE = range(5)
+
 _vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
 _pvp = C.POINTER(C.c_void_p)
 _po = C.POINTER(CSPOptions)
@@ -88,6 +91,7 @@ SYMBOLS = {
     "SB200_d_hss_from_element_blocks_ex": (_i, [_pvp, _i, _vp, _vp, _po, _i, _vp, _vp, _i, _vp]),
     "SB200_d_hss_from_dense_tree": (_i, [_pvp, _i, _vp, _i, _po, _i, _vp, _vp]),
     "SB200_d_hss_node_table": (_i, [_vp, _vp]),
+    "SB200_d_hss_from_kernel_ex": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp, _i]),
     "SB200_d_hss_from_kernel": (_i, [_pvp, _i, _i, _vp, _i, _d, _d, _po, _vp]),
     "SB200_d_blr_compress_and_factor": (_i, [_pvp, _i, _vp, _i, _po, _d]),
     "SB200_d_blr_compress_and_factor_device": (_i, [_pvp, _i, _vp, _i, _po, _d]),
@@ -765,15 +769,16 @@ class HSSMatrix(StructuredMatrix):
         return cls(h.value)
 
     @classmethod
-    def from_kernel(cls, pts, kernel=KERNEL_GAUSS, h=1.0, lam=0.0, opts=None):
+    def from_kernel(cls, pts, kernel=KERNEL_GAUSS, h=1.0, lam=0.0, opts=None, clustering=CLUSTER_KD_TREE):
         """HSSMatrix(kernel::Kernel&, opts) (reference HSSMatrix.cpp:88-106).
-        pts: d x n.  Returns (H, perm, pts_permuted)."""
+        pts: d x n.  clustering: CLUSTER_NATURAL / CLUSTER_TWO_MEANS (the reference's
+        default) / CLUSTER_KD_TREE.  Returns (H, perm, pts_permuted)."""
         pts = np.asfortranarray(np.array(pts, dtype=np.float64))
         d, n = pts.shape
         opts = opts or default_options()
         perm = np.zeros(n, dtype=np.int32)
         hd = C.c_void_p()
-        _check(lib().SB200_d_hss_from_kernel(
+        _check(lib().SB200_d_hss_from_kernel_ex(
             C.byref(hd), n, d, pts.ctypes.data, kernel, h, lam, C.byref(opts),
-            perm.ctypes.data), "from_kernel")
+            perm.ctypes.data, int(clustering)), "from_kernel")
         return cls(hd.value), perm, pts

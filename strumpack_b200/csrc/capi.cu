@@ -354,6 +354,12 @@ int SB200_d_hss_node_table(const CSPStructMat S, long long int* out) {
 int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
                             int kernel_type, double h, double lambda,
                             const CSPOptions* opts, int* perm) {
+  return SB200_d_hss_from_kernel_ex(S, n, d, pts, kernel_type, h, lambda, opts, perm, 2);
+}
+
+int SB200_d_hss_from_kernel_ex(CSPStructMat* S, int n, int d, double* pts,
+                               int kernel_type, double h, double lambda,
+                               const CSPOptions* opts, int* perm, int clustering) {
   return guarded([&] {
     require_gpu();
     auto m = std::make_unique<Mat>();
@@ -363,7 +369,7 @@ int SB200_d_hss_from_kernel(CSPStructMat* S, int n, int d, double* pts,
     co.leaf_size = opts->leaf_size; co.max_rank = opts->max_rank;
     co.verbose = opts->verbose;
     m->hss = std::make_unique<HSSEngine>(
-        compress_kernel(n, d, pts, kernel_type, h, lambda, co, perm));
+        compress_kernel(n, d, pts, kernel_type, h, lambda, co, perm, clustering));
     *S = m.release();
   });
 }

@@ -175,6 +175,67 @@ void build_tree_given(std::vector<TNode>& T, int nnodes, const int* sizes, const
   if (next != nnodes || T[0].hi != n) throw std::invalid_argument("cluster tree does not cover the matrix");
 }
 
+// Recursive 2-means clustering (the reference's default for kernel matrices,
+// src/clustering/KMeans.cpp: k_means with k = 2 + recursive_2_means): Lloyd
+// iterations from a random point and a second one drawn with probability
+// proportional to the squared distance from it; a cluster smaller than `leaf`
+// points is a leaf, so leaves are ragged (roughly leaf/2 .. leaf points).
+void build_tree_2means(std::vector<TNode>& T, std::vector<int>& perm, const double* pts, int d, int lo, int hi,
+                       int parent, int leaf, std::mt19937& gen) {
+  const int me = (int)T.size(), n = hi - lo;
+  T.push_back({lo, hi, parent, -1, -1, 0});
+  if (n < leaf || n < 2) return;
+  auto P = [&](int i, int q) { return pts[q + (size_t)perm[lo + i] * d]; };
+  std::vector<double> c0(d), c1(d), dist(n);
+  const int t = std::uniform_int_distribution<int>(0, n - 1)(gen);
+  for (int i = 0; i < n; i++) {
+    double r2 = 0.;
+    for (int q = 0; q < d; q++) { const double v = P(i, q) - P(t, q); r2 += v * v; }
+    dist[i] = r2;
+  }
+  double tot = 0.;
+  for (double v : dist) tot += v;
+  if (!(tot > 0.)) return;   // all points coincide
+  const int t2 = std::discrete_distribution<int>(dist.begin(), dist.end())(gen);
+  for (int q = 0; q < d; q++) { c0[q] = P(t, q); c1[q] = P(t2, q); }
+  std::vector<char> cl(n, 0);
+  int n0 = 0, n1 = 0;
+  for (int iter = 0; iter < 100; iter++) {
+    bool changes = false;
+    for (int i = 0; i < n; i++) {
+      double a = 0., b = 0.;
+      for (int q = 0; q < d; q++) {
+        const double v = P(i, q);
+        a += (v - c0[q]) * (v - c0[q]);
+        b += (v - c1[q]) * (v - c1[q]);
+      }
+      const char c = b < a ? 1 : 0;
+      if (c != cl[i] || iter == 0) changes = changes || c != cl[i] || iter == 0;
+      cl[i] = c;
+    }
+    std::fill(c0.begin(), c0.end(), 0.);
+    std::fill(c1.begin(), c1.end(), 0.);
+    n0 = n1 = 0;
+    for (int i = 0; i < n; i++) {
+      auto& c = cl[i] ? c1 : c0;
+      (cl[i] ? n1 : n0)++;
+      for (int q = 0; q < d; q++) c[q] += P(i, q);
+    }
+    if (!n0 || !n1) return;
+    for (int q = 0; q < d; q++) { c0[q] /= n0; c1[q] /= n1; }
+    if (!changes) break;
+  }
+  // cluster 0 first, original relative order kept
+  std::vector<int> tmp(perm.begin() + lo, perm.begin() + hi);
+  int a = lo, b = lo + n0;
+  for (int i = 0; i < n; i++) (cl[i] ? perm[b++] : perm[a++]) = tmp[i];
+  const int ch0 = (int)T.size();
+  build_tree_2means(T, perm, pts, d, lo, lo + n0, me, leaf, gen);
+  const int ch1 = (int)T.size();
+  build_tree_2means(T, perm, pts, d, lo + n0, hi, me, leaf, gen);
+  T[me].ch0 = ch0; T[me].ch1 = ch1;
+}
+
 struct Problem {
   int n = 0, d = 1;
   int type = 3;
@@ -641,7 +702,7 @@ HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const Compr
 }
 
 HSSHost compress_kernel(int n, int d, double* pts, int kernel_type, double h,
-                        double lambda, const CompressOptions& o, int* perm) {
+                        double lambda, const CompressOptions& o, int* perm, int clustering) {
   if (kernel_type < 0 || kernel_type > 2) throw std::invalid_argument("unknown kernel type");
   Problem P;
   P.n = n; P.type = kernel_type; P.h = h; P.lambda = lambda; P.symmetric = true;
@@ -655,7 +716,11 @@ HSSHost compress_kernel(int n, int d, double* pts, int kernel_type, double h,
     build_tree_index(T, 0, n, -1, std::max(1, o.leaf_size));
   } else {
     P.d = d;
-    build_tree_kd(T, pm, pts, d, 0, n, -1, std::max(1, o.leaf_size));
+    // HSS::ClusteringAlgorithm of the reference (HSSOptions.hpp): NATURAL 0, TWO_MEANS 1, KD_TREE 2, PCA 3, COBBLE 4
+    if (clustering == 0) build_tree_index(T, 0, n, -1, std::max(1, o.leaf_size));
+    else if (clustering == 1) { std::mt19937 gen(1); build_tree_2means(T, pm, pts, d, 0, n, -1, std::max(1, o.leaf_size), gen); }
+    else if (clustering == 2) build_tree_kd(T, pm, pts, d, 0, n, -1, std::max(1, o.leaf_size));
+    else throw std::invalid_argument("clustering algorithm not implemented (NATURAL, TWO_MEANS and KD_TREE are)");
     P.pts.resize((size_t)d * n);
     for (int i = 0; i < n; i++)
       for (int q = 0; q < d; q++) P.pts[q + (size_t)i * d] = pts[q + (size_t)pm[i] * d];

@@ -65,8 +65,10 @@ HSSHost compress_elements(int rows, int cols, double (*A)(int, int),
 HSSHost compress_element_blocks(int n, BlockElemFn elem, void* user, const CompressOptions& o,
                                 const GivenTree* tree = nullptr, int d = 0, const double* coords = nullptr);
 // kernel matrix on n points (d x n, column-major); pts is reordered in place,
-// perm[new] = old (may be null). kernel_type: SB200_KERNEL_TYPE.
+// perm[new] = old (may be null). kernel_type: SB200_KERNEL_TYPE.  clustering: the
+// reference's HSS::ClusteringAlgorithm (0 natural order, 1 recursive 2-means,
+// 2 kd-tree; PCA / COBBLE are refused).
 HSSHost compress_kernel(int n, int d, double* pts, int kernel_type, double h,
-                        double lambda, const CompressOptions& o, int* perm);
+                        double lambda, const CompressOptions& o, int* perm, int clustering = 2);
 
 }  // namespace sb200

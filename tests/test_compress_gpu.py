@@ -132,3 +132,43 @@ def test_compress_from_element_blocks(built, n, leaf, tol):
     assert rel(H.mult(x, "T"), yt) <= 1e2 * tol
     H.factor()
     assert rel(H.mult(H.solve(y)), y) < 1e-10
+
+
+@pytest.mark.parametrize("clustering", ["two_means", "natural"])
+def test_from_kernel_clustering_options(built, clustering):
+    """HSSOptions::clustering_algorithm is honoured: recursive 2-means (the
+    reference's default, src/clustering/KMeans.cpp) gives ragged leaves like the
+    reference's own tree; NATURAL keeps the caller's order; PCA / COBBLE are
+    refused.  Accuracy bar: the reference's (test_HSS_seq.cpp:143-152)."""
+    sb = built
+    n, h, tol = 6000, 0.1, 1e-4
+    rng = np.random.default_rng(4)
+    pts = rng.random((2, n))
+    if clustering == "natural":
+        pts = pts[:, np.argsort(pts[0])]                    # an order that clusters by itself (slabs in x)
+    o = sb.default_options(type=sb.SP_TYPE_HSS, rel_tol=tol, abs_tol=1e-10, leaf_size=256)
+    cl = sb.CLUSTER_TWO_MEANS if clustering == "two_means" else sb.CLUSTER_NATURAL
+    H, perm, p = sb.HSSMatrix.from_kernel(pts, sb.KERNEL_GAUSS, h, 1.0, o, clustering=cl)
+    assert sorted(perm.tolist()) == list(range(n)) and np.array_equal(p, pts[:, perm])
+    if clustering == "natural":
+        assert np.array_equal(perm, np.arange(n))
+    d2 = ((p[:, :, None] - p[:, None, :]) ** 2).sum(0)
+    K = np.exp(-d2 / (2 * h * h)) + np.eye(n)
+    assert rel(H.dense(), K) <= 1e2 * tol
+    tab = np.zeros((4096, 10), dtype=np.int64)
+    nn = sb.lib().SB200_d_hss_node_table(H._h, tab.ctypes.data)
+    leaves = tab[:nn][tab[:nn, 1] < 0, 3]
+    assert leaves.sum() == n and leaves.max() < 256 + (clustering == "natural") * 256
+    if clustering == "two_means":
+        assert leaves.min() < leaves.max()                  # ragged, unlike the kd tree
+        from conftest import have_ref
+        if have_ref():
+            from oracle import ref
+            R = ref.RefHSS.gauss(pts, h, 1.0, f"--hss_leaf_size 256 --hss_rel_tol {tol}")
+            inf = R.info()
+            assert abs(H.levels - inf["levels"]) <= 2 and abs(H.rank - inf["rank"]) <= 0.35 * inf["rank"]
+    H.factor()
+    x = rng.standard_normal((n, 2))
+    assert rel(H.solve(H.mult(x)), x) < 1e-9
+    with pytest.raises(RuntimeError):
+        sb.HSSMatrix.from_kernel(pts, sb.KERNEL_GAUSS, h, 1.0, o, clustering=sb.CLUSTER_PCA)
