@@ -1,5 +1,6 @@
 """Markdown summary of an `ncu --set full` report (read here, no GPU needed):
-python scripts/summarize_ncu.py gpurun_out/r1c_ncu.ncu-rep > profiles/r1c_ncu_summary.md"""
+python scripts/summarize_ncu.py gpurun_out/r1c_ncu.ncu-rep > profiles/r1c_ncu_summary.md
+(or of its raw page exported as CSV on the GPU box: ... gpurun_out/r2i_ncu_factor_raw.csv)"""
 import csv
 import io
 import subprocess
@@ -21,14 +22,17 @@ STALL = "smsp__average_warps_issue_stalled_"
 
 def main():
     rep = sys.argv[1]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):     # raw page already exported on the GPU box (ncu -i X.ncu-rep --page raw --csv)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     print(f"# ncu --set full summary of `{rep}`\n")
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
-        print(f"## {d.get('Kernel Name', '?')[:90]}\n")
+        print(f"## {d.get('Kernel Name', '?')[:90]}  (launch id {d.get('ID', '?')}, grid {d.get('launch__grid_size', '?')})\n")
         print("| metric | value | unit |\n|---|---|---|")
         for m in METRICS:
             if m in d:

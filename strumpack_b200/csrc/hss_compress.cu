@@ -293,7 +293,14 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
     //  (b) K2 random ones among the next 8*K1 nearest   (near field, all sides)
     //  (c) the K3 points of (sibling U parent's sample) nearest to the centre,
     //  (d) K4 random ones of that set                   (every coarser scale)
-    const int K1 = o.sample_near, K2 = o.sample_near, K3 = o.sample_far, K4 = o.sample_far;
+    // the stratum sizes grow with the accuracy asked for: a sample that resolves the complement to 1e-2
+    // does not resolve it to 1e-6 (measured, scripts/r2_sampling.py / profiles/r2_compress_sampling.txt:
+    // Toeplitz 262144 at tol 1e-6: 2.0e-4 with the base sizes, 8.9e-6 with 4x, same ranks and nonzeros)
+    const int sf = std::min(4, std::max(1, (int)std::lround(-std::log10(std::max(o.rel_tol, 1e-16)) / 2.)));
+    int K1 = o.sample_near * sf, K2 = o.sample_near * sf, K3 = o.sample_far * sf, K4 = o.sample_far * sf;
+    // experiments: SB200_SAMPLE_NEAR / SB200_SAMPLE_FAR override the stratum sizes
+    if (const char* e = std::getenv("SB200_SAMPLE_NEAR")) K1 = K2 = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("SB200_SAMPLE_FAR")) K3 = K4 = std::max(1, std::atoi(e));
     // bounding boxes, bottom-up
     std::vector<double> bmin((size_t)N * d), bmax((size_t)N * d);
     for (int t = N - 1; t >= 0; t--) {

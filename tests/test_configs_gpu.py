@@ -96,15 +96,14 @@ def test_config2_hss_ulv_toeplitz_262144(built):
     assert H.levels >= 10
     x = np.random.default_rng(2).standard_normal(n)
     y = toeplitz_fft_product(x)
-    # construction (not the path this config measures): the sampled-column ID
-    # reaches 2e-4 at this size for the 1/(1+d) kernel (8.9e-6 at N = 32768, see
-    # profiles/r1b_compress_accuracy.txt); the reference builds this case from a randomized
-    # sketch with a fast mat-vec instead
-    assert rel(H.mult(x)[:, 0], y) <= 1e-3
+    # construction: the reference's bound 1e2*tol (test_HSS_seq.cpp:148-152), met since the
+    # sample sizes of the interpolative decomposition grow with the tolerance asked for
+    # (profiles/r2_compress_sampling.txt: 2.0e-4 with the round-1 sizes, 2-7e-5 now)
+    assert rel(H.mult(x)[:, 0], y) <= 1e2 * tol
     H.factor()
     xs = H.solve(y)
     assert rel(H.mult(xs)[:, 0], y) < 1e-12                      # ULV is a direct solver for H
-    assert rel(toeplitz_fft_product(xs[:, 0]), y) <= 1e-2        # and an approximate one for A
+    assert rel(toeplitz_fft_product(xs[:, 0]), y) <= 1e-3        # and an approximate one for A
     assert H.flops("factor") > 0.9e5 * n                         # ~1.03e5 N for leaf 256
 
 
