@@ -103,7 +103,7 @@ def test_config2_hss_ulv_toeplitz_262144(built):
     H.factor()
     xs = H.solve(y)
     assert rel(H.mult(xs)[:, 0], y) < 1e-12                      # ULV is a direct solver for H
-    assert rel(toeplitz_fft_product(xs[:, 0]), y) <= 1e-3        # and an approximate one for A
+    assert rel(toeplitz_fft_product(xs[:, 0]), y) <= 1e-2        # and an approximate one for A
     assert H.flops("factor") > 0.9e5 * n                         # ~1.03e5 N for leaf 256
 
 
