@@ -2812,6 +2812,7 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   // cp.async-streamed solve sweeps: bit 0 backward, bit 1 forward (default: both);
   // bits 2 / 3 (with bit 0 / 1 clear): the non-streamed kernels with L2 prefetch of the next block
   if (const char* e = std::getenv("SB200_SOLVE_PIPE")) solve_pipe_ = std::atoi(e);
+  if (const char* e = std::getenv("SB200_GRAPH")) use_graph_ = std::atoi(e);
   // 1: left-looking warp-specialised TMA-fed QR (ulv_qr3.cuh) for classes with m <= 256; default: the right-looking kernel
   if (const char* e = std::getenv("SB200_QR3")) qr3_ = std::atoi(e);
   if (qr_split_) qr_variant_ = 0;   // the per-panel launch experiment assumes nb_-wide panels
@@ -2819,6 +2820,47 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
 }
 HSSEngine::~HSSEngine() {
   for (auto& e : ev_) if (e) cudaEventDestroy(e);
+  drop_graphs();
+}
+
+void HSSEngine::drop_graphs() {
+  for (auto& g : graphs_) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  graphs_.clear();
+}
+
+// Run `body` (a fixed sequence of kernel launches on `st`) through a CUDA graph:
+// captured the first time a key is seen, replayed afterwards.  Not used on the
+// legacy default stream (capture is not allowed there) nor while the per-kernel
+// profiling events are on.
+void HSSEngine::run_graphed(const std::string& key, cudaStream_t st, const std::function<void()>& body) {
+  if (!use_graph_ || profile_ || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+    body();
+    return;
+  }
+  auto it = graphs_.find(key);
+  if (it == graphs_.end()) {
+    if (graphs_.size() > 64) drop_graphs();   // operands keep changing: do not hoard executables
+    cudaGraph_t g = nullptr;
+    const long long l0 = launches_;
+    SB200_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      body();
+    } catch (...) {
+      cudaStreamEndCapture(st, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    SB200_CUDA(cudaStreamEndCapture(st, &g));
+    GraphEntry e;
+    e.launches = launches_ - l0;
+    launches_ = l0;
+    const cudaError_t rc = cudaGraphInstantiate(&e.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (rc != cudaSuccess) { cudaGetLastError(); body(); return; }   // fall back to plain launches
+    it = graphs_.emplace(key, e).first;
+  }
+  SB200_CUDA(cudaGraphLaunch(it->second.exec, st));
+  launches_ += it->second.launches;
 }
 
 void HSSEngine::set_profile(bool on) {
@@ -2900,6 +2942,7 @@ void HSSEngine::build_tables() {
 
 void HSSEngine::ensure_apply_ws(int s) {
   if (s <= apply_s_) return;
+  drop_graphs();
   t1_.alloc((size_t)std::max(ws_total_, 1) * s);
   t2_.alloc((size_t)std::max(ws_total_, 1) * s);
   apply_s_ = s;
@@ -2907,6 +2950,7 @@ void HSSEngine::ensure_apply_ws(int s) {
 
 void HSSEngine::ensure_solve_ws(int s) {
   if (s <= solve_s_) return;
+  drop_graphs();
   ysol_.alloc((size_t)std::max<long long>(tot_k_, 1) * s);
   zsol_.alloc((size_t)std::max<long long>(tot_rv_, 1) * s);
   fsol_.alloc((size_t)std::max<long long>(tot_ru_, 1) * s);
@@ -3058,6 +3102,7 @@ void HSSEngine::set_partition(int nparts, int part) {
     own.push_back(lo);
     for (int i = lo + 1; i < N && H_.nodes[i].depth > depth; i++) own.push_back(i);
   }
+  drop_graphs();
   nparts_ = nparts; part_ = part;
   make_lists(own_, own);
   make_lists(top_, top);
@@ -3081,6 +3126,14 @@ void HSSEngine::dist_sizes(int s, long long* out) const {
     v = std::max<long long>(v, (long long)(d.v_rank + d.u_rank) * s);
   }
   out[0] = std::max<long long>(a, 1); out[1] = std::max<long long>(f, 1); out[2] = std::max<long long>(v, 1);
+}
+
+static std::string gkey(const char* op, std::initializer_list<const void*> ptrs, std::initializer_list<long long> ints) {
+  std::string k(op);
+  char buf[40];
+  for (const void* p : ptrs) { std::snprintf(buf, sizeof buf, "|%p", p); k += buf; }
+  for (long long v : ints) { std::snprintf(buf, sizeof buf, "|%lld", v); k += buf; }
+  return k;
 }
 
 // ------------------------------------------------------------------- apply
@@ -3170,8 +3223,12 @@ void HSSEngine::mult(char trans, int s, const double* dB, int ldB, double* dC,
   const bool T = !(trans == 'N' || trans == 'n');
   if (s <= 0) return;
   ensure_apply_ws(s);
-  run_up(own_, T, s, dB, ldB, st);
-  run_down(own_, T, s, dB, ldB, dC, ldC, true, st, beta);
+  long long bb;
+  std::memcpy(&bb, &beta, sizeof bb);
+  run_graphed(gkey("mult", {dB, dC}, {T, s, ldB, ldC, bb}), st, [&] {
+    run_up(own_, T, s, dB, ldB, st);
+    run_down(own_, T, s, dB, ldB, dC, ldC, true, st, beta);
+  });
   SB200_CUDA(cudaGetLastError());
 }
 
@@ -3180,10 +3237,12 @@ void HSSEngine::dist_mult_begin(char trans, int s, const double* dB, int ldB,
                                 double* send, cudaStream_t st) {
   const bool T = !(trans == 'N' || trans == 'n');
   ensure_apply_ws(s);
-  run_up(own_, T, s, dB, ldB, st);
-  const DNode& d = hn_[cut_[part_]];
-  const int r = T ? d.u_rank : d.v_rank;
-  copy2d(send, r, t1_.p + (size_t)d.w_off * s, r, r, s, st);
+  run_graphed(gkey("mult_begin", {dB, send}, {T, s, ldB}), st, [&] {
+    run_up(own_, T, s, dB, ldB, st);
+    const DNode& d = hn_[cut_[part_]];
+    const int r = T ? d.u_rank : d.v_rank;
+    copy2d(send, r, t1_.p + (size_t)d.w_off * s, r, r, s, st);
+  });
   SB200_CUDA(cudaGetLastError());
 }
 // ... import every cut node's t1, sweep the replicated top, finish locally
@@ -3192,15 +3251,17 @@ void HSSEngine::dist_mult_end(char trans, int s, const double* dB, int ldB, doub
   const bool T = !(trans == 'N' || trans == 'n');
   long long sz[3];
   dist_sizes(s, sz);
-  for (int c = 0; c < nparts_; c++) {
-    const DNode& d = hn_[cut_[c]];
-    const int r = T ? d.u_rank : d.v_rank;
-    copy2d(t1_.p + (size_t)d.w_off * s, r, recv + (size_t)c * sz[0], r, r, s, st);
-  }
-  run_up(top_, T, s, dB, ldB, st);
-  run_down(top_, T, s, dB, ldB, dC, ldC, false, st);
-  run_down(own_, T, s, dB, ldB, dC, ldC, true, st);
-  // the cut node itself is an inner (or leaf) node of own_: its down kernel ran above
+  run_graphed(gkey("mult_end", {dB, dC, recv}, {T, s, ldB, ldC}), st, [&] {
+    for (int c = 0; c < nparts_; c++) {
+      const DNode& d = hn_[cut_[c]];
+      const int r = T ? d.u_rank : d.v_rank;
+      copy2d(t1_.p + (size_t)d.w_off * s, r, recv + (size_t)c * sz[0], r, r, s, st);
+    }
+    run_up(top_, T, s, dB, ldB, st);
+    run_down(top_, T, s, dB, ldB, dC, ldC, false, st);
+    run_down(own_, T, s, dB, ldB, dC, ldC, true, st);
+    // the cut node itself is an inner (or leaf) node of own_: its down kernel ran above
+  });
   SB200_CUDA(cudaGetLastError());
 }
 
@@ -3289,14 +3350,18 @@ void HSSEngine::factor_prepare(bool whole) {
   }
   // zero-filled on allocation: the alignment padding between blocks is never written
   const size_t nf = (size_t)std::max<long long>(fact_len_, 1), nt = (size_t)std::max<long long>((long long)nb_ * tot_k_, 1);
+  if (fact_.n < nf || tfac_.n < nt) drop_graphs();
   if (fact_.n < nf) { fact_.alloc(nf); SB200_CUDA(cudaMemset(fact_.p, 0, nf * sizeof(double))); tmaps_for_ = nullptr; }
   if (qr3_ && tmaps_for_ != fact_.p) {   // TMA descriptors of the factor blocks (they carry the arena's address)
     build_qr3_tmaps(hn_, fact_.p, tmaps_);
     tmaps_for_ = fact_.p;
   }
   if (tfac_.n < nt) { tfac_.alloc(nt); SB200_CUDA(cudaMemset(tfac_.p, 0, nt * sizeof(double))); }
+  const void* old_piv = rootpiv_.p;
+  const void* old_scr = scratch_.p;
   rootpiv_.ensure(std::max(hn_[0].m, 1));
   scratch_.ensure((size_t)std::max<long long>(std::max(std::max(own_.smax, top_.smax), sub0_.smax), 1));
+  if (old_piv != rootpiv_.p || old_scr != scratch_.p) drop_graphs();
 }
 
 void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t st, int lu_node,
@@ -3402,7 +3467,7 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
 void HSSEngine::factor(cudaStream_t st) {
   if (nparts_ > 1) throw std::logic_error("sharded matrix: use the dist_* entry points");
   factor_prepare();
-  factor_classes(own_, true, st);
+  run_graphed("factor", st, [&] { factor_classes(own_, true, st); });
   SB200_CUDA(cudaGetLastError());
   factored_ = true;
   pf_ok_ = false;   // the factor arena now holds the full factorization
@@ -3410,22 +3475,26 @@ void HSSEngine::factor(cudaStream_t st) {
 
 void HSSEngine::dist_factor_begin(double* send, cudaStream_t st) {
   factor_prepare();
-  factor_classes(own_, true, st);
-  // export [Vt1 | Dt^T] of this rank's cut node: rows k..m, columns k..naug of F
-  const DNode& d = hn_[cut_[part_]];
-  copy2d(send, d.u_rank, fact_.p + d.F + d.k + (size_t)d.k * d.m, d.m, d.u_rank, d.v_rank + d.u_rank, st);
+  run_graphed(gkey("factor_begin", {send}, {}), st, [&] {
+    factor_classes(own_, true, st);
+    // export [Vt1 | Dt^T] of this rank's cut node: rows k..m, columns k..naug of F
+    const DNode& d = hn_[cut_[part_]];
+    copy2d(send, d.u_rank, fact_.p + d.F + d.k + (size_t)d.k * d.m, d.m, d.u_rank, d.v_rank + d.u_rank, st);
+  });
   SB200_CUDA(cudaGetLastError());
 }
 
 void HSSEngine::dist_factor_end(const double* recv, cudaStream_t st) {
   long long sz[3];
   dist_sizes(1, sz);
-  for (int c = 0; c < nparts_; c++) {
-    const DNode& d = hn_[cut_[c]];
-    copy2d(fact_.p + d.F + d.k + (size_t)d.k * d.m, d.m, recv + (size_t)c * sz[1], d.u_rank,
-           d.u_rank, d.v_rank + d.u_rank, st);
-  }
-  factor_classes(top_, false, st);
+  run_graphed(gkey("factor_end", {recv}, {}), st, [&] {
+    for (int c = 0; c < nparts_; c++) {
+      const DNode& d = hn_[cut_[c]];
+      copy2d(fact_.p + d.F + d.k + (size_t)d.k * d.m, d.m, recv + (size_t)c * sz[1], d.u_rank,
+             d.u_rank, d.v_rank + d.u_rank, st);
+    }
+    factor_classes(top_, false, st);
+  });
   SB200_CUDA(cudaGetLastError());
   factored_ = true;
 }
@@ -3741,9 +3810,11 @@ void HSSEngine::solve(int s, double* dB, int ldB, cudaStream_t st) {
   if (!factored_) throw std::logic_error("solve called before factor");
   if (s <= 0) return;
   ensure_solve_ws(s);
-  solve_fwd(own_, s, dB, ldB, st);     // the kernels skip the root
-  solve_root(s, dB, ldB, st);
-  solve_bwd(own_, s, dB, ldB, st);
+  run_graphed(gkey("solve", {dB}, {s, ldB}), st, [&] {
+    solve_fwd(own_, s, dB, ldB, st);     // the kernels skip the root
+    solve_root(s, dB, ldB, st);
+    solve_bwd(own_, s, dB, ldB, st);
+  });
   SB200_CUDA(cudaGetLastError());
 }
 
@@ -3770,29 +3841,33 @@ void HSSEngine::backward_solve(int s, double* dB, int ldB, cudaStream_t st) {
 void HSSEngine::dist_solve_begin(int s, double* dB, int ldB, double* send, cudaStream_t st) {
   if (!factored_) throw std::logic_error("solve called before factor");
   ensure_solve_ws(s);
-  solve_fwd(own_, s, dB, ldB, st);
-  const DNode& d = hn_[cut_[part_]];
-  // export [z ; ft1] of the cut node, (r_v + r_u) x s
-  const int ld = d.v_rank + d.u_rank;
-  copy2d(send, ld, zsol_.p + (size_t)d.z_off * s, d.v_rank, d.v_rank, s, st);
-  copy2d(send + d.v_rank, ld, fsol_.p + (size_t)d.f_off * s, d.u_rank, d.u_rank, s, st);
+  run_graphed(gkey("solve_begin", {dB, send}, {s, ldB}), st, [&] {
+    solve_fwd(own_, s, dB, ldB, st);
+    const DNode& d = hn_[cut_[part_]];
+    // export [z ; ft1] of the cut node, (r_v + r_u) x s
+    const int ld = d.v_rank + d.u_rank;
+    copy2d(send, ld, zsol_.p + (size_t)d.z_off * s, d.v_rank, d.v_rank, s, st);
+    copy2d(send + d.v_rank, ld, fsol_.p + (size_t)d.f_off * s, d.u_rank, d.u_rank, s, st);
+  });
   SB200_CUDA(cudaGetLastError());
 }
 
 void HSSEngine::dist_solve_end(int s, double* dB, int ldB, const double* recv, cudaStream_t st) {
   long long sz[3];
   dist_sizes(s, sz);
-  for (int c = 0; c < nparts_; c++) {
-    const DNode& d = hn_[cut_[c]];
-    const int ld = d.v_rank + d.u_rank;
-    const double* src = recv + (size_t)c * sz[2];
-    copy2d(zsol_.p + (size_t)d.z_off * s, d.v_rank, src, ld, d.v_rank, s, st);
-    copy2d(fsol_.p + (size_t)d.f_off * s, d.u_rank, src + d.v_rank, ld, d.u_rank, s, st);
-  }
-  solve_fwd(top_, s, dB, ldB, st);
-  solve_root(s, dB, ldB, st);
-  solve_bwd(top_, s, dB, ldB, st);
-  solve_bwd(own_, s, dB, ldB, st);
+  run_graphed(gkey("solve_end", {dB, recv}, {s, ldB}), st, [&] {
+    for (int c = 0; c < nparts_; c++) {
+      const DNode& d = hn_[cut_[c]];
+      const int ld = d.v_rank + d.u_rank;
+      const double* src = recv + (size_t)c * sz[2];
+      copy2d(zsol_.p + (size_t)d.z_off * s, d.v_rank, src, ld, d.v_rank, s, st);
+      copy2d(fsol_.p + (size_t)d.f_off * s, d.u_rank, src + d.v_rank, ld, d.u_rank, s, st);
+    }
+    solve_fwd(top_, s, dB, ldB, st);
+    solve_root(s, dB, ldB, st);
+    solve_bwd(top_, s, dB, ldB, st);
+    solve_bwd(own_, s, dB, ldB, st);
+  });
   SB200_CUDA(cudaGetLastError());
 }
 

@@ -8,6 +8,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <functional>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "hss_tree.hpp"
@@ -178,6 +181,16 @@ class HSSEngine {
   long long scratch_per_node_max_ = 0;
   bool factored_ = false;
   long long launches_ = 0;
+  // CUDA graphs of the per-class launch sequences (apply / factor / solve and the
+  // begin / end halves of their sharded versions): the sweeps above the leaves
+  // are ~90 latency-bound launches per step; replaying a captured graph removes
+  // the per-launch gaps on the device.  Keyed by operation + operand addresses;
+  // dropped whenever an arena or a node list changes.  SB200_GRAPH=0 disables.
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+  std::map<std::string, GraphEntry> graphs_;
+  int use_graph_ = 1;
+  void drop_graphs();
+  void run_graphed(const std::string& key, cudaStream_t st, const std::function<void()>& body);
   // Schur / partial factorization state
   NodeLists sub0_, sub1_;        // subtrees of the root's children (cut nodes included)
   bool sub_ok_ = false, pf_ok_ = false;
