@@ -18,19 +18,6 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr size_t kMaxSmem = 200 * 1024;   // dynamic shared memory we ask for at most
 
-// sum over the CTA; every thread gets the result. red: >= 32 doubles of smem.
-// Contains two __syncthreads().
-__device__ __forceinline__ double block_sum(double v, double* red, int tid) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((tid & 31) == 0) red[tid >> 5] = v;
-  __syncthreads();
-  double s = 0.;
-#pragma unroll
-  for (int w = 0; w < kWarps; w++) s += red[w];
-  return s;
-}
-
 // ===========================================================================
 //                                  APPLY
 // ===========================================================================
@@ -559,11 +546,6 @@ __device__ __forceinline__ double child_Dt(const double* f, const DNode& c, int 
   // Dt[a,b] = F[(k+b) + (k+rv+a) m]
   return f[c.F + (c.k + b) + (size_t)(c.k + c.v_rank + a) * c.m];
 }
-__device__ __forceinline__ double child_Vt1(const double* f, const DNode& c, int a, int j) {
-  // Vt1[a,j] = F[(k+a) + (k+j) m]
-  return f[c.F + (c.k + a) + (size_t)(c.k + j) * c.m];
-}
-
 // Inner nodes: Dfull = [Dt0, B01 Vt1(c1)^H; B10 Vt1(c0)^H, Dt1] into `dst`
 // (ld = m) and, for non-root nodes, Vh = [Vt1(c0) Vd_top; Vt1(c1) Vd_bot]
 // into the factor block                         (factor.hpp:68-98)
@@ -1028,21 +1010,12 @@ template <int NB, bool SMALL, int NTH, int MINB = (NTH == 128 ? 4 : 2)>
 __global__ void __launch_bounds__(NTH, MINB)
 ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
               double* __restrict__ fact, double* __restrict__ tfac, int ldv,
-              int pmode, int pidx) {
+              int nowide) {
   static_assert(NTH == 256 || SMALL, "the shared-memory sub-panel variant needs 8 warps");
   constexpr int NWP = NTH / 32;
   extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
   if (nd.parent < 0 || nd.k == 0) return;
-  if (pmode >= 16) {
-    // experiment (SB200_QR_SKEW): de-phase every other CTA so that co-resident
-    // equal-size nodes do not run their panel / trailing phases in lockstep
-    if ((blockIdx.x / 148) & 1) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)(pmode >> 4) * 1000) { }
-    }
-    pmode &= 15;
-  }
   const int m = nd.m, k = nd.k, naug = nd.naug, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
@@ -1058,8 +1031,7 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   double* A = fact + nd.F;
   double* Tg = tfac + nd.T;
   // every column of the factor block starts on a 16-byte boundary (even F, even m)
-  const bool wide = !(pmode & 8) && ((m & 1) == 0) && ((nd.F & 1) == 0);
-  pmode &= 7;
+  const bool wide = !nowide && ((m & 1) == 0) && ((nd.F & 1) == 0);
 #ifdef SB200_QR_TIMING
   long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -1067,29 +1039,9 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
 #else
 #define QR_TICK(p)
 #endif
-  // pmode 0: whole factorization in this launch (small classes);
-  // pmode 1: factor panel pidx only; pmode 2: trailing update with panel pidx
-  // only.  Splitting the leaf class into per-panel launches keeps the
-  // latency-bound Householder chains from sharing the fp64 pipe with the DMMA
-  // stream of a co-resident CTA and balances the slab updates.
-  for (int j0 = pmode ? pidx * NB : 0; j0 < k; j0 += NB) {
+  for (int j0 = 0; j0 < k; j0 += NB) {
     const int jb = min(NB, k - j0), mp = m - j0;
     const int mp8 = (mp + 7) & ~7;
-    if (pmode == 2) {
-      // reload the explicit V (unit lower trapezoid) and T of this panel
-      for (int c = warp; c < NB; c += NWP) {
-        const double* src = A + j0 + (size_t)(j0 + c) * m;
-        double* dst = Vs + c * ldv;
-        const bool cin = c < jb;
-        for (int i = lane; i < mp8; i += 32)
-          dst[i] = (cin && i < mp && i >= c) ? (i == c ? 1. : src[i]) : 0.;
-      }
-      for (int idx = tid; idx < NB * NB; idx += NTH) {
-        const int a = idx % NB, c = idx / NB;
-        Ts[a + c * LDW] = (a < jb && c < jb && a <= c) ? Tg[a + (size_t)(j0 + c) * NB] : 0.;
-      }
-      __syncthreads();
-    } else {
     // ---- load panel (zero padded to mp8 rows / NB columns), clear T.  The
     // panel comes from L2 (it was just written by the trailing update): LDGSTS
     // keeps every element of the panel in flight at once instead of one L2
@@ -1254,11 +1206,7 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
           //   none: straight to the barrier
           const int ww = warp - nupd;
           const bool upd = warp < nupd, lead = upd || (nupd == 0 && warp == 7);
-#ifdef SB200_EXP_NODOT
-          const bool dot = false;
-#else
           const bool dot = !lead && ww < cq;
-#endif
           const bool writer = nupd > 0 ? warp == 0 : warp == 7;
           if (lead || dot) {
             double* oth = upd ? Vs + (c + 1 + warp) * ldv : Vs + (cs + (dot ? ww : 0)) * ldv;
@@ -1301,16 +1249,12 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
               QR_TICK(9)
               const double alpha = x[c];
               double tc = 0., scal = 0., beta = alpha;
-#ifdef SB200_EXP_NOSQRT
-              if (pn > 0.) { beta = -copysign(alpha * alpha + pn, alpha); const double d = alpha - beta; scal = d * 0.5; tc = -d * beta; }
-#else
               if (pn > 0.) {   // dlarfg
                 beta = -copysign(sqrt(alpha * alpha + pn), alpha);
                 const double d = alpha - beta;
                 scal = 1. / d;
                 tc = -d / beta;
               }
-#endif
               QR_TICK(10)
               if (upd) {
                 const double colc = oth[c];
@@ -1344,7 +1288,6 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
           QR_TICK(12)
           __syncthreads();
           QR_TICK(13)
-#ifndef SB200_EXP_NOTCOL
           if (warp == 7 && lane <= cq) {   // column cq of the 8x8 T (dlarft)
             const int a = lane;
             const double tc = tau[c], sc = scals[c];
@@ -1361,7 +1304,6 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
             }
             Ts[(cs + a) + (cs + cq) * LDW] = val;
           }
-#endif
           QR_TICK(14)
         }
         const double scal_prev = scals[cs + sbw - 1];
@@ -1441,9 +1383,7 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
       for (int i = c + 1 + lane; i < mp; i += 32) dst[i] = src[i];
     }
     QR_TICK(5)
-    if (pmode == 1) break;
     __syncthreads();
-    }
     // ---- trailing update: one warp per 8-column slab, no barrier inside
     const int ntrail = naug - (j0 + jb);
     // (the warp that gets the extra slab rotates with the panel index)
@@ -1462,7 +1402,6 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
       }
     }
     QR_TICK(6)
-    if (pmode == 2) break;
     __syncthreads();
     QR_TICK(7)
   }
@@ -1472,511 +1411,6 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
            blockIdx.x, warp, m, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7],
            tph[8], tph[9], tph[10], tph[11], tph[12], tph[13], tph[14]);
   }
-#endif
-}
-
-// ---------------------------------------------------------------------------
-// Left-looking variant for nodes with m <= 256 (the leaf class): 128-thread
-// CTAs, 4 per SM.  The right-looking kernel above keeps 2 Householder chains
-// per SM in flight and re-streams the trailing matrix once per panel; here a
-// 16-column panel lives in shared memory, receives ALL earlier block
-// reflectors (V, T read back from global / L1, every column of the factor
-// block is read once and written once), is factored with the same register
-// sub-panel steps, and four CTAs per SM keep four chains in flight so that the
-// fp64 tensor pipe always has a CTA in its update phase.
-//   rows are owned by warps in 8-row tiles (tile index mod 4 == warp), each
-//   warp updates all 16 columns of its tiles: V fragments are loaded once for
-//   both column slabs; the partial V^T C products of the 4 warps are combined
-//   through shared memory (double buffered, one CTA barrier per application).
-constexpr int kLLThreads = 128;
-constexpr int kLLWarps = 4;
-constexpr int kLLLdw = 20;     // ld of the 16 x 16 panel T in shared memory
-constexpr int kLLWx = 2048;    // exchange / scratch doubles
-
-static size_t qr_ll_smem(int ldc) {
-  return sizeof(double) * ((size_t)ldc * 16 + kLLLdw * 16 + kLLWx);
-}
-
-// C(panel, smem) <- (I - V T^T V^T) C for one block reflector of NBR columns.
-//   Cp   : panel column 0, absolute row 0 (ld = ldc, rows zero padded to 8)
-//   row0 : first row touched (multiple of 8); q0: row/column of V's unit diagonal
-//   VGLOBAL: V read from the factor block (strictly lower part stored, unit
-//            diagonal implicit, Vp = column q0, absolute row 0, ld = ldv)
-//            else explicit V in shared memory
-//   T(a,c) = Tp[a + c*ldt] (upper triangular incl. stored zeros), a,c < jbq
-//   ONLYW: stop after W^T = C^T V (used for S = V1^T V2 of the T merge)
-// wt returns W^T[n = s*8+g][a = at*8+2t+e] (full sum, identical in all warps).
-template <int NBR, int NSLAB, bool VGLOBAL, bool ONLYW>
-__device__ __forceinline__ void ll_apply(double* Cp, int ldc, int m, int row0, int q0,
-                                         const double* Vp, int ldv, int jbq,
-                                         const double* Tp, int ldt,
-                                         double* Wx, int par, int warp, int lane,
-                                         double (&wt)[NSLAB][NBR / 8][2],
-                                         long long* tph = nullptr) {
-#ifdef SB200_QR_TIMING
-  long long tl_ = clock64();
-#define LL_TICK(p) { long long now_ = clock64(); if (tph) tph[p] += now_ - tl_; tl_ = now_; }
-#else
-#define LL_TICK(p)
-#endif
-  constexpr int NT = NBR / 8;
-  const int g = lane >> 2, t = lane & 3;
-  const int nt = (m + 7) >> 3;
-  const int itm = (q0 + NBR) >> 3;        // tiles below need the unit-lower mask
-  const bool ragged = (m & 7) != 0 || jbq < NBR;
-  const int itb = (row0 >> 3) + ((warp - (row0 >> 3)) & 3);
-  auto vld = [&](int i, int a, bool edge) -> double {
-    if (!VGLOBAL) return Vp[i + a * ldv];
-    if (!edge) return Vp[i + (size_t)a * ldv];
-    if (i >= m || a >= jbq) return 0.;
-    const int d = q0 + a;
-    return i > d ? Vp[i + (size_t)a * ldv] : (i == d ? 1. : 0.);
-  };
-  double w[2][NSLAB][NT][2];
-#pragma unroll
-  for (int x = 0; x < 2; x++)
-#pragma unroll
-    for (int s = 0; s < NSLAB; s++)
-#pragma unroll
-      for (int q = 0; q < NT; q++) w[x][s][q][0] = w[x][s][q][1] = 0.;
-  // ---- phase 1: partial W^T over this warp's row tiles
-  for (int it0 = itb; it0 < nt; it0 += 8) {
-    double a[2][NSLAB][2], b[2][NT][2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int it = it0 + 4 * u;
-      const bool in = it < nt;
-      const bool edge = VGLOBAL && (it < itm || (ragged && (it == nt - 1 || jbq < NBR)));
-#pragma unroll
-      for (int ks = 0; ks < 2; ks++) {
-        const int i = it * 8 + ks * 4 + t;
-#pragma unroll
-        for (int s = 0; s < NSLAB; s++) a[u][s][ks] = in ? Cp[i + (s * 8 + g) * ldc] : 0.;
-#pragma unroll
-        for (int at = 0; at < NT; at++) b[u][at][ks] = in ? vld(i, at * 8 + g, edge) : 0.;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; u++)
-      if (it0 + 4 * u < nt) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ks++)
-#pragma unroll
-          for (int s = 0; s < NSLAB; s++)
-#pragma unroll
-            for (int at = 0; at < NT; at++)
-              dmma(w[ks][s][at][0], w[ks][s][at][1], a[u][s][ks], b[u][at][ks]);
-      }
-  }
-  LL_TICK(9)
-  // ---- combine the 4 partial products (fixed order: identical in all warps)
-  {
-    double* mine = Wx + par * 1024 + warp * 256;
-#pragma unroll
-    for (int s = 0; s < NSLAB; s++)
-#pragma unroll
-      for (int at = 0; at < NT; at++)
-#pragma unroll
-        for (int e = 0; e < 2; e++)
-          mine[((s * NT + at) * 2 + e) * 32 + lane] = w[0][s][at][e] + w[1][s][at][e];
-    __syncthreads();
-    const double* all = Wx + par * 1024;
-#pragma unroll
-    for (int s = 0; s < NSLAB; s++)
-#pragma unroll
-      for (int at = 0; at < NT; at++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int idx = ((s * NT + at) * 2 + e) * 32 + lane;
-          wt[s][at][e] = (all[idx] + all[256 + idx]) + (all[512 + idx] + all[768 + idx]);
-        }
-  }
-  LL_TICK(10)
-  if constexpr (ONLYW) return;
-  // ---- phase T: W2^T = W^T T   (A operand straight from the accumulators via
-  //      the K-slot permutation a = 8*at + 2t + e)
-  double bneg[NSLAB][NBR / 4];
-  {
-    double w2[NSLAB][NT][2];
-#pragma unroll
-    for (int s = 0; s < NSLAB; s++)
-#pragma unroll
-      for (int q = 0; q < NT; q++) w2[s][q][0] = w2[s][q][1] = 0.;
-#pragma unroll
-    for (int atp = 0; atp < NT; atp++)
-#pragma unroll
-      for (int at = 0; at < NT; at++)
-        if (at <= atp) {
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int ta = at * 8 + 2 * t + e, tc = atp * 8 + g;
-            const double bb = (ta < jbq && tc < jbq) ? Tp[ta + (size_t)tc * ldt] : 0.;
-#pragma unroll
-            for (int s = 0; s < NSLAB; s++) dmma(w2[s][atp][0], w2[s][atp][1], wt[s][at][e], bb);
-          }
-        }
-    // accumulator layout -> B-fragment layout (natural K order), negated
-#pragma unroll
-    for (int s = 0; s < NSLAB; s++)
-#pragma unroll
-      for (int s4 = 0; s4 < NBR / 4; s4++) {
-        const int src = (g << 2) + ((s4 & 1) << 1) + (t >> 1);
-        const double v0 = __shfl_sync(0xffffffffu, w2[s][s4 >> 1][0], src);
-        const double v1 = __shfl_sync(0xffffffffu, w2[s][s4 >> 1][1], src);
-        bneg[s][s4] = -((t & 1) ? v1 : v0);
-      }
-  }
-  LL_TICK(11)
-  // ---- phase 2: C -= V W2 on this warp's row tiles
-  for (int it0 = itb; it0 < nt; it0 += 8) {
-    double va[2][NBR / 4];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int it = it0 + 4 * u;
-      const bool in = it < nt;
-      const bool edge = VGLOBAL && (it < itm || (ragged && (it == nt - 1 || jbq < NBR)));
-#pragma unroll
-      for (int s4 = 0; s4 < NBR / 4; s4++) va[u][s4] = in ? vld(it * 8 + g, s4 * 4 + t, edge) : 0.;
-    }
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int it = it0 + 4 * u;
-      if (it < nt) {
-#pragma unroll
-        for (int s = 0; s < NSLAB; s++) {
-          double* c0p = Cp + it * 8 + g + (s * 8 + 2 * t) * ldc;
-          double c0 = c0p[0], c1 = c0p[ldc];
-#pragma unroll
-          for (int s4 = 0; s4 < NBR / 4; s4++) dmma(c0, c1, va[u][s4], bneg[s][s4]);
-          c0p[0] = c0;
-          c0p[ldc] = c1;
-        }
-      }
-    }
-  }
-  LL_TICK(12)
-}
-
-__global__ void __launch_bounds__(kLLThreads, 4)
-ulv_qr_ll_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
-                 double* fact, double* tfac, int ldc) {
-  extern __shared__ __align__(16) double sm[];
-  const DNode nd = nodes[list[blockIdx.x]];
-  if (nd.parent < 0 || nd.k == 0) return;
-  const int m = nd.m, k = nd.k, naug = nd.naug, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  constexpr int LDW = kLLLdw;
-  double* Cs = sm;                    // ldc x 16 : the panel, absolute rows
-  double* Ts = Cs + (size_t)ldc * 16; // LDW x 16 : T of the panel being factored
-  double* Wx = Ts + LDW * 16;         // exchange buffers of ll_apply; between
-  double* pair = Wx;                  //   applications: [2][4][8] step partials,
-  double* diag = Wx + 64;             //   [2][8] pivot rows,
-  double* Ss = Wx + 128;              //   [4][64] S partials of the T merge,
-  double* Ys = Wx + 384;              //   8 x 8 (ld 8),
-  double* Xs = Wx + 512;              //   16 x 16 S (ld 16) and
-  double* Y2 = Wx + 768;              //   16 x 16 T1 S   of the 32-wide merge
-  double* A = fact + nd.F;
-  double* Tg = tfac + nd.T;
-  const int m8 = (m + 7) & ~7;
-  const int npan = (k + 15) >> 4, naugp = (naug - k + 15) >> 4;
-  int par = 0;
-#ifdef SB200_QR_TIMING
-  long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long tlast = clock64();
-  const long long tstart = tlast;
-#define TPH tph
-#else
-#define TPH nullptr
-#endif
-  for (int pp = 0; pp < npan + naugp; pp++) {
-    const bool fac = pp < npan;
-    const int c0 = fac ? pp * 16 : k + (pp - npan) * 16;
-    const int jb = min(16, (fac ? k : naug) - c0);
-    // ---- load the panel (all rows), clear T; prefetch the next panel to L2
-    for (int c = warp; c < 16; c += kLLWarps) {
-      const double* src = A + (size_t)(c0 + c) * m;
-      double* dst = Cs + c * ldc;
-      const bool cin = c < jb;
-      for (int i = lane; i < m8; i += 32) dst[i] = (cin && i < m) ? src[i] : 0.;
-    }
-    if (pp + 1 < npan + naugp) {
-      const int cn = (pp + 1 < npan) ? (pp + 1) * 16 : k + (pp + 1 - npan) * 16;
-      const long long nbytes = (long long)min(16, naug - cn) * m * 8;
-      const char* base = reinterpret_cast<const char*>(A + (size_t)cn * m);
-      for (long long o = (long long)tid * 128; o < nbytes; o += kLLThreads * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
-    }
-    for (int idx = tid; idx < LDW * 16; idx += kLLThreads) Ts[idx] = 0.;
-    __syncthreads();
-    QR_TICK(0)
-    // ---- apply the earlier block reflectors
-    const int nq = fac ? pp : npan;
-    for (int q = 0; q < nq; q++) {
-      const int q0 = q * 16;
-      double wt[2][2][2];
-      ll_apply<16, 2, true, false>(Cs, ldc, m, q0, q0, A + (size_t)q0 * m, m, min(16, k - q0),
-                                   Tg + (q & 1) * 16 + (size_t)q0 * 32, 32, Wx, par, warp, lane, wt, TPH);
-      par ^= 1;
-    }
-    __syncthreads();
-    QR_TICK(1)
-    if (!fac) {   // columns of [Vh | W1^T]: Q^T applied, done
-      for (int c = warp; c < jb; c += kLLWarps) {
-        double* dst = A + (size_t)(c0 + c) * m;
-        const double* src = Cs + c * ldc;
-        for (int i = lane; i < m; i += 32) dst[i] = src[i];
-      }
-      __syncthreads();
-      QR_TICK(2)
-      continue;
-    }
-    // ---- rows above the panel are final R entries
-    for (int c = warp; c < jb; c += kLLWarps) {
-      double* dst = A + (size_t)(c0 + c) * m;
-      const double* src = Cs + c * ldc;
-      for (int i = lane; i < c0; i += 32) dst[i] = src[i];
-    }
-    QR_TICK(2)
-    double* Pn = Cs + c0;          // panel top
-    const int mp = m - c0;
-    const int mp8 = m8 - c0;
-    const int nsub = (jb + 7) >> 3;
-    for (int sp = 0; sp < nsub; sp++) {
-      const int cs = sp * 8, sbw = min(8, jb - cs);
-      {
-        // register-resident sub-panel: see ulv_qr_kernel<NB, true>
-        double a[8][2];
-        const int r0 = warp * 64 + lane;
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-#pragma unroll
-          for (int rr = 0; rr < 2; rr++) {
-            const int i = r0 + 32 * rr;
-            a[q][rr] = i < mp ? Pn[i + (cs + q) * ldc] : 0.;
-          }
-        double tr[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) tr[q] = 0.;
-#pragma unroll
-        for (int cq = 0; cq < 8; cq++) {
-          if (cq < sbw) {
-            const int c = cs + cq;   // diagonal row c < 16: warp 0, rr = 0, lane c
-            double p[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) p[q] = 0.;
-#pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-              const int i = r0 + 32 * rr;
-              const double xv = i > c ? a[cq][rr] : 0.;
-#pragma unroll
-              for (int q = 0; q < 8; q++) p[q] += xv * a[q][rr];
-            }
-            double rsum;
-            {
-              const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-              double r1[4], r2[2];
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const double send = b4 ? p[q] : p[q + 4];
-                const double keep = b4 ? p[q + 4] : p[q];
-                r1[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-              }
-#pragma unroll
-              for (int q = 0; q < 2; q++) {
-                const double send = b3 ? r1[q] : r1[q + 2];
-                const double keep = b3 ? r1[q + 2] : r1[q];
-                r2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-              }
-              {
-                const double send = b2 ? r2[0] : r2[1];
-                const double keep = b2 ? r2[1] : r2[0];
-                rsum = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-              }
-              rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
-              rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
-            }
-            double* pw = pair + (cq & 1) * 32 + warp * 8;
-            if ((lane & 3) == 0) pw[lane >> 2] = rsum;
-            if (warp == 0 && lane == c) {
-#pragma unroll
-              for (int q = 0; q < 8; q++) diag[(cq & 1) * 8 + q] = a[q][0];
-            }
-            __syncthreads();
-            const double* pp_ = pair + (cq & 1) * 32;
-            double sm_[8], dg[8];
-            {
-              const double2* p2 = reinterpret_cast<const double2*>(pp_);
-              const double2* d2 = reinterpret_cast<const double2*>(diag + (cq & 1) * 8);
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const double2 a0 = p2[q], a1 = p2[4 + q], a2 = p2[8 + q], a3 = p2[12 + q], dd = d2[q];
-                sm_[2 * q] = (a0.x + a1.x) + (a2.x + a3.x);
-                sm_[2 * q + 1] = (a0.y + a1.y) + (a2.y + a3.y);
-                dg[2 * q] = dd.x; dg[2 * q + 1] = dd.y;
-              }
-            }
-            const double pn = sm_[cq], alpha = dg[cq];
-            double tc = 0., scal = 0., beta = alpha;
-            if (pn > 0.) {   // dlarfg
-              beta = -copysign(sqrt(alpha * alpha + pn), alpha);
-              const double d = alpha - beta;
-              scal = 1. / d;
-              tc = -d / beta;
-            }
-            const bool isdiag = (warp == 0 && lane == c);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              if (q > cq) {
-                const double w = tc * (dg[q] + scal * sm_[q]);
-                const double ws = w * scal;
-#pragma unroll
-                for (int rr = 0; rr < 2; rr++)
-                  if (r0 + 32 * rr > c) a[q][rr] -= ws * a[cq][rr];
-                if (isdiag) a[q][0] -= w;
-              }
-            }
-#pragma unroll
-            for (int rr = 0; rr < 2; rr++)
-              if (r0 + 32 * rr > c) a[cq][rr] *= scal;
-            if (isdiag) a[cq][0] = beta;
-            {
-              double val = (lane == cq) ? tc : 0.;
-              double acc = 0.;
-#pragma unroll
-              for (int b = 0; b < 8; b++)
-                if (b < cq) acc += (b >= lane ? tr[b] : 0.) * (dg[b] + scal * sm_[b]);
-              if (lane < cq) val = -tc * acc;
-              tr[cq] = val;
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-#pragma unroll
-          for (int rr = 0; rr < 2; rr++) {
-            const int i = r0 + 32 * rr;
-            if (i < mp) Pn[i + (cs + q) * ldc] = a[q][rr];
-          }
-        if (warp == 0 && lane < 8) {
-#pragma unroll
-          for (int q = 0; q < 8; q++) Ts[(cs + lane) + (cs + q) * LDW] = (q >= lane) ? tr[q] : 0.;
-        }
-      }
-      __syncthreads();
-      QR_TICK(3)
-      // ---- R entries of these columns to global; V explicit (unit diagonal)
-      for (int cw = warp; cw < sbw; cw += kLLWarps) {
-        const int c = cs + cw;
-        double* dst = A + c0 + (size_t)(c0 + c) * m;
-        if (lane <= c) {
-          dst[lane] = Pn[lane + c * ldc];
-          Pn[lane + c * ldc] = (lane == c) ? 1. : 0.;
-        }
-      }
-      __syncthreads();
-      QR_TICK(4)
-      // ---- second half of the panel <- first sub-panel's block reflector
-      if (sp == 0 && jb > 8) {
-        double wt[1][1][2];
-        ll_apply<8, 1, false, false>(Cs + 8 * ldc, ldc, m, c0, c0, Cs, ldc, 8, Ts, LDW, Wx, par, warp, lane, wt);
-        par ^= 1;
-        __syncthreads();
-        QR_TICK(5)
-      }
-    }
-    // ---- T01 = -T00 (V0^T V1) T11 (block dlarft)
-    if (nsub > 1) {
-      const int cw = jb - 8;
-      {
-        const int g = lane >> 2, t = lane & 3;
-        double s0 = 0., s1 = 0.;
-        const double* va = Pn + t + g * ldc;
-        const double* vb = Pn + t + (8 + g) * ldc;
-        for (int i = 8 + 4 * warp; i < mp8; i += 16) dmma(s0, s1, va[i], vb[i]);
-        Ss[warp * 64 + g + (2 * t) * 8] = s0;
-        Ss[warp * 64 + g + (2 * t + 1) * 8] = s1;
-      }
-      __syncthreads();
-      if (tid < 64) {
-        const int a = tid & 7, cp = tid >> 3;
-        double acc = 0.;
-        for (int b = a; b < 8; b++) {
-          const int si = b + cp * 8;
-          acc += Ts[a + b * LDW] * ((Ss[si] + Ss[64 + si]) + (Ss[128 + si] + Ss[192 + si]));
-        }
-        Ys[a + cp * 8] = acc;
-      }
-      __syncthreads();
-      if (tid < 64) {
-        const int a = tid & 7, cp = tid >> 3;
-        if (cp < cw) {
-          double acc = 0.;
-          for (int d = 0; d <= cp; d++) acc += Ys[a + d * 8] * Ts[(8 + d) + (8 + cp) * LDW];
-          Ts[a + (8 + cp) * LDW] = -acc;
-        }
-      }
-      __syncthreads();
-    }
-    QR_TICK(6)
-    // ---- T to global in the 32-wide format the solve uses: diagonal block ...
-    const int hb = pp & 1;
-    for (int idx = tid; idx < 16 * 16; idx += kLLThreads) {
-      const int a = idx & 15, c = idx >> 4;
-      if (c < jb) {
-        Tg[hb * 16 + a + (size_t)(c0 + c) * 32] = (a < jb) ? Ts[a + c * LDW] : 0.;
-        if (!hb) Tg[16 + a + (size_t)(c0 + c) * 32] = 0.;
-      }
-    }
-    // ---- V (strictly lower part) back to global
-    for (int c = warp; c < jb; c += kLLWarps) {
-      double* dst = A + c0 + (size_t)(c0 + c) * m;
-      const double* src = Pn + c * ldc;
-      for (int i = c + 1 + lane; i < mp; i += 32) dst[i] = src[i];
-    }
-    QR_TICK(7)
-    // ---- ... and for the second half of a pair T12 = -T1 (V1^T V2) T2
-    if (hb) {
-      double wt[2][2][2];
-      __syncthreads();
-      ll_apply<16, 2, true, true>(Cs, ldc, m, c0, c0 - 16, A + (size_t)(c0 - 16) * m, m, 16,
-                                  nullptr, 0, Wx, par, warp, lane, wt);
-      par ^= 1;
-      __syncthreads();   // all warps have read the exchange buffers
-      if (warp == 0) {
-        const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-        for (int s = 0; s < 2; s++)
-#pragma unroll
-          for (int at = 0; at < 2; at++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) Xs[(at * 8 + 2 * t + e) + (s * 8 + g) * 16] = wt[s][at][e];
-      }
-      __syncthreads();
-      const double* T1 = Tg + (size_t)(c0 - 16) * 32;   // rows 0..15 of the pair's first half
-      for (int idx = tid; idx < 256; idx += kLLThreads) {
-        const int a = idx & 15, n = idx >> 4;
-        double acc = 0.;
-        for (int b = a; b < 16; b++) acc += T1[a + (size_t)b * 32] * Xs[b + n * 16];
-        Y2[a + n * 16] = acc;
-      }
-      __syncthreads();
-      for (int idx = tid; idx < 256; idx += kLLThreads) {
-        const int a = idx & 15, c = idx >> 4;
-        if (c < jb) {
-          double acc = 0.;
-          for (int d = 0; d <= c; d++) acc += Y2[a + d * 16] * Ts[d + c * LDW];
-          Tg[a + (size_t)(c0 + c) * 32] = -acc;
-        }
-      }
-    }
-    __syncthreads();
-    QR_TICK(8)
-  }
-#ifdef SB200_QR_TIMING
-  if (lane == 0 && (blockIdx.x < 2 || blockIdx.x == 2000))
-    printf("[ll timing] block %d warp %d m %d k %d total %lld : load %lld apply %lld rstore %lld steps %lld fin %lld inpanel %lld merge %lld tvstore %lld t12 %lld | ph1 %lld xchg %lld phT %lld ph2 %lld\n",
-           blockIdx.x, warp, m, k, clock64() - tstart, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7], tph[8],
-           tph[9], tph[10], tph[11], tph[12]);
 #endif
 }
 
@@ -2799,10 +2233,7 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   int dev = 0;
   SB200_CUDA(cudaGetDevice(&dev));
   SB200_CUDA(cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, dev));
-  if (const char* e = std::getenv("SB200_QR_SPLIT")) qr_split_ = std::atoi(e);
   if (const char* e = std::getenv("SB200_QR_REGPANEL")) qr_regpanel_ = std::atoi(e);
-  if (const char* e = std::getenv("SB200_QR_SKEW")) qr_skew_ = std::atoi(e);   // in 1000 clk
-  if (const char* e = std::getenv("SB200_QR_LL")) qr_ll_ = std::atoi(e);       // 0 off, 1 leaf class, 2 all classes
   // classes with m <= 256: 0 = 32-column panels, 256 threads, 2 CTAs/SM;
   // 1 = 16-column panels, 128 threads, 4 CTAs/SM; 2 = 16-column panels, 256 threads
   if (const char* e = std::getenv("SB200_QR_VARIANT")) qr_variant_ = std::atoi(e);
@@ -2815,7 +2246,6 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
   if (const char* e = std::getenv("SB200_GRAPH")) use_graph_ = std::atoi(e);
   // 1: left-looking warp-specialised TMA-fed QR (ulv_qr3.cuh) for classes with m <= 256; default: the right-looking kernel
   if (const char* e = std::getenv("SB200_QR3")) qr3_ = std::atoi(e);
-  if (qr_split_) qr_variant_ = 0;   // the per-panel launch experiment assumes nb_-wide panels
   build_tables();
 }
 HSSEngine::~HSSEngine() {
@@ -3068,7 +2498,6 @@ void HSSEngine::make_lists(NodeLists& L, const std::vector<int>& nodes) {
 int HSSEngine::class_nb(int h, int max_m) const {
   if (nb_ != 32 || max_m > 256) return nb_;
   if (qr3_) return 16;
-  if (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0)) return 32;   // the left-looking kernel writes 32-wide T
   return (qr_regpanel_ && qr_variant_ >= 1) ? 16 : 32;
 }
 
@@ -3425,40 +2854,28 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
     const bool timed = profile_ && time_leaf && h == 0;
     if (timed) SB200_CUDA(cudaEventRecord(ev_[0], st));
     {
-      // optional: one launch per panel and phase (SB200_QR_SPLIT=1); default fused
-      const int kmax = L.max_k[h];
-      const bool split = qr_split_ && cnt >= 2 * nsm_ && kmax > nb_;
-      const int npan = split ? (kmax + nb_ - 1) / nb_ : 1;
-      for (int pp = 0; pp < npan; pp++)
-        for (int phase0 = split ? 1 : 0; phase0 <= (split ? 2 : 0); phase0++) {
-          const int phase = phase0 + (qr_nowide_ ? 8 : 0) + (h == 0 ? (qr_skew_ << 4) : 0);
-          if (nb_ == 32 && gmm <= 256 && qr3_ && !split) {
-            set_smem(qr3::ulv_qr3_kernel, qr3::SMEM_BYTES);
-            qr3::ulv_qr3_kernel<<<cnt, qr3::NTHREADS, qr3::SMEM_BYTES, st>>>(dn_.p, lst, fact_.p, tfac_.p, tmaps_.p);
-          } else if (nb_ == 32 && gmm <= 256 && !split && (qr_ll_ == 2 || (qr_ll_ == 1 && h == 0))) {
-            const size_t smem = qr_ll_smem(ldv);
-            set_smem(ulv_qr_ll_kernel, smem);
-            if (std::getenv("SB200_DEBUG_OCC")) {
-              int nbk = 0;
-              SB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbk, ulv_qr_ll_kernel, kLLThreads, smem));
-              std::fprintf(stderr, "[sb200] ulv_qr_ll_kernel: %d CTAs/SM (smem %zu B, class %d, %d nodes)\n", nbk, smem, h, cnt);
-            }
-            ulv_qr_ll_kernel<<<cnt, kLLThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv);
-          } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 1) {
-            size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 128>, smem);
-            ulv_qr_kernel<16, true, 128><<<cnt, 128, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 2) {
-            size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 256>, smem);
-            ulv_qr_kernel<16, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true, 256>, smem);
-            ulv_qr_kernel<32, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          } else if (nb_ == 32) { size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, false, 256>, smem);
-            ulv_qr_kernel<32, false, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          } else { size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, false, 256>, smem);
-            ulv_qr_kernel<16, false, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, phase, pp);
-          }
-          launches_++;
-        }
+      // one launch per class: the whole blocked QR of every node of the class
+      const int nowide = qr_nowide_ ? 1 : 0;
+      if (nb_ == 32 && gmm <= 256 && qr3_) {          // optional left-looking TMA-fed kernel
+        set_smem(qr3::ulv_qr3_kernel, qr3::SMEM_BYTES);
+        qr3::ulv_qr3_kernel<<<cnt, qr3::NTHREADS, qr3::SMEM_BYTES, st>>>(dn_.p, lst, fact_.p, tfac_.p, tmaps_.p);
+      } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 1) {   // default for m <= 256
+        size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 128>, smem);
+        ulv_qr_kernel<16, true, 128><<<cnt, 128, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, nowide);
+      } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 2) {
+        size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 256>, smem);
+        ulv_qr_kernel<16, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, nowide);
+      } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_) {
+        size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, true, 256>, smem);
+        ulv_qr_kernel<32, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, nowide);
+      } else if (nb_ == 32) {
+        size_t smem = qr_smem<32>(ldv); set_smem(ulv_qr_kernel<32, false, 256>, smem);
+        ulv_qr_kernel<32, false, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, nowide);
+      } else {
+        size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, false, 256>, smem);
+        ulv_qr_kernel<16, false, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, nowide);
+      }
+      launches_++;
     }
     if (timed) SB200_CUDA(cudaEventRecord(ev_[1], st));
   }
@@ -3958,7 +3375,7 @@ void debug_qr_batch(int m, int k, int naug, int count, const double* hA, double*
     } else {
       size_t smem = qr_smem<16>(ldv);
       set_smem(ulv_qr_kernel<16, true, 128>, smem);
-      ulv_qr_kernel<16, true, 128><<<count, 128, smem>>>(dn.p, dl.p, fact.p, tf.p, ldv, 0, 0);
+      ulv_qr_kernel<16, true, 128><<<count, 128, smem>>>(dn.p, dl.p, fact.p, tf.p, ldv, 0);
     }
     SB200_CUDA(cudaEventRecord(e1, 0));
     SB200_CUDA(cudaEventSynchronize(e1));

@@ -202,7 +202,7 @@ class HSSEngine {
   const double* tmaps_for_ = nullptr;    // the factor arena those descriptors point into
   int qr3_ = 0;        // SB200_QR3=1: ulv_qr3.cuh (left-looking, TMA-fed, warp-specialised) for classes with m <= 256;
                        // measured slower than the right-looking kernel, kept as an option
-  int nsm_ = 148, qr_split_ = 0, qr_regpanel_ = 1, qr_skew_ = 0, qr_ll_ = 0, qr_variant_ = 1, qr_nowide_ = 0;   // switches; env SB200_QR_*
+  int nsm_ = 148, qr_regpanel_ = 1, qr_variant_ = 1, qr_nowide_ = 0;   // switches; env SB200_QR_*
   int elim_variant_ = 0;   // ulv_eliminate_kernel: 0 = 32-column tiles, 1 = 16-column tiles x 4 CTAs/SM, 2 = 16-column tiles prefetched (SB200_ELIM_VARIANT)
   int solve_pipe_ = 3;  // bit 0: ulv_bwd_pipe_kernel, bit 1: ulv_fwd_pipe_kernel (SB200_SOLVE_PIPE; 0 = the non-streamed kernels)
   int mm_min_ = 4;      // >= this many right-hand sides: GEMM-shaped (tensor pipe) apply kernels
