@@ -541,7 +541,7 @@ HSSHost compress_impl(Problem& P, std::vector<TNode>& T, const CompressOptions& 
       size_t smem = (sizeof(double) + sizeof(int)) * (size_t)max_nc + 16;
       if (smem > 48 * 1024)
         SB200_CUDA(cudaFuncSetAttribute(id_cpqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      id_cpqr_kernel<<<cnt, kThreads, smem>>>(dit.p, o.rel_tol, o.abs_tol, o.max_rank);
+      id_cpqr_kernel<<<cnt, kCpqrThreads, smem>>>(dit.p, o.rel_tol, o.abs_tol, o.max_rank);
       SB200_CUDA(cudaGetLastError());
       std::vector<int> hOrder(totI), hRank(cnt);
       SB200_CUDA(cudaMemcpy(hOrder.data(), dOrder.p, sizeof(int) * totI, cudaMemcpyDeviceToHost));

@@ -10,8 +10,8 @@
 namespace sb200 {
 namespace {
 
-constexpr int kCpqrThreads = 256;
-constexpr int kCpqrWarps = 8;
+constexpr int kCpqrThreads = 1024;   // one CTA per matrix: the steps are latency-bound, more warps = more columns in flight
+constexpr int kCpqrWarps = kCpqrThreads / 32;
 
 // ---- batched column-pivoted QR -> interpolative decomposition ----------------
 struct IDTask {
@@ -83,21 +83,52 @@ id_cpqr_kernel(const IDTask* __restrict__ tasks, double rtol, double atol,
     for (int i = tid; i < ns; i += kCpqrThreads) q[i] *= inv;
     if (tid == 0) t.R[j + (size_t)pc * t.rcap] = rjj;
     __syncthreads();
-    // orthogonalise the remaining columns against q, refresh their norms
-    for (int p = j + 1 + warp; p < nc; p += kCpqrWarps) {
-      const int c = ord[p];
-      double* col = t.M + (size_t)c * ns;
-      double r = 0.;
-      for (int i = lane; i < ns; i += 32) r += q[i] * col[i];
-      r = warp_sum(r);
-      double a = 0.;
-      for (int i = lane; i < ns; i += 32) {
-        double v = col[i] - r * q[i];
-        col[i] = v;
-        a += v * v;
+    // orthogonalise the remaining columns against q, refresh their norms.  The
+    // step is bound by the latency of its global / L2 accesses, not by flops: a
+    // warp takes kCG columns at a time so that kCG independent loads per lane are
+    // in flight (q is read once for all of them); the sums of every column are
+    // formed in the same order as one column at a time.
+    constexpr int kCG = 4;
+    for (int p0 = j + 1 + warp * kCG; p0 < nc; p0 += kCpqrWarps * kCG) {
+      double* col[kCG];
+      bool in[kCG];
+      int cidx[kCG];
+#pragma unroll
+      for (int u = 0; u < kCG; u++) {
+        in[u] = p0 + u < nc;
+        cidx[u] = ord[in[u] ? p0 + u : j];
+        col[u] = t.M + (size_t)cidx[u] * ns;
       }
-      a = warp_sum(a);
-      if (lane == 0) { t.R[j + (size_t)c * t.rcap] = r; nrm2[c] = a; }
+      double r[kCG];
+#pragma unroll
+      for (int u = 0; u < kCG; u++) r[u] = 0.;
+      for (int i = lane; i < ns; i += 32) {
+        const double qi = q[i];
+#pragma unroll
+        for (int u = 0; u < kCG; u++) r[u] += qi * col[u][i];
+      }
+#pragma unroll
+      for (int u = 0; u < kCG; u++) r[u] = warp_sum(r[u]);
+      double a[kCG];
+#pragma unroll
+      for (int u = 0; u < kCG; u++) a[u] = 0.;
+      for (int i = lane; i < ns; i += 32) {
+        const double qi = q[i];
+#pragma unroll
+        for (int u = 0; u < kCG; u++)
+          if (in[u]) {
+            const double v = col[u][i] - r[u] * qi;
+            col[u][i] = v;
+            a[u] += v * v;
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < kCG; u++) a[u] = warp_sum(a[u]);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < kCG; u++)
+          if (in[u]) { t.R[j + (size_t)cidx[u] * t.rcap] = r[u]; nrm2[cidx[u]] = a[u]; }
+      }
     }
     __syncthreads();
   }
