@@ -13,6 +13,11 @@
  * every function returns 0 on success and 1 after printing
  * "Operation failed: <what>" (StructuredMatrixC.cpp:107-119).
  *
+ * Limits of this engine (the reference has none of them; its default max_rank is
+ * 5000): a reduced HSS block (a leaf, or the sum of two children's ranks) of at
+ * most 1600 rows, BLR tiles of at most 1024 rows; larger ones are refused with an
+ * error.  Real arithmetic only (SP_d_*, and SP_s_* as a float boundary over fp64).
+ *
  * The SB200_* entry points are engine extensions (device-resident operands,
  * generator import, statistics); they never change the meaning of SP_*.
  *
