@@ -438,6 +438,27 @@ int SB200_d_hss_file_info(const char* path, long long int* out);
 int SB200_d_hss_file_copy(const char* in_path, const char* out_path);
 
 /* Library identification: returns "strumpack_b200 <ver> sm_100a". */
+/* Device-resident extend-add (front assembly): for each of nf parent fronts,
+ * F(I[y], I[x]) += CB(y, x) for the contribution blocks of its left and right
+ * child.  The parent is stored as its four column-major blocks F11 (d1 x d1, ld
+ * d1), F12 (d1 x d2, ld d1), F21 (d2 x d1, ld d2), F22 (d2 x d2, ld d2); CB1 /
+ * CB2 are dCB x dCB (ld dCB) or NULL, I1 / I2 the child's update indices in the
+ * parent's numbering (0 .. d1+d2-1, no repeats).  Every pointer, including
+ * d_fronts itself, is a DEVICE pointer; the work is queued on `stream`.
+ * Replaces extend_add_kernel / AssembleData of src/sparse/fronts/FrontCUDA.cu:60-148
+ * and the extend-add loops of FrontBLR.cpp:338-403. */
+typedef struct {
+  double *F11, *F12, *F21, *F22;
+  int d1, d2;
+  const double* CB1;
+  const int* I1;
+  int dCB1;
+  const double* CB2;
+  const int* I2;
+  int dCB2;
+} SB200FrontAssemble;
+int SB200_d_front_extend_add_device(int nf, const SB200FrontAssemble* d_fronts, int max_dCB, void* stream);
+
 /* The roofline denominator of the factor kernels, measured on the current device
  * when called (about 10 ms): TFLOP/s of a register-resident stream of
  * mma.sync.m8n8k4.f64 (fp64 has no tcgen05 kind; this is the fp64 tensor pipe). */

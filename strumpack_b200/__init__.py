@@ -35,6 +35,14 @@ class CSPOptions(C.Structure):
                 ("max_rank", C.c_int), ("verbose", C.c_int)]
 
 
+class SB200FrontAssemble(C.Structure):
+    """One parent front + the contribution blocks of its two children (device pointers)."""
+    _fields_ = [("F11", C.c_void_p), ("F12", C.c_void_p), ("F21", C.c_void_p), ("F22", C.c_void_p),
+                ("d1", C.c_int), ("d2", C.c_int),
+                ("CB1", C.c_void_p), ("I1", C.c_void_p), ("dCB1", C.c_int),
+                ("CB2", C.c_void_p), ("I2", C.c_void_p), ("dCB2", C.c_int)]
+
+
 class SB200BLRParams(C.Structure):
     """include/sb200_structured.h: BLROptions members CSPOptions does not carry"""
     _fields_ = [("pivot_threshold", C.c_double), ("factor_algorithm", C.c_int),
@@ -60,6 +68,7 @@ _po = C.POINTER(CSPOptions)
 SYMBOLS = {
     "SB200_version": (C.c_char_p, []),
     "SB200_fp64_dmma_peak_tflops": (_d, []),
+    "SB200_d_front_extend_add_device": (_i, [_i, _vp, _i, _vp]),
     "SB200_debug_qr_batch": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "SP_d_struct_default_options": (None, [_po]),
     "SP_d_struct_destroy": (None, [_pvp]),
