@@ -344,8 +344,13 @@ def run_ours(args):
     yT = torch.zeros_like(xT)
     bT = torch.zeros_like(xT)
     if world > 1:
-        from strumpack_b200.dist import GpuShardEngine, ShardedHSS
-        S = ShardedHSS(GpuShardEngine(H, world, rank))
+        from strumpack_b200.dist import GpuShardEngine, ShardedHSS, NcclShardedHSS
+        # default: the exchange inside the engine (one C call = local sweep + ncclAllGather + top, one CUDA graph);
+        # SB200_DIST=py: begin -> torch.distributed all_gather -> end driven from Python (round 1)
+        in_engine = os.environ.get("SB200_DIST", "engine") != "py"
+        make_sharded = (lambda M: NcclShardedHSS(M, world, rank)) if in_engine else \
+                       (lambda M: ShardedHSS(GpuShardEngine(M, world, rank)))
+        S = make_sharded(H)
         lo, hi = S.owned
     else:
         S, lo, hi = None, 0, n
@@ -358,7 +363,7 @@ def run_ours(args):
         try:
             g = np.load(os.path.join(gdir, case + ".npz"))
             Hg = sb.HSSMatrix.read(os.path.join(gdir, case + ".hss"))
-            Sg = ShardedHSS(GpuShardEngine(Hg, world, rank))
+            Sg = make_sharded(Hg)
             xg = torch.tensor(g["x"].T.copy(), device=dev)
             yg = torch.zeros_like(xg)
             Sg.mult(xg, yg)
@@ -508,7 +513,9 @@ def run_ours(args):
                 "workload": workload(n),
                 "N": n, "leaf": LEAF, "rel_tol": TOL, "rank": H.rank, "levels": H.levels,
                 "parallelism": (f"one matrix sharded by subtree over {world} GPUs, replicated top "
-                                f"{world - 1} nodes, one NCCL all-gather per sweep") if world > 1 else "1 GPU",
+                                f"{world - 1} nodes, one NCCL all-gather per sweep "
+                                f"({'issued by the engine, inside its CUDA graph' if in_engine else 'torch.distributed from Python'})"
+                                ) if world > 1 else "1 GPU",
                 "l2": "inputs larger than L2 (generators %.2f GB + ULV factors %.2f GB)" % (
                     H.memory / 1e9, H.factor_nonzeros * 8 / 1e9),
                 "flops_per_step": {"apply": fa, "factor": ff, "solve": fs,

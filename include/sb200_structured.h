@@ -380,6 +380,21 @@ int SB200_d_hss_partial_backward_solve(const CSPStructMat S, int nrhs, double* X
  * device pointers; x/b/y are full-length vectors of which only the owned rows
  * are read/written.  This replaces the reference's MPI/BLACS subtree mapping
  * (src/HSS/HSSMatrixMPI.cpp:317-345, pgemr2d moves HSSMatrixMPI.factor.hpp:63-66). */
+/* The same sharded operations with the exchange INSIDE the engine: local sweep,
+ * one ncclAllGather on `stream`, replicated top and the sweep back down are queued
+ * back to back by one call (and replayed as one CUDA graph from the second call on).
+ * NCCL is bound at run time (dlopen; the copy a host framework has loaded is
+ * shared).  Rank 0 obtains a 128-byte unique id (SB200_nccl_unique_id) and hands
+ * it to the other ranks by any means; every rank then calls SB200_d_hss_dist_init
+ * (partition + communicator).  Operands are DEVICE pointers, full length on every
+ * rank; only the owned rows are read / written. */
+int SB200_nccl_unique_id(char* out128);
+int SB200_d_hss_dist_init(CSPStructMat S, int nparts, int part, const char* unique_id128);
+int SB200_d_hss_dist_mult(const CSPStructMat S, char trans, int m, const double* dB, int ldB, double* dC,
+                          int ldC, void* stream);
+int SB200_d_hss_dist_factor(CSPStructMat S, void* stream);
+int SB200_d_hss_dist_solve(const CSPStructMat S, int nrhs, double* dB, int ldB, void* stream);
+
 int SB200_d_hss_set_partition(CSPStructMat S, int nparts, int part);
 int SB200_d_hss_owned_range(const CSPStructMat S, int* lo, int* hi);
 int SB200_d_hss_dist_sizes(const CSPStructMat S, int nrhs, long long int* out);

@@ -68,6 +68,11 @@ _po = C.POINTER(CSPOptions)
 SYMBOLS = {
     "SB200_version": (C.c_char_p, []),
     "SB200_fp64_dmma_peak_tflops": (_d, []),
+    "SB200_nccl_unique_id": (_i, [_vp]),
+    "SB200_d_hss_dist_init": (_i, [_vp, _i, _i, _vp]),
+    "SB200_d_hss_dist_mult": (_i, [_vp, C.c_char, _i, _vp, _i, _vp, _i, _vp]),
+    "SB200_d_hss_dist_factor": (_i, [_vp, _vp]),
+    "SB200_d_hss_dist_solve": (_i, [_vp, _i, _vp, _i, _vp]),
     "SB200_d_front_extend_add_device": (_i, [_i, _vp, _i, _vp]),
     "SB200_debug_qr_batch": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "SP_d_struct_default_options": (None, [_po]),

@@ -941,6 +941,24 @@ int SB200_d_hss_partial_backward_solve(const CSPStructMat S, int nrhs, double* X
   });
 }
 
+/* ---- sharded operations with the NCCL exchange inside the engine ---------- */
+int SB200_nccl_unique_id(char* out128) {
+  return guarded([&] { HSSEngine::nccl_unique_id(out128); });
+}
+int SB200_d_hss_dist_init(CSPStructMat S, int nparts, int part, const char* unique_id128) {
+  return guarded([&] { require_gpu(); hss(S).dist_init(nparts, part, unique_id128); });
+}
+int SB200_d_hss_dist_mult(const CSPStructMat S, char trans, int m, const double* dB, int ldB, double* dC,
+                          int ldC, void* stream) {
+  return guarded([&] { hss(S).dist_mult(trans, m, dB, ldB, dC, ldC, static_cast<cudaStream_t>(stream)); });
+}
+int SB200_d_hss_dist_factor(CSPStructMat S, void* stream) {
+  return guarded([&] { hss(S).dist_factor(static_cast<cudaStream_t>(stream)); });
+}
+int SB200_d_hss_dist_solve(const CSPStructMat S, int nrhs, double* dB, int ldB, void* stream) {
+  return guarded([&] { hss(S).dist_solve(nrhs, dB, ldB, static_cast<cudaStream_t>(stream)); });
+}
+
 int SB200_d_hss_set_partition(CSPStructMat S, int nparts, int part) {
   return guarded([&] { hss(S).set_partition(nparts, part); });
 }

@@ -4,6 +4,8 @@
 #include "ulv_qr3.cuh"
 
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is bound at run time (dlopen), single-GPU use needs no NCCL
 
 #include <algorithm>
 #include <cmath>
@@ -2251,11 +2253,13 @@ HSSEngine::HSSEngine(HSSHost&& host) : H_(std::move(host)) {
 HSSEngine::~HSSEngine() {
   for (auto& e : ev_) if (e) cudaEventDestroy(e);
   drop_graphs();
+  dist_close();
 }
 
 void HSSEngine::drop_graphs() {
   for (auto& g : graphs_) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   graphs_.clear();
+  seen_.clear();
 }
 
 // Run `body` (a fixed sequence of kernel launches on `st`) through a CUDA graph:
@@ -2268,6 +2272,10 @@ void HSSEngine::run_graphed(const std::string& key, cudaStream_t st, const std::
     return;
   }
   auto it = graphs_.find(key);
+  if (it == graphs_.end() && seen_[key]++ == 0) {   // first time: plain launches (one-off calls never pay for a capture;
+    body();                                         // libraries inside the sequence get their lazy set-up done)
+    return;
+  }
   if (it == graphs_.end()) {
     if (graphs_.size() > 64) drop_graphs();   // operands keep changing: do not hoard executables
     cudaGraph_t g = nullptr;
@@ -2916,6 +2924,157 @@ void HSSEngine::dist_factor_end(const double* recv, cudaStream_t st) {
   factored_ = true;
 }
 
+
+// ---------------------------------------------------------------------------
+// Sharded operations with the exchange inside the engine (NCCL bound at run time)
+// ---------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+const NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool done = false;
+  if (!done) {
+    // the copy a host framework (torch) has already loaded is found by its soname
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) throw std::runtime_error(std::string("NCCL is not available: ") + dlerror());
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy)
+      throw std::runtime_error("NCCL symbols not found");
+    done = true;
+  }
+  return api;
+}
+void nccl_check(ncclResult_t r, const char* what) {
+  if (r != ncclSuccess) {
+    const auto& a = nccl_api();
+    throw std::runtime_error(std::string("NCCL error in ") + what + ": " + (a.GetErrorString ? a.GetErrorString(r) : "?"));
+  }
+}
+}  // namespace
+
+void HSSEngine::nccl_unique_id(char* out128) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  nccl_check(nccl_api().GetUniqueId(&id), "ncclGetUniqueId");
+  std::memcpy(out128, &id, sizeof id);
+}
+
+void HSSEngine::dist_init(int nparts, int part, const char* unique_id128) {
+  set_partition(nparts, part);
+  dist_close();
+  if (nparts <= 1) return;
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id128, sizeof id);
+  ncclComm_t comm = nullptr;
+  nccl_check(nccl_api().CommInitRank(&comm, nparts, id, part), "ncclCommInitRank");
+  nccl_comm_ = comm;
+}
+
+void HSSEngine::dist_close() {
+  if (!nccl_comm_) return;
+  try { nccl_api().CommDestroy(static_cast<ncclComm_t>(nccl_comm_)); } catch (...) { }
+  nccl_comm_ = nullptr;
+}
+
+void HSSEngine::all_gather(int which, long long count, cudaStream_t st) {
+  nccl_check(nccl_api().AllGather(xsend_[which].p, xrecv_[which].p, (size_t)count, ncclDouble,
+                                  static_cast<ncclComm_t>(nccl_comm_), st), "ncclAllGather");
+}
+
+void HSSEngine::dist_mult(char trans, int s, const double* dB, int ldB, double* dC, int ldC, cudaStream_t st) {
+  if (!nccl_comm_) throw std::logic_error("dist_mult: call dist_init first");
+  const bool T = !(trans == 'N' || trans == 'n');
+  if (s <= 0) return;
+  ensure_apply_ws(s);
+  long long sz[3];
+  dist_sizes(s, sz);
+  if (xsend_[0].n < (size_t)sz[0]) { drop_graphs(); xsend_[0].alloc(sz[0]); xrecv_[0].alloc(sz[0] * nparts_); }
+  run_graphed(gkey("dist_mult", {dB, dC}, {T, s, ldB, ldC}), st, [&] {
+    run_up(own_, T, s, dB, ldB, st);
+    {
+      const DNode& d = hn_[cut_[part_]];
+      const int r = T ? d.u_rank : d.v_rank;
+      copy2d(xsend_[0].p, r, t1_.p + (size_t)d.w_off * s, r, r, s, st);
+    }
+    all_gather(0, sz[0], st);
+    for (int c = 0; c < nparts_; c++) {
+      const DNode& d = hn_[cut_[c]];
+      const int r = T ? d.u_rank : d.v_rank;
+      copy2d(t1_.p + (size_t)d.w_off * s, r, xrecv_[0].p + (size_t)c * sz[0], r, r, s, st);
+    }
+    run_up(top_, T, s, dB, ldB, st);
+    run_down(top_, T, s, dB, ldB, dC, ldC, false, st);
+    run_down(own_, T, s, dB, ldB, dC, ldC, true, st);
+  });
+  SB200_CUDA(cudaGetLastError());
+}
+
+void HSSEngine::dist_factor(cudaStream_t st) {
+  if (!nccl_comm_) throw std::logic_error("dist_factor: call dist_init first");
+  factor_prepare();
+  long long sz[3];
+  dist_sizes(1, sz);
+  if (xsend_[1].n < (size_t)sz[1]) { drop_graphs(); xsend_[1].alloc(sz[1]); xrecv_[1].alloc(sz[1] * nparts_); }
+  run_graphed("dist_factor", st, [&] {
+    factor_classes(own_, true, st);
+    {
+      const DNode& d = hn_[cut_[part_]];
+      copy2d(xsend_[1].p, d.u_rank, fact_.p + d.F + d.k + (size_t)d.k * d.m, d.m, d.u_rank, d.v_rank + d.u_rank, st);
+    }
+    all_gather(1, sz[1], st);
+    for (int c = 0; c < nparts_; c++) {
+      const DNode& d = hn_[cut_[c]];
+      copy2d(fact_.p + d.F + d.k + (size_t)d.k * d.m, d.m, xrecv_[1].p + (size_t)c * sz[1], d.u_rank,
+             d.u_rank, d.v_rank + d.u_rank, st);
+    }
+    factor_classes(top_, false, st);
+  });
+  SB200_CUDA(cudaGetLastError());
+  factored_ = true;
+}
+
+void HSSEngine::dist_solve(int s, double* dB, int ldB, cudaStream_t st) {
+  if (!nccl_comm_) throw std::logic_error("dist_solve: call dist_init first");
+  if (!factored_) throw std::logic_error("solve called before factor");
+  if (s <= 0) return;
+  ensure_solve_ws(s);
+  long long sz[3];
+  dist_sizes(s, sz);
+  if (xsend_[2].n < (size_t)sz[2]) { drop_graphs(); xsend_[2].alloc(sz[2]); xrecv_[2].alloc(sz[2] * nparts_); }
+  run_graphed(gkey("dist_solve", {dB}, {s, ldB}), st, [&] {
+    solve_fwd(own_, s, dB, ldB, st);
+    {
+      const DNode& d = hn_[cut_[part_]];
+      const int ld = d.v_rank + d.u_rank;
+      copy2d(xsend_[2].p, ld, zsol_.p + (size_t)d.z_off * s, d.v_rank, d.v_rank, s, st);
+      copy2d(xsend_[2].p + d.v_rank, ld, fsol_.p + (size_t)d.f_off * s, d.u_rank, d.u_rank, s, st);
+    }
+    all_gather(2, sz[2], st);
+    for (int c = 0; c < nparts_; c++) {
+      const DNode& d = hn_[cut_[c]];
+      const int ld = d.v_rank + d.u_rank;
+      const double* src = xrecv_[2].p + (size_t)c * sz[2];
+      copy2d(zsol_.p + (size_t)d.z_off * s, d.v_rank, src, ld, d.v_rank, s, st);
+      copy2d(fsol_.p + (size_t)d.f_off * s, d.u_rank, src + d.v_rank, ld, d.u_rank, s, st);
+    }
+    solve_fwd(top_, s, dB, ldB, st);
+    solve_root(s, dB, ldB, st);
+    solve_bwd(top_, s, dB, ldB, st);
+    solve_bwd(own_, s, dB, ldB, st);
+  });
+  SB200_CUDA(cudaGetLastError());
+}
 
 // ---------------------------------------------------------------------------
 // Schur complement of the (0,0) block (HSS fronts)

@@ -88,6 +88,16 @@ class HSSEngine {
   void dist_factor_end(const double* recv, cudaStream_t st);
   void dist_solve_begin(int s, double* dB, int ldB, double* send, cudaStream_t st);
   void dist_solve_end(int s, double* dB, int ldB, const double* recv, cudaStream_t st);
+  // The same three operations with the exchange done by the engine itself: the
+  // local sweep, ONE ncclAllGather on `st` and the replicated top + the sweep back
+  // down are queued back to back (and replayed as one CUDA graph).  dist_init joins
+  // the communicator (unique id from nccl_unique_id(), shared by the caller) and
+  // sets the partition.
+  static void nccl_unique_id(char* out128);
+  void dist_init(int nparts, int part, const char* unique_id128);
+  void dist_mult(char trans, int s, const double* dB, int ldB, double* dC, int ldC, cudaStream_t st);
+  void dist_factor(cudaStream_t st);
+  void dist_solve(int s, double* dB, int ldB, cudaStream_t st);
 
   // ---- Schur complement of the (0,0) block of H = [H00 H01; H10 H11] (root's
   // children), what the reference's HSS fronts use (reference
@@ -167,6 +177,10 @@ class HSSEngine {
   DevBuf<int32_t> perms_;
   NodeLists own_, top_;
   std::vector<int> cut_;
+  void* nccl_comm_ = nullptr;          // ncclComm_t of the sharded matrix (dist_init)
+  DevBuf<double> xsend_[3], xrecv_[3]; // exchange buffers of dist_mult / dist_factor / dist_solve
+  void all_gather(int which, long long count, cudaStream_t st);
+  void dist_close();
   int nparts_ = 1, part_ = 0;
   // apply workspace
   DevBuf<double> t1_, t2_;
@@ -188,6 +202,7 @@ class HSSEngine {
   // dropped whenever an arena or a node list changes.  SB200_GRAPH=0 disables.
   struct GraphEntry { cudaGraphExec_t exec = nullptr; long long launches = 0; };
   std::map<std::string, GraphEntry> graphs_;
+  std::map<std::string, int> seen_;    // a sequence is captured the second time it is asked for
   int use_graph_ = 1;
   void drop_graphs();
   void run_graphed(const std::string& key, cudaStream_t st, const std::function<void()>& body);

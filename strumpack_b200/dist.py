@@ -122,3 +122,56 @@ class ShardedHSS:
         for l, h, t in parts:
             out[:, l:h] = t
         return out
+
+
+class NcclShardedHSS:
+    """The sharded matrix with the exchange inside the engine (C ABI SB200_d_hss_dist_{init,mult,factor,solve}):
+    one C call per operation queues the local sweep, ONE ncclAllGather and the replicated top on the caller's
+    stream; from the second call on the whole sequence is one CUDA graph.  `torch.distributed` is only used once,
+    to hand rank 0's NCCL unique id to the other ranks."""
+
+    def __init__(self, H, world, rank, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import lib, _check
+        self.H, self.world, self.rank, self.torch = H, world, rank, torch
+        self._lib, self._check = lib(), _check
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            _check(self._lib.SB200_nccl_unique_id(uid), "nccl_unique_id")
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        _check(self._lib.SB200_d_hss_dist_init(H._h, world, rank, box[0]), "dist_init")
+        lo, hi = C.c_int(), C.c_int()
+        _check(self._lib.SB200_d_hss_owned_range(H._h, C.byref(lo), C.byref(hi)), "owned_range")
+        self.lo, self.hi = lo.value, hi.value
+        self._dist, self._group = dist, group
+
+    @property
+    def owned(self):
+        return self.lo, self.hi
+
+    def _st(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def mult(self, xT, yT, trans="N"):
+        s, n = xT.shape
+        self._check(self._lib.SB200_d_hss_dist_mult(self.H._h, trans.encode()[:1], s, C.c_void_p(xT.data_ptr()), n,
+                                                    C.c_void_p(yT.data_ptr()), yT.shape[1], self._st()), "dist_mult")
+
+    def factor(self):
+        self._check(self._lib.SB200_d_hss_dist_factor(self.H._h, self._st()), "dist_factor")
+
+    def solve(self, bT):
+        s, n = bT.shape
+        self._check(self._lib.SB200_d_hss_dist_solve(self.H._h, s, C.c_void_p(bT.data_ptr()), n, self._st()),
+                    "dist_solve")
+
+    def gather_rows(self, vT):
+        import torch
+        parts = [None] * self.world
+        self._dist.all_gather_object(parts, (self.lo, self.hi, vT[:, self.lo:self.hi].cpu()), group=self._group)
+        out = torch.zeros_like(vT, device="cpu")
+        for l, h, t in parts:
+            out[:, l:h] = t
+        return out

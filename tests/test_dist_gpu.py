@@ -72,7 +72,7 @@ def test_unsharded_calls_refuse_sharded_matrix(built, capfd):
     assert "sharded" in capfd.readouterr().err
 
 
-def _nccl_worker(rank, world, port, case, out):
+def _nccl_worker(rank, world, port, case, out, in_engine=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -81,10 +81,12 @@ def _nccl_worker(rank, world, port, case, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import strumpack_b200 as sb
-    from strumpack_b200.dist import GpuShardEngine, ShardedHSS
+    from strumpack_b200.dist import GpuShardEngine, ShardedHSS, NcclShardedHSS
     g = np.load(os.path.join(GOLDEN, case + ".npz"))
     H = sb.HSSMatrix.read(os.path.join(GOLDEN, case + ".hss"))
-    S = ShardedHSS(GpuShardEngine(H, world, rank))
+    S = NcclShardedHSS(H, world, rank) if in_engine else ShardedHSS(GpuShardEngine(H, world, rank))
+    stream = torch.cuda.Stream()          # not the legacy default stream: the engine replays CUDA graphs
+    torch.cuda.set_stream(stream)
     xT = torch.tensor(g["x"].T.copy(), device="cuda")
     yT = torch.zeros_like(xT)
     S.mult(xT, yT)
@@ -93,21 +95,33 @@ def _nccl_worker(rank, world, port, case, out):
     bT = torch.tensor(g["y"].T.copy(), device="cuda")
     S.solve(bT)
     xs = S.gather_rows(bT)
+    for _ in range(3):                    # again: from the second call on the sequences are graph replays
+        yT.zero_()
+        S.mult(xT, yT)
+        S.factor()
+        bT.copy_(torch.tensor(g["y"].T.copy(), device="cuda"))
+        S.solve(bT)
+    y2, xs2 = S.gather_rows(yT), S.gather_rows(bT)
     if rank == 0:
-        torch.save({"y": y, "xs": xs}, out)
+        torch.save({"y": y, "xs": xs, "y2": y2, "xs2": xs2}, out)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_engine_nccl(built, tmp_path):
+@pytest.mark.parametrize("in_engine", [False, True])
+def test_sharded_engine_nccl(built, tmp_path, in_engine):
+    """Real NCCL (needs >= 2 GPUs): the Python-driven begin / all_gather / end protocol and the in-engine
+    exchange (SB200_d_hss_dist_*: ncclAllGather issued by the engine, CUDA-graph replays) against the
+    reference's golden vectors."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world, case = 2, CASES[2]
     out = str(tmp_path / "res.pt")
-    mp.spawn(_nccl_worker, args=(world, 29611, case, out), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, 29611 + int(in_engine), case, out, in_engine), nprocs=world, join=True)
     res = torch.load(out)
     g = np.load(os.path.join(GOLDEN, case + ".npz"))
-    assert rel(res["y"].numpy().T, g["y"]) < 1e-13
-    assert rel(res["xs"].numpy().T, g["xs"]) < 1e-10
+    for ky, kx in (("y", "xs"), ("y2", "xs2")):
+        assert rel(res[ky].numpy().T, g["y"]) < 1e-13
+        assert rel(res[kx].numpy().T, g["xs"]) < 1e-10
