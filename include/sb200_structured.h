@@ -224,6 +224,13 @@ typedef struct SB200BLRParams {
   int factor_algorithm;
   const int* admissible;
   int n_admissible;
+  /* tile partition given by the caller (the reference's tiles1 / tiles2: leaf
+   * sizes of the separator / update cluster trees); NULL / 0: recursive
+   * bisection down to leaf_size.  tiles1 must add up to n (or n1), tiles2 to n2. */
+  const int* tiles1;
+  int n_tiles1;
+  const int* tiles2;
+  int n_tiles2;
 } SB200BLRParams;
 int SB200_d_blr_compress_and_factor_ex(CSPStructMat* S, int n, const double* A, int ldA,
                                        const CSPOptions* opts, const SB200BLRParams* params);

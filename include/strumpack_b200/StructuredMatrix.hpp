@@ -27,6 +27,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -41,7 +42,7 @@ template <typename scalar_t> class DenseMatrix {
  public:
   DenseMatrix() = default;
   DenseMatrix(std::size_t m, std::size_t n) : rows_(m), cols_(n), ld_(m ? m : 1), own_(m * n) {
-    data_ = own_.data();
+    data_ = reinterpret_cast<scalar_t*>(own_.data());
   }
   // copy of a column-major block (reference DenseMatrix(m, n, D, ld))
   DenseMatrix(std::size_t m, std::size_t n, const scalar_t* D, std::size_t ld) : DenseMatrix(m, n) {
@@ -103,18 +104,32 @@ template <typename scalar_t> class DenseMatrix {
   }
   std::size_t nonzeros() const { return rows_ * cols_; }
   void clear() { own_.clear(); own_.shrink_to_fit(); data_ = nullptr; rows_ = cols_ = 0; ld_ = 1; }
+  // DenseMatrix::laswp(P, fwd) (reference DenseMatrix.cpp:288-297): LAPACK row
+  // interchanges, P 1-based.  An EMPTY P is a no-op: BLRMatrix::piv() of this
+  // engine is empty because the interchanges are applied inside its solves.
+  void laswp(const std::vector<int>& P, bool fwd) {
+    if (P.empty()) return;
+    const int n = int(P.size());
+    for (int q = 0; q < n; q++) {
+      const int i = fwd ? q : n - 1 - q, p = P[i] - 1;
+      if (p != i)
+        for (std::size_t c = 0; c < cols_; c++) std::swap((*this)(i, c), (*this)(p, c));
+    }
+  }
 
  protected:
   void swap_in(DenseMatrix&& o) {
     const bool owned = !o.own_.empty() || o.data_ == nullptr;
     own_ = std::move(o.own_);
     rows_ = o.rows_; cols_ = o.cols_; ld_ = o.ld_;
-    data_ = owned ? own_.data() : o.data_;
+    data_ = owned ? reinterpret_cast<scalar_t*>(own_.data()) : o.data_;
     o.data_ = nullptr; o.rows_ = o.cols_ = 0; o.ld_ = 1;
   }
   scalar_t* data_ = nullptr;
   std::size_t rows_ = 0, cols_ = 0, ld_ = 1;
-  std::vector<scalar_t> own_;
+  // (bool is stored as bytes: std::vector<bool> has no contiguous storage; adm_t = DenseMatrix<bool>)
+  using store_t = typename std::conditional<std::is_same<scalar_t, bool>::value, unsigned char, scalar_t>::type;
+  std::vector<store_t> own_;
 };
 
 // non-owning view (reference DenseMatrixWrapper)
@@ -834,8 +849,16 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
   using adm_t = DenseMatrix<bool>;
   BLRMatrix() = default;
   explicit BLRMatrix(CSPStructMat h) : base(h) {}
-  BLRMatrix(BLRMatrix&& o) noexcept = default;
-  BLRMatrix& operator=(BLRMatrix&& o) noexcept = default;
+  BLRMatrix(BLRMatrix&& o) noexcept : base(std::move(o)), view_(o.view_) { o.view_ = false; }
+  BLRMatrix& operator=(BLRMatrix&& o) noexcept {
+    if (this != &o) {
+      if (view_) this->h_ = nullptr;
+      base::operator=(std::move(o));
+      view_ = o.view_;
+      o.view_ = false;
+    }
+    return *this;
+  }
   // BLRMatrix::compress(A, admissible, opts)                   (BLRMatrix.cpp:91-111)
   void compress(const DenseM_t& A, const Opts_t& opts) {
     CSPStructMat s = nullptr;
@@ -856,7 +879,7 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
     if (A.rows() != A.cols()) throw std::invalid_argument("BLR: only square matrices are supported");
     CSPStructMat s = nullptr;
     check_supported(opts);
-    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), nullptr, 0};
+    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), nullptr, 0, nullptr, 0, nullptr, 0};
     if (SB200_d_blr_compress_and_factor_ex(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), &p))
       throw std::invalid_argument("BLRMatrix::compress_and_factor failed");
     reset(s);
@@ -868,7 +891,7 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
     for (std::size_t j = 0; j < admissible.cols(); j++)
       for (std::size_t i = 0; i < admissible.rows(); i++) adm[i + j * admissible.rows()] = admissible(i, j) ? 1 : 0;
     check_supported(opts);
-    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), adm.data(), int(admissible.rows())};
+    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), adm.data(), int(admissible.rows()), nullptr, 0, nullptr, 0};
     CSPStructMat s = nullptr;
     if (SB200_d_blr_compress_and_factor_ex(&s, int(A.rows()), A.data(), int(A.ld()), opts.c(), &p))
       throw std::invalid_argument("BLRMatrix::compress_and_factor failed");
@@ -882,13 +905,58 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
                                                 const Opts_t& opts) {
     CSPStructMat s = nullptr;
     check_supported(opts);
-    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), nullptr, 0};
+    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), nullptr, 0, nullptr, 0, nullptr, 0};
     if (SB200_d_blr_partial_factor_ex(&s, int(A11.rows()), int(A22.rows()), A11.data(), int(A11.ld()), A12.data(),
                                       int(A12.ld()), A21.data(), int(A21.ld()), A22.data(), int(A22.ld()),
                                       opts.c(), &p))
       throw std::invalid_argument("BLRMatrix::construct_and_partial_factor failed");
     A11.clear(); A12.clear(); A21.clear();
     return BLRMatrix(s);
+  }
+  // The reference's own signature (BLRMatrix.hpp:184-191; FrontBLR.cpp:429-433):
+  // three result matrices and the tile partitions of the separator / update
+  // blocks.  B11 owns the factored front; B12 and B21 are views of it (the
+  // engine keeps F11, F12 and F21 in one object), so they must not outlive B11.
+  static void construct_and_partial_factor(DenseM_t& A11, DenseM_t& A12, DenseM_t& A21, DenseM_t& A22,
+                                           BLRMatrix& B11, BLRMatrix& B12, BLRMatrix& B21,
+                                           const std::vector<std::size_t>& tiles1,
+                                           const std::vector<std::size_t>& tiles2, const adm_t& admissible,
+                                           const Opts_t& opts) {
+    check_supported(opts);
+    std::vector<int> t1(tiles1.begin(), tiles1.end()), t2(tiles2.begin(), tiles2.end());
+    std::vector<int> adm(admissible.rows() * admissible.cols());
+    for (std::size_t j = 0; j < admissible.cols(); j++)
+      for (std::size_t i = 0; i < admissible.rows(); i++) adm[i + j * admissible.rows()] = admissible(i, j) ? 1 : 0;
+    SB200BLRParams p{opts.pivot_threshold(), int(opts.BLR_factor_algorithm()), adm.empty() ? nullptr : adm.data(),
+                     int(admissible.rows()), t1.data(), int(t1.size()), t2.empty() ? nullptr : t2.data(), int(t2.size())};
+    CSPStructMat s = nullptr;
+    if (SB200_d_blr_partial_factor_ex(&s, int(A11.rows()), int(A22.rows()), A11.data(), int(A11.ld()), A12.data(),
+                                      int(A12.ld()), A21.data(), int(A21.ld()), A22.data(), int(A22.ld()),
+                                      opts.c(), &p))
+      throw std::invalid_argument("BLRMatrix::construct_and_partial_factor failed");
+    A11.clear(); A12.clear(); A21.clear();
+    B11.reset(s);
+    B12.view(s);
+    B21.view(s);
+  }
+  // pivots of the factored block: empty -- the row interchanges are applied inside
+  // trsmLNU_gemm (DenseMatrix::laswp with an empty vector is a no-op), so the
+  // reference's `bloc.laswp(F11.piv(), true); trsmLNU_gemm(F11, F21, bloc, bupd, d)`
+  // (FrontBLR.cpp:529-531) computes the same thing unchanged
+  const std::vector<int>& piv() const { static const std::vector<int> none; return none; }
+  // B1 <- L11^{-1} P B1, B2 <- B2 - F21 B1                     (BLRMatrix.cpp:1552-1608)
+  static void trsmLNU_gemm(const BLRMatrix& F1, const BLRMatrix& /*F2*/, DenseM_t& B1, DenseM_t& B2,
+                           int /*task_depth*/) {
+    DenseM_t b = stack(B1, B2);
+    F1.trsmLNU_gemm(b);
+    unstack(b, B1, B2);
+  }
+  // B1 <- U11^{-1} (B1 - F12 B2)                               (BLRMatrix.cpp:1610-1665)
+  static void gemm_trsmUNN(const BLRMatrix& F1, const BLRMatrix& /*F2*/, DenseM_t& B1, DenseM_t& B2,
+                           int /*task_depth*/) {
+    DenseM_t b = stack(B1, B2);
+    F1.gemm_trsmUNN(b);
+    unstack(b, B1, B2);
   }
   // the two halves of the front solve on b = [b_sep; b_upd]
   // (laswp + trsmLNU_gemm, gemm_trsmUNN; BLRMatrix.cpp:1552-1665)
@@ -903,8 +971,26 @@ template <typename scalar_t> class BLRMatrix : public structured::StructuredMatr
   std::size_t colblocks() const { return SB200_d_blr_tiles(this->h_); }
   std::size_t dense_tiles() const { return SB200_d_blr_dense_tiles(this->h_); }
 
+  ~BLRMatrix() override { if (view_) this->h_ = nullptr; }   // a view does not own the engine object
+
  private:
-  void reset(CSPStructMat s) { SP_d_struct_destroy(&this->h_); this->h_ = s; }
+  bool view_ = false;
+  void reset(CSPStructMat s) { if (view_) this->h_ = nullptr; SP_d_struct_destroy(&this->h_); this->h_ = s; view_ = false; }
+  void view(CSPStructMat s) { reset(nullptr); this->h_ = s; view_ = true; }
+  static DenseM_t stack(const DenseM_t& B1, const DenseM_t& B2) {
+    DenseM_t b(B1.rows() + B2.rows(), B1.cols());
+    for (std::size_t c = 0; c < B1.cols(); c++) {
+      for (std::size_t i = 0; i < B1.rows(); i++) b(i, c) = B1(i, c);
+      for (std::size_t i = 0; i < B2.rows(); i++) b(B1.rows() + i, c) = B2(i, c);
+    }
+    return b;
+  }
+  static void unstack(const DenseM_t& b, DenseM_t& B1, DenseM_t& B2) {
+    for (std::size_t c = 0; c < B1.cols(); c++) {
+      for (std::size_t i = 0; i < B1.rows(); i++) B1(i, c) = b(i, c);
+      for (std::size_t i = 0; i < B2.rows(); i++) B2(i, c) = b(B1.rows() + i, c);
+    }
+  }
 };
 
 }  // namespace BLR

@@ -46,15 +46,24 @@ class SB200FrontAssemble(C.Structure):
 class SB200BLRParams(C.Structure):
     """include/sb200_structured.h: BLROptions members CSPOptions does not carry"""
     _fields_ = [("pivot_threshold", C.c_double), ("factor_algorithm", C.c_int),
-                ("admissible", C.c_void_p), ("n_admissible", C.c_int)]
+                ("admissible", C.c_void_p), ("n_admissible", C.c_int),
+                ("tiles1", C.c_void_p), ("n_tiles1", C.c_int),
+                ("tiles2", C.c_void_p), ("n_tiles2", C.c_int)]
 
 
-def _blr_params(pivot_threshold, factor_algorithm, admissible):
-    p = SB200BLRParams(float(pivot_threshold), int(factor_algorithm), None, 0)
-    keep = None
+def _blr_params(pivot_threshold, factor_algorithm, admissible, tiles1=None, tiles2=None):
+    p = SB200BLRParams(float(pivot_threshold), int(factor_algorithm), None, 0, None, 0, None, 0)
+    keep = []
     if admissible is not None:
-        keep = np.asfortranarray(np.asarray(admissible) != 0, dtype=np.int32)
-        p.admissible, p.n_admissible = keep.ctypes.data, keep.shape[0]
+        adm = np.asfortranarray(np.asarray(admissible) != 0, dtype=np.int32)
+        p.admissible, p.n_admissible = adm.ctypes.data, adm.shape[0]
+        keep.append(adm)
+    for name, t in (("tiles1", tiles1), ("tiles2", tiles2)):
+        if t is not None:
+            t = np.ascontiguousarray(t, dtype=np.int32)
+            setattr(p, name, t.ctypes.data)
+            setattr(p, "n_" + name, t.size)
+            keep.append(t)
     return p, keep
 
 
@@ -478,14 +487,15 @@ class BLRMatrix(StructuredMatrix):
 
     @classmethod
     def compress_and_factor(cls, A, opts=None, pivot_threshold=-1.0, factor_algorithm=BLR_RL,
-                            admissible=None):
+                            admissible=None, tiles=None):
         """BLRMatrix::compress_and_factor(A, admissible, opts) with tiles from
         ClusterTree(n).refine(leaf) (reference BLRMatrix.cpp:113-241,
         test/test_BLR_seq.cpp:136-156); factor_algorithm: BLR_RL / BLR_LL / ...;
-        admissible: nb x nb matrix (None: weak admissibility)."""
+        admissible: nb x nb matrix (None: weak admissibility); tiles: the caller's
+        tile sizes (the `tiles` vector of BLRMatrix.hpp:91-101) instead of refine(leaf)."""
         A = _fortran(A)
         opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
-        p, keep = _blr_params(pivot_threshold, factor_algorithm, admissible)
+        p, keep = _blr_params(pivot_threshold, factor_algorithm, admissible, tiles)
         h = C.c_void_p()
         _check(lib().SB200_d_blr_compress_and_factor_ex(
             C.byref(h), A.shape[0], A.ctypes.data, A.shape[0], C.byref(opts),
@@ -506,7 +516,7 @@ class BLRMatrix(StructuredMatrix):
 
     @classmethod
     def construct_and_partial_factor(cls, A11, A12, A21, A22, opts=None, pivot_threshold=-1.0,
-                                     factor_algorithm=BLR_RL, admissible=None):
+                                     factor_algorithm=BLR_RL, admissible=None, tiles1=None, tiles2=None):
         """BLRMatrix::construct_and_partial_factor (reference BLRMatrix.cpp:739-1037,
         RL, weak admissibility, tiles from ClusterTree(n1/n2).refine(leaf)).
         Returns (F, S): F holds F11 = LU(A11), F12, F21 in BLR form, S is the dense
@@ -516,7 +526,7 @@ class BLRMatrix(StructuredMatrix):
         n1, n2 = A11.shape[0], S.shape[0]
         opts = opts or default_options(type=SP_TYPE_BLR, leaf_size=256)
         h = C.c_void_p()
-        p, keep = _blr_params(pivot_threshold, factor_algorithm, admissible)
+        p, keep = _blr_params(pivot_threshold, factor_algorithm, admissible, tiles1, tiles2)
         _check(lib().SB200_d_blr_partial_factor_ex(
             C.byref(h), n1, n2, A11.ctypes.data, n1, A12.ctypes.data, max(n1, 1),
             A21.ctypes.data, max(n2, 1), S.ctypes.data, max(n2, 1), C.byref(opts),

@@ -596,7 +596,12 @@ BLREngine::BLREngine(int n, const double* hostA, int ldA, const BLROpts& o, bool
     : n_(n), opts_(o) {
   if (n <= 0) throw std::invalid_argument("empty matrix");
   std::vector<int> tiles;
-  refine(tiles, n, std::max(1, o.leaf_size));
+  if (!o.tiles1.empty()) {
+    long long sum = 0;
+    for (int t : o.tiles1) { if (t <= 0) throw std::invalid_argument("BLR: tile sizes must be positive"); sum += t; }
+    if (sum != n) throw std::invalid_argument("BLR: the given tiles do not add up to the matrix size");
+    tiles = o.tiles1;
+  } else refine(tiles, n, std::max(1, o.leaf_size));
   n1_ = n;
   nsteps_ = int(tiles.size());
   setup(tiles, do_factor);
@@ -612,10 +617,20 @@ BLREngine::BLREngine(int n1, int n2, const double* A11, int ld11, const double* 
     : n_(n1 + n2), opts_(o) {
   if (n1 <= 0 || n2 < 0) throw std::invalid_argument("partial factorization needs n1 > 0, n2 >= 0");
   std::vector<int> tiles;
-  refine(tiles, n1, std::max(1, o.leaf_size));
+  auto given = [&](const std::vector<int>& t, int n) {
+    long long sum = 0;
+    for (int v : t) { if (v <= 0) throw std::invalid_argument("BLR: tile sizes must be positive"); sum += v; }
+    if (sum != n) throw std::invalid_argument("BLR: the given tiles do not add up to the block size");
+    tiles.insert(tiles.end(), t.begin(), t.end());
+  };
+  if (!o.tiles1.empty()) given(o.tiles1, n1);
+  else refine(tiles, n1, std::max(1, o.leaf_size));
   n1_ = n1;
   nsteps_ = int(tiles.size());
-  if (n2 > 0) refine(tiles, n2, std::max(1, o.leaf_size));
+  if (n2 > 0) {
+    if (!o.tiles2.empty()) given(o.tiles2, n2);
+    else refine(tiles, n2, std::max(1, o.leaf_size));
+  }
   setup(tiles, true);
   const cudaMemcpyKind kind = device_input ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const size_t n = (size_t)n_, w = sizeof(double);

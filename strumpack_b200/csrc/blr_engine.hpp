@@ -21,6 +21,10 @@ struct BLROpts {            // reference BLROptions defaults, src/BLR/BLROptions
   // may be compressed.  Empty = weak admissibility (every off-diagonal tile).
   std::vector<int> admissible;
   int nadm = 0;
+  // tile partition given by the caller (the reference passes tiles1 / tiles2 =
+  // the leaf sizes of its separator / update cluster trees, FrontBLR.cpp:58-76);
+  // empty: ClusterTree(n).refine(leaf_size)
+  std::vector<int> tiles1, tiles2;
 };
 
 struct SolveTask { double* B; long long ldb; int ncols; };   // one column block of a batched trsm

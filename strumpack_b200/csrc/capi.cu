@@ -393,6 +393,8 @@ static BLROpts blr_opts(const CSPOptions* opts, const SB200BLRParams* p) {
           " is not implemented by this engine (RL, the reference's default, and LL are)");
     bo.pivot_threshold = p->pivot_threshold;
     bo.factor_algorithm = p->factor_algorithm == 2 ? 1 : 0;
+    if (p->tiles1 && p->n_tiles1 > 0) bo.tiles1.assign(p->tiles1, p->tiles1 + p->n_tiles1);
+    if (p->tiles2 && p->n_tiles2 > 0) bo.tiles2.assign(p->tiles2, p->tiles2 + p->n_tiles2);
     if (p->admissible) {
       if (p->n_admissible <= 0) throw std::invalid_argument("BLR admissibility matrix without a size");
       bo.nadm = p->n_admissible;
@@ -415,7 +417,7 @@ int SB200_d_blr_compress_and_factor_ex(CSPStructMat* S, int n, const double* A, 
 
 int SB200_d_blr_compress_and_factor(CSPStructMat* S, int n, const double* A, int ldA,
                                     const CSPOptions* opts, double pivot_threshold) {
-  SB200BLRParams p{pivot_threshold, 1, nullptr, 0};
+  SB200BLRParams p{pivot_threshold, 1, nullptr, 0, nullptr, 0, nullptr, 0};
   return SB200_d_blr_compress_and_factor_ex(S, n, A, ldA, opts, &p);
 }
 
@@ -454,7 +456,7 @@ int SB200_d_blr_partial_factor(CSPStructMat* S, int n1, int n2, const double* A1
                                double* A22, int ld22, const CSPOptions* opts,
                                double pivot_threshold) {
   return guarded([&] {
-    SB200BLRParams p{pivot_threshold, 1, nullptr, 0};
+    SB200BLRParams p{pivot_threshold, 1, nullptr, 0, nullptr, 0, nullptr, 0};
     blr_partial_impl(S, n1, n2, A11, ld11, A12, ld12, A21, ld21, A22, ld22, opts, &p, false);
   });
 }
@@ -464,7 +466,7 @@ int SB200_d_blr_partial_factor_device(CSPStructMat* S, int n1, int n2, const dou
                                       double* dA22, int ld22, const CSPOptions* opts,
                                       double pivot_threshold) {
   return guarded([&] {
-    SB200BLRParams p{pivot_threshold, 1, nullptr, 0};
+    SB200BLRParams p{pivot_threshold, 1, nullptr, 0, nullptr, 0, nullptr, 0};
     blr_partial_impl(S, n1, n2, dA11, ld11, dA12, ld12, dA21, ld21, dA22, ld22, opts, &p, true);
   });
 }

@@ -173,6 +173,71 @@ int main(int argc, char* argv[]) {
     Hc.compress_with_coordinates(coords, elem, HSSopts);
     CHECK(rel(Hc.dense(), F) < 1e-7, "compress_with_coordinates");
   }
+  // ---- the BLR front, statement by statement as FrontBLR does it --------------------------
+  //   FrontBLR::multifrontal_factorization   src/sparse/fronts/FrontBLR.cpp:422-433
+  //   fwd_solve_phase2 / bwd_solve_phase1     :525-568
+  {
+    using BLRM_t = BLR::BLRMatrix<scalar_t>;
+    BLR::BLROptions<scalar_t> blr_opts;
+    blr_opts.set_rel_tol(1e-9);
+    blr_opts.set_leaf_size(96);
+    structured::ClusterTree st(dim_sep_), ut(dim_upd_);
+    st.refine(blr_opts.leaf_size());
+    ut.refine(blr_opts.leaf_size());
+    auto leaves = [](const structured::ClusterTree& t) { auto v = t.leaf_sizes(); return std::vector<std::size_t>(v.begin(), v.end()); };
+    const std::vector<std::size_t> sep_tiles_ = leaves(st), upd_tiles_ = leaves(ut);
+    DenseMatrix<bool> admissibility_(sep_tiles_.size(), sep_tiles_.size());
+    for (std::size_t j = 0; j < sep_tiles_.size(); j++)
+      for (std::size_t i = 0; i < sep_tiles_.size(); i++) admissibility_(i, j) = i != j;   // weak admissibility
+    DenseM_t F11(dim_sep_, dim_sep_), F12(dim_sep_, dim_upd_), F21(dim_upd_, dim_sep_), F22_(dim_upd_, dim_upd_);
+    for (int j = 0; j < dim_blk; j++)
+      for (int i = 0; i < dim_blk; i++) {
+        const double v = F(i, j);
+        if (i < dim_sep_ && j < dim_sep_) F11(i, j) = v;
+        else if (i < dim_sep_) F12(i, j - dim_sep_) = v;
+        else if (j < dim_sep_) F21(i - dim_sep_, j) = v;
+        else F22_(i - dim_sep_, j - dim_sep_) = v;
+      }
+    BLRM_t F11blr_, F12blr_, F21blr_;
+    {
+      auto nF11 = F11.normF();
+      auto nF12 = F12.normF();
+      auto nF21 = F21.normF();
+      auto nF = std::sqrt(nF11*nF11 + nF12*nF12 + nF21*nF21);
+      auto lopts = blr_opts;
+      lopts.set_abs_tol(lopts.abs_tol() * nF);
+      BLRM_t::construct_and_partial_factor
+        (F11, F12, F21, F22_, F11blr_, F12blr_, F21blr_,
+         sep_tiles_, upd_tiles_, admissibility_, lopts);
+    }
+    CHECK(F11blr_.rowblocks() == sep_tiles_.size() + upd_tiles_.size(), "the engine used the caller's tiles");
+    // F22_ now holds the Schur complement; solve the whole front with the two half solves
+    DenseM_t b(dim_blk, nrhs), y(dim_blk, nrhs);
+    b.random();
+    DenseM_t bcopy(b);
+    DenseM_t bupd(dim_upd_, nrhs);
+    for (int c = 0; c < nrhs; c++)
+      for (int i = 0; i < dim_upd_; i++) bupd(i, c) = b(dim_sep_ + i, c);
+    {   // fwd_solve_phase2
+      DenseMW_t bloc(dim_sep(), b.cols(), b, sep_begin_, 0);
+      bloc.laswp(F11blr_.piv(), true);
+      BLRM_t::trsmLNU_gemm(F11blr_, F21blr_, bloc, bupd, task_depth);
+    }
+    DenseM_t yupd(bupd);
+    dense_solve(F22_, yupd);         // the parent front
+    for (int c = 0; c < nrhs; c++)
+      for (int i = 0; i < dim_sep_; i++) y(i, c) = b(i, c);
+    {   // bwd_solve_phase1
+      DenseMW_t yloc(dim_sep(), y.cols(), y, sep_begin_, 0);
+      BLRM_t::gemm_trsmUNN(F11blr_, F12blr_, yloc, yupd, task_depth);
+    }
+    for (int c = 0; c < nrhs; c++)
+      for (int i = 0; i < dim_upd_; i++) y(dim_sep_ + i, c) = yupd(i, c);
+    DenseM_t xref(bcopy);
+    dense_solve(F, xref);
+    std::printf("# BLR front %d + %d: ||y - F^-1 b|| / ||F^-1 b|| = %.3e\n", dim_sep_, dim_upd_, rel(y, xref));
+    CHECK(rel(y, xref) < 1e-6, "BLR front solve through the reference's static calls");
+  }
   std::printf("# exiting\n");
   return 0;
 }

@@ -344,3 +344,24 @@ def test_blr_from_element_blocks_and_dense(built):
     P2, S2 = sb.BLRMatrix.construct_and_partial_factor(A[:n1, :n1], A[:n1, n1:], A[n1:, :n1], A[n1:, n1:], o)
     assert rel(S, S2) <= 1e-13
     assert rel(S, A[n1:, n1:] - A[n1:, :n1] @ np.linalg.solve(A[:n1, :n1], A[:n1, n1:])) <= 1e2 * tol
+
+
+def test_blr_caller_given_tiles(built):
+    """The `tiles` vectors of BLRMatrix(A, tiles, admissible, opts) and of
+    construct_and_partial_factor(..., tiles1, tiles2, ...) (reference BLRMatrix.hpp:91-101,
+    FrontBLR.cpp:422-433: the separator's own cluster tree leaves, ragged sizes)."""
+    sb = built
+    n1, n2, tol = 900, 500, 1e-6
+    A, A11, A12, A21, A22 = _front(n1, n2)
+    t1, t2 = [100, 250, 37, 313, 200], [300, 200]
+    o = sb.default_options(type=sb.SP_TYPE_BLR, rel_tol=tol, abs_tol=1e-12, leaf_size=128)
+    F, S = sb.BLRMatrix.construct_and_partial_factor(A11, A12, A21, A22, o, tiles1=t1, tiles2=t2)
+    assert F.tiles == len(t1) + len(t2)
+    assert rel(S, A22 - A21 @ np.linalg.solve(A11, A12)) <= 1e2 * tol
+    G = sb.BLRMatrix.compress_and_factor(A11, o, tiles=t1)
+    assert G.tiles == len(t1)
+    B = np.random.default_rng(5).standard_normal((n1, 2))
+    assert rel(A11 @ G.solve(B), B) <= 1e2 * tol
+    for bad in ([100, 250], [900, 0], [1000, -100]):    # wrong sum, empty tile, negative tile
+        with pytest.raises((RuntimeError, ValueError)):
+            sb.BLRMatrix.compress_and_factor(A11, o, tiles=bad)
