@@ -866,17 +866,29 @@ __device__ __forceinline__ double2 ld2(const double* p, bool pred) {
 //  * W^T T is chained through the accumulators with the column permutation
 //    sigma, W2 is already in B-fragment layout for phase 2 (no shuffles).
 // Needs 16-byte aligned columns: ldc even, Cg 16-byte aligned, mp even.
-template <int NB>
+// pf / pfcols / pfmode: the NEXT pair of slabs this warp will update (or null):
+// its lines are requested into L2 (prefetch.global.L2, no register or
+// scoreboard held) at entry (pfmode 1) or between phase 1 and phase 2 (pfmode
+// 2), so that its phase-1 loads find them there instead of in HBM.
+template <int NB, int U1 = (NB <= 16 ? 8 : 4), int U2 = (NB <= 16 ? 4 : 2)>
 __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, int mp,
                                              int cw0, int cw1,
                                              const double* __restrict__ Vs, int ldv,
                                              const double* __restrict__ Ts, int ldt,
-                                             int lane) {
+                                             int lane, const double* pf = nullptr,
+                                             int pfcols = 0, int pfmode = 0) {
   constexpr int NT = NB / 8;
-  // row blocks per load group: with 16-column panels there are 4 CTAs of 4
-  // warps per SM and on average ~2 warps per scheduler in this phase, so each
-  // warp must keep more of the slab in flight to cover the L2 round trip
-  constexpr int U1 = NB <= 16 ? 8 : 4, U2 = NB <= 16 ? 4 : 2;
+  // U1 / U2 = row blocks per load group: with 16-column panels there are 4 CTAs
+  // of 4 warps per SM and on average ~2 warps per scheduler in this phase, so
+  // each warp must keep more of the slab in flight to cover the L2 round trip
+  auto request_next = [&]() {
+    const int lpc = ((mp + 15) >> 4) + 1;          // 128-byte lines per column (unaligned start)
+    for (int idx = lane; idx < lpc * pfcols; idx += 32) {
+      const int c = idx / lpc, l = idx - c * lpc;
+      prefetch_l2(pf + (size_t)c * ldc + min(l * 16, mp - 1));
+    }
+  };
+  if (pfmode == 1 && pf) request_next();
   const int g = lane >> 2, t = lane & 3;
   const int sg = sig8(g), s0 = sig8(2 * t), s1 = sig8(2 * t + 1);
   double wt[2][NT][2];
@@ -942,6 +954,7 @@ __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, i
   for (int s = 0; s < 2; s++)
 #pragma unroll
     for (int q = 0; q < NT; q++) { w2[s][q][0] = -w2[s][q][0]; w2[s][q][1] = -w2[s][q][1]; }
+  if (pfmode == 2 && pf) request_next();
   // ---- phase 2: C -= V W2 on 16-row blocks; DMMA row tile u holds rows
   // r0 + 2g + u, so a lane owns rows (2g, 2g+1) of columns 2t and 2t+1
   {
@@ -1033,7 +1046,9 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   double* A = fact + nd.F;
   double* Tg = tfac + nd.T;
   // every column of the factor block starts on a 16-byte boundary (even F, even m)
-  const bool wide = !nowide && ((m & 1) == 0) && ((nd.F & 1) == 0);
+  // nowide: bit 0 = 64-bit one-slab trailing update; bits 1-2 = L2 prefetch mode of slab2_update
+  const bool wide = !(nowide & 1) && ((m & 1) == 0) && ((nd.F & 1) == 0);
+  const int pfmode = (nowide >> 1) & 3;
 #ifdef SB200_QR_TIMING
   long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -1392,10 +1407,13 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
     if (wide) {
       // 16-byte aligned columns: two slabs per warp, 128-bit C and V accesses
       const int npair = (ntrail + 15) >> 4;
+      constexpr int U1 = MINB >= 5 ? 4 : (NB <= 16 ? 8 : 4), U2 = MINB >= 5 ? 2 : (NB <= 16 ? 4 : 2);
       for (int pr = (warp + (j0 / NB) * 3) % NWP; pr < npair; pr += NWP) {
         const int c0 = j0 + jb + pr * 16;
-        slab2_update<NB>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0),
-                         max(0, min(8, naug - c0 - 8)), Vs, ldv, Ts, LDW, lane);
+        const int cn = c0 + NWP * 16;           // this warp's next pair
+        slab2_update<NB, U1, U2>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0),
+                                 max(0, min(8, naug - c0 - 8)), Vs, ldv, Ts, LDW, lane,
+                                 cn < naug ? A + j0 + (size_t)cn * m : nullptr, min(16, naug - cn), pfmode);
       }
     } else {
       for (int sl = (warp + (j0 / NB) * 3) % NWP; sl * 8 < ntrail; sl += NWP) {

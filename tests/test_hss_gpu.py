@@ -276,10 +276,11 @@ def test_two_handles_from_two_threads(sb):
     the host-pointer C ABI at the same time, and two threads share ONE matrix;
     every result equals the single-threaded one."""
     import threading
-    g = np.load(os.path.join(GOLDEN, CASES[0] + ".npz"))
+    # arrays materialised up front: an NpzFile reads lazily from one zip handle, which threads must not share
+    g = dict(np.load(os.path.join(GOLDEN, CASES[0] + ".npz")))
     H1 = sb.HSSMatrix.read(os.path.join(GOLDEN, CASES[0] + ".hss"))
     H2 = sb.HSSMatrix.read(os.path.join(GOLDEN, CASES[2] + ".hss"))
-    g2 = np.load(os.path.join(GOLDEN, CASES[2] + ".npz"))
+    g2 = dict(np.load(os.path.join(GOLDEN, CASES[2] + ".npz")))
     H1.factor()
     H2.factor()
     errs = []
