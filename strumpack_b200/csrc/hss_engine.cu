@@ -866,7 +866,7 @@ __device__ __forceinline__ double2 ld2(const double* p, bool pred) {
 //  * W^T T is chained through the accumulators with the column permutation
 //    sigma, W2 is already in B-fragment layout for phase 2 (no shuffles).
 // Needs 16-byte aligned columns: ldc even, Cg 16-byte aligned, mp even.
-template <int NB>
+template <int NB, bool TWO = true>
 __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, int mp,
                                              int cw0, int cw1,
                                              const double* __restrict__ Vs, int ldv,
@@ -888,7 +888,7 @@ __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, i
   // i0 are rows i0 + 2t + e; B column g is reflector 8 at + sigma(g)
   {
     const int nb8 = (mp + 7) >> 3;
-    const bool in0 = g < cw0, in1 = g < cw1;
+    const bool in0 = g < cw0, in1 = TWO && g < cw1;
     const double* C0 = Cg + (size_t)g * ldc + 2 * t;
     const double* C1 = Cg + (size_t)(8 + g) * ldc + 2 * t;
     const double* Vb = Vs + 2 * t + sg * ldv;
@@ -899,7 +899,7 @@ __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, i
         const int i0 = (ib0 + u) * 8;
         const bool rin = i0 + 2 * t < mp;
         c[u][0] = ld2(C0 + i0, rin && in0);
-        c[u][1] = ld2(C1 + i0, rin && in1);
+        if (TWO) c[u][1] = ld2(C1 + i0, rin && in1);
       }
 #pragma unroll
       for (int u = 0; u < U1; u++) {
@@ -910,9 +910,9 @@ __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, i
             if (at <= ib) {   // V[i][a] = 0 for a > i
               const double2 v = *reinterpret_cast<const double2*>(Vb + ib * 8 + at * 8 * ldv);
               dmma(wt[0][at][0], wt[0][at][1], c[u][0].x, v.x);
-              dmma(wt[1][at][0], wt[1][at][1], c[u][1].x, v.x);
+              if (TWO) dmma(wt[1][at][0], wt[1][at][1], c[u][1].x, v.x);
               dmma(wt[0][at][0], wt[0][at][1], c[u][0].y, v.y);
-              dmma(wt[1][at][0], wt[1][at][1], c[u][1].y, v.y);
+              if (TWO) dmma(wt[1][at][0], wt[1][at][1], c[u][1].y, v.y);
             }
         }
       }
@@ -935,7 +935,7 @@ __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, i
         for (int e = 0; e < 2; e++) {
           const double bb = Ts[(at * 8 + (e ? s1 : s0)) + (atp * 8 + sg) * ldt];
           dmma(w2[0][atp][0], w2[0][atp][1], wt[0][at][e], bb);
-          dmma(w2[1][atp][0], w2[1][atp][1], wt[1][at][e], bb);
+          if (TWO) dmma(w2[1][atp][0], w2[1][atp][1], wt[1][at][e], bb);
         }
       }
 #pragma unroll
@@ -946,7 +946,7 @@ __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, i
   // r0 + 2g + u, so a lane owns rows (2g, 2g+1) of columns 2t and 2t+1
   {
     const int nb16 = (mp + 15) >> 4;
-    const bool k00 = 2 * t < cw0, k01 = 2 * t + 1 < cw0, k10 = 2 * t < cw1, k11 = 2 * t + 1 < cw1;
+    const bool k00 = 2 * t < cw0, k01 = 2 * t + 1 < cw0, k10 = TWO && 2 * t < cw1, k11 = TWO && 2 * t + 1 < cw1;
     double* P00 = Cg + (size_t)(2 * t) * ldc + 2 * g;
     double* P01 = P00 + ldc;
     double* P10 = Cg + (size_t)(8 + 2 * t) * ldc + 2 * g;
@@ -961,8 +961,10 @@ __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, i
         const bool rin = r0 + 2 * g < mp;
         a[u][0] = ld2(P00 + r0, rin && k00);
         a[u][1] = ld2(P01 + r0, rin && k01);
-        a[u][2] = ld2(P10 + r0, rin && k10);
-        a[u][3] = ld2(P11 + r0, rin && k11);
+        if (TWO) {
+          a[u][2] = ld2(P10 + r0, rin && k10);
+          a[u][3] = ld2(P11 + r0, rin && k11);
+        }
       }
 #pragma unroll
       for (int u = 0; u < U2; u++) {
@@ -976,189 +978,19 @@ __device__ __forceinline__ void slab2_update(double* __restrict__ Cg, int ldc, i
               for (int e = 0; e < 2; e++) {
                 const double2 v = *reinterpret_cast<const double2*>((e ? Va1 : Va0) + r0 + atp * 8 * ldv);
                 dmma(a[u][0].x, a[u][1].x, v.x, w2[0][atp][e]);
-                dmma(a[u][2].x, a[u][3].x, v.x, w2[1][atp][e]);
+                if (TWO) dmma(a[u][2].x, a[u][3].x, v.x, w2[1][atp][e]);
                 dmma(a[u][0].y, a[u][1].y, v.y, w2[0][atp][e]);
-                dmma(a[u][2].y, a[u][3].y, v.y, w2[1][atp][e]);
+                if (TWO) dmma(a[u][2].y, a[u][3].y, v.y, w2[1][atp][e]);
               }
             }
           const bool rin = r0 + 2 * g < mp;
           if (rin && k00) *reinterpret_cast<double2*>(P00 + r0) = a[u][0];
           if (rin && k01) *reinterpret_cast<double2*>(P01 + r0) = a[u][1];
-          if (rin && k10) *reinterpret_cast<double2*>(P10 + r0) = a[u][2];
-          if (rin && k11) *reinterpret_cast<double2*>(P11 + r0) = a[u][3];
+          if (TWO && rin && k10) *reinterpret_cast<double2*>(P10 + r0) = a[u][2];
+          if (TWO && rin && k11) *reinterpret_cast<double2*>(P11 + r0) = a[u][3];
         }
       }
     }
-  }
-}
-
-// Trailing update by the WHOLE CTA (4 warps), one 16-column group after the
-// other, C read from global ONCE: every warp takes up to four 16-row blocks of
-// the group into registers (LDG.256: lane (g, t) holds rows 4t..4t+3 of
-// columns g and 8+g of each block), and those registers are
-//   phase 1  the A fragments of  W^T = C^T V   (K slot t of k-step q <-> row 4t+q),
-//   phase 2  the ACCUMULATORS of C^T -= W2^T V^T  (DMMA h of a block covers rows
-//            4 (j >> 1) + 2h + (j & 1), so a lane's accumulator pair is the register
-//            pair (4t+2h, 4t+2h+1) exactly as the load delivered it: no moves),
-// so C is never re-read (slab2_update re-reads it for phase 2, and with 16
-// warps x 32 KB in flight per SM that second read misses L1: ncu shows both
-// reads waiting on L2 equally long).  As soon as a block of group cg is
-// stored, the same registers take the block of group cg+1: its L2 round trip
-// runs under the rest of phase 2 and the start of the next phase 1.  The four
-// partial W^T (one per warp) meet in shared memory behind ONE 128-thread named
-// barrier per group (two buffers); W2^T = W^T T is formed by every warp from the
-// accumulators.  Work is split by rows, so the four warps are balanced
-// whatever the number of column groups.
-// Needs ldv % 16 == 2 (the V fragment loads are conflict free: phase 1 128-bit
-// at 4t + g ldv, phase 2 64-bit at {0,1,4,5}(g) + {0,1,4,5}(t) ldv), 32-byte aligned
-// columns (m % 4 == 0, F % 4 == 0, j0 % 16 == 0), V zero-padded to a multiple
-// of 16 rows.  Ct = first trailing column (row j0), ntrail columns.
-__device__ __forceinline__ void coop_trailing16(double* __restrict__ Ct, int ldc, int mp, int ntrail,
-                                                const double* __restrict__ Vs, int ldv,
-                                                const double* __restrict__ Ts, int ldt,
-                                                double2* __restrict__ red, int warp, int lane
-#ifdef SB200_QR_TIMING
-                                                , long long* tph, long long& tlast
-#define CO_TICK(p) { long long now_ = clock64(); tph[p] += now_ - tlast; tlast = now_; }
-#else
-#define CO_TICK(p)
-#endif
-                                                ) {
-  constexpr int UB = 4;
-  const int g = lane >> 2, t = lane & 3;
-  const int nb16 = (mp + 15) >> 4, bpw = (nb16 + 3) >> 2;
-  const int b0 = warp * bpw, nbw = max(0, min(bpw, nb16 - b0));
-  const int ngr = (ntrail + 15) >> 4;
-  double c[UB][2][4];
-  auto load_block = [&](int u, const double* P0, bool in0, bool in1) {
-    const int r0 = (b0 + u) * 16;
-    const bool rin = u < nbw && r0 + 4 * t < mp;
-    double4r v0{0., 0., 0., 0.}, v1{0., 0., 0., 0.};
-    if (rin && in0) v0 = ld256(P0 + r0);
-    if (rin && in1) v1 = ld256(P0 + (size_t)8 * ldc + r0);
-    c[u][0][0] = v0.x; c[u][0][1] = v0.y; c[u][0][2] = v0.z; c[u][0][3] = v0.w;
-    c[u][1][0] = v1.x; c[u][1][1] = v1.y; c[u][1][2] = v1.z; c[u][1][3] = v1.w;
-  };
-  double* P0 = Ct + (size_t)g * ldc + 4 * t;   // this lane's rows of column g of the current group
-  bool in0 = g < ntrail, in1 = 8 + g < ntrail;
-#pragma unroll
-  for (int u = 0; u < UB; u++) load_block(u, P0, in0, in1);
-  const double* Vb = Vs + 4 * t + g * ldv;
-  // phase 2: row of V for D column g is 4 (g >> 1) + (g & 1) (+ 2h), reflector of K slot t is 4 (t >> 1) + (t & 1) (+ 2e);
-  // phase T delivers W2 in that K order when column g of its B operand is reflector rg
-  const double* Va = Vs + (4 * (g >> 1) + (g & 1)) + (4 * (t >> 1) + (t & 1)) * ldv;
-  const int rg = (g & 4) | ((g & 1) << 1) | ((g >> 1) & 1);
-  CO_TICK(8)
-  for (int cg = 0; cg < ngr; cg++) {
-    // ---- phase 1: wt[s][at][e] = W^T[column 8s+g][reflector 8at + 2t + e] (this warp's rows)
-    double wt[2][2][2];
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-#pragma unroll
-      for (int q = 0; q < 2; q++) wt[s][q][0] = wt[s][q][1] = 0.;
-#pragma unroll
-    for (int u = 0; u < UB; u++)
-      if (u < nbw) {
-        const double* vb = Vb + (b0 + u) * 16;
-        const double2 a01 = *reinterpret_cast<const double2*>(vb);
-        const double2 a23 = *reinterpret_cast<const double2*>(vb + 2);
-        const double2 b01 = *reinterpret_cast<const double2*>(vb + 8 * ldv);
-        const double2 b23 = *reinterpret_cast<const double2*>(vb + 8 * ldv + 2);
-        dmma(wt[0][0][0], wt[0][0][1], c[u][0][0], a01.x);
-        dmma(wt[1][0][0], wt[1][0][1], c[u][1][0], a01.x);
-        dmma(wt[0][1][0], wt[0][1][1], c[u][0][0], b01.x);
-        dmma(wt[1][1][0], wt[1][1][1], c[u][1][0], b01.x);
-        dmma(wt[0][0][0], wt[0][0][1], c[u][0][1], a01.y);
-        dmma(wt[1][0][0], wt[1][0][1], c[u][1][1], a01.y);
-        dmma(wt[0][1][0], wt[0][1][1], c[u][0][1], b01.y);
-        dmma(wt[1][1][0], wt[1][1][1], c[u][1][1], b01.y);
-        dmma(wt[0][0][0], wt[0][0][1], c[u][0][2], a23.x);
-        dmma(wt[1][0][0], wt[1][0][1], c[u][1][2], a23.x);
-        dmma(wt[0][1][0], wt[0][1][1], c[u][0][2], b23.x);
-        dmma(wt[1][1][0], wt[1][1][1], c[u][1][2], b23.x);
-        dmma(wt[0][0][0], wt[0][0][1], c[u][0][3], a23.y);
-        dmma(wt[1][0][0], wt[1][0][1], c[u][1][3], a23.y);
-        dmma(wt[0][1][0], wt[0][1][1], c[u][0][3], b23.y);
-        dmma(wt[1][1][0], wt[1][1][1], c[u][1][3], b23.y);
-      }
-    CO_TICK(9)
-    // ---- the four partial sums meet in shared memory: buf[warp][q][lane]
-    {
-      double2* buf = red + (cg & 1) * 512;
-      double2* mine = buf + warp * 128 + lane;
-      mine[0] = make_double2(wt[0][0][0], wt[0][0][1]);
-      mine[32] = make_double2(wt[0][1][0], wt[0][1][1]);
-      mine[64] = make_double2(wt[1][0][0], wt[1][0][1]);
-      mine[96] = make_double2(wt[1][1][0], wt[1][1][1]);
-      CO_TICK(10)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      CO_TICK(11)
-      const double2* all = buf + lane;
-#pragma unroll
-      for (int s = 0; s < 2; s++)
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int o = (2 * s + q) * 32;
-          const double2 p0 = all[o], p1 = all[128 + o], p2 = all[256 + o], p3 = all[384 + o];
-          wt[s][q][0] = (p0.x + p1.x) + (p2.x + p3.x);
-          wt[s][q][1] = (p0.y + p1.y) + (p2.y + p3.y);
-        }
-    }
-    CO_TICK(12)
-    // ---- phase T: w2[s][atp][e] = -(W^T T)[column 8s+g][reflector 8atp + 2t + e]
-    double w2[2][2][2];
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-#pragma unroll
-      for (int q = 0; q < 2; q++) w2[s][q][0] = w2[s][q][1] = 0.;
-#pragma unroll
-    for (int atp = 0; atp < 2; atp++)
-#pragma unroll
-      for (int at = 0; at < 2; at++)
-        if (at <= atp) {
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const double bb = Ts[(at * 8 + 2 * t + e) + (atp * 8 + rg) * ldt];
-            dmma(w2[0][atp][0], w2[0][atp][1], wt[0][at][e], bb);
-            dmma(w2[1][atp][0], w2[1][atp][1], wt[1][at][e], bb);
-          }
-        }
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-#pragma unroll
-      for (int q = 0; q < 2; q++) { w2[s][q][0] = -w2[s][q][0]; w2[s][q][1] = -w2[s][q][1]; }
-    CO_TICK(13)
-    // ---- phase 2: C^T -= W2^T V^T with the loaded registers as accumulators, the only
-    // store, and the same registers reloaded with the next group's block
-    const int nrem = ntrail - (cg + 1) * 16;                 // columns after this group
-    const bool more = nrem > 0, nin0 = g < nrem, nin1 = 8 + g < nrem;
-    double* Pn = P0 + (size_t)16 * ldc;
-#pragma unroll
-    for (int u = 0; u < UB; u++) {
-      if (u < nbw) {
-        const int r0 = (b0 + u) * 16;
-#pragma unroll
-        for (int atp = 0; atp < 2; atp++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const double* pv = Va + r0 + (atp * 8 + 2 * e) * ldv;
-            const double v0 = pv[0], v1 = pv[2];
-            dmma(c[u][0][0], c[u][0][1], w2[0][atp][e], v0);
-            dmma(c[u][1][0], c[u][1][1], w2[1][atp][e], v0);
-            dmma(c[u][0][2], c[u][0][3], w2[0][atp][e], v1);
-            dmma(c[u][1][2], c[u][1][3], w2[1][atp][e], v1);
-          }
-        if (r0 + 4 * t < mp) {
-          if (in0) st256(P0 + r0, c[u][0][0], c[u][0][1], c[u][0][2], c[u][0][3]);
-          if (in1) st256(P0 + (size_t)8 * ldc + r0, c[u][1][0], c[u][1][1], c[u][1][2], c[u][1][3]);
-        }
-      }
-      // reloads in two batches (after blocks 1 and 3): one scoreboard each, so that the V fragment loads
-      // of the blocks still to come never share a scoreboard with a global load in flight
-      if (more && (u & 1)) { load_block(u - 1, Pn, nin0, nin1); load_block(u, Pn, nin0, nin1); }
-    }
-    P0 = Pn; in0 = nin0; in1 = nin1;
-    CO_TICK(14)
   }
 }
 
@@ -1178,13 +1010,12 @@ __device__ __forceinline__ void coop_trailing16(double* __restrict__ Ct, int ldc
 //  NTH = 256: 2 CTAs per SM; NTH = 128 (register sub-panel only, NB = 16): 4
 //  CTAs per SM, i.e. four Householder column chains in flight per SM, so that
 //  the fp64 tensor pipe always finds a CTA in its trailing update.
-template <int NB, bool SMALL, int NTH, int MINB = (NTH == 128 ? 4 : 2), bool COOP = false>
+template <int NB, bool SMALL, int NTH, int MINB = (NTH == 128 ? 4 : 2)>
 __global__ void __launch_bounds__(NTH, MINB)
 ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
               double* __restrict__ fact, double* __restrict__ tfac, int ldv,
               int nowide) {
   static_assert(NTH == 256 || SMALL, "the shared-memory sub-panel variant needs 8 warps");
-  static_assert(!COOP || (NB == 16 && NTH == 128), "coop_update16: 16-column panels, 4 warps");
   constexpr int NWP = NTH / 32;
   extern __shared__ __align__(16) double sm[];
   const DNode nd = nodes[list[blockIdx.x]];
@@ -1200,14 +1031,11 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   double* betas = tau + NB;              // NB
   double* nrm2s = betas + NB;            // NB
   double* scals = nrm2s;                 // NB (1/(alpha-beta) per column)
-  double* zs = nrm2s + NB;               // 2 x 16 (2 x 32 for the register sub-panel)
-  double2* red = reinterpret_cast<double2*>(zs + 64);   // COOP: 2 buffers x 4 warps x 4 x 32 double2 (16 KB)
+  double* zs = nrm2s + NB;               // 2 x 16
   double* A = fact + nd.F;
   double* Tg = tfac + nd.T;
   // every column of the factor block starts on a 16-byte boundary (even F, even m)
   const bool wide = !nowide && ((m & 1) == 0) && ((nd.F & 1) == 0);
-  // the CTA-cooperative update needs 32-byte aligned columns (the panels start at multiples of 16 rows)
-  const bool coop = COOP && !nowide && ((m & 3) == 0) && ((nd.F & 3) == 0);
 #ifdef SB200_QR_TIMING
   long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -1218,7 +1046,6 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
   for (int j0 = 0; j0 < k; j0 += NB) {
     const int jb = min(NB, k - j0), mp = m - j0;
     const int mp8 = (mp + 7) & ~7;
-    const int mpz = COOP ? ((mp + 15) & ~15) : mp8;   // rows of V the trailing update may touch (zero padded)
     // ---- load panel (zero padded to mp8 rows / NB columns), clear T.  The
     // panel comes from L2 (it was just written by the trailing update): LDGSTS
     // keeps every element of the panel in flight at once instead of one L2
@@ -1227,7 +1054,7 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
       const double* src = A + j0 + (size_t)(j0 + c) * m;
       double* dst = Vs + c * ldv;
       const bool cin = c < jb;
-      for (int i = lane; i < mpz; i += 32) cp_async8(dst + i, src + i, cin && i < mp);
+      for (int i = lane; i < mp8; i += 32) cp_async8(dst + i, src + i, cin && i < mp);
     }
     cp_async_wait_all();
     for (int idx = tid; idx < NB * NB; idx += NTH) Ts[(idx % NB) + (idx / NB) * LDW] = 0.;
@@ -1564,19 +1391,23 @@ ulv_qr_kernel(const DNode* __restrict__ nodes, const int* __restrict__ list,
     // ---- trailing update: one warp per 8-column slab, no barrier inside
     const int ntrail = naug - (j0 + jb);
     // (the warp that gets the extra slab rotates with the panel index)
-    if (COOP && coop) {
-      if (ntrail > 0) coop_trailing16(A + j0 + (size_t)(j0 + jb) * m, m, mp, ntrail, Vs, ldv, Ts, LDW, red, warp, lane
-#ifdef SB200_QR_TIMING
-                                      , tph, tlast
-#endif
-                                      );
-    } else if (wide) {
+    if (wide) {
       // 16-byte aligned columns: two slabs per warp, 128-bit C and V accesses
-      const int npair = (ntrail + 15) >> 4;
-      for (int pr = (warp + (j0 / NB) * 3) % NWP; pr < npair; pr += NWP) {
-        const int c0 = j0 + jb + pr * 16;
-        slab2_update<NB>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0),
-                         max(0, min(8, naug - c0 - 8)), Vs, ldv, Ts, LDW, lane);
+      // the slabs are dealt out in contiguous runs whose lengths differ by at most one (pairs of slabs
+      // dealt round-robin leave a warp with up to two slabs more than another: 13 % of the update time at
+      // m = 256); a run is worked off in pairs, its odd slab alone
+      const int nslab = (ntrail + 7) >> 3;
+      const int wr = (warp + (j0 / NB) * 3) % NWP;
+      const int base = nslab / NWP, rem = nslab - base * NWP;
+      int sl = wr * base + min(wr, rem);
+      const int send = sl + base + (wr < rem ? 1 : 0);
+      for (; sl + 1 < send; sl += 2) {
+        const int c0 = j0 + jb + sl * 8;
+        slab2_update<NB>(A + j0 + (size_t)c0 * m, m, mp, 8, min(8, naug - c0 - 8), Vs, ldv, Ts, LDW, lane);
+      }
+      if (sl < send) {
+        const int c0 = j0 + jb + sl * 8;
+        slab2_update<NB, false>(A + j0 + (size_t)c0 * m, m, mp, min(8, naug - c0), 0, Vs, ldv, Ts, LDW, lane);
       }
     } else {
       for (int sl = (warp + (j0 / NB) * 3) % NWP; sl * 8 < ntrail; sl += NWP) {
@@ -2540,7 +2371,7 @@ void HSSEngine::build_tables() {
       d.naug = d.k + n.v_rank + n.u_rank;
     }
     d.F = foff;
-    foff += ((long long)d.m * d.naug + 3) & ~3LL;   // offsets % 4 == 0: 32-byte aligned columns when m % 4 == 0 (LDG.256)
+    foff += ((long long)d.m * d.naug + 1) & ~1LL;   // even offsets: 16-byte aligned columns when m is even
     d.T = toff;
     toff += (long long)nb_ * d.k;
     d.y_off = yoff; yoff += d.k;
@@ -2905,12 +2736,10 @@ void HSSEngine::export_ulv(double* factors, double* tfactors, long long* sizes) 
   if (tfactors) SB200_CUDA(cudaMemcpy(tfactors, tfac_.p, nt * sizeof(double), cudaMemcpyDeviceToHost));
 }
 
-template <int NB> static size_t qr_smem(int ldv, bool coop = false) {
+template <int NB> static size_t qr_smem(int ldv) {
   constexpr int LDW = ((NB + 15) / 16) * 16 + 4;
-  return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 64 + (coop ? 2048 : 0));
+  return sizeof(double) * ((size_t)ldv * NB + 2 * LDW * NB + LDW * 8 + 3 * NB + 64);
 }
-// leading dimension of the panel for the CTA-cooperative trailing update (coop_update16): % 16 == 2
-static int coop_ld(int rows) { return (rows + 15) / 16 * 16 + 2; }
 
 // ------------------------------------------------------------------ extract
 void HSSEngine::extract(int nI, const int* I, int nJ, const int* J, double* dB, int ldB,
@@ -3053,10 +2882,6 @@ void HSSEngine::factor_classes(const NodeLists& L, bool time_leaf, cudaStream_t 
       } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 1) {   // default for m <= 256
         size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 128>, smem);
         ulv_qr_kernel<16, true, 128><<<cnt, 128, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, nowide);
-      } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 5) {   // CTA-cooperative trailing update
-        const int ldc = coop_ld(mm);
-        size_t smem = qr_smem<16>(ldc, true); set_smem(ulv_qr_kernel<16, true, 128, 4, true>, smem);
-        ulv_qr_kernel<16, true, 128, 4, true><<<cnt, 128, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldc, nowide);
       } else if (nb_ == 32 && gmm <= 256 && qr_regpanel_ && qr_variant_ == 2) {
         size_t smem = qr_smem<16>(ldv); set_smem(ulv_qr_kernel<16, true, 256>, smem);
         ulv_qr_kernel<16, true, 256><<<cnt, kThreads, smem, st>>>(dn_.p, lst, fact_.p, tfac_.p, ldv, nowide);
@@ -3683,8 +3508,7 @@ double measure_fp64_dmma_peak_tflops() {
 // ---------------------------------------------------------------------------
 // Test / microbenchmark hook: `count` copies of one m x naug block (QR of the
 // first k columns) through the leaf QR kernels, outside any HSS tree.
-// variant 0: ulv_qr_kernel<16, true, 128> (right-looking), 1: qr3::ulv_qr3_kernel,
-// 2: the right-looking kernel with the CTA-cooperative trailing update (coop_update16)
+// variant 0: ulv_qr_kernel<16, true, 128> (right-looking), 1: qr3::ulv_qr3_kernel
 // ---------------------------------------------------------------------------
 void debug_qr_batch(int m, int k, int naug, int count, const double* hA, double* hOut, double* hT, int variant,
                     int reps, float* ms) {
@@ -3719,11 +3543,6 @@ void debug_qr_batch(int m, int k, int naug, int count, const double* hA, double*
     if (variant == 1) {
       set_smem(qr3::ulv_qr3_kernel, qr3::SMEM_BYTES);
       qr3::ulv_qr3_kernel<<<count, qr3::NTHREADS, qr3::SMEM_BYTES>>>(dn.p, dl.p, fact.p, tf.p, tmaps.p);
-    } else if (variant == 2) {
-      const int ldc = coop_ld(m);
-      size_t smem = qr_smem<16>(ldc, true);
-      set_smem(ulv_qr_kernel<16, true, 128, 4, true>, smem);
-      ulv_qr_kernel<16, true, 128, 4, true><<<count, 128, smem>>>(dn.p, dl.p, fact.p, tf.p, ldc, 0);
     } else {
       size_t smem = qr_smem<16>(ldv);
       set_smem(ulv_qr_kernel<16, true, 128>, smem);

@@ -83,17 +83,6 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// 256-bit global accesses (LDG.256 / STG.256, sm_100): four consecutive doubles, 32-byte aligned
-struct double4r { double x, y, z, w; };
-__device__ __forceinline__ double4r ld256(const double* p) {
-  double4r v;
-  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];\n" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st256(double* p, double x, double y, double z, double w) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
-}
-
 // pull one 128-byte line into L2 ahead of a dependent load
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));

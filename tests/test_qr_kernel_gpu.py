@@ -36,7 +36,7 @@ def check(A, k, out, T):
     return e_r, e_aug, e_nrm
 
 
-@pytest.mark.parametrize("variant", [2, 1, 0])
+@pytest.mark.parametrize("variant", [1, 0])
 @pytest.mark.parametrize("m,k,naug", SHAPES)
 def test_leaf_qr_kernel(built, m, k, naug, variant):
     sb = built
