@@ -668,20 +668,31 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
     }
     cp_async_commit();
   };
+  auto load_e = [&](double (&bn)[KS], int i0, int l0) {
+#pragma unroll
+    for (int s = 0; s < KS; s++) {
+      const int l = l0 + 4 * s + t;
+      // B[k=l][n=i] = -E[i, l]
+      bn[s] = (l < r && i0 + g < k) ? E[(i0 + g) + (size_t)l * k] : 0.;
+    }
+  };
+  const bool onepass = r <= 4 * KS;
+  double bnext[KS];
   if (PIPE) issue(0, 0);
   int buf = 0;
   for (int j0 = 0; j0 < m; j0 += TJ, buf ^= (PIPE ? 1 : 0)) {
     const int tj = min(TJ, m - j0);
     __syncthreads();
     if (PIPE) {
+      if (onepass && warp * 8 < k) load_e(bnext, warp * 8, 0);
       if (j0 + TJ < m) { issue(j0 + TJ, buf ^ 1); cp_async_wait<1>(); }
       else cp_async_wait<0>();
     } else {
-      for (int jj = warp; jj < TJ; jj += kWarps) {
-        const double* src = Dsrc + (size_t)(j0 + jj) * m;
-        const bool jin = jj < tj;
-        for (int i = lane; i < m; i += 32) Dn0[i * LD + jj] = jin ? src[i] : 0.;
-      }
+      // one buffer, but the whole tile in flight at once (LDGSTS): loads through registers kept 4 per thread
+      // in flight and exposed 8 HBM round trips per tile (ncu source page: 39 % of the samples on their STS)
+      issue(j0, 0);
+      if (onepass && warp * 8 < k) load_e(bnext, warp * 8, 0);   // under the tile's HBM round trip
+      cp_async_wait<0>();
     }
     __syncthreads();
     const double* Dn = Dn0 + (size_t)buf * m * LD;
@@ -690,7 +701,10 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
       const double* src = Dn + Ps[l] * LD;
       for (int jj = lane; jj < tj; jj += 32) W1t[(j0 + jj) + (size_t)l * m] = src[jj];
     }
-    // W0^T tile (tj x k), 8-column slabs over the warps
+    // W0^T tile (tj x k), 8-column slabs over the warps.  The E fragment of a slab (B operand, -E^T) does not
+    // depend on the column tile but cannot stay in registers for all slabs of a warp: it comes from L2 once per
+    // tile, and the fragment of the NEXT slab is requested before the products of the current one (ncu source
+    // page: 17 % of the samples waited on these loads when they were issued right before their first use).
     for (int i0 = warp * 8; i0 < k; i0 += kWarps * 8) {
       double acc[RT][2];
       const int ia = i0 + 2 * t, ib = ia + 1;       // output columns of this lane
@@ -701,11 +715,18 @@ ulv_eliminate_kernel(const DNode* __restrict__ nodes, const int* __restrict__ li
       for (int l0 = 0; l0 < r; l0 += 4 * KS) {
         double bneg[KS];
         int prow[KS];
+        if (onepass) {
+#pragma unroll
+          for (int s = 0; s < KS; s++) bneg[s] = -bnext[s];
+          if (i0 + kWarps * 8 < k) load_e(bnext, i0 + kWarps * 8, 0);
+        } else {
+          load_e(bneg, i0, l0);
+#pragma unroll
+          for (int s = 0; s < KS; s++) bneg[s] = -bneg[s];
+        }
 #pragma unroll
         for (int s = 0; s < KS; s++) {
           const int l = l0 + 4 * s + t;
-          // B[k=l][n=i] = -E[i, l]
-          bneg[s] = (l < r && i0 + g < k) ? -E[(i0 + g) + (size_t)l * k] : 0.;
           prow[s] = (l < r ? Ps[l] : 0) * LD + g;
         }
 #pragma unroll
