@@ -24,6 +24,10 @@ import time
 
 import numpy as np
 
+# stdout carries the one JSON line and nothing else: NCCL's own banner ("NCCL version ...", printed to stdout
+# when the environment sets NCCL_DEBUG=VERSION) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.setrecursionlimit(100000)
