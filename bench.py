@@ -24,9 +24,23 @@ import time
 
 import numpy as np
 
-# stdout carries the one JSON line and nothing else: NCCL's own banner ("NCCL version ...", printed to stdout
-# when the environment sets NCCL_DEBUG=VERSION) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries the one JSON line and nothing else: whatever native libraries print to fd 1 (NCCL's
+# "NCCL version ..." banner at communicator creation) is sent to stderr; the JSON line goes to the saved descriptor
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -186,7 +200,7 @@ def run_reference(args):
     reexec_with_all_cores()
     from oracle import ref
     if not ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built"})
         return
     cores = os.cpu_count() or 1
     n = args.n
@@ -239,7 +253,7 @@ def run_reference(args):
         np.save(args.dump_results + ".y.npy", y)
         np.save(args.dump_results + ".x.npy", xs)
     gf = (fa + ff + fs) / dt / 1e9
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "HSS apply+ULV GFLOP/s", "value": gf, "unit": "GFLOP/s",
         "n_gpus": 0, "steps": len(ts), "steps_requested": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3,
@@ -255,7 +269,7 @@ def run_reference(args):
                                    f"{cores}-core host (runtime max threads {got})"},
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
     if tmp is not None:
         tmp.cleanup()
 
@@ -296,6 +310,7 @@ def cpu_baseline(H, n, xs_dev, y_dev, steps=3, budget_s=30.0):
 
 # ----------------------------------------------------------------------- ours
 def run_ours(args):
+    _claim_stdout()   # before any communicator is created
     import torch
     import torch.distributed as dist
     import strumpack_b200 as sb
@@ -539,7 +554,7 @@ def run_ours(args):
             "parity": parity,
             "dist_parity": dist_parity,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -549,6 +564,7 @@ def run_blr(args):
     """configs[3]: BLRMatrix LU (compress_and_factor, RL, weak admissibility) of the root frontal matrix of the
     7-point Laplacian on a 181^3 grid (N = 32761), tile 256, tol 1e-4, one B200.  One step = one factorization.
     value: matrix resident in HBM; e2e: through SB200_d_blr_compress_and_factor with a HOST matrix (H2D inside)."""
+    _claim_stdout()
     import torch
     import strumpack_b200 as sb
     from strumpack_b200.fronts import laplacian_root_front
@@ -619,7 +635,7 @@ def run_blr(args):
                         "rank_reference": R.info()["rank"], "rank_engine": Bs.rank}
         except Exception as e:
             base = {"error": str(e)[:200]}
-    print(json.dumps({
+    emit({
         "metric": "BLR LU (compress_and_factor) time", "value": ms, "unit": "ms", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": False,
         "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -636,7 +652,7 @@ def run_blr(args):
                              "tiles read+written once (+ the input read and written once) / time",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
         "cpu_baseline": base,
-    }))
+    })
 
 
 def main():
