@@ -54,6 +54,36 @@ int main() {
   CHECK(M.rows() == 3 && C.rows() == 0 && M(2, 1) == 5.);
   A.clear();
   CHECK(A.rows() == 0 && A.data() == nullptr);
+
+  // laswp with LAPACK's 1-based pivot vector: forward applies the interchanges in order, backward undoes them
+  // (FrontBLR.cpp:527, 566 call it around trsmLNU_gemm / gemm_trsmUNN)
+  DenseMatrix<double> L(4, 2);
+  for (int i = 0; i < 4; i++) { L(i, 0) = i; L(i, 1) = 10 + i; }
+  const std::vector<int> piv = {3, 3, 4, 4};
+  L.laswp(piv, true);
+  CHECK(L(0, 0) == 2. && L(1, 0) == 0. && L(2, 0) == 3. && L(3, 0) == 1. && L(0, 1) == 12.);
+  L.laswp(piv, false);
+  for (int i = 0; i < 4; i++) CHECK(L(i, 0) == i && L(i, 1) == 10 + i);
+
+  // the admissibility matrix type of the BLR constructors (adm_t = DenseMatrix<bool>, BLRMatrix.hpp:78)
+  DenseMatrix<bool> adm(3, 3);
+  adm.fill(true);
+  for (int i = 0; i < 3; i++) adm(i, i) = false;
+  CHECK(adm(0, 1) && !adm(2, 2) && adm.rows() == 3 && adm.ld() == 3);
+
+  // ClusterTree: recursive bisection down to leaf_size (ClusterTree.hpp:104-114), leaves in order, pre-order export
+  structured::ClusterTree tree(1000);
+  tree.refine(128);
+  const std::vector<int> leaves = tree.leaf_sizes();
+  int sum = 0;
+  for (int v : leaves) { sum += v; CHECK(v >= 128 && v < 256); }
+  CHECK(sum == 1000 && leaves.size() == 4 && leaves[0] == 250);
+  std::vector<int> sizes, nchild;
+  tree.serialize(sizes, nchild);
+  CHECK(sizes.size() == 7 && sizes[0] == 1000 && nchild[0] == 2 && sizes[1] == 500 && nchild[2] == 0);
+  structured::ClusterTree flat(100);
+  flat.refine(128);
+  CHECK(flat.leaf_sizes().size() == 1 && flat.leaf_sizes()[0] == 100);
   std::printf("options ok\n");
   return 0;
 }
